@@ -1,0 +1,103 @@
+/*
+ * resr.h — C ABI of libresr.so: the sm_100a (B200) implementation of the two hot paths of
+ * Lornatang/Real_ESRGAN-PyTorch.
+ *
+ * The reference has no FFI layer: its boundary is the Python module API. Each entry point below
+ * names the reference call site it replaces (file:line under /root/reference). The reference-side binding a
+ * maintainer would add is a ctypes stub; see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - the caller owns all memory; the library never frees caller memory and never allocates across the ABI
+ *     (handles own their packed weights and cached tensor maps only);
+ *   - every function returns 0 on success, non-zero on failure; resr_last_error() gives the message
+ *     (thread-local). There is no CPU fallback: without a CUDA device every compute call fails with RESR_E_CUDA.
+ *   - image tensors are fp32 NCHW contiguous in [0,1] exactly as the reference scripts hold them.
+ */
+#ifndef RESR_H_
+#define RESR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RESR_OK 0
+#define RESR_E_INVALID 1  /* bad argument (the reference would raise ValueError / a shape error) */
+#define RESR_E_CUDA 2     /* CUDA runtime / launch failure */
+#define RESR_E_NOMEM 3    /* workspace too small */
+
+int resr_version(void);
+const char* resr_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Hot path 1 — RRDBNet x4 generator. Replaces model.Generator(3, 3, 4).forward (model.py:206-275),
+ * ResidualResidualDenseBlock.forward (model.py:123-132) and ResidualDenseBlock.forward (model.py:87-98).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct resr_generator resr_generator_t;
+
+/* model.py:207-252. Only (in=3, out=3, upscale=4) — the configuration the north star names — is implemented;
+ * anything else returns RESR_E_INVALID. */
+int resr_generator_create(resr_generator_t** out, int in_channels, int out_channels, int upscale_factor);
+void resr_generator_destroy(resr_generator_t* g);
+
+/* Number of fp32 parameters (16,697,987) and of parameter tensors (702) in state_dict order:
+ * conv1.{weight,bias}, trunk.{0..22}.rdb{1,2,3}.conv{1..5}.{weight,bias}, conv2.*, upsampling1.0.*,
+ * upsampling2.0.*, conv3.0.*, conv4.*  (model.py:223-252). */
+size_t resr_generator_num_params(void);
+int resr_generator_num_tensors(void);
+/* Element offset of tensor `index` (0..701) inside the flat parameter vector, and its element count. */
+int resr_generator_tensor_span(int index, size_t* offset, size_t* count);
+
+/* Repack OIHW fp32 weights (flat vector in state_dict order, device memory) into the tap-major 16-bit swizzled
+ * tiles the tensor-core kernel streams. Replaces load_state_dict (inference.py:32-33). */
+int resr_generator_load_params(resr_generator_t* g, const float* flat_params, void* stream);
+
+size_t resr_generator_workspace_bytes(int n, int h, int w);
+
+/* y[n,3,4h,4w] = clamp(G(x[n,3,h,w]), 0, 1). x, y fp32 NCHW contiguous. model.py:255-275. */
+int resr_generator_forward(resr_generator_t* g, const float* x, float* y, int n, int h, int w, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
+/* Same, but x_host / y_host are (pinned) HOST buffers: H2D, forward, D2H on `stream`, then a stream synchronise.
+ * This is the call inference.py:46-56 turns into. */
+int resr_generator_forward_host(resr_generator_t* g, const float* x_host, float* y_host, int n, int h, int w,
+                                void* workspace, size_t workspace_bytes, void* stream);
+
+/* Number of kernels of this library that one resr_generator_forward launches (for bench accounting). */
+int resr_generator_launches_per_forward(void);
+
+/* One 3x3 convolution through the same tensor-core kernel (test / building block).
+ * in16: NHWC 16-bit activations [n,h,w,c_total]; the first `cin` channels are convolved.
+ * weight: OIHW fp32 [cout,cin,3,3]; bias: fp32 [cout] or NULL. */
+typedef struct resr_conv_desc {
+    const void* in16;
+    int n, h, w, c_total, cin, cout;
+    int fmt_in;  /* 0 fp16, 1 bf16 */
+    int mode;    /* -1 auto, 0 shifted-descriptor loads, 1 three loads per row */
+    const float* weight;
+    const float* bias;
+    int ep_mode; /* 0 plain, 1 rdb: 0.2*v+res1, 2 rrdb: 0.2*(0.2*v+res1)+res2, 3 skip: res1+v */
+    int lrelu, clamp01;
+    void* out16;
+    int out16_fmt, out16_cstride, out16_choff, out16_up2;
+    float* outf;
+    int outf_cstride, outf_choff;
+    const float* res1;
+    const float* res2;
+    int res_cstride, res_choff;
+    float* out_nchw;
+    int out_nchw_c;
+} resr_conv_desc;
+int resr_conv3x3(const resr_conv_desc* d, void* stream);
+
+/* Layout helpers used by the generator (exposed for tests): NCHW fp32 -> NHWC 16-bit, channels zero-padded. */
+int resr_nchw_to_nhwc16(const float* x, void* out16, int n, int c, int h, int w, int c_pad, int fmt, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RESR_H_ */

@@ -1,0 +1,12 @@
+"""resr_b200 — sm_100a (B200) implementation of the two hot paths of Lornatang/Real_ESRGAN-PyTorch.
+
+Host-side mirror of the reference's Python API for those paths (same names, arguments and error behaviour):
+  model.Generator / ResidualDenseBlock / ResidualResidualDenseBlock      (/root/reference/model.py)
+  imgproc.filter2d_torch / USMSharp / DiffJPEG / random_add_*_noise_torch / random_crop (/root/reference/imgproc.py)
+Everything dispatches through ctypes into the C ABI of lib/libresr.so (include/resr.h). There is no CPU
+fallback: importing works anywhere, computing needs the built library and a B200.
+"""
+from . import _lib  # noqa: F401
+from . import model  # noqa: F401
+
+__all__ = ["_lib", "model"]

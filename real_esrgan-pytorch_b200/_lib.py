@@ -1,0 +1,86 @@
+"""ctypes binding of libresr.so (C ABI declared in include/resr.h). torch is used only for device memory and streams."""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libresr.so")
+
+
+class ResrError(RuntimeError):
+    pass
+
+
+class ConvDesc(Structure):
+    """struct resr_conv_desc (include/resr.h)."""
+    _fields_ = [
+        ("in16", c_void_p),
+        ("n", c_int), ("h", c_int), ("w", c_int), ("c_total", c_int), ("cin", c_int), ("cout", c_int),
+        ("fmt_in", c_int), ("mode", c_int),
+        ("weight", c_void_p), ("bias", c_void_p),
+        ("ep_mode", c_int), ("lrelu", c_int), ("clamp01", c_int),
+        ("out16", c_void_p),
+        ("out16_fmt", c_int), ("out16_cstride", c_int), ("out16_choff", c_int), ("out16_up2", c_int),
+        ("outf", c_void_p),
+        ("outf_cstride", c_int), ("outf_choff", c_int),
+        ("res1", c_void_p), ("res2", c_void_p),
+        ("res_cstride", c_int), ("res_choff", c_int),
+        ("out_nchw", c_void_p),
+        ("out_nchw_c", c_int),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/resr.h declares must be listed here (tests check both ways).
+SIGNATURES = {
+    "resr_version": (c_int, []),
+    "resr_last_error": (c_char_p, []),
+    "resr_generator_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int]),
+    "resr_generator_destroy": (None, [c_void_p]),
+    "resr_generator_num_params": (c_size_t, []),
+    "resr_generator_num_tensors": (c_int, []),
+    "resr_generator_tensor_span": (c_int, [c_int, POINTER(c_size_t), POINTER(c_size_t)]),
+    "resr_generator_load_params": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "resr_generator_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "resr_generator_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "resr_generator_forward_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "resr_generator_launches_per_forward": (c_int, []),
+    "resr_conv3x3": (c_int, [POINTER(ConvDesc), c_void_p]),
+    "resr_nchw_to_nhwc16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+}
+
+_lib = None
+
+
+def lib():
+    """Loads libresr.so on first use. Fails loudly: there is no other implementation to fall back to."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ResrError(
+                f"{LIB_PATH} is missing: build it with `make` (or `python -c 'import __graft_entry__ as g; g.build()'`). "
+                "resr_b200 has no CPU / PyTorch fallback.")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().resr_last_error()
+        raise ResrError(f"libresr error {rc}: {msg.decode() if msg else '?'}")
+
+
+def stream_ptr():
+    import torch
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device (or host) pointer of a torch tensor as c_void_p; None -> NULL."""
+    if t is None:
+        return c_void_p(0)
+    return c_void_p(t.data_ptr())

@@ -1,0 +1,527 @@
+// RRDBNet x4 generator forward: host orchestration + layout / weight-packing kernels + C ABI.
+// Reference: /root/reference/model.py:64-132 (RDB, RRDB), :206-275 (Generator). See DESIGN.md §3-4.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../include/resr.h"
+#include "conv3x3.cuh"
+#include "errors.h"
+
+namespace resr {
+
+// ------------------------------------------------------------------------------------------- layer table
+struct ConvSpec {
+    int cin, cout;
+    int nout;      // channels per CTA slice (32, or 16 for the 3-channel output conv)
+    int nslices;
+    int nchunks;   // ceil(cin / 64)
+    int fmt;       // operand format: 0 fp16, 1 bf16
+    size_t p_off;  // offset of weight in the flat fp32 parameter vector (bias follows the weight)
+    size_t w_off;  // byte offset of the packed weights
+    size_t b_off;  // float offset of the padded bias
+};
+
+static const int kNumConvs = 351;
+static const int kNumRRDB = 23;
+
+struct Table {
+    ConvSpec c[kNumConvs];
+    size_t n_params, pack_bytes, bias_floats;
+    Table() {
+        int i = 0;
+        auto add = [&](int cin, int cout, int fmt) {
+            ConvSpec& s = c[i++];
+            s.cin = cin;
+            s.cout = cout;
+            s.nout = cout >= 32 ? 32 : 16;
+            s.nslices = (cout + s.nout - 1) / s.nout;
+            s.nchunks = (cin + 63) / 64;
+            s.fmt = fmt;
+        };
+        add(3, 64, 0);  // conv1 (input image kept in fp16: 11 significant bits for [0,1] pixels)
+        for (int r = 0; r < kNumRRDB * 3; ++r) {
+            for (int k = 0; k < 4; ++k) add(64 + 32 * k, 32, 1);
+            add(192, 64, 1);
+        }
+        add(64, 64, 1);  // conv2 reads the bf16 trunk output
+        add(64, 64, 0);  // upsampling1.0   (tail runs with fp16 operands)
+        add(64, 64, 0);  // upsampling2.0
+        add(64, 64, 0);  // conv3.0
+        add(64, 3, 0);   // conv4
+        size_t p = 0, w = 0, b = 0;
+        for (int k = 0; k < kNumConvs; ++k) {
+            c[k].p_off = p;
+            p += static_cast<size_t>(c[k].cout) * c[k].cin * 9 + c[k].cout;
+            c[k].w_off = w;
+            w += static_cast<size_t>(c[k].nslices) * c[k].nchunks * 3 * (3 * c[k].nout) * 128;
+            c[k].b_off = b;
+            b += static_cast<size_t>(c[k].nslices) * c[k].nout;
+        }
+        n_params = p;
+        pack_bytes = w;
+        bias_floats = b;
+    }
+};
+static const Table& table() {
+    static Table t;
+    return t;
+}
+
+// ------------------------------------------------------------------------------------------- small kernels
+
+// OIHW fp32 -> [slice][chunk][dx][n = dy*NOUT + co][64 ch] 16-bit with the 128B shared-memory swizzle applied, so a
+// plain bulk copy drops a ready-to-use UMMA B operand into shared memory.
+__global__ void pack_conv_kernel(const float* __restrict__ w, const float* __restrict__ bias, uint16_t* __restrict__ wp,
+                                 float* __restrict__ bp, int cin, int cout, int nout, int nslices, int nchunks, int fmt) {
+    const int NT = 3 * nout;
+    const size_t total = static_cast<size_t>(nslices) * nchunks * 3 * NT * 64;
+    for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int k = idx % 64;
+        size_t t = idx / 64;
+        const int n = t % NT;
+        t /= NT;
+        const int dx = t % 3;
+        t /= 3;
+        const int chunk = t % nchunks;
+        const int slice = static_cast<int>(t / nchunks);
+        const int co = slice * nout + n % nout;
+        const int dy = n / nout;
+        const int ci = chunk * 64 + k;
+        float v = 0.f;
+        if (co < cout && ci < cin) v = w[((static_cast<size_t>(co) * cin + ci) * 3 + dy) * 3 + dx];
+        uint16_t bits;
+        if (fmt == 1) {
+            __nv_bfloat16 h = __float2bfloat16_rn(v);
+            bits = *reinterpret_cast<uint16_t*>(&h);
+        } else {
+            __half h = __float2half_rn(v);
+            bits = *reinterpret_cast<uint16_t*>(&h);
+        }
+        const size_t tile = ((static_cast<size_t>(slice) * nchunks + chunk) * 3 + dx) * NT * 64;  // elements
+        const size_t off = tile + static_cast<size_t>(n) * 64 + ((((k >> 3) ^ (n & 7)) << 3) | (k & 7));
+        wp[off] = bits;
+    }
+    const int nb = nslices * nout;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nb; i += gridDim.x * blockDim.x)
+        bp[i] = (i < cout && bias) ? bias[i] : 0.f;
+}
+
+// NCHW fp32 -> NHWC 16-bit with channels zero-padded to c_pad (multiple of 8).
+__global__ void nchw_to_nhwc16_kernel(const float* __restrict__ x, uint16_t* __restrict__ out, int N, int C, int H, int W,
+                                      int c_pad, int fmt) {
+    const size_t npix = static_cast<size_t>(N) * H * W;
+    const int groups = c_pad / 8;
+    const size_t total = npix * groups;
+    const size_t plane = static_cast<size_t>(H) * W;
+    for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int gch = idx % groups;
+        const size_t pix = idx / groups;
+        const size_t n = pix / plane, rem = pix % plane;
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float v[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int c = gch * 8 + 2 * j + e;
+                v[e] = c < C ? x[(n * C + c) * plane + rem] : 0.f;
+            }
+            if (fmt == 1) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(v[0], v[1]);
+                pk[j] = *reinterpret_cast<uint32_t*>(&h);
+            } else {
+                __half2 h = __floats2half2_rn(v[0], v[1]);
+                pk[j] = *reinterpret_cast<uint32_t*>(&h);
+            }
+        }
+        reinterpret_cast<uint4*>(out + pix * c_pad)[gch] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+}
+
+static int grid_for(size_t total, int block) {
+    size_t g = (total + block - 1) / block;
+    if (g > 148 * 16) g = 148 * 16;
+    if (g < 1) g = 1;
+    return static_cast<int>(g);
+}
+
+// ------------------------------------------------------------------------------------------- generator object
+struct Step {
+    int tmap;   // index into Plan::tmaps
+    int conv;   // index into the layer table
+    ConvArgs a;
+};
+
+struct Plan {
+    int N = 0, H = 0, W = 0;
+    void* ws = nullptr;
+    CUtensorMap tmaps[7];
+    std::vector<Step> steps;
+    uint16_t* xin = nullptr;
+    bool valid = false;
+};
+
+}  // namespace resr
+
+struct resr_generator {
+    uint8_t* wpack = nullptr;
+    float* bias = nullptr;
+    bool loaded = false;
+    int num_sms = 148;
+    int force_mode = -1;
+    resr::Plan plan;
+};
+
+namespace resr {
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct WsLayout {
+    size_t xin, ca, cb, f[4], t1, t2, t3, t4, total;
+};
+static WsLayout ws_layout(size_t N, size_t H, size_t W) {
+    const size_t P = N * H * W;
+    WsLayout L;
+    size_t o = 0;
+    auto take = [&](size_t bytes) {
+        const size_t at = o;
+        o = align_up(o + bytes, 1024);
+        return at;
+    };
+    L.xin = take(P * 64 * 2);
+    L.ca = take(P * 192 * 2);
+    L.cb = take(P * 192 * 2);
+    for (int i = 0; i < 4; ++i) L.f[i] = take(P * 64 * 4);
+    L.t1 = take(4 * P * 64 * 2);
+    L.t2 = take(16 * P * 64 * 2);
+    L.t3 = take(16 * P * 64 * 2);
+    L.t4 = take(16 * P * 64 * 2);
+    L.total = o;
+    return L;
+}
+
+static int build_plan(resr_generator* g, int N, int H, int W, void* ws) {
+    Plan& p = g->plan;
+    p.valid = false;
+    p.steps.clear();
+    p.N = N; p.H = H; p.W = W; p.ws = ws;
+    const WsLayout L = ws_layout(N, H, W);
+    uint8_t* base = static_cast<uint8_t*>(ws);
+    uint16_t* xin = reinterpret_cast<uint16_t*>(base + L.xin);
+    uint16_t* cbuf[2] = {reinterpret_cast<uint16_t*>(base + L.ca), reinterpret_cast<uint16_t*>(base + L.cb)};
+    float* F[4];
+    for (int i = 0; i < 4; ++i) F[i] = reinterpret_cast<float*>(base + L.f[i]);
+    uint16_t* t1 = reinterpret_cast<uint16_t*>(base + L.t1);
+    uint16_t* t2 = reinterpret_cast<uint16_t*>(base + L.t2);
+    uint16_t* t3 = reinterpret_cast<uint16_t*>(base + L.t3);
+    uint16_t* t4 = reinterpret_cast<uint16_t*>(base + L.t4);
+    p.xin = xin;
+
+    struct Geo { int H, W, BW, BN, mode; };
+    Geo geo[3];
+    for (int s = 0; s < 3; ++s) {
+        geo[s].H = H << s;
+        geo[s].W = W << s;
+        conv3x3_pick_tile(geo[s].W, &geo[s].BW, &geo[s].BN);
+        geo[s].mode = geo[s].BN == 1 ? 0 : 1;
+        if (g->force_mode >= 0) geo[s].mode = (geo[s].BN == 1) ? g->force_mode : 1;
+    }
+    // tensor maps: 0 xin, 1 ca, 2 cb (LR); 3 t1 (2x); 4 t2, 5 t3, 6 t4 (4x)
+    struct TM { const void* ptr; int C; int s; };
+    const TM tm[7] = {{xin, 64, 0}, {cbuf[0], 192, 0}, {cbuf[1], 192, 0}, {t1, 64, 1}, {t2, 64, 2}, {t3, 64, 2}, {t4, 64, 2}};
+    for (int i = 0; i < 7; ++i) {
+        const Geo& q = geo[tm[i].s];
+        const int rc = conv3x3_make_tmap(&p.tmaps[i], tm[i].ptr, N, q.H, q.W, tm[i].C, q.mode, q.BW, q.BN);
+        if (rc != 0) return set_error(RESR_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", rc);
+    }
+    // The zero-padded K chunks of conv2/conv4 of each RDB read growth channels that the current RDB has not written
+    // yet: they are multiplied by zero weights, so they only have to be finite.
+    cudaMemsetAsync(cbuf[0], 0, static_cast<size_t>(N) * H * W * 192 * 2, 0);
+    cudaMemsetAsync(cbuf[1], 0, static_cast<size_t>(N) * H * W * 192 * 2, 0);
+
+    const Table& T = table();
+    auto base_args = [&](int conv, int s) {
+        const ConvSpec& cs = T.c[conv];
+        const Geo& q = geo[s];
+        ConvArgs a;
+        memset(&a, 0, sizeof(a));
+        a.N = N; a.H = q.H; a.W = q.W; a.BW = q.BW; a.BN = q.BN;
+        a.nxs = (q.W + q.BW - 1) / q.BW;
+        a.ncg = ((N + q.BN - 1) / q.BN) * a.nxs;
+        a.nchunks = cs.nchunks;
+        a.mode = q.mode;
+        a.nstages = conv3x3_pick_stages(cs.nchunks, cs.nout);
+        a.fmt_in = cs.fmt;
+        a.rows_total = static_cast<long long>(a.ncg) * q.H;
+        a.wpack = g->wpack + cs.w_off;
+        a.bias = g->bias + cs.b_off;
+        return a;
+    };
+    auto push = [&](int tmap, int conv, const ConvArgs& a) { p.steps.push_back(Step{tmap, conv, a}); };
+
+    int conv = 0;
+    {   // conv1: model.py:258
+        ConvArgs a = base_args(conv, 0);
+        a.ep_mode = EP_PLAIN;
+        a.outf = F[0]; a.outf_cstride = 64; a.outf_choff = 0;
+        a.out16 = cbuf[0]; a.out16_fmt = 1; a.out16_cstride = 192; a.out16_choff = 0;
+        push(0, conv, a);
+        ++conv;
+    }
+    int cur = 0;  // concat buffer holding the current RDB input
+    for (int i = 0; i < kNumRRDB; ++i) {
+        float* X0 = (i == 0) ? F[0] : F[3];
+        for (int j = 0; j < 3; ++j) {
+            float* xin_master = (j == 0) ? X0 : F[j];
+            for (int k = 0; k < 4; ++k) {  // model.py:90-93
+                ConvArgs a = base_args(conv, 0);
+                a.ep_mode = EP_PLAIN; a.lrelu = 1;
+                a.out16 = cbuf[cur]; a.out16_fmt = 1; a.out16_cstride = 192; a.out16_choff = 64 + 32 * k;
+                push(1 + cur, conv, a);
+                ++conv;
+            }
+            ConvArgs a = base_args(conv, 0);  // model.py:94-96 (+ :129-130 for the third RDB)
+            a.res1 = xin_master; a.res_cstride = 64; a.res_choff = 0;
+            if (j < 2) {
+                a.ep_mode = EP_RDB;
+                a.outf = F[j + 1];
+            } else {
+                a.ep_mode = EP_RRDB;
+                a.res2 = X0;
+                a.outf = F[3];
+            }
+            a.outf_cstride = 64; a.outf_choff = 0;
+            a.out16 = cbuf[cur ^ 1]; a.out16_fmt = 1; a.out16_cstride = 192; a.out16_choff = 0;
+            push(1 + cur, conv, a);
+            ++conv;
+            cur ^= 1;
+        }
+    }
+    {   // conv2 + skip (model.py:260-262), written nearest-upsampled x2 (model.py:264) in fp16
+        ConvArgs a = base_args(conv, 0);
+        a.ep_mode = EP_SKIP; a.res1 = F[0]; a.res_cstride = 64; a.res_choff = 0;
+        a.out16 = t1; a.out16_fmt = 0; a.out16_cstride = 64; a.out16_choff = 0; a.out16_up2 = 1;
+        push(1 + cur, conv, a);
+        ++conv;
+    }
+    {   // upsampling1 conv + LeakyReLU (model.py:264), output written upsampled x2 again (model.py:265)
+        ConvArgs a = base_args(conv, 1);
+        a.lrelu = 1;
+        a.out16 = t2; a.out16_fmt = 0; a.out16_cstride = 64; a.out16_up2 = 1;
+        push(3, conv, a);
+        ++conv;
+    }
+    {   // upsampling2 conv + LeakyReLU (model.py:265)
+        ConvArgs a = base_args(conv, 2);
+        a.lrelu = 1;
+        a.out16 = t3; a.out16_fmt = 0; a.out16_cstride = 64;
+        push(4, conv, a);
+        ++conv;
+    }
+    {   // conv3 + LeakyReLU (model.py:267)
+        ConvArgs a = base_args(conv, 2);
+        a.lrelu = 1;
+        a.out16 = t4; a.out16_fmt = 0; a.out16_cstride = 64;
+        push(5, conv, a);
+        ++conv;
+    }
+    {   // conv4 + clamp (model.py:268-270): fp32 NCHW result, pointer patched per call
+        ConvArgs a = base_args(conv, 2);
+        a.clamp01 = 1;
+        a.out_nchw = nullptr; a.out_nchw_c = 3;
+        push(6, conv, a);
+        ++conv;
+    }
+    if (cudaStreamSynchronize(0) != cudaSuccess) return set_error(RESR_E_CUDA, "workspace init failed");
+    p.valid = true;
+    return RESR_OK;
+}
+
+}  // namespace resr
+
+using namespace resr;
+
+extern "C" {
+
+int resr_version(void) { return 1; }
+
+size_t resr_generator_num_params(void) { return table().n_params; }
+int resr_generator_num_tensors(void) { return 2 * kNumConvs; }
+int resr_generator_launches_per_forward(void) { return 1 + kNumConvs; }
+
+int resr_generator_tensor_span(int index, size_t* offset, size_t* count) {
+    if (index < 0 || index >= 2 * kNumConvs || !offset || !count) return set_error(RESR_E_INVALID, "bad tensor index");
+    const ConvSpec& c = table().c[index / 2];
+    const size_t wn = static_cast<size_t>(c.cout) * c.cin * 9;
+    if (index % 2 == 0) { *offset = c.p_off; *count = wn; }
+    else { *offset = c.p_off + wn; *count = c.cout; }
+    return RESR_OK;
+}
+
+int resr_generator_create(resr_generator_t** out, int in_channels, int out_channels, int upscale_factor) {
+    if (!out) return set_error(RESR_E_INVALID, "null out");
+    if (in_channels != 3 || out_channels != 3 || upscale_factor != 4)
+        return set_error(RESR_E_INVALID, "only Generator(3, 3, 4) is implemented (got %d, %d, %d)", in_channels,
+                         out_channels, upscale_factor);
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return set_error(RESR_E_CUDA, "no CUDA device: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return set_error(RESR_E_CUDA, "cudaGetDeviceProperties failed");
+    if (prop.major != 10) return set_error(RESR_E_CUDA, "libresr needs an sm_100a device (found sm_%d%d)", prop.major, prop.minor);
+    resr_generator* g = new resr_generator();
+    g->num_sms = prop.multiProcessorCount;
+    const char* fm = getenv("RESR_CONV_MODE");
+    if (fm) g->force_mode = atoi(fm);
+    if (cudaMalloc(&g->wpack, table().pack_bytes) != cudaSuccess || cudaMalloc(&g->bias, table().bias_floats * 4) != cudaSuccess) {
+        delete g;
+        return set_error(RESR_E_CUDA, "cudaMalloc of packed weights failed");
+    }
+    *out = g;
+    return RESR_OK;
+}
+
+void resr_generator_destroy(resr_generator_t* g) {
+    if (!g) return;
+    cudaFree(g->wpack);
+    cudaFree(g->bias);
+    delete g;
+}
+
+int resr_generator_load_params(resr_generator_t* g, const float* flat, void* stream) {
+    if (!g || !flat) return set_error(RESR_E_INVALID, "null argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const Table& T = table();
+    for (int k = 0; k < kNumConvs; ++k) {
+        const ConvSpec& c = T.c[k];
+        const size_t total = static_cast<size_t>(c.nslices) * c.nchunks * 3 * (3 * c.nout) * 64;
+        const float* w = flat + c.p_off;
+        const float* b = w + static_cast<size_t>(c.cout) * c.cin * 9;
+        pack_conv_kernel<<<grid_for(total, 256), 256, 0, s>>>(w, b, reinterpret_cast<uint16_t*>(g->wpack + c.w_off),
+                                                             g->bias + c.b_off, c.cin, c.cout, c.nout, c.nslices,
+                                                             c.nchunks, c.fmt);
+    }
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(RESR_E_CUDA, "pack kernels: %s", cudaGetErrorString(e));
+    g->loaded = true;
+    return RESR_OK;
+}
+
+size_t resr_generator_workspace_bytes(int n, int h, int w) {
+    if (n <= 0 || h <= 0 || w <= 0) return 0;
+    return ws_layout(n, h, w).total;
+}
+
+int resr_generator_forward(resr_generator_t* g, const float* x, float* y, int n, int h, int w, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+    if (!g || !x || !y || !workspace) return set_error(RESR_E_INVALID, "null argument");
+    if (n <= 0 || h <= 0 || w <= 0) return set_error(RESR_E_INVALID, "bad shape %dx3x%dx%d", n, h, w);
+    if (!g->loaded) return set_error(RESR_E_INVALID, "resr_generator_load_params has not been called");
+    if (workspace_bytes < resr_generator_workspace_bytes(n, h, w)) return set_error(RESR_E_NOMEM, "workspace too small");
+    if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0) return set_error(RESR_E_INVALID, "workspace must be 1024-byte aligned");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    Plan& p = g->plan;
+    if (!p.valid || p.N != n || p.H != h || p.W != w || p.ws != workspace) {
+        const int rc = build_plan(g, n, h, w, workspace);
+        if (rc != RESR_OK) return rc;
+    }
+    const size_t total = static_cast<size_t>(n) * h * w * 8;
+    nchw_to_nhwc16_kernel<<<grid_for(total, 256), 256, 0, s>>>(x, p.xin, n, 3, h, w, 64, 0);
+    const Table& T = table();
+    for (size_t i = 0; i < p.steps.size(); ++i) {
+        Step& st = p.steps[i];
+        if (i + 1 == p.steps.size()) st.a.out_nchw = y;
+        const ConvSpec& cs = T.c[st.conv];
+        const cudaError_t e = conv3x3_launch(p.tmaps[st.tmap], st.a, cs.nout, cs.nslices, g->num_sms, s);
+        if (e != cudaSuccess) return set_error(RESR_E_CUDA, "conv %d launch: %s", st.conv, cudaGetErrorString(e));
+    }
+    return RESR_OK;
+}
+
+int resr_generator_forward_host(resr_generator_t* g, const float* x_host, float* y_host, int n, int h, int w,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+    if (!x_host || !y_host) return set_error(RESR_E_INVALID, "null argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t in_bytes = static_cast<size_t>(n) * 3 * h * w * 4, out_bytes = in_bytes * 16;
+    const size_t need = resr_generator_workspace_bytes(n, h, w);
+    // device staging for x and y lives at the end of the caller's workspace
+    const size_t off_x = (need + 1023) / 1024 * 1024, off_y = off_x + (in_bytes + 1023) / 1024 * 1024;
+    if (workspace_bytes < off_y + out_bytes) return set_error(RESR_E_NOMEM, "workspace too small for host staging (need %zu)", off_y + out_bytes);
+    float* xd = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + off_x);
+    float* yd = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + off_y);
+    if (cudaMemcpyAsync(xd, x_host, in_bytes, cudaMemcpyHostToDevice, s) != cudaSuccess) return set_error(RESR_E_CUDA, "H2D failed");
+    const int rc = resr_generator_forward(g, xd, yd, n, h, w, workspace, need, stream);
+    if (rc != RESR_OK) return rc;
+    if (cudaMemcpyAsync(y_host, yd, out_bytes, cudaMemcpyDeviceToHost, s) != cudaSuccess) return set_error(RESR_E_CUDA, "D2H failed");
+    const cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return set_error(RESR_E_CUDA, "forward_host: %s", cudaGetErrorString(e));
+    return RESR_OK;
+}
+
+int resr_nchw_to_nhwc16(const float* x, void* out16, int n, int c, int h, int w, int c_pad, int fmt, void* stream) {
+    if (!x || !out16 || c_pad % 8 != 0 || c > c_pad) return set_error(RESR_E_INVALID, "bad argument");
+    const size_t total = static_cast<size_t>(n) * h * w * (c_pad / 8);
+    nchw_to_nhwc16_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, static_cast<uint16_t*>(out16), n, c, h, w, c_pad, fmt);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(RESR_E_CUDA, "nchw_to_nhwc16: %s", cudaGetErrorString(e));
+    return RESR_OK;
+}
+
+int resr_conv3x3(const resr_conv_desc* d, void* stream) {
+    if (!d || !d->in16 || !d->weight) return set_error(RESR_E_INVALID, "null argument");
+    if (d->cin > d->c_total || d->c_total % 8 != 0) return set_error(RESR_E_INVALID, "bad channel counts");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int nout = d->cout >= 32 ? 32 : 16;
+    const int nslices = (d->cout + nout - 1) / nout;
+    const int nchunks = (d->cin + 63) / 64;
+    if (nchunks * 64 > d->c_total) return set_error(RESR_E_INVALID, "c_total must cover cin rounded up to 64");
+    const size_t pack_bytes = static_cast<size_t>(nslices) * nchunks * 3 * (3 * nout) * 128;
+    uint8_t* wp = nullptr;
+    float* bp = nullptr;
+    if (cudaMalloc(&wp, pack_bytes) != cudaSuccess || cudaMalloc(&bp, nslices * nout * 4) != cudaSuccess)
+        return set_error(RESR_E_CUDA, "cudaMalloc failed");
+    pack_conv_kernel<<<grid_for(pack_bytes / 2, 256), 256, 0, s>>>(d->weight, d->bias, reinterpret_cast<uint16_t*>(wp), bp,
+                                                                 d->cin, d->cout, nout, nslices, nchunks, d->fmt_in);
+    ConvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.N = d->n; a.H = d->h; a.W = d->w;
+    conv3x3_pick_tile(d->w, &a.BW, &a.BN);
+    a.mode = d->mode >= 0 ? d->mode : (a.BN == 1 ? 0 : 1);
+    if (a.BN != 1) a.mode = 1;
+    a.nxs = (d->w + a.BW - 1) / a.BW;
+    a.ncg = ((d->n + a.BN - 1) / a.BN) * a.nxs;
+    a.nchunks = nchunks;
+    a.nstages = conv3x3_pick_stages(nchunks, nout);
+    a.fmt_in = d->fmt_in;
+    a.rows_total = static_cast<long long>(a.ncg) * d->h;
+    a.wpack = wp; a.bias = bp;
+    a.ep_mode = d->ep_mode; a.lrelu = d->lrelu; a.clamp01 = d->clamp01;
+    a.out16 = d->out16; a.out16_fmt = d->out16_fmt; a.out16_cstride = d->out16_cstride; a.out16_choff = d->out16_choff;
+    a.out16_up2 = d->out16_up2;
+    a.outf = d->outf; a.outf_cstride = d->outf_cstride; a.outf_choff = d->outf_choff;
+    a.res1 = d->res1; a.res2 = d->res2; a.res_cstride = d->res_cstride; a.res_choff = d->res_choff;
+    a.out_nchw = d->out_nchw; a.out_nchw_c = d->out_nchw_c;
+    CUtensorMap tm;
+    int rc = conv3x3_make_tmap(&tm, d->in16, d->n, d->h, d->w, d->c_total, a.mode, a.BW, a.BN);
+    cudaError_t e = cudaSuccess;
+    if (rc == 0) e = conv3x3_launch(tm, a, nout, nslices, sms, s);
+    const cudaError_t e2 = cudaStreamSynchronize(s);
+    cudaFree(wp);
+    cudaFree(bp);
+    if (rc != 0) return set_error(RESR_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", rc);
+    if (e != cudaSuccess) return set_error(RESR_E_CUDA, "conv launch: %s", cudaGetErrorString(e));
+    if (e2 != cudaSuccess) return set_error(RESR_E_CUDA, "conv run: %s", cudaGetErrorString(e2));
+    return RESR_OK;
+}
+
+}  // extern "C"

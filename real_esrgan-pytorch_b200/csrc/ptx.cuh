@@ -1,0 +1,164 @@
+// Raw PTX wrappers for sm_100a: mbarrier, TMA (cp.async.bulk[.tensor]), tcgen05 (alloc / mma / commit / ld).
+// Hand-written for this project; nothing here is portable below compute_100a.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace resr {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n"
+        ".reg .b32 rx;\n"
+        ".reg .pred px;\n"
+        "elect.sync rx|px, %1;\n"
+        "selp.b32 %0, 1, 0, px;\n"
+        "}\n"
+        : "=r"(pred)
+        : "r"(0xFFFFFFFFu));
+    return pred != 0;
+}
+
+// ---------------------------------------------------------------- mbarrier
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.b32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Spin with a hang guard: a protocol bug must surface as a trap (sticky launch error reported through the
+// C ABI), never as a wedged GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 255u) == 0 && clock64() - t0 > 4000000000ll) { __trap(); }  // ~2 s at 2 GHz
+    }
+}
+
+// ---------------------------------------------------------------- TMA
+__device__ __forceinline__ void prefetch_tmap(const void* desc) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(desc)) : "memory");
+}
+// 4-D tiled tensor load global -> shared, completion on an mbarrier (bytes).
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* desc, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
+        "r"(c2), "r"(c3)
+        : "memory");
+}
+// 1-D bulk copy global -> shared (no tensor map), completion on an mbarrier.
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---------------------------------------------------------------- tcgen05 / TMEM
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+                 "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]; kind::f16 covers bf16 and fp16 operands with fp32 accumulate.
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Arrive once on an mbarrier when every previously issued tcgen05.mma of this thread has completed.
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+// Shared-memory matrix descriptor, K-major operand, rows of `swz_bytes` (128 or 64) with the matching hardware
+// swizzle; groups of 8 rows are `sbo` bytes apart. Field layout: cute/arch/mma_sm100_desc.hpp SmemDescriptor.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo, uint32_t swz_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);        // start address  [0,14)
+    d |= static_cast<uint64_t>(0) << 16;                         // LBO (unused for swizzled K-major)
+    d |= static_cast<uint64_t>((sbo >> 4) & 0x3FFFu) << 32;      // SBO            [32,46)
+    d |= static_cast<uint64_t>(1) << 46;                         // descriptor version (sm_100)
+    d |= static_cast<uint64_t>(swz_bytes == 128 ? 2 : (swz_bytes == 64 ? 4 : 6)) << 61;  // layout type
+    return d;
+}
+// Instruction descriptor for kind::f16: fp32 accumulate, A/B both K-major, M x N tile.
+// fmt: 0 = fp16 operands, 1 = bf16 operands.
+__host__ __device__ __forceinline__ uint32_t make_idesc_f16(int fmt, int M, int N) {
+    return (1u << 4) | (static_cast<uint32_t>(fmt) << 7) | (static_cast<uint32_t>(fmt) << 10) |
+           (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+// TMEM -> registers: 32 lanes (this warp's quadrant) x 32 consecutive fp32 columns.
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+
+}  // namespace resr

@@ -1,0 +1,164 @@
+"""Host-side mirror of the reference generator API (/root/reference/model.py:64-132, 206-275).
+
+`Generator(in_channels, out_channels, upscale_factor)` is an nn.Module whose parameters carry exactly the reference
+names, shapes, initialisation and RNG consumption order (so `torch.manual_seed(s); Generator(3, 3, 4)` reproduces
+the reference weights and reference checkpoints load unchanged), but whose forward is ONE call into the C ABI
+(`resr_generator_forward`, include/resr.h) running hand-written sm_100a kernels. The sub-modules exist only to own
+parameters; they have no forward of their own — there is no PyTorch fallback path.
+"""
+import ctypes
+
+import torch
+from torch import nn
+
+from . import _lib
+
+__all__ = ["ResidualDenseBlock", "ResidualResidualDenseBlock", "Generator"]
+
+
+def _conv(cin: int, cout: int) -> nn.Conv2d:
+    return nn.Conv2d(cin, cout, (3, 3), (1, 1), (1, 1))
+
+
+class _ParamsOnly(nn.Module):
+    def forward(self, *args, **kwargs):  # pragma: no cover - guard
+        raise _lib.ResrError(
+            f"{type(self).__name__} only owns parameters; run the whole Generator (C ABI resr_generator_forward). "
+            "There is no per-block PyTorch path.")
+
+
+class ResidualDenseBlock(_ParamsOnly):
+    """Parameter container of one RDB (reference model.py:64-106): conv1..4 (C+32k -> 32), conv5 (C+128 -> C)."""
+
+    def __init__(self, channels: int, growth_channels: int) -> None:
+        super().__init__()
+        for k in range(5):
+            setattr(self, f"conv{k + 1}",
+                    _conv(channels + growth_channels * k, growth_channels if k < 4 else channels))
+        # reference model.py:100-106: kaiming_normal * 0.1, zero bias, in module order
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight)
+                m.weight.data *= 0.1
+                nn.init.constant_(m.bias, 0)
+
+
+class ResidualResidualDenseBlock(_ParamsOnly):
+    """Parameter container of one RRDB (reference model.py:109-132)."""
+
+    def __init__(self, channels: int, growth_channels: int) -> None:
+        super().__init__()
+        self.rdb1 = ResidualDenseBlock(channels, growth_channels)
+        self.rdb2 = ResidualDenseBlock(channels, growth_channels)
+        self.rdb3 = ResidualDenseBlock(channels, growth_channels)
+
+
+class Generator(nn.Module):
+    """RRDBNet x4 (23 RRDB, nf=64, gc=32). Reference: model.py:206-275."""
+
+    def __init__(self, in_channels: int, out_channels: int, upscale_factor: int) -> None:
+        super().__init__()
+        if (in_channels, out_channels, upscale_factor) != (3, 3, 4):
+            # the reference also supports x2/x1 through PixelUnshuffle (model.py:209-217); out of scope
+            raise ValueError("resr_b200.Generator implements the x4 RGB configuration Generator(3, 3, 4) only")
+        self.conv1 = _conv(in_channels, 64)
+        self.trunk = nn.Sequential(*[ResidualResidualDenseBlock(64, 32) for _ in range(23)])
+        self.conv2 = _conv(64, 64)
+        self.upsampling1 = nn.Sequential(_conv(64, 64), nn.LeakyReLU(0.2, True))
+        self.upsampling2 = nn.Sequential(_conv(64, 64), nn.LeakyReLU(0.2, True))
+        self.conv3 = nn.Sequential(_conv(64, 64), nn.LeakyReLU(0.2, True))
+        self.conv4 = _conv(64, out_channels)
+        self._handle = None
+        self._packed_version = None
+        self._flat = None
+        self._workspace = None
+
+    # ------------------------------------------------------------------ native plumbing
+    def _native(self):
+        if self._handle is None:
+            h = ctypes.c_void_p()
+            _lib.check(_lib.lib().resr_generator_create(ctypes.byref(h), 3, 3, 4))
+            self._handle = h
+        return self._handle
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h is not None:
+            try:
+                _lib.lib().resr_generator_destroy(h)
+            except Exception:
+                pass
+
+    def _param_version(self):
+        return tuple(p._version for p in self.parameters()) + (next(self.parameters()).device,)
+
+    def flat_parameters(self) -> torch.Tensor:
+        """All parameters in state_dict order as one contiguous fp32 device vector (layout of resr_generator_tensor_span)."""
+        ps = [p.detach().reshape(-1).float() for p in self.parameters()]
+        flat = torch.cat(ps)
+        assert flat.numel() == _lib.lib().resr_generator_num_params()
+        return flat
+
+    def _ensure_packed(self):
+        ver = self._param_version()
+        if self._packed_version != ver:
+            self._flat = self.flat_parameters()
+            _lib.check(_lib.lib().resr_generator_load_params(self._native(), _lib.ptr(self._flat), _lib.stream_ptr()))
+            self._packed_version = ver
+
+    def _get_workspace(self, n: int, h: int, w: int, device, extra: int = 0) -> torch.Tensor:
+        need = _lib.lib().resr_generator_workspace_bytes(n, h, w) + extra
+        ws = self._workspace
+        if ws is None or ws.numel() < need + 1024 or ws.device != device:
+            ws = torch.empty(need + 1024, dtype=torch.uint8, device=device)
+            self._workspace = ws
+        return ws
+
+    @staticmethod
+    def _aligned(ws: torch.Tensor):
+        base = ws.data_ptr()
+        off = (-base) % 1024
+        return ctypes.c_void_p(base + off), ws.numel() - off
+
+    # ------------------------------------------------------------------ reference API
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self._forward_impl(x)
+
+    def _forward_impl(self, x: torch.Tensor) -> torch.Tensor:
+        if x.dim() != 4 or x.size(1) != 3:
+            raise ValueError(f"expected [N, 3, H, W] input, got {tuple(x.shape)}")
+        if not x.is_cuda:
+            raise _lib.ResrError("resr_b200.Generator runs on a CUDA (sm_100a) device only; there is no CPU path")
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            from . import autograd  # training path
+            return autograd.generator_apply(self, x)
+        return self.infer(x)
+
+    @torch.no_grad()
+    def infer(self, x: torch.Tensor) -> torch.Tensor:
+        n, _, h, w = x.shape
+        xc = x.detach().contiguous(memory_format=torch.contiguous_format).float()
+        self._ensure_packed()
+        y = torch.empty((n, 3, 4 * h, 4 * w), dtype=torch.float32, device=x.device)
+        ws = self._get_workspace(n, h, w, x.device)
+        wp, wbytes = self._aligned(ws)
+        _lib.check(_lib.lib().resr_generator_forward(self._native(), _lib.ptr(xc), _lib.ptr(y), n, h, w, wp, wbytes,
+                                                     _lib.stream_ptr()))
+        return y
+
+    @torch.no_grad()
+    def infer_host(self, x_host: torch.Tensor, y_host: torch.Tensor = None, device=None) -> torch.Tensor:
+        """End-to-end call with HOST tensors (pinned recommended): H2D + forward + D2H inside the C ABI."""
+        device = device or next(self.parameters()).device
+        n, _, h, w = x_host.shape
+        xc = x_host.contiguous().float()
+        if y_host is None:
+            y_host = torch.empty((n, 3, 4 * h, 4 * w), dtype=torch.float32, pin_memory=True)
+        self._ensure_packed()
+        extra = xc.numel() * 4 * 17 + 4096
+        ws = self._get_workspace(n, h, w, device, extra)
+        wp, wbytes = self._aligned(ws)
+        with torch.cuda.device(device):
+            _lib.check(_lib.lib().resr_generator_forward_host(self._native(), _lib.ptr(xc), _lib.ptr(y_host), n, h, w,
+                                                              wp, wbytes, _lib.stream_ptr()))
+        return y_host

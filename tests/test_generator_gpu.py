@@ -1,0 +1,76 @@
+"""GPU parity of the RRDBNet x4 forward (C ABI resr_generator_forward behind resr_b200.model.Generator) against the
+fp32 oracle. Contract (BASELINE.json north_star): max-abs <= 2e-2 on [0,1] outputs and PSNR >= 45 dB."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+MAX_ABS = 2e-2
+MIN_PSNR = 45.0
+
+
+def _psnr(a, b):
+    mse = torch.mean((a.double() - b.double()) ** 2).item()
+    return 99.0 if mse == 0 else 10 * math.log10(1.0 / mse)
+
+
+def _make(seed):
+    import resr_b200
+    from oracle import generator as og
+    sd = og.random_state_dict(seed)
+    g = resr_b200.model.Generator(3, 3, 4)
+    g.load_state_dict(sd)
+    return g.cuda().eval(), sd
+
+
+@pytest.mark.parametrize("seed,shape", [(0, (1, 3, 32, 32)), (1, (2, 3, 24, 40)), (2, (3, 3, 16, 64)), (3, (1, 3, 20, 128))])
+def test_generator_vs_oracle(seed, shape):
+    from oracle import generator as og
+    g, sd = _make(seed)
+    torch.manual_seed(100 + seed)
+    x = torch.rand(*shape)
+    ref = og.generator_forward(x, sd)
+    with torch.no_grad():
+        y = g(x.cuda()).cpu()
+    assert y.shape == ref.shape
+    err = (y - ref).abs().max().item()
+    ps = _psnr(y, ref)
+    print(f"seed {seed} shape {shape}: max-abs {err:.3e}  psnr {ps:.2f} dB")
+    assert err <= MAX_ABS and ps >= MIN_PSNR
+
+
+def test_generator_golden_reference_vectors(golden_dir):
+    """Committed outputs of the UNMODIFIED reference (oracle/make_golden.py)."""
+    path = os.path.join(golden_dir, "generator.npz")
+    z = np.load(path)
+    for tag in ("a", "b"):
+        seed = int(z[f"{tag}_seed"])
+        g, _ = _make(seed)
+        x = torch.from_numpy(z[f"{tag}_x"])
+        ref = torch.from_numpy(z[f"{tag}_y"])
+        with torch.no_grad():
+            y = g(x.cuda()).cpu()
+        err = (y - ref).abs().max().item()
+        ps = _psnr(y, ref)
+        print(f"golden {tag}: max-abs {err:.3e} psnr {ps:.2f} dB")
+        assert err <= MAX_ABS and ps >= MIN_PSNR
+
+
+def test_generator_cfg1_shape_channels_last_and_modes(golden_dir):
+    """cfg1 (1x3x128x128): channels_last input accepted; both activation-load modes agree to fp32 noise."""
+    from oracle import generator as og
+    z = np.load(os.path.join(golden_dir, "generator.npz"))
+    g, sd = _make(0)
+    torch.manual_seed(0)
+    x = torch.rand(1, 3, 128, 128)
+    with torch.no_grad():
+        y = g(x.cuda().contiguous(memory_format=torch.channels_last)).cpu()
+    sub = torch.from_numpy(z["cfg1_y_sub"])  # reference output, every 4th pixel
+    err = (y[:, :, ::4, ::4] - sub).abs().max().item()
+    ps = _psnr(y[:, :, ::4, ::4], sub)
+    print(f"cfg1: max-abs {err:.3e} psnr {ps:.2f} dB")
+    assert err <= MAX_ABS and ps >= MIN_PSNR
