@@ -104,7 +104,8 @@ def test_conv_epilogues():
     up = torch.zeros(n, 2 * h, 2 * w, cout, device=dev, dtype=torch.float16)
     _run_conv(x16, cin, wt, b, fmt=1, ep_mode=3, res1=r1, out16=up, out16_fmt=0, out16_up2=1)
     ref_up = (r1 + conv).half().repeat_interleave(2, 1).repeat_interleave(2, 2)
-    assert (up.float() - ref_up.float()).abs().max().item() < 2e-3
+    # one fp16 ulp: the kernel rounds its own fp32 sum, which may differ from torch's in the last bit
+    assert ((up.float() - ref_up.float()).abs() <= ref_up.float().abs() * 2 ** -9 + 1e-6).all()
     # lrelu
     outf.zero_()
     _run_conv(x16, cin, wt, b, fmt=1, lrelu=1, outf=outf)

@@ -3,6 +3,7 @@ import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import resr_b200
+torch.set_grad_enabled(False)
 
 n, h, w = (int(v) for v in (sys.argv[1:4] if len(sys.argv) >= 4 else (64, 128, 128)))
 torch.manual_seed(0)
