@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of BASELINE.json ("x4 RRDBNet LR Mpix/s + degraded pairs/s ... % of roofline").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Our arm (default): one step = one RRDBNet x4 forward of a 64x3x128x128 LR batch (BASELINE.json configs[2]) per GPU,
+batch-sharded (every rank owns its own 64 images, no collective on the data path). Rank 0 prints ONE JSON line:
+  value      device-timed LR Mpix/s, inputs resident in HBM (CUDA events on the launch stream, max over ranks)
+  e2e        the same through the host-buffer C ABI call (pinned H2D + forward + D2H inside the timed region)
+  roofline   tensor-core roofline of the conv kernel against MEASURED_PEAKS.json
+  cpu_baseline  the fp32 oracle port of the reference forward on this box's host cores (bounded sample)
+  degradation   secondary object: degraded pairs/s of the second-order pipeline (configs[1], canonical plan S0)
+                with its HBM roofline (stage-sum bytes)
+`--impl reference`: the reference's own CPU implementation of the path (oracle port; /root/reference does not exist
+on the GPU box) timed on the host cores, one 1x3x128x128 image per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+FLOP_PER_LR_PIXEL = 35853696.0  # SURVEY.md §8a layer table
+METRIC = "x4 RRDBNet LR Mpix/s"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d["bf16_tflops_sustained"],
+                "source": "MEASURED_PEAKS.json"}
+    return {"hbm": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    def __init__(self, index):
+        self.rows, self.stop, self.index = [], threading.Event(), index
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_generator_baseline(seconds_budget=20.0, max_iters=5):
+    """Oracle port of the reference forward (plain torch fp32, all host cores) on cfg1 (1x3x128x128)."""
+    from oracle import generator as og
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = og.random_state_dict(0)
+    torch.manual_seed(0)
+    x = torch.rand(1, 3, 128, 128)
+    og.generator_forward(x[:, :, :32, :32], sd)  # warm-up
+    times = []
+    t_all = time.perf_counter()
+    while len(times) < max_iters and (time.perf_counter() - t_all) < seconds_budget:
+        t0 = time.perf_counter()
+        og.generator_forward(x, sd)
+        times.append(time.perf_counter() - t0)
+    med = sorted(times)[len(times) // 2]
+    return {"value": 128 * 128 / med / 1e6, "unit": "LR Mpix/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{len(times)} fp32 forwards of 1x3x128x128 (BASELINE configs[0]), median {med:.3f} s"}
+
+
+# ------------------------------------------------------------------------------------------------- degradation
+
+
+def degradation_bench(device, steps, warmup, peaks):
+    """configs[1]: 16 x 3 x 256 x 256 HR crops through the canonical plan S0; device-timed with resident inputs."""
+    import resr_b200
+    from oracle import plan as oplan
+    ip = resr_b200.imgproc
+    B, H, W = 16, 256, 256
+    plan = oplan.canonical_plan_s0(B, H, W, seed=0)
+    g = torch.Generator(device="cpu").manual_seed(0)
+    hr = torch.rand(B, 3, H, W, generator=g).to(device)
+    k = torch.zeros(B, 21, 21)
+    ax = torch.arange(21) - 10.0
+    for i in range(B):  # isotropic Gaussians of assorted support, zero-padded to 21 (dataset.py:102-103)
+        ks = 7 + 2 * (i % 8)
+        s = 0.5 + 0.3 * i
+        kk = torch.exp(-(ax[:, None] ** 2 + ax[None] ** 2) / (2 * s * s))
+        kk[(ax.abs() > ks // 2)[:, None] | (ax.abs() > ks // 2)[None]] = 0
+        k[i] = kk / kk.sum()
+    k1 = k.to(device)
+    k2 = k.flip(0).contiguous().to(device)
+    sk = torch.zeros(B, 21, 21)
+    sk[:, 10, 10] = 1
+    sk = sk.to(device)
+    # move every plan tensor to the device once (they are part of the resident input)
+    for key in ("noise1", "noise2"):
+        for kk_, v in list(plan[key].items()):
+            if isinstance(v, np.ndarray):
+                plan[key][kk_] = torch.from_numpy(v).to(device)
+    plan["jpeg1_quality"] = torch.from_numpy(plan["jpeg1_quality"]).to(device)
+    plan["jpeg2_quality"] = torch.from_numpy(plan["jpeg2_quality"]).to(device)
+
+    def step():
+        return ip.degrade_batch(hr, k1, k2, sk, plan)
+
+    for _ in range(max(3, warmup)):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        lr, hrc = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    # stage-sum algorithmic bytes of S0: 4 B x (elements read + written) per executed stage
+    E0 = B * 3 * H * W
+    e1_, e2_ = E0 // 4, E0 // 16
+    stage_bytes = 4 * (2 * E0 + 2 * E0 + (E0 + e1_) + (2 * e1_ + e1_) + 2 * e1_ + 2 * e1_ + (e1_ + e2_) + (2 * e2_ + e2_)
+                       + 2 * e2_ + 2 * e2_ + 2 * e2_ + 2 * e2_)
+    gbs = stage_bytes / (ms * 1e-3) / 1e9
+    return {"metric": "degraded pairs/s", "value": B / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms,
+            "config": {"workload": "second-order degradation, 16x3x256x256 HR -> 16x3x64x64 LR, canonical plan S0 "
+                                   "(SURVEY.md §8d), noise tensors host-fed and resident"},
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
+                         "traffic": None, "algorithmic_bytes_per_step": stage_bytes,
+                         "note": "stage-sum bytes / whole-pipeline time; blur stencils are FMA-bound (SURVEY.md §8d caveat)"}}
+
+
+# ------------------------------------------------------------------------------------------------- arms
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import generator as og
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = og.random_state_dict(0)
+    torch.manual_seed(0)
+    x = torch.rand(1, 3, 128, 128)
+    for _ in range(max(1, min(args.warmup, 2))):
+        og.generator_forward(x, sd)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        og.generator_forward(x, sd)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = 128 * 128 / dt / 1e6
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "LR Mpix/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "RRDBNet x4 (23 RRDB, nf=64, gc=32) forward, random init; each step a bounded sample "
+                                   "of the 64x3x128x128 workload: one 1x3x128x128 image on the host CPU"},
+            "cpu_baseline": {"value": val, "unit": "LR Mpix/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": "1x3x128x128 fp32 forward per step, oracle port of model.py (reference tree is not on the GPU box)"},
+            "e2e": {"value": val, "unit": "LR Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA (B200) device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    import resr_b200
+    L = resr_b200._lib
+    peaks = measured_peaks()
+    torch.set_grad_enabled(False)
+
+    N, H, W = args.batch, 128, 128
+    torch.manual_seed(0)
+    gen = resr_b200.model.Generator(3, 3, 4).to(device).eval()
+    gcpu = torch.Generator().manual_seed(1234 + rank)
+    x_host = torch.rand(N, 3, H, W, generator=gcpu).pin_memory()
+    y_host = torch.empty(N, 3, 4 * H, 4 * W).pin_memory()
+    x = x_host.to(device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing
+    for _ in range(max(3, args.warmup)):
+        y = gen(x)
+    barrier()
+    with ClockSampler(local) as clocks:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            y = gen(x)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+    t = torch.tensor([ms], device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    barrier()
+    # ---- end-to-end through the host-buffer ABI call
+    for _ in range(2):
+        gen.infer_host(x_host, y_host, device)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_steps = max(2, min(args.steps, 10))
+    e0.record()
+    for _ in range(e2e_steps):
+        gen.infer_host(x_host, y_host, device)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / e2e_steps], device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_e2e = float(t.item())
+    checksum = float(y_host[0, :, ::64, ::64].double().sum())
+
+    if rank == 0:
+        px = N * H * W
+        launches = L.lib().resr_generator_launches_per_forward()
+        tflops = FLOP_PER_LR_PIXEL * px / (ms * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": world * px / (ms * 1e-3) / 1e6, "unit": "LR Mpix/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"RRDBNet x4 (23 RRDB, nf=64, gc=32) inference, {N}x3x{H}x{W} LR per GPU, random init "
+                                   "(BASELINE.json configs[2]); batch-sharded, no collective",
+                       "precision": "bf16 MMA operands + fp32 residual stream in the trunk, fp16 operands in conv1 and the 4 tail convs, fp32 accumulate",
+                       "l2": "working set (9 GB of activations per forward) is far larger than the 126 MB L2; no flush needed"},
+            "e2e": {"value": world * px / (ms_e2e * 1e-3) / 1e6, "unit": "LR Mpix/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": y_host.numel() * 4,
+                    "api": "resr_generator_forward_host (pinned host buffers)", "checksum": checksum},
+            "gpu_launches": launches * args.steps,
+            "clocks": clocks.summary(),
+            "roofline": {"bound": "tensor", "achieved": tflops, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                         "frac": tflops / peaks["tf_sustained"], "traffic": None,
+                         "kernel": "conv3x3_tc_kernel (351 launches per forward; algorithmic FLOPs 35,853,696 per LR pixel)",
+                         "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)"},
+        }
+        if not args.no_degrade:
+            try:
+                line["degradation"] = degradation_bench(device, max(10, args.steps), args.warmup, peaks)
+            except Exception as e:  # keep the headline even if the secondary leg breaks
+                line["degradation"] = {"error": repr(e)}
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_generator_baseline()
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="LR images per GPU (64 = BASELINE configs[2])")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-degrade", action="store_true", help="skip the secondary degradation leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

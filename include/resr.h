@@ -97,6 +97,63 @@ int resr_conv3x3(const resr_conv_desc* d, void* stream);
 /* Layout helpers used by the generator (exposed for tests): NCHW fp32 -> NHWC 16-bit, channels zero-padded. */
 int resr_nchw_to_nhwc16(const float* x, void* out16, int n, int c, int h, int w, int c_pad, int fmt, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Hot path 2 — second-order degradation synthesis (train_realesrnet.py:267-377 and the imgproc.py ops it calls).
+ * Images: fp32 NCHW contiguous, device memory. Random decisions and random tensors are INPUTS (drawn by the
+ * caller: torch RNG on the host side, or recorded from the reference for parity).
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* imgproc.filter2d_torch (imgproc.py:1089-1121): reflect-pad k/2, cross-correlation; kernel [kernel_batch,k,k] with
+ * kernel_batch == b (one kernel per sample, all channels) or 1 (shared). Even k -> RESR_E_INVALID "Wrong kernel size."
+ * (the reference raises ValueError, imgproc.py:1106). */
+int resr_filter2d(const float* image, const float* kernel, float* out, int b, int c, int h, int w, int k,
+                  int kernel_batch, void* stream);
+
+/* imgproc.USMSharp(radius, sigma).forward(image, weight, threshold) (imgproc.py:1514-1537). Workspace: 3 images. */
+size_t resr_usm_workspace_bytes(int b, int c, int h, int w);
+int resr_usm_sharp(const float* image, float* out, int b, int c, int h, int w, int radius, int sigma, float weight,
+                   float threshold, void* workspace, size_t workspace_bytes, void* stream);
+
+/* torch.nn.functional.interpolate(image, size= | scale_factor=, mode=) as called at train_realesrnet.py:288, 326,
+ * 349, 366. mode: 0 area, 1 bilinear, 2 bicubic (align_corners=False, no antialias). scale_h/scale_w: the
+ * scale_factor when the reference call used scale_factor= (coordinate scale is then 1/scale_factor), or 0 when
+ * it used size= (coordinate scale in/out). planes = b*c. */
+int resr_resize(const float* image, float* out, int planes, int h_in, int w_in, int h_out, int w_out, int mode,
+                double scale_h, double scale_w, void* stream);
+
+/* imgproc.random_add_gaussian_noise_torch(clip, rounds) with its draws fed in (imgproc.py:829-863,
+ * 1029-1057): sigma[b], gray[b] in {0,1}, noise_color = randn(b,c,h,w), noise_gray = randn(h,w) or NULL when no
+ * sample drew gray. */
+int resr_gaussian_noise_apply(const float* image, float* out, const float* sigma, const float* gray,
+                              const float* noise_color, const float* noise_gray, int b, int c, int h, int w, int clip,
+                              int rounds, void* stream);
+
+/* Poisson branch (imgproc.py:866-916, 1060-1086). */
+size_t resr_poisson_workspace_bytes(int b);
+/* len(torch.unique(...)) of the u8-quantised colour image / luma per sample (imgproc.py:892, 903), no host sync.
+ * counts_gray may be NULL. */
+int resr_unique_count_u8(const float* image, int* counts_color, int* counts_gray, int b, int c, int h, int w,
+                         void* workspace, size_t workspace_bytes, void* stream);
+/* The rate tensors the reference hands to torch.poisson: q*vals [b,3,h,w] and (optional) q_gray*vals_gray [b,1,h,w]. */
+int resr_poisson_rates(const float* image, float* rate_color, float* rate_gray, int b, int c, int h, int w,
+                       void* workspace, size_t workspace_bytes, void* stream);
+/* random_add_poisson_noise_torch(clip, rounds) with its draws fed in: scale[b], gray[b],
+ * samples_color = poisson(rate_color), samples_gray = poisson(rate_gray) or NULL. */
+int resr_poisson_noise_apply(const float* image, float* out, const float* scale, const float* gray,
+                             const float* samples_color, const float* samples_gray, int b, int c, int h, int w, int clip,
+                             int rounds, void* workspace, size_t workspace_bytes, void* stream);
+
+/* imgproc.DiffJPEG(differentiable=False).forward(image, quality[b]) (imgproc.py:1462-1494). quality is NOT modified;
+ * the factor the reference writes back in place (imgproc.py:1478-1479) is returned in factor_out[b] (may be NULL).
+ * clamp_input=1 fuses the torch.clamp(out, 0, 1) of train_realesrnet.py:308. q_y/q_cb/q_cr (all or none): dump of the
+ * quantised coefficients, [b, (hp/8)*(wp/8), 8, 8] and [b, (hp/16)*(wp/16), 8, 8] with hp, wp = h, w rounded up to 16. */
+int resr_jpeg(const float* image, float* out, const float* quality, float* factor_out, int b, int h, int w,
+              int clamp_input, float* q_y, float* q_cb, float* q_cr, void* stream);
+
+/* Paired crop (imgproc.random_crop, imgproc.py:1894-1934) and the u8-grid rounding of train_realesrnet.py:374. */
+int resr_crop(const float* image, float* out, int planes, int h_in, int w_in, int top, int left, int h_out, int w_out,
+              int round_to_u8, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,707 @@
+// Hot path 2: second-order degradation ops as CUDA kernels for sm_100a (fp32 NCHW images, as the reference holds
+// them). Reference: /root/reference/imgproc.py (filter2d_torch :1089, USMSharp :1514, noise :829-1086, DiffJPEG
+// :1124-1494, random_crop :1894) and the sequencing in train_realesrnet.py:267-377. See DESIGN.md §5.
+#include <cmath>
+#include <cstring>
+
+#include "../../include/resr.h"
+#include "errors.h"
+
+namespace resr {
+
+#define RESR_LAUNCH_CHECK(what)                                                                   \
+    do {                                                                                          \
+        const cudaError_t e__ = cudaGetLastError();                                               \
+        if (e__ != cudaSuccess) return set_error(RESR_E_CUDA, what ": %s", cudaGetErrorString(e__)); \
+    } while (0)
+
+__device__ __forceinline__ int reflect_idx(int i, int n) {  // ATen reflection_pad2d rule (imgproc.py:1104)
+    i = i < 0 ? -i : i;
+    return i >= n ? 2 * (n - 1) - i : i;
+}
+
+// ===================================================================================== filter2d (a8)
+// One block = 32 x 32 output tile of one (sample, channel) plane; 256 threads, each owns 4 consecutive rows of one
+// column. The reflect-padded (32+k-1)^2 input tile and the k x k taps live in shared memory; zero rows/columns
+// at the border of the (zero-padded 7..21 -> 21) kernel are trimmed per sample.
+static constexpr int kF2dTile = 32;
+static constexpr int kF2dRows = 4;
+
+__global__ void __launch_bounds__(256) filter2d_kernel(const float* __restrict__ in, const float* __restrict__ kern,
+                                                       float* __restrict__ out, int B, int C, int H, int W, int k,
+                                                       int kern_batched) {
+    extern __shared__ float sm[];
+    const int r = k / 2;
+    const int tw = kF2dTile + k - 1;
+    float* tile = sm;                 // [tw][tw + 1]
+    float* taps = sm + tw * (tw + 1);  // [k][k]
+    __shared__ int s_lo_y, s_hi_y, s_lo_x, s_hi_x;
+    const int plane = blockIdx.z;     // b * C + c
+    const int b = plane / C;
+    const int x0 = blockIdx.x * kF2dTile, y0 = blockIdx.y * kF2dTile;
+    const float* src = in + static_cast<size_t>(plane) * H * W;
+    const float* kp = kern + (kern_batched ? static_cast<size_t>(b) * k * k : 0);
+    if (threadIdx.x == 0) { s_lo_y = k; s_hi_y = -1; s_lo_x = k; s_hi_x = -1; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < k * k; i += blockDim.x) {
+        const float v = kp[i];
+        taps[i] = v;
+        if (v != 0.f) {
+            atomicMin(&s_lo_y, i / k); atomicMax(&s_hi_y, i / k);
+            atomicMin(&s_lo_x, i % k); atomicMax(&s_hi_x, i % k);
+        }
+    }
+    for (int i = threadIdx.x; i < tw * tw; i += blockDim.x) {
+        const int ty = i / tw, tx = i % tw;
+        const int gy = reflect_idx(y0 + ty - r, H), gx = reflect_idx(x0 + tx - r, W);
+        // rows/cols beyond the image that the tile overhang would touch are clamped: their outputs are never stored
+        const int cy = min(max(gy, 0), H - 1), cx = min(max(gx, 0), W - 1);
+        tile[ty * (tw + 1) + tx] = src[static_cast<size_t>(cy) * W + cx];
+    }
+    __syncthreads();
+    const int lo_y = s_lo_y, hi_y = s_hi_y, lo_x = s_lo_x, hi_x = s_hi_x;
+    const int tx = threadIdx.x & 31;
+    const int ty0 = (threadIdx.x >> 5) * kF2dRows;
+    float acc[kF2dRows];
+#pragma unroll
+    for (int j = 0; j < kF2dRows; ++j) acc[j] = 0.f;
+    if (hi_y >= lo_y) {
+        for (int kx = lo_x; kx <= hi_x; ++kx) {
+            // sliding window down the column: input row (ty0 + rr) feeds output j with tap ky = rr - j
+            for (int rr = lo_y; rr <= hi_y + kF2dRows - 1; ++rr) {
+                const float v = tile[(ty0 + rr) * (tw + 1) + tx + kx];
+#pragma unroll
+                for (int j = 0; j < kF2dRows; ++j) {
+                    const int ky = rr - j;
+                    if (ky >= lo_y && ky <= hi_y) acc[j] = fmaf(v, taps[ky * k + kx], acc[j]);
+                }
+            }
+        }
+    }
+    const int gx = x0 + tx;
+    if (gx < W) {
+#pragma unroll
+        for (int j = 0; j < kF2dRows; ++j) {
+            const int gy = y0 + ty0 + j;
+            if (gy < H) out[static_cast<size_t>(plane) * H * W + static_cast<size_t>(gy) * W + gx] = acc[j];
+        }
+    }
+}
+
+static int filter2d_impl(const float* in, const float* kern, float* out, int B, int C, int H, int W, int k, int kb,
+                         cudaStream_t s) {
+    if (k % 2 != 1) return set_error(RESR_E_INVALID, "Wrong kernel size.");  // imgproc.py:1106 ValueError
+    if (k > 63) return set_error(RESR_E_INVALID, "kernel size %d > 63 unsupported", k);
+    if (k / 2 >= H || k / 2 >= W) return set_error(RESR_E_INVALID, "reflect padding %d needs a larger image (%dx%d)", k / 2, H, W);
+    const int tw = kF2dTile + k - 1;
+    const size_t smem = (static_cast<size_t>(tw) * (tw + 1) + static_cast<size_t>(k) * k) * sizeof(float);
+    static size_t attr_set = 0;
+    if (smem > 48 * 1024 && smem > attr_set) {
+        cudaFuncSetAttribute(filter2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        attr_set = smem;
+    }
+    dim3 grid((W + kF2dTile - 1) / kF2dTile, (H + kF2dTile - 1) / kF2dTile, B * C);
+    filter2d_kernel<<<grid, 256, smem, s>>>(in, kern, out, B, C, H, W, k, kb);
+    RESR_LAUNCH_CHECK("filter2d");
+    return RESR_OK;
+}
+
+// ===================================================================================== USM sharpen (a7)
+// The 51 x 51 kernel is an exact outer product (imgproc.py:1522-1523), so both blurs run as a horizontal and a
+// vertical 51-tap pass. Taps: cv2.getGaussianKernel(51, 0) restated on the host in double, stored as fp32.
+static constexpr int kUsmMaxTaps = 129;
+__constant__ float c_usm_taps[kUsmMaxTaps];
+
+// out = conv_x(in) with reflect padding; one block = one row segment of 256 outputs.
+__global__ void __launch_bounds__(256) usm_hpass_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W,
+                                                        int k) {
+    extern __shared__ float row[];
+    const int r = k / 2;
+    const size_t line = static_cast<size_t>(blockIdx.z) * H + blockIdx.y;
+    const int x0 = blockIdx.x * 256;
+    const float* src = in + line * W;
+    for (int i = threadIdx.x; i < 256 + k - 1; i += 256) {
+        const int gx = reflect_idx(x0 + i - r, W);
+        row[i] = src[min(max(gx, 0), W - 1)];
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x;
+    if (x < W) {
+        float acc = 0.f;
+        for (int t = 0; t < k; ++t) acc = fmaf(row[threadIdx.x + t], c_usm_taps[t], acc);
+        out[line * W + x] = acc;
+    }
+}
+
+// Vertical pass over a 32-wide x 64-tall output tile, then the fused pointwise tail.
+//   stage 0: blur = conv_y(tmp); res = x - blur; mask = |res| * 255 > threshold     -> res_out, mask_out
+//   stage 1: soft = conv_y(tmp); out = soft * clip(x + weight * res, 0, 1) + (1 - soft) * x
+__global__ void __launch_bounds__(256) usm_vpass_kernel(const float* __restrict__ tmp, const float* __restrict__ x,
+                                                        float* __restrict__ res, float* __restrict__ mask_or_out, int H,
+                                                        int W, int k, int stage, float weight, float threshold) {
+    extern __shared__ float tile[];  // [64 + k - 1][32]
+    const int r = k / 2;
+    const int plane = blockIdx.z;
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 64;
+    const size_t pbase = static_cast<size_t>(plane) * H * W;
+    const int tx = threadIdx.x & 31, tyb = threadIdx.x >> 5;  // 8 row groups
+    const int gx = min(x0 + tx, W - 1);
+    for (int i = tyb; i < 64 + k - 1; i += 8) {
+        const int gy = reflect_idx(y0 + i - r, H);
+        tile[i * 32 + tx] = tmp[pbase + static_cast<size_t>(min(max(gy, 0), H - 1)) * W + gx];
+    }
+    __syncthreads();
+    if (x0 + tx >= W) return;
+#pragma unroll 1
+    for (int j = 0; j < 8; ++j) {
+        const int ly = tyb * 8 + j;
+        const int gy = y0 + ly;
+        if (gy >= H) break;
+        float acc = 0.f;
+        for (int t = 0; t < k; ++t) acc = fmaf(tile[(ly + t) * 32 + tx], c_usm_taps[t], acc);
+        const size_t o = pbase + static_cast<size_t>(gy) * W + x0 + tx;
+        const float xv = x[o];
+        if (stage == 0) {
+            const float rv = xv - acc;                                     // imgproc.py:1528
+            res[o] = rv;
+            mask_or_out[o] = (fabsf(rv) * 255.f > threshold) ? 1.f : 0.f;  // imgproc.py:1530-1531
+        } else {
+            const float rv = res[o];
+            float sh = __fadd_rn(xv, __fmul_rn(weight, rv));                // imgproc.py:1533 (separate mul, add)
+            sh = fminf(fmaxf(sh, 0.f), 1.f);                               // imgproc.py:1534
+            mask_or_out[o] = __fadd_rn(__fmul_rn(acc, sh), __fmul_rn(1.f - acc, xv));  // imgproc.py:1535
+        }
+    }
+}
+
+static int usm_set_taps(int radius, int sigma, int* k_out) {
+    if (radius % 2 == 0) radius += 1;  // imgproc.py:1518-1519
+    if (radius > kUsmMaxTaps) return set_error(RESR_E_INVALID, "USM radius %d too large", radius);
+    double sg = sigma;
+    if (sg <= 0) sg = 0.3 * ((radius - 1) * 0.5 - 1) + 0.8;  // cv2.getGaussianKernel
+    double taps[kUsmMaxTaps], sum = 0;
+    for (int i = 0; i < radius; ++i) {
+        const double d = i - (radius - 1) * 0.5;
+        taps[i] = std::exp(-(d * d) / (2.0 * sg * sg));
+        sum += taps[i];
+    }
+    float tf[kUsmMaxTaps];
+    for (int i = 0; i < radius; ++i) tf[i] = static_cast<float>(taps[i] / sum);
+    static int cached_radius = -1, cached_sigma = -1;
+    if (cached_radius != radius || cached_sigma != sigma) {
+        if (cudaMemcpyToSymbol(c_usm_taps, tf, radius * sizeof(float)) != cudaSuccess)
+            return set_error(RESR_E_CUDA, "cudaMemcpyToSymbol failed");
+        cached_radius = radius;
+        cached_sigma = sigma;
+    }
+    *k_out = radius;
+    return RESR_OK;
+}
+
+static int usm_impl(const float* x, float* out, float* ws, int B, int C, int H, int W, int radius, int sigma, float weight,
+                    float threshold, cudaStream_t s) {
+    int k = 0;
+    const int rc = usm_set_taps(radius, sigma, &k);
+    if (rc != RESR_OK) return rc;
+    if (k / 2 >= H || k / 2 >= W) return set_error(RESR_E_INVALID, "USM reflect padding %d needs a larger image (%dx%d)", k / 2, H, W);
+    const size_t E = static_cast<size_t>(B) * C * H * W;
+    float* tmp = ws;
+    float* res = ws + E;
+    float* mask = ws + 2 * E;
+    const dim3 gh((W + 255) / 256, H, B * C), gv((W + 31) / 32, (H + 63) / 64, B * C);
+    const size_t sh = (256 + k - 1) * sizeof(float), sv = static_cast<size_t>(64 + k - 1) * 32 * sizeof(float);
+    usm_hpass_kernel<<<gh, 256, sh, s>>>(x, tmp, H, W, k);
+    usm_vpass_kernel<<<gv, 256, sv, s>>>(tmp, x, res, mask, H, W, k, 0, weight, threshold);
+    usm_hpass_kernel<<<gh, 256, sh, s>>>(mask, tmp, H, W, k);
+    usm_vpass_kernel<<<gv, 256, sv, s>>>(tmp, x, res, out, H, W, k, 1, weight, threshold);
+    RESR_LAUNCH_CHECK("usm");
+    return RESR_OK;
+}
+
+// ===================================================================================== resize (a9)
+// One thread per output element; ATen index rules in fp32 (see oracle/degrade.py resize()).
+__device__ __forceinline__ float cubic1(float x) { const float A = -0.75f; return ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f; }
+__device__ __forceinline__ float cubic2(float x) { const float A = -0.75f; return ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A; }
+
+__global__ void __launch_bounds__(256) resize_kernel(const float* __restrict__ in, float* __restrict__ out, int planes, int Hi,
+                                                     int Wi, int Ho, int Wo, int mode, float sy, float sx) {
+    const size_t total = static_cast<size_t>(planes) * Ho * Wo;
+    for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int ox = idx % Wo;
+        const int oy = (idx / Wo) % Ho;
+        const size_t p = idx / (static_cast<size_t>(Wo) * Ho);
+        const float* src = in + p * Hi * Wi;
+        float v;
+        if (mode == 0) {  // area == adaptive_avg_pool2d
+            const int ys = (oy * Hi) / Ho, ye = ((oy + 1) * Hi + Ho - 1) / Ho;
+            const int xs = (ox * Wi) / Wo, xe = ((ox + 1) * Wi + Wo - 1) / Wo;
+            float acc = 0.f;
+            for (int y = ys; y < ye; ++y)
+                for (int x = xs; x < xe; ++x) acc += src[static_cast<size_t>(y) * Wi + x];
+            v = acc / static_cast<float>((ye - ys) * (xe - xs));
+        } else if (mode == 1) {  // bilinear, align_corners=False
+            const float fy = fmaxf(fmaf(sy, oy + 0.5f, -0.5f), 0.f), fx = fmaxf(fmaf(sx, ox + 0.5f, -0.5f), 0.f);
+            const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+            const int y1 = y0 + (y0 < Hi - 1), x1 = x0 + (x0 < Wi - 1);
+            const float ly1 = fy - y0, lx1 = fx - x0, ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+            const float top = lx0 * src[static_cast<size_t>(y0) * Wi + x0] + lx1 * src[static_cast<size_t>(y0) * Wi + x1];
+            const float bot = lx0 * src[static_cast<size_t>(y1) * Wi + x0] + lx1 * src[static_cast<size_t>(y1) * Wi + x1];
+            v = ly0 * top + ly1 * bot;
+        } else {  // bicubic A=-0.75, indices clamped
+            const float fy = fmaf(sy, oy + 0.5f, -0.5f), fx = fmaf(sx, ox + 0.5f, -0.5f);
+            const float fly = floorf(fy), flx = floorf(fx);
+            const int iy = static_cast<int>(fly), ix = static_cast<int>(flx);
+            const float ty = fy - fly, tx = fx - flx;
+            const float wy[4] = {cubic2(ty + 1.f), cubic1(ty), cubic1(1.f - ty), cubic2(2.f - ty)};
+            const float wx[4] = {cubic2(tx + 1.f), cubic1(tx), cubic1(1.f - tx), cubic2(2.f - tx)};
+            v = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int yy = min(max(iy - 1 + i, 0), Hi - 1);
+                float rowacc = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int xx = min(max(ix - 1 + j, 0), Wi - 1);
+                    rowacc += src[static_cast<size_t>(yy) * Wi + xx] * wx[j];
+                }
+                v += rowacc * wy[i];
+            }
+        }
+        out[idx] = v;
+    }
+}
+
+static int grid1d(size_t total, int block = 256) {
+    size_t g = (total + block - 1) / block;
+    if (g > 148 * 32) g = 148 * 32;
+    return static_cast<int>(g < 1 ? 1 : g);
+}
+
+static int resize_impl(const float* in, float* out, int planes, int Hi, int Wi, int Ho, int Wo, int mode, double scale_h,
+                       double scale_w, cudaStream_t s) {
+    if (mode < 0 || mode > 2 || Ho <= 0 || Wo <= 0) return set_error(RESR_E_INVALID, "bad resize arguments");
+    // ATen area_pixel_compute_scale: 1/scale_factor when the caller passed scale_factor, else in/out, as float
+    const float sy = scale_h > 0 ? static_cast<float>(1.0 / scale_h) : static_cast<float>(Hi) / static_cast<float>(Ho);
+    const float sx = scale_w > 0 ? static_cast<float>(1.0 / scale_w) : static_cast<float>(Wi) / static_cast<float>(Wo);
+    const size_t total = static_cast<size_t>(planes) * Ho * Wo;
+    resize_kernel<<<grid1d(total), 256, 0, s>>>(in, out, planes, Hi, Wi, Ho, Wo, mode, sy, sx);
+    RESR_LAUNCH_CHECK("resize");
+    return RESR_OK;
+}
+
+// ===================================================================================== noise (a10, a11)
+__device__ __forceinline__ float round_u8(float x) {  // clamp(round(x*255), 0, 255) / 255, half-to-even
+    return __fdiv_rn(fminf(fmaxf(rintf(__fmul_rn(x, 255.f)), 0.f), 255.f), 255.f);
+}
+__device__ __forceinline__ float gray_of(float r, float g, float b) {  // torchvision rgb_to_grayscale
+    return __fadd_rn(__fadd_rn(__fmul_rn(0.2989f, r), __fmul_rn(0.587f, g)), __fmul_rn(0.114f, b));
+}
+
+// clip / rounds tail shared by both noise ops (imgproc.py:1048-1055, 1080-1085)
+__device__ __forceinline__ float noise_post(float v, int clip, int rounds) {
+    if (clip && rounds) return __fdiv_rn(fminf(fmaxf(rintf(__fmul_rn(v, 255.f)), 0.f), 255.f), 255.f);
+    if (clip) return fminf(fmaxf(v, 0.f), 1.f);
+    if (rounds) return __fdiv_rn(rintf(__fmul_rn(v, 255.f)), 255.f);
+    return v;
+}
+
+__global__ void __launch_bounds__(256) gaussian_noise_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                                             const float* __restrict__ sigma, const float* __restrict__ gray,
+                                                             const float* __restrict__ ncolor,
+                                                             const float* __restrict__ ngray, int B, int C, int HW, int clip,
+                                                             int rounds) {
+    const size_t total = static_cast<size_t>(B) * C * HW;
+    for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int b = idx / (static_cast<size_t>(C) * HW);
+        const int p = idx % HW;
+        const float sg = sigma[b];
+        float n = __fdiv_rn(__fmul_rn(ncolor[idx], sg), 255.f);  // imgproc.py:858
+        if (ngray) {                                             // imgproc.py:853-861
+            const float g = gray[b];
+            const float ng = __fdiv_rn(__fmul_rn(ngray[p], sg), 255.f);
+            n = __fadd_rn(__fmul_rn(n, 1.f - g), __fmul_rn(ng, g));
+        }
+        out[idx] = noise_post(__fadd_rn(x[idx], n), clip, rounds);
+    }
+}
+
+// Presence bitmap of the 256 u8 levels per sample, colour image (all channels) and luma: replaces the per-sample
+// torch.unique host syncs of imgproc.py:892, 903. bitmaps: [B][2][8] uint32 (0 = colour, 1 = gray), pre-zeroed.
+__global__ void __launch_bounds__(256) u8_presence_kernel(const float* __restrict__ x, unsigned* __restrict__ bitmaps, int C,
+                                                          int HW, int want_gray) {
+    __shared__ unsigned sbits[16];
+    if (threadIdx.x < 16) sbits[threadIdx.x] = 0;
+    __syncthreads();
+    const int b = blockIdx.y;
+    const float* src = x + static_cast<size_t>(b) * C * HW;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
+        float ch[3];
+        for (int c = 0; c < C; ++c) {
+            ch[c < 3 ? c : 2] = src[static_cast<size_t>(c) * HW + p];
+            const int lv = static_cast<int>(fminf(fmaxf(rintf(__fmul_rn(src[static_cast<size_t>(c) * HW + p], 255.f)), 0.f), 255.f));
+            atomicOr(&sbits[lv >> 5], 1u << (lv & 31));
+        }
+        if (want_gray && C == 3) {
+            const int lv = static_cast<int>(fminf(fmaxf(rintf(__fmul_rn(gray_of(ch[0], ch[1], ch[2]), 255.f)), 0.f), 255.f));
+            atomicOr(&sbits[8 + (lv >> 5)], 1u << (lv & 31));
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 16 && sbits[threadIdx.x]) atomicOr(&bitmaps[b * 16 + threadIdx.x], sbits[threadIdx.x]);
+}
+
+__global__ void unique_counts_kernel(const unsigned* __restrict__ bitmaps, int* __restrict__ counts, float* __restrict__ vals,
+                                     int B) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // b*2 + which
+    if (i >= 2 * B) return;
+    int n = 0;
+    for (int w = 0; w < 8; ++w) n += __popc(bitmaps[i * 8 + w]);
+    counts[i] = n;
+    // 2 ** ceil(log2(n)) (imgproc.py:893, 904): smallest power of two >= n
+    int v = 1;
+    while (v < n) v <<= 1;
+    vals[i] = static_cast<float>(v);
+}
+
+__global__ void __launch_bounds__(256) poisson_noise_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                                            const float* __restrict__ scale, const float* __restrict__ gray,
+                                                            const float* __restrict__ scolor,
+                                                            const float* __restrict__ sgray, const float* __restrict__ vals,
+                                                            int B, int HW, int clip, int rounds) {
+    const size_t total = static_cast<size_t>(B) * HW;
+    for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int b = idx / HW;
+        const int p = idx % HW;
+        const size_t base = static_cast<size_t>(b) * 3 * HW + p;
+        const float r = x[base], g = x[base + HW], bl = x[base + 2 * static_cast<size_t>(HW)];
+        const float vc = vals[2 * b], sc = scale[b];
+        float ng = 0.f, gm = 0.f;
+        if (sgray) {  // imgproc.py:886-897
+            gm = gray[b];
+            const float qg = round_u8(gray_of(r, g, bl));
+            ng = __fsub_rn(__fdiv_rn(sgray[idx], vals[2 * b + 1]), qg);
+        }
+        const float in3[3] = {r, g, bl};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const size_t o = base + static_cast<size_t>(c) * HW;
+            const float q = round_u8(in3[c]);                                   // imgproc.py:901
+            float n = __fsub_rn(__fdiv_rn(scolor[o], vc), q);                   // imgproc.py:906-907
+            if (sgray) n = __fadd_rn(__fmul_rn(n, 1.f - gm), __fmul_rn(ng, gm));  // imgproc.py:910
+            n = __fmul_rn(n, sc);                                               // imgproc.py:914
+            out[o] = noise_post(__fadd_rn(in3[c], n), clip, rounds);
+        }
+    }
+}
+
+// Rates handed to the Poisson sampler: rate = q * vals (imgproc.py:895, 906). Used to replay host-fed draws.
+__global__ void __launch_bounds__(256) poisson_rates_kernel(const float* __restrict__ x, const float* __restrict__ vals,
+                                                            float* __restrict__ rate_color, float* __restrict__ rate_gray,
+                                                            int B, int HW) {
+    const size_t total = static_cast<size_t>(B) * HW;
+    for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int b = idx / HW;
+        const int p = idx % HW;
+        const size_t base = static_cast<size_t>(b) * 3 * HW + p;
+        const float r = x[base], g = x[base + HW], bl = x[base + 2 * static_cast<size_t>(HW)];
+        const float vc = vals[2 * b];
+        rate_color[base] = __fmul_rn(round_u8(r), vc);
+        rate_color[base + HW] = __fmul_rn(round_u8(g), vc);
+        rate_color[base + 2 * static_cast<size_t>(HW)] = __fmul_rn(round_u8(bl), vc);
+        if (rate_gray) rate_gray[idx] = __fmul_rn(round_u8(gray_of(r, g, bl)), vals[2 * b + 1]);
+    }
+}
+
+// ===================================================================================== JPEG (a12)
+// One 256-thread block loops over 16 x 16 MCUs (4 Y blocks + Cb + Cr). DCT / IDCT are the reference's direct 64-term
+// contractions with its own cos-product table (imgproc.py:1238-1243), held in shared memory.
+__device__ float g_dct_table[4096];   // [x][y][u][v] = cos((2x+1)u pi/16) cos((2y+1)v pi/16), float64 -> float32
+__device__ float g_idct_table[4096];  // transpose: [x][y][u][v] = cos((2u+1)x pi/16) cos((2v+1)y pi/16)
+__constant__ float c_ytab[64];       // transposed Annex-K luma table (imgproc.py:40-45), [u][v]
+__constant__ float c_ctab[64];       // chroma table (imgproc.py:46-49)
+
+__global__ void __launch_bounds__(256) jpeg_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                                   const float* __restrict__ quality, float* __restrict__ factor_out,
+                                                   int B, int H, int W, int clamp_in, float* __restrict__ qy,
+                                                   float* __restrict__ qcb, float* __restrict__ qcr) {
+    __shared__ float T[4096];
+    __shared__ float Ti[4096];
+    __shared__ float pix[6][64];   // level-shifted samples of the 6 blocks, [x*8+y] = row-major inside the block
+    __shared__ float coef[6][64];  // dequantised, alpha-scaled coefficients
+    __shared__ float cbf[16][17], crf[16][17];
+    for (int i = threadIdx.x; i < 4096; i += 256) { T[i] = g_dct_table[i]; Ti[i] = g_idct_table[i]; }
+    const int Hp = (H + 15) / 16 * 16, Wp = (W + 15) / 16 * 16;
+    const int mw = Wp / 16, mh = Hp / 16;
+    const int nmcu = B * mh * mw;
+    const int t = threadIdx.x;
+    const int py = t >> 4, px = t & 15;
+    const size_t HW = static_cast<size_t>(H) * W;
+    __syncthreads();
+    for (int m = blockIdx.x; m < nmcu; m += gridDim.x) {
+        const int b = m / (mh * mw);
+        const int my = (m / mw) % mh, mx = m % mw;
+        // quality -> factor in fp32 tensor arithmetic (imgproc.py:1124-1141 applied per element at :1478-1479)
+        const float q = quality[b];
+        const float factor = __fdiv_rn(q < 50.f ? __fdiv_rn(5000.f, q) : __fsub_rn(200.f, __fmul_rn(q, 2.f)), 100.f);
+        if (factor_out && my == 0 && mx == 0 && t == 0) factor_out[b] = factor;
+        const int gy = my * 16 + py, gx = mx * 16 + px;
+        float r = 0.f, g = 0.f, bl = 0.f;  // zero padding to a multiple of 16 (imgproc.py:1489)
+        if (gy < H && gx < W) {
+            const size_t o = static_cast<size_t>(b) * 3 * HW + static_cast<size_t>(gy) * W + gx;
+            r = x[o]; g = x[o + HW]; bl = x[o + 2 * HW];
+            if (clamp_in) { r = fminf(fmaxf(r, 0.f), 1.f); g = fminf(fmaxf(g, 0.f), 1.f); bl = fminf(fmaxf(bl, 0.f), 1.f); }
+        }
+        r = __fmul_rn(r, 255.f); g = __fmul_rn(g, 255.f); bl = __fmul_rn(bl, 255.f);  // imgproc.py:1318
+        // imgproc.py:1195-1208 (matrix rows as float32 constants)
+        const float yv = 0.299f * r + 0.587f * g + 0.114f * bl;
+        const float cb = -0.168736f * r + -0.331264f * g + 0.5f * bl + 128.f;
+        const float cr = 0.5f * r + -0.418688f * g + -0.081312f * bl + 128.f;
+        pix[(py >> 3) * 2 + (px >> 3)][(py & 7) * 8 + (px & 7)] = yv - 128.f;
+        cbf[py][px] = cb;
+        crf[py][px] = cr;
+        __syncthreads();
+        if (t < 128) {  // 2x2 mean (imgproc.py:1216-1219)
+            const int c = t >> 6, i = t & 63, cy = i >> 3, cx = i & 7;
+            float (*src)[17] = c ? crf : cbf;
+            const float s = (src[2 * cy][2 * cx] + src[2 * cy][2 * cx + 1]) + (src[2 * cy + 1][2 * cx] + src[2 * cy + 1][2 * cx + 1]);
+            pix[4 + c][i] = s * 0.25f - 128.f;
+        }
+        __syncthreads();
+        // forward DCT + quantise + dequantise: 384 coefficients over 256 threads (two rounds)
+        for (int ci = t; ci < 384; ci += 256) {
+            const int blk = ci >> 6, uv = ci & 63;
+            float acc = 0.f;
+#pragma unroll 8
+            for (int xy = 0; xy < 64; ++xy) acc = fmaf(pix[blk][xy], T[xy * 64 + uv], acc);
+            const int u = uv >> 3, v = uv & 7;
+            const float alpha = (u == 0 ? 0.70710678118654752f : 1.f) * (v == 0 ? 0.70710678118654752f : 1.f);
+            const float scale = (u == 0 && v == 0) ? 0.125f : ((u == 0 || v == 0) ? static_cast<float>(0.25 * 0.70710678118654752) : 0.25f);
+            const float d = __fmul_rn(scale, acc);                                // imgproc.py:1249
+            const float tq = __fmul_rn(blk < 4 ? c_ytab[uv] : c_ctab[uv], factor);  // imgproc.py:1270, 1289
+            const float qc = rintf(__fdiv_rn(d, tq));                             // imgproc.py:1272-1274
+            if (qy) {  // optional dump of the quantised coefficients (tests)
+                if (blk < 4) {
+                    const int byi = my * 2 + (blk >> 1), bxi = mx * 2 + (blk & 1);
+                    qy[(static_cast<size_t>(b) * (Hp / 8) * (Wp / 8) + static_cast<size_t>(byi) * (Wp / 8) + bxi) * 64 + uv] = qc;
+                } else {
+                    float* dst = blk == 4 ? qcb : qcr;
+                    dst[(static_cast<size_t>(b) * mh * mw + static_cast<size_t>(my) * mw + mx) * 64 + uv] = qc;
+                }
+            }
+            coef[blk][uv] = __fmul_rn(__fmul_rn(qc, tq), alpha);                  // imgproc.py:1331, 1366
+        }
+        __syncthreads();
+        // inverse DCT per pixel: out[u,v] = 0.25 * sum_{x,y} coef[x,y] * cos((2u+1)x..)cos((2v+1)y..) + 128
+        float rec[3];
+        {
+            const int blk = (py >> 3) * 2 + (px >> 3), uv = (py & 7) * 8 + (px & 7);
+            float acc = 0.f;
+#pragma unroll 8
+            for (int xy = 0; xy < 64; ++xy) acc = fmaf(coef[blk][xy], Ti[xy * 64 + uv], acc);
+            rec[0] = __fadd_rn(__fmul_rn(0.25f, acc), 128.f);
+        }
+        __syncthreads();  // everyone is done reading pix[] as forward-DCT input; reuse cbf/crf for decoded chroma
+        if (t < 128) {
+            const int c = t >> 6, uv = t & 63;
+            float acc = 0.f;
+#pragma unroll 8
+            for (int xy = 0; xy < 64; ++xy) acc = fmaf(coef[4 + c][xy], Ti[xy * 64 + uv], acc);
+            (c ? crf : cbf)[uv >> 3][uv & 7] = __fadd_rn(__fmul_rn(0.25f, acc), 128.f);
+        }
+        __syncthreads();
+        rec[1] = cbf[py >> 1][px >> 1] - 128.f;  // nearest 2x repeat (imgproc.py:1392-1400) + shift (:1412)
+        rec[2] = crf[py >> 1][px >> 1] - 128.f;
+        if (gy < H && gx < W) {
+            // imgproc.py:1405-1419
+            const float ro = rec[0] + 1.402f * rec[2];
+            const float go = rec[0] + -0.344136f * rec[1] + -0.714136f * rec[2];
+            const float bo = rec[0] + 1.772f * rec[1];
+            const size_t o = static_cast<size_t>(b) * 3 * HW + static_cast<size_t>(gy) * W + gx;
+            out[o] = __fdiv_rn(fminf(255.f, fmaxf(0.f, ro)), 255.f);  // imgproc.py:1453-1455
+            out[o + HW] = __fdiv_rn(fminf(255.f, fmaxf(0.f, go)), 255.f);
+            out[o + 2 * HW] = __fdiv_rn(fminf(255.f, fmaxf(0.f, bo)), 255.f);
+        }
+        __syncthreads();
+    }
+}
+
+static int jpeg_init_tables() {
+    static bool done = false;
+    if (done) return RESR_OK;
+    static float T[4096], Ti[4096];
+    const double pi = 3.14159265358979323846;
+    for (int x = 0; x < 8; ++x)
+        for (int y = 0; y < 8; ++y)
+            for (int u = 0; u < 8; ++u)
+                for (int v = 0; v < 8; ++v)
+                    T[((x * 8 + y) * 8 + u) * 8 + v] =
+                        static_cast<float>(std::cos((2 * x + 1) * u * pi / 16) * std::cos((2 * y + 1) * v * pi / 16));
+    for (int a = 0; a < 64; ++a)
+        for (int b = 0; b < 64; ++b) Ti[a * 64 + b] = T[b * 64 + a];
+    static const float ybase[64] = {16, 11, 10, 16, 24, 40, 51, 61, 12, 12, 14, 19, 26, 58, 60, 55, 14, 13, 16, 24, 40, 57,
+                                    69, 56, 14, 17, 22, 29, 51, 87, 80, 62, 18, 22, 37, 56, 68, 109, 103, 77, 24, 35, 55,
+                                    64, 81, 104, 113, 92, 49, 64, 78, 87, 103, 121, 120, 101, 72, 92, 95, 98, 112, 100, 103, 99};
+    static const float cbase[16] = {17, 18, 24, 47, 18, 21, 26, 66, 24, 26, 56, 99, 47, 66, 99, 99};
+    float yt[64], ct[64];
+    for (int u = 0; u < 8; ++u)
+        for (int v = 0; v < 8; ++v) {
+            yt[u * 8 + v] = ybase[v * 8 + u];  // .T (imgproc.py:45)
+            ct[u * 8 + v] = (u < 4 && v < 4) ? cbase[v * 4 + u] : 99.f;
+        }
+    if (cudaMemcpyToSymbol(g_dct_table, T, sizeof(T)) != cudaSuccess || cudaMemcpyToSymbol(g_idct_table, Ti, sizeof(Ti)) != cudaSuccess || cudaMemcpyToSymbol(c_ytab, yt, sizeof(yt)) != cudaSuccess ||
+        cudaMemcpyToSymbol(c_ctab, ct, sizeof(ct)) != cudaSuccess)
+        return set_error(RESR_E_CUDA, "JPEG table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    done = true;
+    return RESR_OK;
+}
+
+static int jpeg_impl(const float* x, float* out, const float* quality, float* factor_out, int B, int H, int W, int clamp_in,
+                     float* qy, float* qcb, float* qcr, cudaStream_t s) {
+    const int rc = jpeg_init_tables();
+    if (rc != RESR_OK) return rc;
+    const int nmcu = B * ((H + 15) / 16) * ((W + 15) / 16);
+    const int grid = nmcu < 148 * 4 ? nmcu : 148 * 4;
+    jpeg_kernel<<<grid, 256, 0, s>>>(x, out, quality, factor_out, B, H, W, clamp_in, qy, qcb, qcr);
+    RESR_LAUNCH_CHECK("jpeg");
+    return RESR_OK;
+}
+
+// ===================================================================================== round + crop (a13)
+__global__ void __launch_bounds__(256) crop_kernel(const float* __restrict__ in, float* __restrict__ out, int planes, int Hi,
+                                                   int Wi, int top, int left, int Ho, int Wo, int round_to_u8) {
+    const size_t total = static_cast<size_t>(planes) * Ho * Wo;
+    for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int ox = idx % Wo;
+        const int oy = (idx / Wo) % Ho;
+        const size_t p = idx / (static_cast<size_t>(Wo) * Ho);
+        float v = in[(p * Hi + top + oy) * Wi + left + ox];
+        if (round_to_u8) v = round_u8(v);  // train_realesrnet.py:374
+        out[idx] = v;
+    }
+}
+
+}  // namespace resr
+
+using namespace resr;
+
+extern "C" {
+
+int resr_filter2d(const float* image, const float* kernel, float* out, int b, int c, int h, int w, int k, int kernel_batch,
+                  void* stream) {
+    if (!image || !kernel || !out) return set_error(RESR_E_INVALID, "null argument");
+    if (kernel_batch != 1 && kernel_batch != b) return set_error(RESR_E_INVALID, "kernel batch %d must be 1 or %d", kernel_batch, b);
+    return filter2d_impl(image, kernel, out, b, c, h, w, k, kernel_batch != 1, static_cast<cudaStream_t>(stream));
+}
+
+size_t resr_usm_workspace_bytes(int b, int c, int h, int w) { return static_cast<size_t>(b) * c * h * w * 4 * 3; }
+
+int resr_usm_sharp(const float* image, float* out, int b, int c, int h, int w, int radius, int sigma, float weight,
+                   float threshold, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!image || !out || !workspace) return set_error(RESR_E_INVALID, "null argument");
+    if (workspace_bytes < resr_usm_workspace_bytes(b, c, h, w)) return set_error(RESR_E_NOMEM, "USM workspace too small");
+    return usm_impl(image, out, static_cast<float*>(workspace), b, c, h, w, radius, sigma, weight, threshold,
+                    static_cast<cudaStream_t>(stream));
+}
+
+int resr_resize(const float* image, float* out, int planes, int h_in, int w_in, int h_out, int w_out, int mode,
+                double scale_h, double scale_w, void* stream) {
+    if (!image || !out) return set_error(RESR_E_INVALID, "null argument");
+    return resize_impl(image, out, planes, h_in, w_in, h_out, w_out, mode, scale_h, scale_w, static_cast<cudaStream_t>(stream));
+}
+
+int resr_gaussian_noise_apply(const float* image, float* out, const float* sigma, const float* gray,
+                              const float* noise_color, const float* noise_gray, int b, int c, int h, int w, int clip,
+                              int rounds, void* stream) {
+    if (!image || !out || !sigma || !noise_color) return set_error(RESR_E_INVALID, "null argument");
+    if (noise_gray && !gray) return set_error(RESR_E_INVALID, "noise_gray needs gray flags");
+    const size_t total = static_cast<size_t>(b) * c * h * w;
+    gaussian_noise_kernel<<<grid1d(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(image, out, sigma, gray, noise_color,
+                                                                                       noise_gray, b, c, h * w, clip, rounds);
+    RESR_LAUNCH_CHECK("gaussian_noise");
+    return RESR_OK;
+}
+
+size_t resr_poisson_workspace_bytes(int b) { return static_cast<size_t>(b) * (16 * 4 + 2 * 4 + 2 * 4); }
+
+static int poisson_prepare(const float* image, int b, int c, int h, int w, int want_gray, void* workspace, size_t wsb,
+                           cudaStream_t s, unsigned** bm, int** counts, float** vals) {
+    if (c != 3) return set_error(RESR_E_INVALID, "Poisson noise expects RGB images");
+    if (wsb < resr_poisson_workspace_bytes(b)) return set_error(RESR_E_NOMEM, "Poisson workspace too small");
+    *bm = static_cast<unsigned*>(workspace);
+    *counts = reinterpret_cast<int*>(*bm + static_cast<size_t>(b) * 16);
+    *vals = reinterpret_cast<float*>(*counts + 2 * b);
+    cudaMemsetAsync(*bm, 0, static_cast<size_t>(b) * 16 * 4, s);
+    const int HW = h * w;
+    int gx = (HW + 255) / 256;
+    if (gx > 64) gx = 64;
+    u8_presence_kernel<<<dim3(gx, b), 256, 0, s>>>(image, *bm, c, HW, want_gray);
+    unique_counts_kernel<<<(2 * b + 127) / 128, 128, 0, s>>>(*bm, *counts, *vals, b);
+    RESR_LAUNCH_CHECK("poisson_prepare");
+    return RESR_OK;
+}
+
+int resr_unique_count_u8(const float* image, int* counts_color, int* counts_gray, int b, int c, int h, int w, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+    if (!image || !counts_color || !workspace) return set_error(RESR_E_INVALID, "null argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    unsigned* bm; int* counts; float* vals;
+    const int rc = poisson_prepare(image, b, c, h, w, counts_gray != nullptr, workspace, workspace_bytes, s, &bm, &counts, &vals);
+    if (rc != RESR_OK) return rc;
+    cudaMemcpy2DAsync(counts_color, 4, counts, 8, 4, b, cudaMemcpyDeviceToDevice, s);
+    if (counts_gray) cudaMemcpy2DAsync(counts_gray, 4, counts + 1, 8, 4, b, cudaMemcpyDeviceToDevice, s);
+    RESR_LAUNCH_CHECK("unique_count");
+    return RESR_OK;
+}
+
+int resr_poisson_rates(const float* image, float* rate_color, float* rate_gray, int b, int c, int h, int w, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+    if (!image || !rate_color || !workspace) return set_error(RESR_E_INVALID, "null argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    unsigned* bm; int* counts; float* vals;
+    const int rc = poisson_prepare(image, b, c, h, w, rate_gray != nullptr, workspace, workspace_bytes, s, &bm, &counts, &vals);
+    if (rc != RESR_OK) return rc;
+    poisson_rates_kernel<<<grid1d(static_cast<size_t>(b) * h * w), 256, 0, s>>>(image, vals, rate_color, rate_gray, b, h * w);
+    RESR_LAUNCH_CHECK("poisson_rates");
+    return RESR_OK;
+}
+
+int resr_poisson_noise_apply(const float* image, float* out, const float* scale, const float* gray, const float* samples_color,
+                             const float* samples_gray, int b, int c, int h, int w, int clip, int rounds, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+    if (!image || !out || !scale || !samples_color || !workspace) return set_error(RESR_E_INVALID, "null argument");
+    if (samples_gray && !gray) return set_error(RESR_E_INVALID, "samples_gray needs gray flags");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    unsigned* bm; int* counts; float* vals;
+    const int rc = poisson_prepare(image, b, c, h, w, samples_gray != nullptr, workspace, workspace_bytes, s, &bm, &counts, &vals);
+    if (rc != RESR_OK) return rc;
+    poisson_noise_kernel<<<grid1d(static_cast<size_t>(b) * h * w), 256, 0, s>>>(image, out, scale, gray, samples_color,
+                                                                              samples_gray, vals, b, h * w, clip, rounds);
+    RESR_LAUNCH_CHECK("poisson_noise");
+    return RESR_OK;
+}
+
+int resr_jpeg(const float* image, float* out, const float* quality, float* factor_out, int b, int h, int w, int clamp_input,
+              float* q_y, float* q_cb, float* q_cr, void* stream) {
+    if (!image || !out || !quality) return set_error(RESR_E_INVALID, "null argument");
+    if ((q_y != nullptr) != (q_cb != nullptr) || (q_y != nullptr) != (q_cr != nullptr))
+        return set_error(RESR_E_INVALID, "pass all three coefficient dumps or none");
+    return jpeg_impl(image, out, quality, factor_out, b, h, w, clamp_input, q_y, q_cb, q_cr, static_cast<cudaStream_t>(stream));
+}
+
+int resr_crop(const float* image, float* out, int planes, int h_in, int w_in, int top, int left, int h_out, int w_out,
+              int round_to_u8, void* stream) {
+    if (!image || !out) return set_error(RESR_E_INVALID, "null argument");
+    if (top < 0 || left < 0 || top + h_out > h_in || left + w_out > w_in) return set_error(RESR_E_INVALID, "crop window out of range");
+    const size_t total = static_cast<size_t>(planes) * h_out * w_out;
+    crop_kernel<<<grid1d(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(image, out, planes, h_in, w_in, top, left, h_out,
+                                                                            w_out, round_to_u8);
+    RESR_LAUNCH_CHECK("crop");
+    return RESR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,318 @@
+"""Host-side mirror of the reference degradation API (/root/reference/imgproc.py) — same names, arguments and error
+behaviour — dispatching into the C ABI (include/resr.h). CUDA fp32 tensors in, new CUDA tensors out; random numbers
+come from the global torch / `random` generators in the reference's draw order. No CPU / PyTorch fallback.
+
+  filter2d_torch                     imgproc.py:1089-1121
+  USMSharp                           imgproc.py:1514-1537
+  DiffJPEG                           imgproc.py:1462-1494
+  random_add_gaussian_noise_torch    imgproc.py:1029-1057 (-> :919-940 -> :829-863)
+  random_add_poisson_noise_torch     imgproc.py:1060-1086 (-> :943-964 -> :866-916)
+  random_crop                        imgproc.py:1894-1934
+  interpolate                        torch.nn.functional.interpolate as called by train_realesrnet.py:288,326,349,366
+  degrade_batch                      the whole block train_realesrnet.py:267-377 driven by a plan
+"""
+import ctypes
+import math
+import random
+
+import torch
+from torch import nn
+
+from . import _lib
+
+__all__ = ["filter2d_torch", "USMSharp", "DiffJPEG", "random_add_gaussian_noise_torch",
+           "random_add_poisson_noise_torch", "random_crop", "interpolate", "degrade_batch"]
+
+_MODES = {"area": 0, "bilinear": 1, "bicubic": 2}
+
+
+def _prep(image: torch.Tensor) -> torch.Tensor:
+    if not image.is_cuda:
+        raise _lib.ResrError("resr_b200.imgproc runs on CUDA tensors only; there is no CPU path")
+    return image.detach().contiguous().float()
+
+
+_ws_cache = {}
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    key = (device.type, device.index)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def filter2d_torch(image: torch.Tensor, kernel: torch.Tensor) -> torch.Tensor:
+    """PyTorch-API twin of cv2.filter2D: reflect pad + cross-correlation (reference imgproc.py:1089-1121)."""
+    k = kernel.size(-1)
+    b, c, h, w = image.size()
+    if k % 2 != 1:
+        raise ValueError("Wrong kernel size.")
+    x = _prep(image)
+    kern = _prep(kernel).view(-1, k, k)
+    kb = kern.size(0)
+    if kb != 1 and kb != b:
+        raise RuntimeError(f"kernel batch {kb} does not match image batch {b}")
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().resr_filter2d(_lib.ptr(x), _lib.ptr(kern), _lib.ptr(out), b, c, h, w, k, kb, _lib.stream_ptr()))
+    return out
+
+
+class USMSharp(nn.Module):
+    """Unsharp-mask sharpening (reference imgproc.py:1514-1537)."""
+
+    def __init__(self, radius: int, sigma: int) -> None:
+        super().__init__()
+        if radius % 2 == 0:
+            radius += 1
+        self.radius = radius
+        self.sigma = sigma
+        # same buffer as the reference (imgproc.py:1522-1524) so state_dict()/.to() behave alike; the CUDA path
+        # rebuilds the separable taps from (radius, sigma)
+        s = sigma if sigma > 0 else 0.3 * ((radius - 1) * 0.5 - 1) + 0.8
+        xs = torch.arange(radius, dtype=torch.float64) - (radius - 1) * 0.5
+        k1 = torch.exp(-(xs * xs) / (2.0 * s * s))
+        k1 = k1 / k1.sum()
+        self.register_buffer("kernel", torch.outer(k1, k1).float().unsqueeze_(0))
+
+    def forward(self, x: torch.Tensor, weight: float, threshold: int) -> torch.Tensor:
+        b, c, h, w = x.size()
+        xi = _prep(x)
+        out = torch.empty_like(xi)
+        need = _lib.lib().resr_usm_workspace_bytes(b, c, h, w)
+        ws = _workspace(need, xi.device)
+        _lib.check(_lib.lib().resr_usm_sharp(_lib.ptr(xi), _lib.ptr(out), b, c, h, w, self.radius, int(self.sigma),
+                                             float(weight), float(threshold), _lib.ptr(ws), ws.numel(),
+                                             _lib.stream_ptr()))
+        return out
+
+
+class DiffJPEG(nn.Module):
+    """JPEG compress + decompress round trip (reference imgproc.py:1462-1494). differentiable=True (the cubic
+    rounding surrogate, imgproc.py:1180-1192) is not on the degradation path and is not implemented."""
+
+    def __init__(self, differentiable: bool) -> None:
+        super().__init__()
+        if differentiable:
+            raise NotImplementedError("resr_b200.DiffJPEG implements differentiable=False (the path the training loops use)")
+
+    def forward(self, x: torch.Tensor, quality, *, return_coefficients: bool = False, clamp_input: bool = False):
+        """clamp_input=True fuses the torch.clamp(out, 0, 1) the training loop applies first (train_realesrnet.py:308)."""
+        b, c, h, w = x.size()
+        if c != 3:
+            raise ValueError("DiffJPEG expects RGB input")
+        xi = _prep(x)
+        if isinstance(quality, (int, float)):
+            q = torch.full((b,), float(quality), dtype=torch.float32, device=xi.device)
+            write_back = None
+        else:
+            write_back = quality
+            q = quality.detach().to(device=xi.device, dtype=torch.float32).contiguous()
+        out = torch.empty_like(xi)
+        factor = torch.empty(b, dtype=torch.float32, device=xi.device)
+        qy = qcb = qcr = None
+        if return_coefficients:
+            hp, wp = (h + 15) // 16 * 16, (w + 15) // 16 * 16
+            qy = torch.empty(b, (hp // 8) * (wp // 8), 8, 8, device=xi.device)
+            qcb = torch.empty(b, (hp // 16) * (wp // 16), 8, 8, device=xi.device)
+            qcr = torch.empty_like(qcb)
+        _lib.check(_lib.lib().resr_jpeg(_lib.ptr(xi), _lib.ptr(out), _lib.ptr(q), _lib.ptr(factor), b, h, w, int(clamp_input),
+                                        _lib.ptr(qy), _lib.ptr(qcb), _lib.ptr(qcr), _lib.stream_ptr()))
+        if write_back is not None:
+            # the reference overwrites the caller's quality tensor with the factor (imgproc.py:1474-1479)
+            write_back.copy_(factor.to(write_back.device))
+        if return_coefficients:
+            return out, factor, qy, qcb, qcr
+        return out
+
+
+def gaussian_noise_apply(image, sigma, gray, noise_color, noise_gray, clip=True, rounds=False):
+    """Deterministic core of random_add_gaussian_noise_torch: all draws are arguments."""
+    b, c, h, w = image.size()
+    x = _prep(image)
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().resr_gaussian_noise_apply(
+        _lib.ptr(x), _lib.ptr(out), _lib.ptr(_prep(sigma)), _lib.ptr(None if gray is None else _prep(gray)),
+        _lib.ptr(_prep(noise_color)), _lib.ptr(None if noise_gray is None else _prep(noise_gray)), b, c, h, w,
+        int(bool(clip)), int(bool(rounds)), _lib.stream_ptr()))
+    return out
+
+
+def random_add_gaussian_noise_torch(image: torch.Tensor, sigma_range: tuple = (0, 1.0), gray_prob: int = 0,
+                                    clip: bool = True, rounds: bool = False) -> torch.Tensor:
+    """Reference imgproc.py:1029-1057; draws in the reference order: sigma, gray flags, [gray field], colour field."""
+    b, _, h, w = image.size()
+    kw = dict(dtype=image.dtype, device=image.device)
+    sigma = torch.rand(b, **kw) * (sigma_range[1] - sigma_range[0]) + sigma_range[0]
+    gray = (torch.rand(b, **kw) < gray_prob).float()
+    noise_gray = None
+    if torch.sum(gray) > 0:  # the reference branches on this too (imgproc.py:849-855), one host sync
+        noise_gray = torch.randn(h, w, **kw)
+    noise_color = torch.randn(*image.size(), **kw)
+    return gaussian_noise_apply(image, sigma, gray, noise_color, noise_gray, clip, rounds)
+
+
+def unique_count_u8(image: torch.Tensor, with_gray: bool = True):
+    """Per-sample number of distinct u8 levels of the colour image and of its luma (reference imgproc.py:892, 903),
+    computed on the device without host syncs. Returns int32 tensors (colour, gray)."""
+    b, c, h, w = image.size()
+    x = _prep(image)
+    cc = torch.empty(b, dtype=torch.int32, device=x.device)
+    cg = torch.empty(b, dtype=torch.int32, device=x.device) if with_gray else None
+    ws = _workspace(_lib.lib().resr_poisson_workspace_bytes(b), x.device)
+    _lib.check(_lib.lib().resr_unique_count_u8(_lib.ptr(x), _lib.ptr(cc), _lib.ptr(cg), b, c, h, w, _lib.ptr(ws),
+                                               ws.numel(), _lib.stream_ptr()))
+    return cc, cg
+
+
+def poisson_rates(image: torch.Tensor, with_gray: bool):
+    b, c, h, w = image.size()
+    x = _prep(image)
+    rc = torch.empty_like(x)
+    rg = torch.empty(b, 1, h, w, device=x.device) if with_gray else None
+    ws = _workspace(_lib.lib().resr_poisson_workspace_bytes(b), x.device)
+    _lib.check(_lib.lib().resr_poisson_rates(_lib.ptr(x), _lib.ptr(rc), _lib.ptr(rg), b, c, h, w, _lib.ptr(ws),
+                                             ws.numel(), _lib.stream_ptr()))
+    return rc, rg
+
+
+def poisson_noise_apply(image, scale, gray, samples_color, samples_gray, clip=True, rounds=False):
+    """Deterministic core of random_add_poisson_noise_torch: all draws are arguments."""
+    b, c, h, w = image.size()
+    x = _prep(image)
+    out = torch.empty_like(x)
+    ws = _workspace(_lib.lib().resr_poisson_workspace_bytes(b), x.device)
+    _lib.check(_lib.lib().resr_poisson_noise_apply(
+        _lib.ptr(x), _lib.ptr(out), _lib.ptr(_prep(scale)), _lib.ptr(None if gray is None else _prep(gray)),
+        _lib.ptr(_prep(samples_color)), _lib.ptr(None if samples_gray is None else _prep(samples_gray)), b, c, h, w,
+        int(bool(clip)), int(bool(rounds)), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+    return out
+
+
+def random_add_poisson_noise_torch(image: torch.Tensor, scale_range: tuple = (0, 1.0), gray_prob: int = 0,
+                                   clip: bool = True, rounds: bool = False) -> torch.Tensor:
+    """Reference imgproc.py:1060-1086; draws in the reference order: scale, gray flags, [gray Poisson], colour Poisson."""
+    b = image.size(0)
+    kw = dict(dtype=image.dtype, device=image.device)
+    scale = torch.rand(b, **kw) * (scale_range[1] - scale_range[0]) + scale_range[0]
+    gray = (torch.rand(b, **kw) < gray_prob).float()
+    with_gray = bool(torch.sum(gray) > 0)  # imgproc.py:884-886
+    rate_c, rate_g = poisson_rates(image, with_gray)
+    samples_gray = torch.poisson(rate_g) if with_gray else None
+    samples_color = torch.poisson(rate_c)
+    return poisson_noise_apply(image, scale, gray, samples_color, samples_gray, clip, rounds)
+
+
+def _crop(image, top, left, h_out, w_out, round_to_u8=False):
+    b, c, h, w = image.size()
+    x = _prep(image)
+    out = torch.empty(b, c, h_out, w_out, dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().resr_crop(_lib.ptr(x), _lib.ptr(out), b * c, h, w, top, left, h_out, w_out,
+                                    int(round_to_u8), _lib.stream_ptr()))
+    return out
+
+
+def random_crop(lr_images: torch.Tensor, hr_images: torch.Tensor, hr_image_size: int, upscale_factor: int):
+    """Reference imgproc.py:1894-1934: ONE (top, left) per batch from `random.randint`, LR offset = HR offset // scale."""
+    hr_h, hr_w = hr_images[0].size()[1:]
+    hr_top = random.randint(0, hr_h - hr_image_size)
+    hr_left = random.randint(0, hr_w - hr_image_size)
+    lr_size = hr_image_size // upscale_factor
+    lr = _crop(lr_images, hr_top // upscale_factor, hr_left // upscale_factor, lr_size, lr_size)
+    hr = _crop(hr_images, hr_top, hr_left, hr_image_size, hr_image_size)
+    return lr, hr
+
+
+def interpolate(image: torch.Tensor, size=None, scale_factor=None, mode: str = "bilinear") -> torch.Tensor:
+    """torch.nn.functional.interpolate for modes area / bilinear / bicubic (align_corners=False, no antialias) with
+    ATen's index rules; scale_factor= uses 1/scale_factor as the coordinate scale, size= uses in/out."""
+    if mode not in _MODES:
+        raise NotImplementedError(f"mode {mode!r}: the degradation path uses area / bilinear / bicubic")
+    b, c, h, w = image.size()
+    if (size is None) == (scale_factor is None):
+        raise ValueError("only one of size or scale_factor should be defined")
+    if size is not None:
+        oh, ow = (size, size) if isinstance(size, int) else size
+        sh = sw = 0.0
+    else:
+        sh, sw = (scale_factor, scale_factor) if not isinstance(scale_factor, (tuple, list)) else scale_factor
+        oh, ow = int(math.floor(float(h) * sh)), int(math.floor(float(w) * sw))
+    x = _prep(image)
+    out = torch.empty(b, c, oh, ow, dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().resr_resize(_lib.ptr(x), _lib.ptr(out), b * c, h, w, oh, ow, _MODES[mode], float(sh), float(sw),
+                                      _lib.stream_ptr()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+
+
+def _dev(t, device):
+    if t is None:
+        return None
+    if not torch.is_tensor(t):
+        t = torch.as_tensor(t)
+    return t.to(device=device, dtype=torch.float32).contiguous()
+
+
+def _noise(x, p):
+    dev = x.device
+    if p["type"] == "gaussian":
+        return gaussian_noise_apply(x, _dev(p["sigma"], dev), _dev(p["gray"], dev), _dev(p["noise_color"], dev),
+                                    _dev(p.get("noise_gray"), dev))
+    sc, sg = p.get("samples_color"), p.get("samples_gray")
+    gray = _dev(p["gray"], dev)
+    if sc is None:  # plan without recorded draws: sample from the rates with the torch generator
+        with_gray = bool(gray.sum() > 0)
+        rc, rg = poisson_rates(x, with_gray)
+        sg = torch.poisson(rg) if with_gray else None
+        sc = torch.poisson(rc)
+    return poisson_noise_apply(x, _dev(p["scale"], dev), gray, _dev(sc, dev), _dev(sg, dev))
+
+
+def degrade_batch(hr: torch.Tensor, kernel1: torch.Tensor, kernel2: torch.Tensor, sinc_kernel: torch.Tensor, plan: dict,
+                  stages: list = None):
+    """The reference's second-order degradation block (train_realesrnet.py:267-377) with every host decision and
+    random tensor taken from `plan` (layout: oracle/plan.py). Returns (lr, hr_crop); lr is detached and on the u8 grid."""
+    usm = USMSharp(50, 0)
+    jpeger = DiffJPEG(False)
+    dev = hr.device
+
+    def rec(name, t):
+        if stages is not None:
+            stages.append((name, t))
+        return t
+
+    def jpeg(x, q):
+        return jpeger(x, _dev(q, dev).clone(), clamp_input=True)
+
+    def resize(x, r):
+        if r.get("scale") is not None:
+            return interpolate(x, scale_factor=r["scale"], mode=("area", "bilinear", "bicubic")[r["mode"]])
+        return interpolate(x, size=(r["out_h"], r["out_w"]), mode=("area", "bilinear", "bicubic")[r["mode"]])
+
+    out = rec("usm", usm(hr, 0.5, 10))
+    if plan["blur1"]:
+        out = rec("blur1", filter2d_torch(out, kernel1))
+    out = rec("resize1", resize(out, plan["resize1"]))
+    out = rec("noise1", _noise(out, plan["noise1"]))
+    out = rec("jpeg1", jpeg(out, plan["jpeg1_quality"]))
+    if plan["blur2"]:
+        out = rec("blur2", filter2d_torch(out, kernel2))
+    out = rec("resize2", resize(out, plan["resize2"]))
+    out = rec("noise2", _noise(out, plan["noise2"]))
+    if plan["final_order"] == 0:
+        out = rec("resize3", resize(out, plan["resize3"]))
+        out = rec("sinc", filter2d_torch(out, sinc_kernel))
+        out = rec("jpeg2", jpeg(out, plan["jpeg2_quality"]))
+    else:
+        out = rec("jpeg2", jpeg(out, plan["jpeg2_quality"]))
+        out = rec("resize3", resize(out, plan["resize3"]))
+        out = rec("sinc", filter2d_torch(out, sinc_kernel))
+    c = plan["crop"]
+    ls = c["image_size"] // c["upscale"]
+    lr = _crop(out, c["hr_top"] // c["upscale"], c["hr_left"] // c["upscale"], ls, ls, round_to_u8=True)
+    hr_c = _crop(hr, c["hr_top"], c["hr_left"], c["image_size"], c["image_size"])
+    return lr, hr_c

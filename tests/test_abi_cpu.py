@@ -1,0 +1,94 @@
+"""CPU: libresr.so loads, exports exactly the symbols include/resr.h declares, and refuses to compute without a GPU
+(no CPU fallback). Also host-side logic that needs no device."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "resr.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(resr_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    import resr_b200
+    L = resr_b200._lib
+    lib = L.lib()
+    declared = _declared()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/resr.h but not exported by libresr.so"
+    assert sorted(L.SIGNATURES) == declared, "ctypes SIGNATURES and include/resr.h disagree"
+
+
+def test_abi_constants():
+    import resr_b200
+    lib = resr_b200._lib.lib()
+    assert lib.resr_version() >= 1
+    assert lib.resr_generator_num_params() == 16697987
+    assert lib.resr_generator_num_tensors() == 702
+    off, cnt = ctypes.c_size_t(), ctypes.c_size_t()
+    assert lib.resr_generator_tensor_span(0, ctypes.byref(off), ctypes.byref(cnt)) == 0
+    assert (off.value, cnt.value) == (0, 64 * 3 * 9)
+    assert lib.resr_generator_tensor_span(701, ctypes.byref(off), ctypes.byref(cnt)) == 0
+    assert off.value + cnt.value == 16697987 and cnt.value == 3
+    assert lib.resr_generator_tensor_span(702, ctypes.byref(off), ctypes.byref(cnt)) != 0
+    assert lib.resr_generator_workspace_bytes(64, 128, 128) > 8 * 2 ** 30
+    assert lib.resr_generator_workspace_bytes(0, 1, 1) == 0
+
+
+def test_tensor_spans_follow_state_dict_order():
+    import resr_b200
+    lib = resr_b200._lib.lib()
+    g = resr_b200.model.Generator(3, 3, 4)
+    off, cnt = ctypes.c_size_t(), ctypes.c_size_t()
+    pos = 0
+    for i, (name, p) in enumerate(g.named_parameters()):
+        assert lib.resr_generator_tensor_span(i, ctypes.byref(off), ctypes.byref(cnt)) == 0
+        assert (off.value, cnt.value) == (pos, p.numel()), name
+        pos += p.numel()
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    import resr_b200
+    L = resr_b200._lib
+    h = ctypes.c_void_p()
+    rc = L.lib().resr_generator_create(ctypes.byref(h), 3, 3, 4)
+    assert rc == 2, "without a CUDA device creation must fail with RESR_E_CUDA"
+    assert b"CUDA" in L.lib().resr_last_error() or b"device" in L.lib().resr_last_error()
+    g = resr_b200.model.Generator(3, 3, 4)
+    with pytest.raises(L.ResrError):
+        g(torch.rand(1, 3, 8, 8))
+    with pytest.raises(L.ResrError):
+        resr_b200.imgproc.filter2d_torch(torch.rand(1, 3, 32, 32), torch.ones(1, 3, 3) / 9)
+
+
+def test_generator_mirror_matches_reference_layout():
+    import resr_b200
+    from oracle import generator as og
+    torch.manual_seed(3)
+    g = resr_b200.model.Generator(3, 3, 4)
+    sd = og.random_state_dict(3)
+    msd = g.state_dict()
+    assert list(msd.keys()) == list(sd.keys())
+    assert all(torch.equal(msd[k], sd[k]) for k in sd)  # same init, same RNG consumption order as the reference
+    with pytest.raises(ValueError):
+        resr_b200.model.Generator(3, 3, 2)
+    with pytest.raises(ValueError):
+        resr_b200.imgproc.filter2d_torch(torch.rand(1, 3, 8, 8), torch.ones(1, 4, 4))
+
+
+def test_invalid_arguments_are_rejected():
+    import resr_b200
+    L = resr_b200._lib
+    h = ctypes.c_void_p()
+    assert L.lib().resr_generator_create(ctypes.byref(h), 3, 3, 2) == 1  # RESR_E_INVALID before touching the device
+    assert b"Generator(3, 3, 4)" in L.lib().resr_last_error()
+    assert L.lib().resr_filter2d(None, None, None, 1, 3, 8, 8, 3, 1, None) == 1
