@@ -24,35 +24,46 @@ struct ConvArgs {
     int mode;       // 0: one TMA load of BW+2 px per (row, chunk), dx taken by shifting the smem descriptor
                     // 1: three TMA loads per (row, chunk), one per dx (any BW x BN split)
     int nstages;    // activation ring depth
+    int nepi;       // epilogue warp groups (1 or 2), rows alternate between them
     int fmt_in;     // MMA operand format: 0 fp16, 1 bf16
     long long rows_total;  // ncg * H
     const uint8_t* wpack;  // [slice][chunk][dx][(dy,co) x 64ch] 16-bit, 128B-swizzled, ready for a bulk copy
     const float* bias;     // [nslices * NOUT]
     // epilogue
     int ep_mode, lrelu, clamp01;
-    void* out16;           // NHWC 16-bit output (or null)
+    int has_out16;         // 16-bit NHWC output through tmapO16 (TMA store from a staging tile)
     int out16_fmt;         // 0 fp16, 1 bf16
-    int out16_cstride;     // channels per pixel of the destination tensor
     int out16_choff;       // first destination channel of slice 0
     int out16_up2;         // 1: destination is [N,2H,2W,*]; every pixel is written to its 2x2 nearest-upsampled sites
-    float* outf;           // NHWC fp32 output (or null)
-    int outf_cstride, outf_choff;
-    const float* res1;     // NHWC fp32 residual inputs
-    const float* res2;
-    int res_cstride, res_choff;
+    int has_outf;          // fp32 NHWC output through tmapOF
+    int outf_choff;
+    int has_res1;          // fp32 NHWC residual through tmapR1 (TMA load into the fp32 staging tile)
+    int res_choff;
+    const float* res2;     // second residual (EP_RRDB only): plain global loads
+    int res2_cstride;
     float* out_nchw;       // NCHW fp32 output with out_nchw_c channels (or null)
     int out_nchw_c;
 };
 
+struct ConvMaps {
+    CUtensorMap a;    // activations (load)
+    CUtensorMap o16;  // 16-bit output (store), 4-D or 5-D (up2)
+    CUtensorMap of;   // fp32 output (store)
+    CUtensorMap r1;   // fp32 residual (load)
+};
+
 // Launch one convolution. `cout_slice` is 32 or 16 (channels per CTA slice), `nslices` slices cover Cout.
-cudaError_t conv3x3_launch(const CUtensorMap& tmapA, const ConvArgs& args, int cout_slice, int nslices, int num_sms,
+cudaError_t conv3x3_launch(const ConvMaps& maps, const ConvArgs& args, int cout_slice, int nslices, int num_sms,
                            cudaStream_t stream);
 
-// Shared-memory / pipeline planning for a convolution with `nchunks` K-chunks.
-int conv3x3_pick_stages(int nchunks, int cout_slice);
+// Fills nstages / nepi from the shared-memory budget. Returns false if the configuration does not fit.
+bool conv3x3_plan_smem(ConvArgs* args, int cout_slice);
 
-// Builds the activation tensor map for `conv3x3_launch`. base: NHWC 16-bit tensor [N,H,W,C].
-int conv3x3_make_tmap(CUtensorMap* out, const void* base, int N, int H, int W, int C, int mode, int BW, int BN);
+// Tensor maps. base: NHWC tensor [N,H,W,C].
+int conv3x3_make_tmap_act(CUtensorMap* out, const void* base, int N, int H, int W, int C, int mode, int BW, int BN);
+int conv3x3_make_tmap_out16(CUtensorMap* out, const void* base, int N, int H, int W, int C, int nout, int BW, int BN,
+                            int up2);  // N,H,W = geometry of the CONVOLUTION (destination is 2H x 2W when up2)
+int conv3x3_make_tmap_f32(CUtensorMap* out, const void* base, int N, int H, int W, int C, int BW, int BN);
 
 // Chooses the lane split for an image width.
 void conv3x3_pick_tile(int W, int* BW, int* BN);

@@ -6,18 +6,25 @@
 //   * One M tile = 128 output columns of ONE image row (or BW columns x BN images when W < 128): TMEM lane = pixel.
 //   * The three vertical taps are folded into the MMA N dimension: for input row r the tensor core computes
 //         D'_r[x, (dy, co)] = sum_{dx, ci} in[r, x + dx - 1, ci] * w[co, ci, dy, dx]            (N = 3 * Cout_slice)
-//     so every activation row is read from shared memory once per dx instead of once per tap, and
-//         out[y] = D'_{y-1}[dy=0] + D'_y[dy=1] + D'_{y+1}[dy=2]
-//     is a same-lane sum that the epilogue warps keep in registers while rows roll through a TMEM ring.
+//     so every activation row is read from shared memory once per dx instead of once per tap.
+//   * out[y] = D'_{y-1}[dy=0] + D'_y[dy=1] + D'_{y+1}[dy=2] is summed BY THE TENSOR CORE: output-row accumulators live
+//     in a ring of 16 TMEM slots laid out in descending row order, so the (dy=0, dy=1, dy=2) column blocks of one MMA
+//     land exactly on the accumulators of rows (r+1, r, r-1). Every MMA accumulates; the epilogue zeroes a slot after
+//     draining it. (At the ring seam the N = 3*NOUT MMA is split into an N = NOUT and an N = 2*NOUT MMA.)
 //   * Horizontal taps: mode 0 loads BW+2 pixels once (TMA zero-fills x = -1 and x = W) and shifts the UMMA
 //     shared-memory descriptor by dx * 128 B; mode 1 issues one TMA load per dx (used when the lanes span images).
-//   * Weights of the CTA's Cout slice stay resident in shared memory for the whole launch (one bulk copy).
+//   * Weights of the CTA's Cout slice stay resident in shared memory for the whole launch (bulk copies).
 //   * CTAs are persistent over a contiguous range of (column group, row) work; grid = #SMs / #slices.
+//   * Epilogue: one or two groups of 4 warps take alternate output rows: TMEM -> registers -> bias / LeakyReLU /
+//     residual -> shared-memory staging tile -> TMA store (coalesced NHWC writes, also the 2x nearest-upsampled
+//     variant); the fp32 residual tile arrives by TMA load while the row's MMAs are still running.
 //
-// Warp roles (256 threads): warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer, warp 2 = TMEM allocator,
-// warps 4-7 = epilogue (TMEM -> registers -> bias / LeakyReLU / residual -> global).
+// Warp roles: warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer, warp 2 = TMEM allocator,
+// warps 4-7 (and 8-11) = epilogue groups.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+
+#include <cstring>
 
 #include "conv3x3.cuh"
 #include "ptx.cuh"
@@ -26,10 +33,10 @@ namespace resr {
 
 static constexpr int kStageBytes = 17408;  // 136 rows x 128 B (mode 0 uses 130 rows, mode 1 uses 128)
 static constexpr int kMaxStages = 12;
-static constexpr int kTmemSlots = 4;
-static constexpr int kTmemSlotCols = 128;
+static constexpr int kSlots = 16;          // TMEM accumulator ring
 static constexpr int kMiscBytes = 1024;
-static constexpr int kSmemMax = 232448;  // 227 KB opt-in limit per CTA
+static constexpr int kSmemMax = 232448;    // 227 KB opt-in limit per CTA
+static constexpr int kTileFBytes = 16384;  // 128 px x 32 fp32
 
 struct RowRange {
     long long g0, g1;
@@ -42,133 +49,92 @@ __device__ __forceinline__ RowRange cta_rows(const ConvArgs& a) {
     return r;
 }
 
-template <int NOUT>
-struct Emit {
-    const ConvArgs& a;
-    const float* bias_s;
-    int slice;
-    __device__ __forceinline__ void operator()(int n, int y, int x, float* v) const {
-        const size_t pix = (static_cast<size_t>(n) * a.H + y) * a.W + x;
+__device__ __forceinline__ uint32_t slot_of(long long v) { return static_cast<uint32_t>((16 - (v & 15)) & 15); }
+
+__host__ __device__ inline int epi_group_bytes(const ConvArgs& a, int nout) {
+    const int f = (a.has_outf || a.has_res1) ? kTileFBytes : 0;
+    const int h = a.has_out16 ? 128 * nout * 2 : 0;
+    return f + (h + 1023) / 1024 * 1024;
+}
+
+
+// K-major, 128B-swizzled operand descriptor: constant high word (SBO = 1024 B, version 1, SWIZZLE_128B) + low word.
+static constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint64_t desc_of(uint32_t lo) { return (static_cast<uint64_t>(kDescHi) << 32) | lo; }
+
+// All MMAs of one pipeline stage, straight-line. SPLIT: 0 = one N=3*NOUT MMA at d0; 1 / 2 = ring seam (slot 14 / 15),
+// the (dy=0,1 | dy=2) resp. (dy=0 | dy=1,2) column blocks go to d0 and to the start of the ring. NDX: horizontal taps
+// served by this stage (3 in mode 0: descriptor shifted by dx pixels; 1 in mode 1).
+template <int NOUT, int SPLIT, int NDX>
+__device__ __forceinline__ void issue_stage(uint32_t d0, uint32_t ring0, uint32_t a_lo, uint32_t b_lo, uint32_t idesc3,
+                                            uint32_t idesc2, uint32_t idesc1) {
+    constexpr uint32_t WT = (3 * NOUT * 128) >> 4;   // one (chunk, dx) weight tile, in 16-byte units
+    constexpr uint32_t ROWS = (NOUT * 128) >> 4;     // NOUT weight rows
 #pragma unroll
-        for (int i = 0; i < NOUT; ++i) v[i] = __fadd_rn(v[i], bias_s[i]);
-        if (a.ep_mode != EP_PLAIN) {
-            const float4* r1 = reinterpret_cast<const float4*>(a.res1 + pix * a.res_cstride + a.res_choff + slice * NOUT);
+    for (int dx = 0; dx < NDX; ++dx) {
 #pragma unroll
-            for (int i = 0; i < NOUT / 4; ++i) {
-                const float4 q = __ldg(r1 + i);
-                if (a.ep_mode == EP_SKIP) {
-                    v[4 * i + 0] = __fadd_rn(q.x, v[4 * i + 0]);
-                    v[4 * i + 1] = __fadd_rn(q.y, v[4 * i + 1]);
-                    v[4 * i + 2] = __fadd_rn(q.z, v[4 * i + 2]);
-                    v[4 * i + 3] = __fadd_rn(q.w, v[4 * i + 3]);
-                } else {
-                    v[4 * i + 0] = __fadd_rn(__fmul_rn(v[4 * i + 0], 0.2f), q.x);
-                    v[4 * i + 1] = __fadd_rn(__fmul_rn(v[4 * i + 1], 0.2f), q.y);
-                    v[4 * i + 2] = __fadd_rn(__fmul_rn(v[4 * i + 2], 0.2f), q.z);
-                    v[4 * i + 3] = __fadd_rn(__fmul_rn(v[4 * i + 3], 0.2f), q.w);
-                }
-            }
-            if (a.ep_mode == EP_RRDB) {
-                const float4* r2 =
-                    reinterpret_cast<const float4*>(a.res2 + pix * a.res_cstride + a.res_choff + slice * NOUT);
-#pragma unroll
-                for (int i = 0; i < NOUT / 4; ++i) {
-                    const float4 q = __ldg(r2 + i);
-                    v[4 * i + 0] = __fadd_rn(__fmul_rn(v[4 * i + 0], 0.2f), q.x);
-                    v[4 * i + 1] = __fadd_rn(__fmul_rn(v[4 * i + 1], 0.2f), q.y);
-                    v[4 * i + 2] = __fadd_rn(__fmul_rn(v[4 * i + 2], 0.2f), q.z);
-                    v[4 * i + 3] = __fadd_rn(__fmul_rn(v[4 * i + 3], 0.2f), q.w);
-                }
-            }
-        }
-        if (a.lrelu) {
-#pragma unroll
-            for (int i = 0; i < NOUT; ++i) v[i] = v[i] > 0.f ? v[i] : __fmul_rn(v[i], 0.2f);
-        }
-        if (a.clamp01) {
-#pragma unroll
-            for (int i = 0; i < NOUT; ++i) v[i] = fminf(fmaxf(v[i], 0.f), 1.f);
-        }
-        if (a.outf) {
-            float4* o = reinterpret_cast<float4*>(a.outf + pix * a.outf_cstride + a.outf_choff + slice * NOUT);
-#pragma unroll
-            for (int i = 0; i < NOUT / 4; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        }
-        if (a.out16) {
-            uint32_t pk[NOUT / 2];
-#pragma unroll
-            for (int i = 0; i < NOUT / 2; ++i) {
-                if (a.out16_fmt == 1) {
-                    __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-                    pk[i] = *reinterpret_cast<uint32_t*>(&h);
-                } else {
-                    __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-                    pk[i] = *reinterpret_cast<uint32_t*>(&h);
-                }
-            }
-            uint16_t* base = reinterpret_cast<uint16_t*>(a.out16);
-            if (!a.out16_up2) {
-                uint4* o = reinterpret_cast<uint4*>(base + pix * a.out16_cstride + a.out16_choff + slice * NOUT);
-#pragma unroll
-                for (int i = 0; i < NOUT / 8; ++i) o[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+        for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t ad = desc_of(a_lo + dx * 8 + ks * 2);
+            const uint32_t bl = b_lo + dx * WT + ks * 2;
+            if (SPLIT == 0) {
+                umma_f16(d0, ad, desc_of(bl), idesc3, 1);
+            } else if (SPLIT == 1) {
+                umma_f16(d0, ad, desc_of(bl), idesc2, 1);
+                umma_f16(ring0, ad, desc_of(bl + 2 * ROWS), idesc1, 1);
             } else {
-                const int Ho = 2 * a.H, Wo = 2 * a.W;
-#pragma unroll
-                for (int s = 0; s < 4; ++s) {
-                    const size_t po = (static_cast<size_t>(n) * Ho + 2 * y + (s >> 1)) * Wo + 2 * x + (s & 1);
-                    uint4* o = reinterpret_cast<uint4*>(base + po * a.out16_cstride + a.out16_choff + slice * NOUT);
-#pragma unroll
-                    for (int i = 0; i < NOUT / 8; ++i)
-                        o[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-                }
-            }
-        }
-        if (a.out_nchw) {
-            const size_t plane = static_cast<size_t>(a.H) * a.W;
-            float* o = a.out_nchw + static_cast<size_t>(n) * a.out_nchw_c * plane + static_cast<size_t>(y) * a.W + x;
-#pragma unroll
-            for (int c = 0; c < NOUT; ++c) {
-                const int cc = slice * NOUT + c;
-                if (cc < a.out_nchw_c) o[static_cast<size_t>(cc) * plane] = v[c];
+                umma_f16(d0, ad, desc_of(bl), idesc1, 1);
+                umma_f16(ring0, ad, desc_of(bl + ROWS), idesc2, 1);
             }
         }
     }
-};
+}
 
 template <int NOUT>
-__global__ void __launch_bounds__(256, 1) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvArgs a) {
-    constexpr int NT = 3 * NOUT;        // MMA N: (dy, co)
-    constexpr int WTILE = NT * 128;     // bytes of one (chunk, dx) weight tile: NT rows x 64 ch x 2 B
+__global__ void __launch_bounds__(384, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapO16,
+                  const __grid_constant__ CUtensorMap tmapOF, const __grid_constant__ CUtensorMap tmapR1,
+                  const ConvArgs a) {
+    constexpr int NT = 3 * NOUT;     // MMA N: (dy, co)
+    constexpr int WTILE = NT * 128;  // bytes of one (chunk, dx) weight tile: NT rows x 64 ch x 2 B
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
-    const int warp = threadIdx.x >> 5;
+    // warp-uniform role index (shuffle => provably uniform: TMA / MMA operands then live in uniform registers)
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
     const int slice = blockIdx.y;
     const uint32_t wbytes = static_cast<uint32_t>(a.nchunks) * 3u * WTILE;
+    const int epi_bytes = epi_group_bytes(a, NOUT);
 
     uint8_t* wsm = smem;
     uint8_t* stg = smem + wbytes;
-    uint8_t* misc = stg + a.nstages * kStageBytes;
+    uint8_t* epi = stg + a.nstages * kStageBytes;
+    uint8_t* misc = epi + a.nepi * epi_bytes;
     uint64_t* full = reinterpret_cast<uint64_t*>(misc);
     uint64_t* empty = full + kMaxStages;
-    uint64_t* tfull = empty + kMaxStages;
-    uint64_t* tempty = tfull + kTmemSlots;
-    uint64_t* wbar = tempty + kTmemSlots;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(wbar + 1);
+    uint64_t* acc_full = empty + kMaxStages;
+    uint64_t* slot_free = acc_full + kSlots;
+    uint64_t* wbar = slot_free + kSlots;
+    uint64_t* res_full = wbar + 1;  // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full + 2);
     float* bias_s = reinterpret_cast<float*>(misc + 512);
 
     if (threadIdx.x == 0) {
         prefetch_tmap(&tmapA);
+        if (a.has_out16) prefetch_tmap(&tmapO16);
+        if (a.has_outf) prefetch_tmap(&tmapOF);
+        if (a.has_res1) prefetch_tmap(&tmapR1);
         for (int i = 0; i < a.nstages; ++i) {
             mbar_init(full + i, 1);
             mbar_init(empty + i, 1);
         }
-        for (int i = 0; i < kTmemSlots; ++i) {
-            mbar_init(tfull + i, 1);
-            mbar_init(tempty + i, 128);
+        for (int i = 0; i < kSlots; ++i) {
+            mbar_init(acc_full + i, 1);
+            mbar_init(slot_free + i, 128);
         }
         mbar_init(wbar, 1);
+        mbar_init(res_full, 1);
+        mbar_init(res_full + 1, 1);
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -180,17 +146,27 @@ __global__ void __launch_bounds__(256, 1) conv3x3_tc_kernel(const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tbase = *tmem_ptr;
+    // Programmatic dependent launch: the next kernel in the stream may take over SMs as soon as CTAs of this grid
+    // retire (it parks in griddepcontrol.wait until this whole grid has completed and flushed).
+    grid_dep_launch();
 
     const RowRange rr = cta_rows(a);
     const int H = a.H;
 
-    if (threadIdx.x == 0) {
-        // ------------------------------------------------------------------ TMA producer
-        mbar_expect_tx(wbar, wbytes);
-        const uint8_t* wsrc = a.wpack + static_cast<size_t>(slice) * wbytes;
-        for (int c = 0; c < a.nchunks; ++c) bulk_load_1d(wsm + c * 3 * WTILE, wsrc + static_cast<size_t>(c) * 3 * WTILE, 3 * WTILE, wbar);
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer (whole warp, one elected lane issues)
+        // weights do not depend on the previous kernel: fetch them before the grid dependency resolves
+        if (elect_one()) {
+            mbar_expect_tx(wbar, wbytes);
+            const uint8_t* wsrc = a.wpack + static_cast<size_t>(slice) * wbytes;
+            for (int c = 0; c < a.nchunks; ++c) bulk_load_1d(wsm + c * 3 * WTILE, wsrc + static_cast<size_t>(c) * 3 * WTILE, 3 * WTILE, wbar);
+        }
+        __syncwarp();
+        grid_dep_wait();
         int stage = 0;
         uint32_t phase = 0;
+        const int ndx = a.mode == 0 ? 1 : 3;
+        const uint32_t tx_bytes = a.mode == 0 ? (a.BW + 2) * 128 : 128 * 128;
         for (long long g = rr.g0; g < rr.g1;) {
             const int cg = static_cast<int>(g / H);
             const int ya = static_cast<int>(g % H);
@@ -200,123 +176,241 @@ __global__ void __launch_bounds__(256, 1) conv3x3_tc_kernel(const __grid_constan
             const int ra = max(ya - 1, 0), rb = min(yb, H - 1);
             for (int r = ra; r <= rb; ++r) {
                 for (int c = 0; c < a.nchunks; ++c) {
-                    if (a.mode == 0) {
+                    for (int dx = 0; dx < ndx; ++dx) {
                         mbar_wait(empty + stage, phase ^ 1);
-                        mbar_expect_tx(full + stage, (a.BW + 2) * 128);
-                        tma_load_4d(stg + stage * kStageBytes, &tmapA, full + stage, c * 64, x0 - 1, r, n0);
-                        if (++stage == a.nstages) { stage = 0; phase ^= 1; }
-                    } else {
-                        for (int dx = 0; dx < 3; ++dx) {
-                            mbar_wait(empty + stage, phase ^ 1);
-                            mbar_expect_tx(full + stage, 128 * 128);
-                            tma_load_4d(stg + stage * kStageBytes, &tmapA, full + stage, c * 64, x0 + dx - 1, r, n0);
-                            if (++stage == a.nstages) { stage = 0; phase ^= 1; }
+                        if (elect_one()) {
+                            mbar_expect_tx(full + stage, tx_bytes);
+                            tma_load_4d(stg + stage * kStageBytes, &tmapA, full + stage, c * 64,
+                                        a.mode == 0 ? x0 - 1 : x0 + dx - 1, r, n0);
                         }
+                        __syncwarp();
+                        if (++stage == a.nstages) { stage = 0; phase ^= 1; }
                     }
                 }
             }
             g += yb - ya;
         }
-    } else if (threadIdx.x == 32) {
-        // ------------------------------------------------------------------ MMA issuer
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (whole warp, one elected lane issues)
+        // ONE thread feeds the tensor core, so its instruction count per MMA is the critical path: descriptors are
+        // (constant high word, 32-bit low word = smem address >> 4) and every MMA costs two integer adds.
         mbar_wait(wbar, 0);
         tc_fence_after();
-        const uint32_t idesc = make_idesc_f16(a.fmt_in, 128, NT);
-        const uint32_t w_addr = smem_u32(wsm);
-        const uint32_t s_addr = smem_u32(stg);
+        const uint32_t idesc3 = make_idesc_f16(a.fmt_in, 128, 3 * NOUT);
+        const uint32_t idesc2 = make_idesc_f16(a.fmt_in, 128, 2 * NOUT);
+        const uint32_t idesc1 = make_idesc_f16(a.fmt_in, 128, NOUT);
+        const uint32_t w_lo = (smem_u32(wsm) & 0x3FFFFu) >> 4;
+        const uint32_t s_lo = (smem_u32(stg) & 0x3FFFFu) >> 4;
+        const int nsteps = a.mode == 0 ? a.nchunks : a.nchunks * 3;  // pipeline stages per input row
         int stage = 0;
         uint32_t phase = 0;
-        uint32_t it = 0;
+        long long v0 = 0, acq = 0;
         for (long long g = rr.g0; g < rr.g1;) {
             const int ya = static_cast<int>(g % H);
             const int yb = static_cast<int>(min(static_cast<long long>(H), ya + (rr.g1 - g)));
             const int ra = max(ya - 1, 0), rb = min(yb, H - 1);
-            for (int r = ra; r <= rb; ++r, ++it) {
-                const uint32_t slot = it % kTmemSlots;
-                mbar_wait(tempty + slot, ((it / kTmemSlots) & 1) ^ 1);
+            for (int r = ra; r <= rb; ++r) {
+                const long long vr = v0 + (r - ra) + 1;  // virtual index of output row r
+                while (acq <= vr + 1) {                  // accumulators of rows r-1, r, r+1 must be zeroed & free
+                    mbar_wait(slot_free + slot_of(acq), static_cast<uint32_t>(acq >> 4) & 1);
+                    ++acq;
+                }
                 tc_fence_after();
-                const uint32_t d_addr = tbase + slot * kTmemSlotCols;
-                uint32_t acc = 0;
-                for (int c = 0; c < a.nchunks; ++c) {
-                    if (a.mode == 0) {
-                        mbar_wait(full + stage, phase);
-                        tc_fence_after();
-                        const uint32_t abase = s_addr + stage * kStageBytes;
-#pragma unroll
-                        for (int dx = 0; dx < 3; ++dx) {
-                            const uint32_t bbase = w_addr + (c * 3 + dx) * WTILE;
-#pragma unroll
-                            for (int ks = 0; ks < 4; ++ks) {
-                                umma_f16(d_addr, make_smem_desc(abase + dx * 128 + ks * 32, 1024, 128),
-                                         make_smem_desc(bbase + ks * 32, 1024, 128), idesc, acc);
-                                acc = 1;
-                            }
+                const uint32_t s0 = slot_of(vr + 1);
+                const uint32_t d0 = tbase + s0 * NOUT;
+                for (int st = 0; st < nsteps; ++st) {
+                    mbar_wait(full + stage, phase);
+                    tc_fence_after();
+                    const uint32_t a_lo = s_lo + stage * (kStageBytes >> 4);
+                    const uint32_t b_lo = w_lo + st * ((a.mode == 0 ? 3 : 1) * (WTILE >> 4));
+                    if (elect_one()) {
+                        if (a.mode == 0) {
+                            if (s0 <= 13) issue_stage<NOUT, 0, 3>(d0, tbase, a_lo, b_lo, idesc3, idesc2, idesc1);
+                            else if (s0 == 14) issue_stage<NOUT, 1, 3>(d0, tbase, a_lo, b_lo, idesc3, idesc2, idesc1);
+                            else issue_stage<NOUT, 2, 3>(d0, tbase, a_lo, b_lo, idesc3, idesc2, idesc1);
+                        } else {
+                            if (s0 <= 13) issue_stage<NOUT, 0, 1>(d0, tbase, a_lo, b_lo, idesc3, idesc2, idesc1);
+                            else if (s0 == 14) issue_stage<NOUT, 1, 1>(d0, tbase, a_lo, b_lo, idesc3, idesc2, idesc1);
+                            else issue_stage<NOUT, 2, 1>(d0, tbase, a_lo, b_lo, idesc3, idesc2, idesc1);
                         }
                         umma_commit(empty + stage);
-                        if (++stage == a.nstages) { stage = 0; phase ^= 1; }
-                    } else {
-                        for (int dx = 0; dx < 3; ++dx) {
-                            mbar_wait(full + stage, phase);
-                            tc_fence_after();
-                            const uint32_t abase = s_addr + stage * kStageBytes;
-                            const uint32_t bbase = w_addr + (c * 3 + dx) * WTILE;
-#pragma unroll
-                            for (int ks = 0; ks < 4; ++ks) {
-                                umma_f16(d_addr, make_smem_desc(abase + ks * 32, 1024, 128),
-                                         make_smem_desc(bbase + ks * 32, 1024, 128), idesc, acc);
-                                acc = 1;
+                        if (st == nsteps - 1) {
+                            umma_commit(acc_full + slot_of(vr - 1));  // row r-1 has its last contribution
+                            if (r == rb) {
+                                umma_commit(acc_full + slot_of(vr));
+                                umma_commit(acc_full + slot_of(vr + 1));
                             }
-                            umma_commit(empty + stage);
-                            if (++stage == a.nstages) { stage = 0; phase ^= 1; }
                         }
                     }
+                    __syncwarp();
+                    if (++stage == a.nstages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(tfull + slot);
             }
+            v0 += rb - ra + 3;
             g += yb - ya;
         }
     } else if (warp >= 4) {
-        // ------------------------------------------------------------------ epilogue warps
-        const int q = warp - 4;            // TMEM lane quadrant
-        const int m = q * 32 + lane;       // M row == TMEM lane == pixel of the tile
+        // ------------------------------------------------------------------ epilogue groups
+        const int gi = (warp - 4) >> 2;
+        const int q = warp & 3;        // TMEM lane quadrant this warp may access
+        const int m = q * 32 + lane;   // M row == TMEM lane == pixel of the tile
+        const bool lead_warp = ((warp - 4) & 3) == 0;  // first warp of the group issues its TMA traffic
+        const bool staged = a.has_out16 || a.has_outf || a.has_res1;
+        uint8_t* tileF = epi + gi * epi_bytes;
+        uint8_t* tile16 = tileF + ((a.has_outf || a.has_res1) ? kTileFBytes : 0);
+        uint64_t* rbar = res_full + gi;
+        uint32_t res_phase = 0;
+        const uint32_t lane_base = tbase + (static_cast<uint32_t>(q * 32) << 16);
         const int img_in_tile = m / a.BW;
         const int x_in_tile = m % a.BW;
-        const Emit<NOUT> emit{a, bias_s, slice};
-        uint32_t it = 0;
+        {   // zero this group's share of the accumulator ring, then hand the slots to the MMA issuer
+            const int s_lo = gi * kSlots / a.nepi, s_hi = (gi + 1) * kSlots / a.nepi;
+            for (int s = s_lo; s < s_hi; ++s) {
+                if (NOUT == 32) tmem_st_zero32(lane_base + s * NOUT); else tmem_st_zero16(lane_base + s * NOUT);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            for (int s = s_lo; s < s_hi; ++s) mbar_arrive(slot_free + s);
+        }
+        grid_dep_wait();  // residual reads / output writes below touch buffers of the previous kernel
+        long long v0 = 0;
         for (long long g = rr.g0; g < rr.g1;) {
             const int cg = static_cast<int>(g / H);
             const int ya = static_cast<int>(g % H);
             const int yb = static_cast<int>(min(static_cast<long long>(H), ya + (rr.g1 - g)));
-            const int n = (cg / a.nxs) * a.BN + img_in_tile;
-            const int x = (cg % a.nxs) * a.BW + x_in_tile;
+            const int n0 = (cg / a.nxs) * a.BN;
+            const int x0 = (cg % a.nxs) * a.BW;
+            const int n = n0 + img_in_tile;
+            const int x = x0 + x_in_tile;
             const bool valid = (n < a.N) && (x < a.W);
             const int ra = max(ya - 1, 0), rb = min(yb, H - 1);
-            float s0[NOUT], s1[NOUT];
-#pragma unroll
-            for (int i = 0; i < NOUT; ++i) { s0[i] = 0.f; s1[i] = 0.f; }
-            for (int r = ra; r <= rb; ++r, ++it) {
-                const uint32_t slot = it % kTmemSlots;
-                mbar_wait(tfull + slot, (it / kTmemSlots) & 1);
-                tc_fence_after();
-                const uint32_t taddr = tbase + (static_cast<uint32_t>(q * 32) << 16) + slot * kTmemSlotCols;
-                float fin[NOUT], t[NOUT];
-                if (NOUT == 32) tmem_ld32(taddr + 2 * NOUT, fin); else tmem_ld16(taddr + 2 * NOUT, fin);
-                if (NOUT == 32) tmem_ld32(taddr + NOUT, t); else tmem_ld16(taddr + NOUT, t);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < NOUT; ++i) {
-                    fin[i] = __fadd_rn(s1[i], fin[i]);   // out[r-1] = (D'_{r-2}[0] + D'_{r-1}[1]) + D'_r[2]
-                    s1[i] = __fadd_rn(s0[i], t[i]);      // partial of out[r]
+            const int n_acc = rb - ra + 3;
+            for (int j = 0; j < n_acc; ++j) {
+                const long long v = v0 + j;
+                if (static_cast<int>(v % a.nepi) != gi) continue;
+                const int y = ra - 1 + j;
+                const bool emit = (y >= ya) && (y < yb);
+                const uint32_t slot = slot_of(v);
+                if (emit && staged) {
+                    if (lead_warp) tma_store_wait_read();  // previous stores of this group have drained the tiles
+                    named_bar_sync(1 + gi, 128);
+                    if (lead_warp && a.has_res1) {
+                        if (elect_one()) {
+                            mbar_expect_tx(rbar, 128 * 128);
+                            tma_load_4d(tileF, &tmapR1, rbar, a.res_choff + slice * NOUT, x0, y, n0);
+                        }
+                        __syncwarp();
+                    }
                 }
-                if (NOUT == 32) tmem_ld32(taddr, s0); else tmem_ld16(taddr, s0);   // partial of out[r+1]
+                mbar_wait(acc_full + slot, static_cast<uint32_t>(v >> 4) & 1);
+                tc_fence_after();
+                float val[NOUT];
+                if (NOUT == 32) tmem_ld32(lane_base + slot * NOUT, val); else tmem_ld16(lane_base + slot * NOUT, val);
                 tmem_ld_wait();
+                if (NOUT == 32) tmem_st_zero32(lane_base + slot * NOUT); else tmem_st_zero16(lane_base + slot * NOUT);
+                tmem_st_wait();
                 tc_fence_before();
-                mbar_arrive(tempty + slot);
-                if (valid && r - 1 >= ya) emit(n, r - 1, x, fin);
+                mbar_arrive(slot_free + slot);
+                if (!emit) continue;
+
+#pragma unroll
+                for (int i = 0; i < NOUT; ++i) val[i] = __fadd_rn(val[i], bias_s[i]);
+                if (a.has_res1) {
+                    mbar_wait(rbar, res_phase);
+                    res_phase ^= 1;
+#pragma unroll
+                    for (int i = 0; i < NOUT / 4; ++i) {
+                        const float4 r4 = *reinterpret_cast<const float4*>(tileF + m * 128 + ((i ^ (m & 7)) << 4));
+                        if (a.ep_mode == EP_SKIP) {
+                            val[4 * i + 0] = __fadd_rn(r4.x, val[4 * i + 0]);
+                            val[4 * i + 1] = __fadd_rn(r4.y, val[4 * i + 1]);
+                            val[4 * i + 2] = __fadd_rn(r4.z, val[4 * i + 2]);
+                            val[4 * i + 3] = __fadd_rn(r4.w, val[4 * i + 3]);
+                        } else {
+                            val[4 * i + 0] = __fadd_rn(__fmul_rn(val[4 * i + 0], 0.2f), r4.x);
+                            val[4 * i + 1] = __fadd_rn(__fmul_rn(val[4 * i + 1], 0.2f), r4.y);
+                            val[4 * i + 2] = __fadd_rn(__fmul_rn(val[4 * i + 2], 0.2f), r4.z);
+                            val[4 * i + 3] = __fadd_rn(__fmul_rn(val[4 * i + 3], 0.2f), r4.w);
+                        }
+                    }
+                }
+                if (a.ep_mode == EP_RRDB) {
+                    const size_t pix = (static_cast<size_t>(valid ? n : 0) * a.H + y) * a.W + (valid ? x : 0);
+                    const float4* r2 = reinterpret_cast<const float4*>(a.res2 + pix * a.res2_cstride + a.res_choff + slice * NOUT);
+#pragma unroll
+                    for (int i = 0; i < NOUT / 4; ++i) {
+                        const float4 r4 = __ldg(r2 + i);
+                        val[4 * i + 0] = __fadd_rn(__fmul_rn(val[4 * i + 0], 0.2f), r4.x);
+                        val[4 * i + 1] = __fadd_rn(__fmul_rn(val[4 * i + 1], 0.2f), r4.y);
+                        val[4 * i + 2] = __fadd_rn(__fmul_rn(val[4 * i + 2], 0.2f), r4.z);
+                        val[4 * i + 3] = __fadd_rn(__fmul_rn(val[4 * i + 3], 0.2f), r4.w);
+                    }
+                }
+                if (a.lrelu) {
+#pragma unroll
+                    for (int i = 0; i < NOUT; ++i) val[i] = val[i] > 0.f ? val[i] : __fmul_rn(val[i], 0.2f);
+                }
+                if (a.clamp01) {
+#pragma unroll
+                    for (int i = 0; i < NOUT; ++i) val[i] = fminf(fmaxf(val[i], 0.f), 1.f);
+                }
+                if (a.has_outf) {
+#pragma unroll
+                    for (int i = 0; i < NOUT / 4; ++i)
+                        *reinterpret_cast<float4*>(tileF + m * 128 + ((i ^ (m & 7)) << 4)) =
+                            make_float4(val[4 * i], val[4 * i + 1], val[4 * i + 2], val[4 * i + 3]);
+                }
+                if (a.has_out16) {
+                    uint32_t pk[NOUT / 2];
+#pragma unroll
+                    for (int i = 0; i < NOUT / 2; ++i) {
+                        if (a.out16_fmt == 1) {
+                            __nv_bfloat162 h = __floats2bfloat162_rn(val[2 * i], val[2 * i + 1]);
+                            pk[i] = *reinterpret_cast<uint32_t*>(&h);
+                        } else {
+                            __half2 h = __floats2half2_rn(val[2 * i], val[2 * i + 1]);
+                            pk[i] = *reinterpret_cast<uint32_t*>(&h);
+                        }
+                    }
+                    // rotate the 16-byte chunk order per lane so that a quarter-warp does not hammer two bank groups
+                    uint4* dst = reinterpret_cast<uint4*>(tile16 + m * (NOUT * 2));
+#pragma unroll
+                    for (int i = 0; i < NOUT / 8; ++i) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+                }
+                if (staged) {
+                    fence_proxy_async_smem();
+                    named_bar_sync(1 + gi, 128);
+                    if (lead_warp) {
+                      if (elect_one()) {
+                        if (a.has_outf) tma_store_4d(&tmapOF, tileF, a.outf_choff + slice * NOUT, x0, y, n0);
+                        if (a.has_out16) {
+                            const int c0 = a.out16_choff + slice * NOUT;
+                            if (!a.out16_up2) {
+                                tma_store_4d(&tmapO16, tile16, c0, x0, y, n0);
+                            } else {
+#pragma unroll
+                                for (int s = 0; s < 4; ++s) tma_store_5d(&tmapO16, tile16, c0, s & 1, x0, 2 * y + (s >> 1), n0);
+                            }
+                        }
+                        tma_store_commit();
+                      }
+                      __syncwarp();
+                    }
+                }
+                if (a.out_nchw && valid) {
+                    const size_t plane = static_cast<size_t>(a.H) * a.W;
+                    float* o = a.out_nchw + static_cast<size_t>(n) * a.out_nchw_c * plane + static_cast<size_t>(y) * a.W + x;
+#pragma unroll
+                    for (int c = 0; c < NOUT; ++c) {
+                        const int cc = slice * NOUT + c;
+                        if (cc < a.out_nchw_c) o[static_cast<size_t>(cc) * plane] = val[c];
+                    }
+                }
             }
-            if (valid && yb == H && rb >= ra) emit(n, H - 1, x, s1);
+            v0 += n_acc;
             g += yb - ya;
         }
+        if (lead_warp) tma_store_wait_all();
     }
 
     tc_fence_before();
@@ -326,11 +420,21 @@ __global__ void __launch_bounds__(256, 1) conv3x3_tc_kernel(const __grid_constan
 
 // --------------------------------------------------------------------------------------------- host side
 
-int conv3x3_pick_stages(int nchunks, int cout_slice) {
-    const int wbytes = nchunks * 3 * (3 * cout_slice) * 128;
-    int ns = (kSmemMax - 1024 /*alignment slack*/ - kMiscBytes - wbytes) / kStageBytes;
-    if (ns > kMaxStages) ns = kMaxStages;
-    return ns;
+bool conv3x3_plan_smem(ConvArgs* a, int cout_slice) {
+    const int wbytes = a->nchunks * 3 * (3 * cout_slice) * 128;
+    const int per_stage_cycles = 12 * (3 * cout_slice / 2);  // MMA cycles one stage feeds (mode 0)
+    // two epilogue groups when a row's MMAs are shorter than one group's drain latency, and staging is cheap
+    int nepi = (a->nchunks * per_stage_cycles < 1500 && !a->has_outf && !a->has_res1) ? 2 : 1;
+    for (;; --nepi) {
+        a->nepi = nepi;
+        const int fixed = 1024 + wbytes + nepi * epi_group_bytes(*a, cout_slice) + kMiscBytes;
+        int ns = (kSmemMax - fixed) / kStageBytes;
+        if (ns > kMaxStages) ns = kMaxStages;
+        if (ns >= 3 || nepi == 1) {
+            a->nstages = ns;
+            return ns >= 2;
+        }
+    }
 }
 
 void conv3x3_pick_tile(int W, int* BW, int* BN) {
@@ -359,24 +463,14 @@ static PFN_encodeTiled get_encode_fn() {
     return fn;
 }
 
-int conv3x3_make_tmap(CUtensorMap* out, const void* base, int N, int H, int W, int C, int mode, int BW, int BN) {
+int conv3x3_make_tmap_act(CUtensorMap* out, const void* base, int N, int H, int W, int C, int mode, int BW, int BN) {
     PFN_encodeTiled enc = get_encode_fn();
     if (!enc) return -1;
     const cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
                                 static_cast<cuuint64_t>(N)};
     const cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(W) * C * 2,
                                    static_cast<cuuint64_t>(H) * W * C * 2};
-    cuuint32_t box[4];
-    box[0] = 64;
-    if (mode == 0) {
-        box[1] = static_cast<cuuint32_t>(BW + 2);
-        box[2] = 1;
-        box[3] = 1;
-    } else {
-        box[1] = static_cast<cuuint32_t>(BW);
-        box[2] = 1;
-        box[3] = static_cast<cuuint32_t>(BN);
-    }
+    cuuint32_t box[4] = {64, static_cast<cuuint32_t>(mode == 0 ? BW + 2 : BW), 1, static_cast<cuuint32_t>(mode == 0 ? 1 : BN)};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -384,40 +478,87 @@ int conv3x3_make_tmap(CUtensorMap* out, const void* base, int N, int H, int W, i
     return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
 }
 
-cudaError_t conv3x3_launch(const CUtensorMap& tmapA, const ConvArgs& args, int cout_slice, int nslices, int num_sms,
+int conv3x3_make_tmap_out16(CUtensorMap* out, const void* base, int N, int H, int W, int C, int nout, int BW, int BN,
+                            int up2) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) return -1;
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r;
+    if (!up2) {
+        const cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                                    static_cast<cuuint64_t>(N)};
+        const cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(W) * C * 2,
+                                       static_cast<cuuint64_t>(H) * W * C * 2};
+        const cuuint32_t box[4] = {static_cast<cuuint32_t>(nout), static_cast<cuuint32_t>(BW), 1, static_cast<cuuint32_t>(BN)};
+        r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+        // destination [N, 2H, 2W, C] viewed as (c, b, x, Y' = 2y + a, n): pixel (Y', 2x + b)
+        const cuuint64_t dims[5] = {static_cast<cuuint64_t>(C), 2, static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(2 * H),
+                                    static_cast<cuuint64_t>(N)};
+        const cuuint64_t strides[4] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(C) * 4,
+                                       static_cast<cuuint64_t>(2 * W) * C * 2, static_cast<cuuint64_t>(2 * H) * 2 * W * C * 2};
+        const cuuint32_t box[5] = {static_cast<cuuint32_t>(nout), 1, static_cast<cuuint32_t>(BW), 1, static_cast<cuuint32_t>(BN)};
+        r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
+}
+
+int conv3x3_make_tmap_f32(CUtensorMap* out, const void* base, int N, int H, int W, int C, int BW, int BN) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) return -1;
+    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                                static_cast<cuuint64_t>(N)};
+    const cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 4, static_cast<cuuint64_t>(W) * C * 4,
+                                   static_cast<cuuint64_t>(H) * W * C * 4};
+    const cuuint32_t box[4] = {32, static_cast<cuuint32_t>(BW), 1, static_cast<cuuint32_t>(BN)};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
+}
+
+template <int NOUT>
+static cudaError_t launch_t(const ConvMaps& maps, const ConvArgs& args, dim3 grid, int threads, cudaStream_t stream) {
+    static bool attr = false;
+    if (!attr) {
+        const cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(threads, 1, 1);
+    cfg.dynamicSmemBytes = kSmemMax;  // always the full 227 KB: exactly one CTA (one 512-column TMEM allocation) per SM
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<NOUT>, maps.a, maps.o16, maps.of, maps.r1, args);
+}
+
+cudaError_t conv3x3_launch(const ConvMaps& maps, const ConvArgs& args, int cout_slice, int nslices, int num_sms,
                            cudaStream_t stream) {
     const int wbytes = args.nchunks * 3 * (3 * cout_slice) * 128;
-    const int smem = 1024 + wbytes + args.nstages * kStageBytes + kMiscBytes;
-    if (args.nstages < 2 || smem > kSmemMax) return cudaErrorInvalidConfiguration;
-    // Always request the full 227 KB so that exactly one CTA (one 512-column TMEM allocation) lives on an SM.
-    const int smem_req = kSmemMax;
+    const int smem = 1024 + wbytes + args.nstages * kStageBytes + args.nepi * epi_group_bytes(args, cout_slice) + kMiscBytes;
+    if (args.nstages < 2 || args.nepi < 1 || args.nepi > 2 || smem > kSmemMax) return cudaErrorInvalidConfiguration;
     long long gx = num_sms / nslices;
     const long long min_rows = 4;  // do not shred tiny problems into 1-row strips (2 halo rows each)
     const long long cap = (args.rows_total + min_rows - 1) / min_rows;
     if (gx > cap) gx = cap;
     if (gx < 1) gx = 1;
-    dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(nslices), 1);
-    cudaError_t e;
-    if (cout_slice == 32) {
-        static bool attr32 = false;
-        if (!attr32) {
-            e = cudaFuncSetAttribute(conv3x3_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
-            if (e != cudaSuccess) return e;
-            attr32 = true;
-        }
-        conv3x3_tc_kernel<32><<<grid, 256, smem_req, stream>>>(tmapA, args);
-    } else if (cout_slice == 16) {
-        static bool attr16 = false;
-        if (!attr16) {
-            e = cudaFuncSetAttribute(conv3x3_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
-            if (e != cudaSuccess) return e;
-            attr16 = true;
-        }
-        conv3x3_tc_kernel<16><<<grid, 256, smem_req, stream>>>(tmapA, args);
-    } else {
-        return cudaErrorInvalidValue;
-    }
-    return cudaGetLastError();
+    const dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(nslices), 1);
+    const int threads = 128 + 128 * args.nepi;
+    if (cout_slice == 32) return launch_t<32>(maps, args, grid, threads, stream);
+    if (cout_slice == 16) return launch_t<16>(maps, args, grid, threads, stream);
+    return cudaErrorInvalidValue;
 }
 
 }  // namespace resr

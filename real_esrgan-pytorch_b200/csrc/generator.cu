@@ -154,15 +154,14 @@ static int grid_for(size_t total, int block) {
 
 // ------------------------------------------------------------------------------------------- generator object
 struct Step {
-    int tmap;   // index into Plan::tmaps
     int conv;   // index into the layer table
+    ConvMaps maps;
     ConvArgs a;
 };
 
 struct Plan {
     int N = 0, H = 0, W = 0;
     void* ws = nullptr;
-    CUtensorMap tmaps[7];
     std::vector<Step> steps;
     uint16_t* xin = nullptr;
     bool valid = false;
@@ -233,46 +232,58 @@ static int build_plan(resr_generator* g, int N, int H, int W, void* ws) {
         geo[s].mode = geo[s].BN == 1 ? 0 : 1;
         if (g->force_mode >= 0) geo[s].mode = (geo[s].BN == 1) ? g->force_mode : 1;
     }
-    // tensor maps: 0 xin, 1 ca, 2 cb (LR); 3 t1 (2x); 4 t2, 5 t3, 6 t4 (4x)
-    struct TM { const void* ptr; int C; int s; };
-    const TM tm[7] = {{xin, 64, 0}, {cbuf[0], 192, 0}, {cbuf[1], 192, 0}, {t1, 64, 1}, {t2, 64, 2}, {t3, 64, 2}, {t4, 64, 2}};
-    for (int i = 0; i < 7; ++i) {
-        const Geo& q = geo[tm[i].s];
-        const int rc = conv3x3_make_tmap(&p.tmaps[i], tm[i].ptr, N, q.H, q.W, tm[i].C, q.mode, q.BW, q.BN);
-        if (rc != 0) return set_error(RESR_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", rc);
-    }
     // The zero-padded K chunks of conv2/conv4 of each RDB read growth channels that the current RDB has not written
     // yet: they are multiplied by zero weights, so they only have to be finite.
     cudaMemsetAsync(cbuf[0], 0, static_cast<size_t>(N) * H * W * 192 * 2, 0);
     cudaMemsetAsync(cbuf[1], 0, static_cast<size_t>(N) * H * W * 192 * 2, 0);
 
     const Table& T = table();
-    auto base_args = [&](int conv, int s) {
+    int map_rc = 0;
+    // in16: source activations [N, H<<s, W<<s, cin_total]
+    auto make_step = [&](int conv, int s, const void* in16, int cin_total) {
         const ConvSpec& cs = T.c[conv];
         const Geo& q = geo[s];
-        ConvArgs a;
-        memset(&a, 0, sizeof(a));
+        Step st;
+        memset(&st, 0, sizeof(st));
+        st.conv = conv;
+        ConvArgs& a = st.a;
         a.N = N; a.H = q.H; a.W = q.W; a.BW = q.BW; a.BN = q.BN;
         a.nxs = (q.W + q.BW - 1) / q.BW;
         a.ncg = ((N + q.BN - 1) / q.BN) * a.nxs;
         a.nchunks = cs.nchunks;
         a.mode = q.mode;
-        a.nstages = conv3x3_pick_stages(cs.nchunks, cs.nout);
         a.fmt_in = cs.fmt;
         a.rows_total = static_cast<long long>(a.ncg) * q.H;
         a.wpack = g->wpack + cs.w_off;
         a.bias = g->bias + cs.b_off;
-        return a;
+        map_rc |= conv3x3_make_tmap_act(&st.maps.a, in16, N, q.H, q.W, cin_total, q.mode, q.BW, q.BN);
+        return st;
     };
-    auto push = [&](int tmap, int conv, const ConvArgs& a) { p.steps.push_back(Step{tmap, conv, a}); };
+    auto set_out16 = [&](Step& st, int s, void* dst, int c_total, int choff, int fmt, int up2) {
+        const Geo& q = geo[s];
+        st.a.has_out16 = 1; st.a.out16_fmt = fmt; st.a.out16_choff = choff; st.a.out16_up2 = up2;
+        map_rc |= conv3x3_make_tmap_out16(&st.maps.o16, dst, N, q.H, q.W, c_total, T.c[st.conv].nout, q.BW, q.BN, up2);
+    };
+    auto set_outf = [&](Step& st, float* dst) {
+        st.a.has_outf = 1; st.a.outf_choff = 0;
+        map_rc |= conv3x3_make_tmap_f32(&st.maps.of, dst, N, geo[0].H, geo[0].W, 64, geo[0].BW, geo[0].BN);
+    };
+    auto set_res1 = [&](Step& st, const float* src) {
+        st.a.has_res1 = 1; st.a.res_choff = 0;
+        map_rc |= conv3x3_make_tmap_f32(&st.maps.r1, src, N, geo[0].H, geo[0].W, 64, geo[0].BW, geo[0].BN);
+    };
+    auto push = [&](Step& st) {
+        if (!conv3x3_plan_smem(&st.a, T.c[st.conv].nout)) map_rc |= 1 << 20;
+        p.steps.push_back(st);
+    };
 
     int conv = 0;
     {   // conv1: model.py:258
-        ConvArgs a = base_args(conv, 0);
-        a.ep_mode = EP_PLAIN;
-        a.outf = F[0]; a.outf_cstride = 64; a.outf_choff = 0;
-        a.out16 = cbuf[0]; a.out16_fmt = 1; a.out16_cstride = 192; a.out16_choff = 0;
-        push(0, conv, a);
+        Step st = make_step(conv, 0, xin, 64);
+        st.a.ep_mode = EP_PLAIN;
+        set_outf(st, F[0]);
+        set_out16(st, 0, cbuf[0], 192, 0, 1, 0);
+        push(st);
         ++conv;
     }
     int cur = 0;  // concat buffer holding the current RDB input
@@ -281,64 +292,65 @@ static int build_plan(resr_generator* g, int N, int H, int W, void* ws) {
         for (int j = 0; j < 3; ++j) {
             float* xin_master = (j == 0) ? X0 : F[j];
             for (int k = 0; k < 4; ++k) {  // model.py:90-93
-                ConvArgs a = base_args(conv, 0);
-                a.ep_mode = EP_PLAIN; a.lrelu = 1;
-                a.out16 = cbuf[cur]; a.out16_fmt = 1; a.out16_cstride = 192; a.out16_choff = 64 + 32 * k;
-                push(1 + cur, conv, a);
+                Step st = make_step(conv, 0, cbuf[cur], 192);
+                st.a.ep_mode = EP_PLAIN; st.a.lrelu = 1;
+                set_out16(st, 0, cbuf[cur], 192, 64 + 32 * k, 1, 0);
+                push(st);
                 ++conv;
             }
-            ConvArgs a = base_args(conv, 0);  // model.py:94-96 (+ :129-130 for the third RDB)
-            a.res1 = xin_master; a.res_cstride = 64; a.res_choff = 0;
+            Step st = make_step(conv, 0, cbuf[cur], 192);  // model.py:94-96 (+ :129-130 for the third RDB)
+            set_res1(st, xin_master);
             if (j < 2) {
-                a.ep_mode = EP_RDB;
-                a.outf = F[j + 1];
+                st.a.ep_mode = EP_RDB;
+                set_outf(st, F[j + 1]);
             } else {
-                a.ep_mode = EP_RRDB;
-                a.res2 = X0;
-                a.outf = F[3];
+                st.a.ep_mode = EP_RRDB;
+                st.a.res2 = X0; st.a.res2_cstride = 64;
+                set_outf(st, F[3]);
             }
-            a.outf_cstride = 64; a.outf_choff = 0;
-            a.out16 = cbuf[cur ^ 1]; a.out16_fmt = 1; a.out16_cstride = 192; a.out16_choff = 0;
-            push(1 + cur, conv, a);
+            set_out16(st, 0, cbuf[cur ^ 1], 192, 0, 1, 0);
+            push(st);
             ++conv;
             cur ^= 1;
         }
     }
     {   // conv2 + skip (model.py:260-262), written nearest-upsampled x2 (model.py:264) in fp16
-        ConvArgs a = base_args(conv, 0);
-        a.ep_mode = EP_SKIP; a.res1 = F[0]; a.res_cstride = 64; a.res_choff = 0;
-        a.out16 = t1; a.out16_fmt = 0; a.out16_cstride = 64; a.out16_choff = 0; a.out16_up2 = 1;
-        push(1 + cur, conv, a);
+        Step st = make_step(conv, 0, cbuf[cur], 192);
+        st.a.ep_mode = EP_SKIP;
+        set_res1(st, F[0]);
+        set_out16(st, 0, t1, 64, 0, 0, 1);
+        push(st);
         ++conv;
     }
     {   // upsampling1 conv + LeakyReLU (model.py:264), output written upsampled x2 again (model.py:265)
-        ConvArgs a = base_args(conv, 1);
-        a.lrelu = 1;
-        a.out16 = t2; a.out16_fmt = 0; a.out16_cstride = 64; a.out16_up2 = 1;
-        push(3, conv, a);
+        Step st = make_step(conv, 1, t1, 64);
+        st.a.lrelu = 1;
+        set_out16(st, 1, t2, 64, 0, 0, 1);
+        push(st);
         ++conv;
     }
     {   // upsampling2 conv + LeakyReLU (model.py:265)
-        ConvArgs a = base_args(conv, 2);
-        a.lrelu = 1;
-        a.out16 = t3; a.out16_fmt = 0; a.out16_cstride = 64;
-        push(4, conv, a);
+        Step st = make_step(conv, 2, t2, 64);
+        st.a.lrelu = 1;
+        set_out16(st, 2, t3, 64, 0, 0, 0);
+        push(st);
         ++conv;
     }
     {   // conv3 + LeakyReLU (model.py:267)
-        ConvArgs a = base_args(conv, 2);
-        a.lrelu = 1;
-        a.out16 = t4; a.out16_fmt = 0; a.out16_cstride = 64;
-        push(5, conv, a);
+        Step st = make_step(conv, 2, t3, 64);
+        st.a.lrelu = 1;
+        set_out16(st, 2, t4, 64, 0, 0, 0);
+        push(st);
         ++conv;
     }
     {   // conv4 + clamp (model.py:268-270): fp32 NCHW result, pointer patched per call
-        ConvArgs a = base_args(conv, 2);
-        a.clamp01 = 1;
-        a.out_nchw = nullptr; a.out_nchw_c = 3;
-        push(6, conv, a);
+        Step st = make_step(conv, 2, t4, 64);
+        st.a.clamp01 = 1;
+        st.a.out_nchw = nullptr; st.a.out_nchw_c = 3;
+        push(st);
         ++conv;
     }
+    if (map_rc != 0) return set_error(RESR_E_CUDA, "tensor map / shared memory planning failed (%d)", map_rc);
     if (cudaStreamSynchronize(0) != cudaSuccess) return set_error(RESR_E_CUDA, "workspace init failed");
     p.valid = true;
     return RESR_OK;
@@ -438,7 +450,7 @@ int resr_generator_forward(resr_generator_t* g, const float* x, float* y, int n,
         Step& st = p.steps[i];
         if (i + 1 == p.steps.size()) st.a.out_nchw = y;
         const ConvSpec& cs = T.c[st.conv];
-        const cudaError_t e = conv3x3_launch(p.tmaps[st.tmap], st.a, cs.nout, cs.nslices, g->num_sms, s);
+        const cudaError_t e = conv3x3_launch(st.maps, st.a, cs.nout, cs.nslices, g->num_sms, s);
         if (e != cudaSuccess) return set_error(RESR_E_CUDA, "conv %d launch: %s", st.conv, cudaGetErrorString(e));
     }
     return RESR_OK;
@@ -492,8 +504,11 @@ int resr_conv3x3(const resr_conv_desc* d, void* stream) {
         return set_error(RESR_E_CUDA, "cudaMalloc failed");
     pack_conv_kernel<<<grid_for(pack_bytes / 2, 256), 256, 0, s>>>(d->weight, d->bias, reinterpret_cast<uint16_t*>(wp), bp,
                                                                  d->cin, d->cout, nout, nslices, nchunks, d->fmt_in);
+    cudaStreamSynchronize(s);  // the conv prefetches its weights before the programmatic grid dependency resolves
     ConvArgs a;
+    ConvMaps maps;
     memset(&a, 0, sizeof(a));
+    memset(&maps, 0, sizeof(maps));
     a.N = d->n; a.H = d->h; a.W = d->w;
     conv3x3_pick_tile(d->w, &a.BW, &a.BN);
     a.mode = d->mode >= 0 ? d->mode : (a.BN == 1 ? 0 : 1);
@@ -501,24 +516,33 @@ int resr_conv3x3(const resr_conv_desc* d, void* stream) {
     a.nxs = (d->w + a.BW - 1) / a.BW;
     a.ncg = ((d->n + a.BN - 1) / a.BN) * a.nxs;
     a.nchunks = nchunks;
-    a.nstages = conv3x3_pick_stages(nchunks, nout);
     a.fmt_in = d->fmt_in;
     a.rows_total = static_cast<long long>(a.ncg) * d->h;
     a.wpack = wp; a.bias = bp;
     a.ep_mode = d->ep_mode; a.lrelu = d->lrelu; a.clamp01 = d->clamp01;
-    a.out16 = d->out16; a.out16_fmt = d->out16_fmt; a.out16_cstride = d->out16_cstride; a.out16_choff = d->out16_choff;
-    a.out16_up2 = d->out16_up2;
-    a.outf = d->outf; a.outf_cstride = d->outf_cstride; a.outf_choff = d->outf_choff;
-    a.res1 = d->res1; a.res2 = d->res2; a.res_cstride = d->res_cstride; a.res_choff = d->res_choff;
+    int rc = conv3x3_make_tmap_act(&maps.a, d->in16, d->n, d->h, d->w, d->c_total, a.mode, a.BW, a.BN);
+    if (d->out16) {
+        a.has_out16 = 1; a.out16_fmt = d->out16_fmt; a.out16_choff = d->out16_choff; a.out16_up2 = d->out16_up2;
+        rc |= conv3x3_make_tmap_out16(&maps.o16, d->out16, d->n, d->h, d->w, d->out16_cstride, nout, a.BW, a.BN, d->out16_up2);
+    }
+    if (d->outf) {
+        a.has_outf = 1; a.outf_choff = d->outf_choff;
+        rc |= conv3x3_make_tmap_f32(&maps.of, d->outf, d->n, d->h, d->w, d->outf_cstride, a.BW, a.BN);
+    }
+    if (d->res1) {
+        a.has_res1 = 1; a.res_choff = d->res_choff;
+        rc |= conv3x3_make_tmap_f32(&maps.r1, d->res1, d->n, d->h, d->w, d->res_cstride, a.BW, a.BN);
+    }
+    a.res2 = d->res2; a.res2_cstride = d->res_cstride;
     a.out_nchw = d->out_nchw; a.out_nchw_c = d->out_nchw_c;
-    CUtensorMap tm;
-    int rc = conv3x3_make_tmap(&tm, d->in16, d->n, d->h, d->w, d->c_total, a.mode, a.BW, a.BN);
+    if (!conv3x3_plan_smem(&a, nout)) rc |= 1 << 20;
+    if (nout == 16 && (d->out16 || d->outf || d->res1)) rc |= 1 << 21;  // the 16-wide slice only feeds the NCHW output
     cudaError_t e = cudaSuccess;
-    if (rc == 0) e = conv3x3_launch(tm, a, nout, nslices, sms, s);
+    if (rc == 0) e = conv3x3_launch(maps, a, nout, nslices, sms, s);
     const cudaError_t e2 = cudaStreamSynchronize(s);
     cudaFree(wp);
     cudaFree(bp);
-    if (rc != 0) return set_error(RESR_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", rc);
+    if (rc != 0) return set_error(RESR_E_CUDA, "tensor map / shared memory planning failed (%d)", rc);
     if (e != cudaSuccess) return set_error(RESR_E_CUDA, "conv launch: %s", cudaGetErrorString(e));
     if (e2 != cudaSuccess) return set_error(RESR_E_CUDA, "conv run: %s", cudaGetErrorString(e2));
     return RESR_OK;

@@ -104,8 +104,8 @@ def test_conv_epilogues():
     up = torch.zeros(n, 2 * h, 2 * w, cout, device=dev, dtype=torch.float16)
     _run_conv(x16, cin, wt, b, fmt=1, ep_mode=3, res1=r1, out16=up, out16_fmt=0, out16_up2=1)
     ref_up = (r1 + conv).half().repeat_interleave(2, 1).repeat_interleave(2, 2)
-    # one fp16 ulp: the kernel rounds its own fp32 sum, which may differ from torch's in the last bit
-    assert ((up.float() - ref_up.float()).abs() <= ref_up.float().abs() * 2 ** -9 + 1e-6).all()
+    # fp16 ulp of the result plus fp32 accumulation-order noise (which dominates where r1 + conv cancels)
+    assert ((up.float() - ref_up.float()).abs() <= ref_up.float().abs() * 2 ** -9 + 2e-4).all()
     # lrelu
     outf.zero_()
     _run_conv(x16, cin, wt, b, fmt=1, lrelu=1, outf=outf)
@@ -124,3 +124,20 @@ def test_conv_rgb_out_clamped():
     _run_conv(x16, cin, wt, b, fmt=0, clamp01=1, out_nchw=y)
     ref = F.conv2d(x, wt, b, padding=1).clamp(0, 1)
     assert (y - ref).abs().max().item() < 2e-4
+
+
+@pytest.mark.parametrize("n,h,w,cin,c_total,cout", [(2, 40, 128, 64, 192, 32), (1, 33, 256, 128, 128, 64), (3, 9, 64, 64, 64, 32)])
+def test_conv_out16_only_two_epilogue_groups(n, h, w, cin, c_total, cout):
+    """16-bit NHWC output only: the configuration that runs two epilogue groups on alternating rows."""
+    torch.manual_seed(h + w)
+    dev = "cuda"
+    x = torch.randn(n, cin, h, w, device=dev).bfloat16().float()
+    wt = (torch.randn(cout, cin, 3, 3, device=dev) * 0.05).bfloat16().float()
+    b = torch.randn(cout, device=dev)
+    x16 = _nhwc16(x, c_total, torch.bfloat16)
+    o16 = torch.zeros(n, h, w, 192, device=dev, dtype=torch.bfloat16)
+    _run_conv(x16, cin, wt, b, fmt=1, lrelu=1, out16=o16, out16_choff=96)
+    ref = F.leaky_relu(F.conv2d(x, wt, b, padding=1), 0.2).permute(0, 2, 3, 1)
+    got = o16[..., 96:96 + cout].float()
+    assert ((got - ref).abs() <= ref.abs() * 2 ** -7 + 2e-4).all()
+    assert o16[..., :96].abs().max().item() == 0 and o16[..., 96 + cout:].abs().max().item() == 0

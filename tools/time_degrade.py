@@ -1,0 +1,31 @@
+"""Device-timed degradation pipeline on cfg2 (development aid)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import resr_b200
+from oracle import plan as oplan
+ip = resr_b200.imgproc
+B, H, W = 16, 256, 256
+dev = torch.device("cuda")
+plan = oplan.canonical_plan_s0(B, H, W, seed=0)
+hr = torch.rand(B, 3, H, W, device=dev)
+k = torch.zeros(B, 21, 21); ax = torch.arange(21) - 10.0
+for i in range(B):
+    ks = 7 + 2 * (i % 8); s = 0.5 + 0.3 * i
+    kk = torch.exp(-(ax[:, None] ** 2 + ax[None] ** 2) / (2 * s * s))
+    kk[(ax.abs() > ks // 2)[:, None] | (ax.abs() > ks // 2)[None]] = 0
+    k[i] = kk / kk.sum()
+k1 = k.to(dev); k2 = k.flip(0).contiguous().to(dev)
+sk = torch.zeros(B, 21, 21); sk[:, 10, 10] = 1; sk = sk.to(dev)
+for key in ("noise1", "noise2"):
+    for kk_, v in list(plan[key].items()):
+        if isinstance(v, np.ndarray): plan[key][kk_] = torch.from_numpy(v).to(dev)
+plan["jpeg1_quality"] = torch.from_numpy(plan["jpeg1_quality"]).to(dev)
+plan["jpeg2_quality"] = torch.from_numpy(plan["jpeg2_quality"]).to(dev)
+for _ in range(3): ip.degrade_batch(hr, k1, k2, sk, plan)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(20): ip.degrade_batch(hr, k1, k2, sk, plan)
+e1.record(); torch.cuda.synchronize()
+print(f"degrade_batch 16x3x256x256 S0: {e0.elapsed_time(e1)/20*1e3:.1f} us/batch")
