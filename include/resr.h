@@ -91,6 +91,8 @@ typedef struct resr_conv_desc {
     int res_cstride, res_choff;
     float* out_nchw;
     int out_nchw_c;
+    int dbg_flags;           /* experiments only (0 in production) */
+    unsigned long long* dbg; /* optional device buffer of 16 u64: phase timestamps of CTA (0,0), or NULL */
 } resr_conv_desc;
 int resr_conv3x3(const resr_conv_desc* d, void* stream);
 

@@ -27,6 +27,8 @@ class ConvDesc(Structure):
         ("res_cstride", c_int), ("res_choff", c_int),
         ("out_nchw", c_void_p),
         ("out_nchw_c", c_int),
+        ("dbg_flags", c_int),
+        ("dbg", c_void_p),
     ]
 
 

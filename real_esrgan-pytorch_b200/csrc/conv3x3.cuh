@@ -43,6 +43,8 @@ struct ConvArgs {
     int res2_cstride;
     float* out_nchw;       // NCHW fp32 output with out_nchw_c channels (or null)
     int out_nchw_c;
+    int dbg_flags;            // experiments only: 1 = skip output stores, 2 = producer re-reads row 0, 4 = issue 1/4 of the MMAs
+    unsigned long long* dbg;  // optional: CTA (0,0) writes phase timestamps (globaltimer ns) here, 16 slots
 };
 
 struct ConvMaps {

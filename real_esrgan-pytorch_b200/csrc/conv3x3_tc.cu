@@ -24,6 +24,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "conv3x3.cuh"
@@ -49,10 +50,17 @@ __device__ __forceinline__ RowRange cta_rows(const ConvArgs& a) {
     return r;
 }
 
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define RESR_DBG(slot) do { if (a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0) a.dbg[slot] = gtimer(); } while (0)
+
 __device__ __forceinline__ uint32_t slot_of(long long v) { return static_cast<uint32_t>((16 - (v & 15)) & 15); }
 
 __host__ __device__ inline int epi_group_bytes(const ConvArgs& a, int nout) {
-    const int f = (a.has_outf || a.has_res1) ? kTileFBytes : 0;
+    const int f = (a.has_outf ? kTileFBytes : 0) + (a.has_res1 ? kTileFBytes : 0);
     const int h = a.has_out16 ? 128 * nout * 2 : 0;
     return f + (h + 1023) / 1024 * 1024;
 }
@@ -65,32 +73,38 @@ __device__ __forceinline__ uint64_t desc_of(uint32_t lo) { return (static_cast<u
 // All MMAs of one pipeline stage, straight-line. SPLIT: 0 = one N=3*NOUT MMA at d0; 1 / 2 = ring seam (slot 14 / 15),
 // the (dy=0,1 | dy=2) resp. (dy=0 | dy=1,2) column blocks go to d0 and to the start of the ring. NDX: horizontal taps
 // served by this stage (3 in mode 0: descriptor shifted by dx pixels; 1 in mode 1).
-template <int NOUT, int SPLIT, int NDX>
-__device__ __forceinline__ void issue_stage(uint32_t d0, uint32_t ring0, uint32_t a_lo, uint32_t b_lo, uint32_t idesc3,
+template <int NOUT, int SPLIT, int I0, int I1>
+__device__ __forceinline__ void issue_range(uint32_t d0, uint32_t ring0, uint32_t a_lo, uint32_t b_lo, uint32_t idesc3,
                                             uint32_t idesc2, uint32_t idesc1) {
     constexpr uint32_t WT = (3 * NOUT * 128) >> 4;   // one (chunk, dx) weight tile, in 16-byte units
     constexpr uint32_t ROWS = (NOUT * 128) >> 4;     // NOUT weight rows
 #pragma unroll
-    for (int dx = 0; dx < NDX; ++dx) {
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t ad = desc_of(a_lo + dx * 8 + ks * 2);
-            const uint32_t bl = b_lo + dx * WT + ks * 2;
-            if (SPLIT == 0) {
-                umma_f16(d0, ad, desc_of(bl), idesc3, 1);
-            } else if (SPLIT == 1) {
-                umma_f16(d0, ad, desc_of(bl), idesc2, 1);
-                umma_f16(ring0, ad, desc_of(bl + 2 * ROWS), idesc1, 1);
-            } else {
-                umma_f16(d0, ad, desc_of(bl), idesc1, 1);
-                umma_f16(ring0, ad, desc_of(bl + ROWS), idesc2, 1);
-            }
+    for (int i = I0; i < I1; ++i) {                  // i = dx * 4 + ks
+        const int dx = i >> 2, ks = i & 3;
+        const uint64_t ad = desc_of(a_lo + dx * 8 + ks * 2);
+        const uint32_t bl = b_lo + dx * WT + ks * 2;
+        if (SPLIT == 0) {
+            umma_f16(d0, ad, desc_of(bl), idesc3, 1);
+        } else if (SPLIT == 1) {
+            umma_f16(d0, ad, desc_of(bl), idesc2, 1);
+            umma_f16(ring0, ad, desc_of(bl + 2 * ROWS), idesc1, 1);
+        } else {
+            umma_f16(d0, ad, desc_of(bl), idesc1, 1);
+            umma_f16(ring0, ad, desc_of(bl + ROWS), idesc2, 1);
         }
     }
 }
+// MMAs [I0, I1) of a stage, dispatching on the ring-seam case (uniform per output row).
+template <int NOUT, int I0, int I1>
+__device__ __forceinline__ void issue_part(uint32_t s0, uint32_t d0, uint32_t ring0, uint32_t a_lo, uint32_t b_lo,
+                                           uint32_t idesc3, uint32_t idesc2, uint32_t idesc1) {
+    if (s0 <= 13) issue_range<NOUT, 0, I0, I1>(d0, ring0, a_lo, b_lo, idesc3, idesc2, idesc1);
+    else if (s0 == 14) issue_range<NOUT, 1, I0, I1>(d0, ring0, a_lo, b_lo, idesc3, idesc2, idesc1);
+    else issue_range<NOUT, 2, I0, I1>(d0, ring0, a_lo, b_lo, idesc3, idesc2, idesc1);
+}
 
 template <int NOUT>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(512, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapO16,
                   const __grid_constant__ CUtensorMap tmapOF, const __grid_constant__ CUtensorMap tmapR1,
                   const ConvArgs a) {
@@ -103,6 +117,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
     const int slice = blockIdx.y;
+    if (threadIdx.x == 0) RESR_DBG(0);  // kernel entry
     const uint32_t wbytes = static_cast<uint32_t>(a.nchunks) * 3u * WTILE;
     const int epi_bytes = epi_group_bytes(a, NOUT);
 
@@ -115,8 +130,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     uint64_t* acc_full = empty + kMaxStages;
     uint64_t* slot_free = acc_full + kSlots;
     uint64_t* wbar = slot_free + kSlots;
-    uint64_t* res_full = wbar + 1;  // [2]
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full + 2);
+    uint64_t* res_full = wbar + 1;  // [4]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full + 4);
     float* bias_s = reinterpret_cast<float*>(misc + 512);
 
     if (threadIdx.x == 0) {
@@ -133,8 +148,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
             mbar_init(slot_free + i, 128);
         }
         mbar_init(wbar, 1);
-        mbar_init(res_full, 1);
-        mbar_init(res_full + 1, 1);
+        for (int i = 0; i < 4; ++i) mbar_init(res_full + i, 1);
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -146,6 +160,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tbase = *tmem_ptr;
+    if (threadIdx.x == 0) RESR_DBG(1);  // setup done (barriers, TMEM)
     // Programmatic dependent launch: the next kernel in the stream may take over SMs as soon as CTAs of this grid
     // retire (it parks in griddepcontrol.wait until this whole grid has completed and flushed).
     grid_dep_launch();
@@ -163,6 +178,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         }
         __syncwarp();
         grid_dep_wait();
+        RESR_DBG(2);  // previous grid complete
         int stage = 0;
         uint32_t phase = 0;
         const int ndx = a.mode == 0 ? 1 : 3;
@@ -181,7 +197,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
                         if (elect_one()) {
                             mbar_expect_tx(full + stage, tx_bytes);
                             tma_load_4d(stg + stage * kStageBytes, &tmapA, full + stage, c * 64,
-                                        a.mode == 0 ? x0 - 1 : x0 + dx - 1, r, n0);
+                                        a.mode == 0 ? x0 - 1 : x0 + dx - 1, (a.dbg_flags & 2) ? 0 : r, (a.dbg_flags & 2) ? 0 : n0);
                         }
                         __syncwarp();
                         if (++stage == a.nstages) { stage = 0; phase ^= 1; }
@@ -192,9 +208,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (whole warp, one elected lane issues)
-        // ONE thread feeds the tensor core, so its instruction count per MMA is the critical path: descriptors are
-        // (constant high word, 32-bit low word = smem address >> 4) and every MMA costs two integer adds.
+        // The tensor core is fed by ONE instruction stream, so everything that is not an MMA is latency the tensor pipe
+        // sees: descriptors are (constant high word, 32-bit low word) = two uniform adds per MMA, and the barrier of
+        // the NEXT pipeline step / accumulator slot is probed (non-blocking test_wait) in the middle of the current
+        // step's MMAs, so that in steady state no blocking wait sits between two steps.
         mbar_wait(wbar, 0);
+        RESR_DBG(3);  // weights resident
         tc_fence_after();
         const uint32_t idesc3 = make_idesc_f16(a.fmt_in, 128, 3 * NOUT);
         const uint32_t idesc2 = make_idesc_f16(a.fmt_in, 128, 2 * NOUT);
@@ -202,8 +221,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         const uint32_t w_lo = (smem_u32(wsm) & 0x3FFFFu) >> 4;
         const uint32_t s_lo = (smem_u32(stg) & 0x3FFFFu) >> 4;
         const int nsteps = a.mode == 0 ? a.nchunks : a.nchunks * 3;  // pipeline stages per input row
+        const uint32_t b_step = (a.mode == 0 ? 3 : 1) * (WTILE >> 4);
         int stage = 0;
         uint32_t phase = 0;
+        bool full_ready = false, slot_ready = false;
         long long v0 = 0, acq = 0;
         for (long long g = rr.g0; g < rr.g1;) {
             const int ya = static_cast<int>(g % H);
@@ -211,28 +232,43 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
             const int ra = max(ya - 1, 0), rb = min(yb, H - 1);
             for (int r = ra; r <= rb; ++r) {
                 const long long vr = v0 + (r - ra) + 1;  // virtual index of output row r
-                while (acq <= vr + 1) {                  // accumulators of rows r-1, r, r+1 must be zeroed & free
-                    mbar_wait(slot_free + slot_of(acq), static_cast<uint32_t>(acq >> 4) & 1);
-                    ++acq;
+                // accumulators of rows r-1, r, r+1 must be zeroed & free
+                if (slot_ready && acq == vr + 1) {
+                    ++acq;  // probed during the previous row
+                } else {
+                    while (acq <= vr + 1) {
+                        mbar_wait(slot_free + slot_of(acq), static_cast<uint32_t>(acq >> 4) & 1);
+                        ++acq;
+                    }
                 }
+                slot_ready = false;
                 tc_fence_after();
                 const uint32_t s0 = slot_of(vr + 1);
                 const uint32_t d0 = tbase + s0 * NOUT;
-                for (int st = 0; st < nsteps; ++st) {
-                    mbar_wait(full + stage, phase);
+                uint32_t b_lo = w_lo;
+                for (int st = 0; st < nsteps; ++st, b_lo += b_step) {
+                    if (!full_ready) mbar_wait(full + stage, phase);
+                    if (v0 == 0 && r == ra && st == 0) RESR_DBG(4);  // first activation stage landed
                     tc_fence_after();
                     const uint32_t a_lo = s_lo + stage * (kStageBytes >> 4);
-                    const uint32_t b_lo = w_lo + st * ((a.mode == 0 ? 3 : 1) * (WTILE >> 4));
+                    const int nstage = (stage + 1 == a.nstages) ? 0 : stage + 1;
+                    const uint32_t nphase = phase ^ (nstage == 0 ? 1u : 0u);
+                    if (a.dbg_flags & 4) {
+                        if (elect_one()) issue_part<NOUT, 0, 3>(s0, d0, tbase, a_lo, b_lo, idesc3, idesc2, idesc1);
+                    } else if (a.mode == 0) {
+                        if (elect_one()) issue_part<NOUT, 0, 6>(s0, d0, tbase, a_lo, b_lo, idesc3, idesc2, idesc1);
+                    } else {
+                        if (elect_one()) issue_part<NOUT, 0, 2>(s0, d0, tbase, a_lo, b_lo, idesc3, idesc2, idesc1);
+                    }
+                    __syncwarp();
+                    // probes for the next step, hidden behind the MMAs just queued
+                    full_ready = mbar_test_wait(full + nstage, nphase);
+                    if (st == nsteps - 1 && r < rb)
+                        slot_ready = mbar_test_wait(slot_free + slot_of(vr + 2), static_cast<uint32_t>((vr + 2) >> 4) & 1);
                     if (elect_one()) {
-                        if (a.mode == 0) {
-                            if (s0 <= 13) issue_stage<NOUT, 0, 3>(d0, tbase, a_lo, b_lo, idesc3, idesc2, idesc1);
-                            else if (s0 == 14) issue_stage<NOUT, 1, 3>(d0, tbase, a_lo, b_lo, idesc3, idesc2, idesc1);
-                            else issue_stage<NOUT, 2, 3>(d0, tbase, a_lo, b_lo, idesc3, idesc2, idesc1);
-                        } else {
-                            if (s0 <= 13) issue_stage<NOUT, 0, 1>(d0, tbase, a_lo, b_lo, idesc3, idesc2, idesc1);
-                            else if (s0 == 14) issue_stage<NOUT, 1, 1>(d0, tbase, a_lo, b_lo, idesc3, idesc2, idesc1);
-                            else issue_stage<NOUT, 2, 1>(d0, tbase, a_lo, b_lo, idesc3, idesc2, idesc1);
-                        }
+                        if (a.dbg_flags & 4) {}
+                        else if (a.mode == 0) issue_part<NOUT, 6, 12>(s0, d0, tbase, a_lo, b_lo, idesc3, idesc2, idesc1);
+                        else issue_part<NOUT, 2, 4>(s0, d0, tbase, a_lo, b_lo, idesc3, idesc2, idesc1);
                         umma_commit(empty + stage);
                         if (st == nsteps - 1) {
                             umma_commit(acc_full + slot_of(vr - 1));  // row r-1 has its last contribution
@@ -243,12 +279,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
                         }
                     }
                     __syncwarp();
-                    if (++stage == a.nstages) { stage = 0; phase ^= 1; }
+                    stage = nstage;
+                    phase = nphase;
                 }
             }
             v0 += rb - ra + 3;
             g += yb - ya;
         }
+        RESR_DBG(5);  // all MMAs issued
     } else if (warp >= 4) {
         // ------------------------------------------------------------------ epilogue groups
         const int gi = (warp - 4) >> 2;
@@ -256,10 +294,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         const int m = q * 32 + lane;   // M row == TMEM lane == pixel of the tile
         const bool lead_warp = ((warp - 4) & 3) == 0;  // first warp of the group issues its TMA traffic
         const bool staged = a.has_out16 || a.has_outf || a.has_res1;
-        uint8_t* tileF = epi + gi * epi_bytes;
-        uint8_t* tile16 = tileF + ((a.has_outf || a.has_res1) ? kTileFBytes : 0);
+        uint8_t* tileR = epi + gi * epi_bytes;                       // fp32 residual tile (TMA load)
+        uint8_t* tileF = tileR + (a.has_res1 ? kTileFBytes : 0);     // fp32 output tile (TMA store)
+        uint8_t* tile16 = tileF + (a.has_outf ? kTileFBytes : 0);    // 16-bit output tile (TMA store)
         uint64_t* rbar = res_full + gi;
         uint32_t res_phase = 0;
+        bool res_inflight = false;  // the residual tile of the row about to be processed was prefetched
         const uint32_t lane_base = tbase + (static_cast<uint32_t>(q * 32) << 16);
         const int img_in_tile = m / a.BW;
         const int x_in_tile = m % a.BW;
@@ -291,13 +331,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
                 const int y = ra - 1 + j;
                 const bool emit = (y >= ya) && (y < yb);
                 const uint32_t slot = slot_of(v);
-                if (emit && staged) {
-                    if (lead_warp) tma_store_wait_read();  // previous stores of this group have drained the tiles
-                    named_bar_sync(1 + gi, 128);
-                    if (lead_warp && a.has_res1) {
+                if (emit && a.has_res1 && !res_inflight) {  // first row of a strip for this group: nothing prefetched
+                    if (lead_warp) {
                         if (elect_one()) {
                             mbar_expect_tx(rbar, 128 * 128);
-                            tma_load_4d(tileF, &tmapR1, rbar, a.res_choff + slice * NOUT, x0, y, n0);
+                            tma_load_4d(tileR, &tmapR1, rbar, a.res_choff + slice * NOUT, x0, y, n0);
                         }
                         __syncwarp();
                     }
@@ -315,12 +353,35 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
 
 #pragma unroll
                 for (int i = 0; i < NOUT; ++i) val[i] = __fadd_rn(val[i], bias_s[i]);
+                float4 resv[NOUT / 4];
                 if (a.has_res1) {
                     mbar_wait(rbar, res_phase);
                     res_phase ^= 1;
 #pragma unroll
+                    for (int i = 0; i < NOUT / 4; ++i)
+                        resv[i] = *reinterpret_cast<const float4*>(tileR + m * 128 + ((i ^ (m & 7)) << 4));
+                }
+                if (staged) {
+                    // tiles are free once the previous TMA stores have read them and (residual tile) everyone has
+                    // copied its row to registers; then the NEXT row's residual is fetched behind this row's math
+                    if (lead_warp) tma_store_wait_read();
+                    named_bar_sync(1 + gi, 128);
+                    res_inflight = false;
+                    if (a.has_res1 && y + a.nepi < yb) {
+                        res_inflight = true;
+                        if (lead_warp) {
+                            if (elect_one()) {
+                                mbar_expect_tx(rbar, 128 * 128);
+                                tma_load_4d(tileR, &tmapR1, rbar, a.res_choff + slice * NOUT, x0, y + a.nepi, n0);
+                            }
+                            __syncwarp();
+                        }
+                    }
+                }
+                if (a.has_res1) {
+#pragma unroll
                     for (int i = 0; i < NOUT / 4; ++i) {
-                        const float4 r4 = *reinterpret_cast<const float4*>(tileF + m * 128 + ((i ^ (m & 7)) << 4));
+                        const float4 r4 = resv[i];
                         if (a.ep_mode == EP_SKIP) {
                             val[4 * i + 0] = __fadd_rn(r4.x, val[4 * i + 0]);
                             val[4 * i + 1] = __fadd_rn(r4.y, val[4 * i + 1]);
@@ -380,7 +441,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
                 if (staged) {
                     fence_proxy_async_smem();
                     named_bar_sync(1 + gi, 128);
-                    if (lead_warp) {
+                    if (lead_warp && !(a.dbg_flags & 1)) {
                       if (elect_one()) {
                         if (a.has_outf) tma_store_4d(&tmapOF, tileF, a.outf_choff + slice * NOUT, x0, y, n0);
                         if (a.has_out16) {
@@ -411,10 +472,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
             g += yb - ya;
         }
         if (lead_warp) tma_store_wait_all();
+        if (gi == 0 && lead_warp) RESR_DBG(6);  // epilogue group 0 drained
     }
 
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) RESR_DBG(7);  // CTA done
     if (warp == 2) tmem_dealloc(tbase, 512);
 }
 
@@ -422,15 +485,20 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
 
 bool conv3x3_plan_smem(ConvArgs* a, int cout_slice) {
     const int wbytes = a->nchunks * 3 * (3 * cout_slice) * 128;
-    const int per_stage_cycles = 12 * (3 * cout_slice / 2);  // MMA cycles one stage feeds (mode 0)
-    // two epilogue groups when a row's MMAs are shorter than one group's drain latency, and staging is cheap
-    int nepi = (a->nchunks * per_stage_cycles < 1500 && !a->has_outf && !a->has_res1) ? 2 : 1;
+    // The per-row epilogue latency (TMEM drain, staging, TMA store; ~1.6k cycles, ~3.6k with the fp32 residual tile) is
+    // hidden by running several epilogue groups on consecutive rows; a row's MMAs take nchunks * 672 cycles.
+    const bool fp32_tiles = a->has_outf || a->has_res1;
+    int nepi = fp32_tiles ? 2 : (a->nchunks == 1 ? 3 : 2);
+    const char* env = getenv("RESR_CONV_NEPI");
+    if (env) nepi = atoi(env);
+    if (nepi < 1) nepi = 1;
+    if (nepi > 3) nepi = 3;
     for (;; --nepi) {
         a->nepi = nepi;
         const int fixed = 1024 + wbytes + nepi * epi_group_bytes(*a, cout_slice) + kMiscBytes;
         int ns = (kSmemMax - fixed) / kStageBytes;
         if (ns > kMaxStages) ns = kMaxStages;
-        if (ns >= 3 || nepi == 1) {
+        if (ns >= 4 || nepi == 1) {
             a->nstages = ns;
             return ns >= 2;
         }
@@ -548,7 +616,7 @@ cudaError_t conv3x3_launch(const ConvMaps& maps, const ConvArgs& args, int cout_
                            cudaStream_t stream) {
     const int wbytes = args.nchunks * 3 * (3 * cout_slice) * 128;
     const int smem = 1024 + wbytes + args.nstages * kStageBytes + args.nepi * epi_group_bytes(args, cout_slice) + kMiscBytes;
-    if (args.nstages < 2 || args.nepi < 1 || args.nepi > 2 || smem > kSmemMax) return cudaErrorInvalidConfiguration;
+    if (args.nstages < 2 || args.nepi < 1 || args.nepi > 3 || smem > kSmemMax) return cudaErrorInvalidConfiguration;
     long long gx = num_sms / nslices;
     const long long min_rows = 4;  // do not shred tiny problems into 1-row strips (2 halo rows each)
     const long long cap = (args.rows_total + min_rows - 1) / min_rows;

@@ -535,6 +535,8 @@ int resr_conv3x3(const resr_conv_desc* d, void* stream) {
     }
     a.res2 = d->res2; a.res2_cstride = d->res_cstride;
     a.out_nchw = d->out_nchw; a.out_nchw_c = d->out_nchw_c;
+    a.dbg = d->dbg;
+    a.dbg_flags = d->dbg_flags;
     if (!conv3x3_plan_smem(&a, nout)) rc |= 1 << 20;
     if (nout == 16 && (d->out16 || d->outf || d->res1)) rc |= 1 << 21;  // the 16-wide slice only feeds the NCHW output
     cudaError_t e = cudaSuccess;
