@@ -103,6 +103,91 @@ __device__ __forceinline__ void issue_part(uint32_t s0, uint32_t d0, uint32_t ri
     else issue_range<NOUT, 2, I0, I1>(d0, ring0, a_lo, b_lo, idesc3, idesc2, idesc1);
 }
 
+
+// The MMA-issuing warp. The tensor core is fed by ONE instruction stream with a shallow queue, so every non-MMA
+// instruction of this warp is tensor-pipe idle time (tools/mma_bench3.cu): the loop keeps 32-bit incremental
+// bookkeeping, probes the NEXT step's barriers (non-blocking test_wait) between the two halves of the current step's
+// MMAs, and spaces the two tcgen05.commit of a row (stage release of the previous step, accumulator completion) at
+// least six MMAs apart (back-to-back commits cost ~190 cycles each, spaced ones ~90).
+template <int NOUT, int MODE>
+__device__ __forceinline__ void mma_role(const ConvArgs& a, const RowRange rr, const uint32_t tbase, const uint32_t wsm_addr,
+                                         const uint32_t stg_addr, const uint32_t full_a, const uint32_t empty_a,
+                                         const uint32_t accfull_a, const uint32_t slotfree_a) {
+    constexpr int NMMA = MODE == 0 ? 12 : 4;  // MMAs per pipeline step
+    constexpr uint32_t WT = (3 * NOUT * 128) >> 4;
+    const uint32_t idesc3 = make_idesc_f16(a.fmt_in, 128, 3 * NOUT);
+    const uint32_t idesc2 = make_idesc_f16(a.fmt_in, 128, 2 * NOUT);
+    const uint32_t idesc1 = make_idesc_f16(a.fmt_in, 128, NOUT);
+    const uint32_t w_lo = (wsm_addr & 0x3FFFFu) >> 4;
+    const uint32_t s_lo = (stg_addr & 0x3FFFFu) >> 4;
+    const int nsteps = MODE == 0 ? a.nchunks : a.nchunks * 3;
+    const uint32_t b_step = (MODE == 0 ? 3 : 1) * WT;
+    const int nstages = a.nstages;
+    const int H = a.H;
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t a_lo = s_lo;
+    int pending_empty = -1;          // stage whose release commit has not been issued yet
+    bool full_ready = false, slot_ready = false;
+    uint32_t vnew = 1;               // virtual index of the NEWEST accumulator the next row touches (out row r+1)
+    uint32_t acq = 0;                // accumulators acquired so far (virtual indices < acq)
+    for (long long g = rr.g0; g < rr.g1;) {
+        const int ya = static_cast<int>(g % H);
+        const int yb = static_cast<int>(min(static_cast<long long>(H), ya + (rr.g1 - g)));
+        const int ra = max(ya - 1, 0), rb = min(yb, H - 1);
+        vnew += 1;                   // a strip touches rows ra-1 .. rb+1: first row's newest accumulator is v0 + 2
+        for (int r = ra; r <= rb; ++r, ++vnew) {
+            // accumulators of rows r-1, r, r+1 (virtual vnew-2 .. vnew) must be zeroed & free
+            if (slot_ready && acq == vnew) {
+                ++acq;
+            } else {
+                while (static_cast<int>(vnew - acq) >= 0) {
+                    mbar_wait_a(slotfree_a + (((0u - acq) & 15u) << 3), (acq >> 4) & 1u);
+                    ++acq;
+                }
+            }
+            slot_ready = false;
+            tc_fence_after();
+            const uint32_t s0 = (0u - vnew) & 15u;
+            const uint32_t d0 = tbase + s0 * NOUT;
+            uint32_t b_lo = w_lo;
+            for (int st = 0; st < nsteps; ++st, b_lo += b_step) {
+                if (!full_ready) mbar_wait_a(full_a + (stage << 3), phase);
+                tc_fence_after();
+                const bool last = (st == nsteps - 1);
+                if (elect_one()) {
+                    issue_part<NOUT, 0, NMMA / 2>(s0, d0, tbase, a_lo, b_lo, idesc3, idesc2, idesc1);
+                    if (pending_empty >= 0) umma_commit_a(empty_a + (pending_empty << 3));
+                }
+                __syncwarp();
+                pending_empty = stage;
+                // advance the ring, then probe the next step's barriers behind the MMAs just queued
+                const uint32_t a_cur = a_lo;
+                if (++stage == nstages) { stage = 0; phase ^= 1u; a_lo = s_lo; } else { a_lo += kStageBytes >> 4; }
+                full_ready = mbar_test_wait_a(full_a + (stage << 3), phase);
+                if (last && r < rb) slot_ready = mbar_test_wait_a(slotfree_a + (((0u - (vnew + 1)) & 15u) << 3), ((vnew + 1) >> 4) & 1u);
+                if (elect_one()) {
+                    issue_part<NOUT, NMMA / 2, NMMA>(s0, d0, tbase, a_cur, b_lo, idesc3, idesc2, idesc1);
+                    if (last) {
+                        umma_commit_a(accfull_a + (((s0 + 2) & 15u) << 3));      // row r-1 has its last contribution
+                        if (r == rb) {                                            // strip end: rows rb, rb+1 get no more
+                            umma_commit_a(accfull_a + (((s0 + 1) & 15u) << 3));
+                            umma_commit_a(accfull_a + (s0 << 3));
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        vnew += 1;                   // strip used rb-ra+3 virtual indices
+        g += yb - ya;
+    }
+    if (pending_empty >= 0) {
+        if (elect_one()) umma_commit_a(empty_a + (pending_empty << 3));
+        __syncwarp();
+    }
+}
+
 template <int NOUT>
 __global__ void __launch_bounds__(512, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapO16,
@@ -197,7 +282,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
                         if (elect_one()) {
                             mbar_expect_tx(full + stage, tx_bytes);
                             tma_load_4d(stg + stage * kStageBytes, &tmapA, full + stage, c * 64,
-                                        a.mode == 0 ? x0 - 1 : x0 + dx - 1, (a.dbg_flags & 2) ? 0 : r, (a.dbg_flags & 2) ? 0 : n0);
+                                        a.mode == 0 ? x0 - 1 : x0 + dx - 1, r, n0);
                         }
                         __syncwarp();
                         if (++stage == a.nstages) { stage = 0; phase ^= 1; }
@@ -208,84 +293,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (whole warp, one elected lane issues)
-        // The tensor core is fed by ONE instruction stream, so everything that is not an MMA is latency the tensor pipe
-        // sees: descriptors are (constant high word, 32-bit low word) = two uniform adds per MMA, and the barrier of
-        // the NEXT pipeline step / accumulator slot is probed (non-blocking test_wait) in the middle of the current
-        // step's MMAs, so that in steady state no blocking wait sits between two steps.
         mbar_wait(wbar, 0);
         RESR_DBG(3);  // weights resident
         tc_fence_after();
-        const uint32_t idesc3 = make_idesc_f16(a.fmt_in, 128, 3 * NOUT);
-        const uint32_t idesc2 = make_idesc_f16(a.fmt_in, 128, 2 * NOUT);
-        const uint32_t idesc1 = make_idesc_f16(a.fmt_in, 128, NOUT);
-        const uint32_t w_lo = (smem_u32(wsm) & 0x3FFFFu) >> 4;
-        const uint32_t s_lo = (smem_u32(stg) & 0x3FFFFu) >> 4;
-        const int nsteps = a.mode == 0 ? a.nchunks : a.nchunks * 3;  // pipeline stages per input row
-        const uint32_t b_step = (a.mode == 0 ? 3 : 1) * (WTILE >> 4);
-        int stage = 0;
-        uint32_t phase = 0;
-        bool full_ready = false, slot_ready = false;
-        long long v0 = 0, acq = 0;
-        for (long long g = rr.g0; g < rr.g1;) {
-            const int ya = static_cast<int>(g % H);
-            const int yb = static_cast<int>(min(static_cast<long long>(H), ya + (rr.g1 - g)));
-            const int ra = max(ya - 1, 0), rb = min(yb, H - 1);
-            for (int r = ra; r <= rb; ++r) {
-                const long long vr = v0 + (r - ra) + 1;  // virtual index of output row r
-                // accumulators of rows r-1, r, r+1 must be zeroed & free
-                if (slot_ready && acq == vr + 1) {
-                    ++acq;  // probed during the previous row
-                } else {
-                    while (acq <= vr + 1) {
-                        mbar_wait(slot_free + slot_of(acq), static_cast<uint32_t>(acq >> 4) & 1);
-                        ++acq;
-                    }
-                }
-                slot_ready = false;
-                tc_fence_after();
-                const uint32_t s0 = slot_of(vr + 1);
-                const uint32_t d0 = tbase + s0 * NOUT;
-                uint32_t b_lo = w_lo;
-                for (int st = 0; st < nsteps; ++st, b_lo += b_step) {
-                    if (!full_ready) mbar_wait(full + stage, phase);
-                    if (v0 == 0 && r == ra && st == 0) RESR_DBG(4);  // first activation stage landed
-                    tc_fence_after();
-                    const uint32_t a_lo = s_lo + stage * (kStageBytes >> 4);
-                    const int nstage = (stage + 1 == a.nstages) ? 0 : stage + 1;
-                    const uint32_t nphase = phase ^ (nstage == 0 ? 1u : 0u);
-                    if (a.dbg_flags & 4) {
-                        if (elect_one()) issue_part<NOUT, 0, 3>(s0, d0, tbase, a_lo, b_lo, idesc3, idesc2, idesc1);
-                    } else if (a.mode == 0) {
-                        if (elect_one()) issue_part<NOUT, 0, 6>(s0, d0, tbase, a_lo, b_lo, idesc3, idesc2, idesc1);
-                    } else {
-                        if (elect_one()) issue_part<NOUT, 0, 2>(s0, d0, tbase, a_lo, b_lo, idesc3, idesc2, idesc1);
-                    }
-                    __syncwarp();
-                    // probes for the next step, hidden behind the MMAs just queued
-                    full_ready = mbar_test_wait(full + nstage, nphase);
-                    if (st == nsteps - 1 && r < rb)
-                        slot_ready = mbar_test_wait(slot_free + slot_of(vr + 2), static_cast<uint32_t>((vr + 2) >> 4) & 1);
-                    if (elect_one()) {
-                        if (a.dbg_flags & 4) {}
-                        else if (a.mode == 0) issue_part<NOUT, 6, 12>(s0, d0, tbase, a_lo, b_lo, idesc3, idesc2, idesc1);
-                        else issue_part<NOUT, 2, 4>(s0, d0, tbase, a_lo, b_lo, idesc3, idesc2, idesc1);
-                        umma_commit(empty + stage);
-                        if (st == nsteps - 1) {
-                            umma_commit(acc_full + slot_of(vr - 1));  // row r-1 has its last contribution
-                            if (r == rb) {
-                                umma_commit(acc_full + slot_of(vr));
-                                umma_commit(acc_full + slot_of(vr + 1));
-                            }
-                        }
-                    }
-                    __syncwarp();
-                    stage = nstage;
-                    phase = nphase;
-                }
-            }
-            v0 += rb - ra + 3;
-            g += yb - ya;
-        }
+        if (a.mode == 0) mma_role<NOUT, 0>(a, rr, tbase, smem_u32(wsm), smem_u32(stg), smem_u32(full), smem_u32(empty), smem_u32(acc_full), smem_u32(slot_free));
+        else mma_role<NOUT, 1>(a, rr, tbase, smem_u32(wsm), smem_u32(stg), smem_u32(full), smem_u32(empty), smem_u32(acc_full), smem_u32(slot_free));
         RESR_DBG(5);  // all MMAs issued
     } else if (warp >= 4) {
         // ------------------------------------------------------------------ epilogue groups
@@ -441,7 +453,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
                 if (staged) {
                     fence_proxy_async_smem();
                     named_bar_sync(1 + gi, 128);
-                    if (lead_warp && !(a.dbg_flags & 1)) {
+                    if (lead_warp) {
                       if (elect_one()) {
                         if (a.has_outf) tma_store_4d(&tmapOF, tileF, a.outf_choff + slice * NOUT, x0, y, n0);
                         if (a.has_out16) {

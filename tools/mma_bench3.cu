@@ -77,6 +77,17 @@ __global__ void __launch_bounds__(128, 1) bench(int variant, int iters, long lon
             } else if (variant == 5) {  // no waits at all, 1 commit
                 if (elect_one()) { issue<0, 12>(d, a_lo, b_lo, idesc); umma_commit(&done_bar[i & 7]); }
                 __syncwarp();
+            } else if (variant == 7) {  // 6 MMA, commit, 6 MMA, commit (spaced commits)
+                if (elect_one()) { issue<0, 6>(d, a_lo, b_lo, idesc); umma_commit(&done_bar[i & 7]); issue<6, 12>(d, a_lo, b_lo, idesc); umma_commit(&done_bar[(i + 4) & 7]); }
+                __syncwarp();
+            } else if (variant == 8) {  // 12 MMA, then 2 commits issued by ANOTHER elected pass after a syncwarp
+                if (elect_one()) { issue<0, 12>(d, a_lo, b_lo, idesc); }
+                __syncwarp();
+                if (elect_one()) { umma_commit(&done_bar[i & 7]); }
+                __syncwarp();
+            } else if (variant == 9) {  // 24 MMAs then 1 commit
+                if (elect_one()) { issue<0, 12>(d, a_lo, b_lo, idesc); issue<0, 12>(d, a_lo, b_lo, idesc); umma_commit(&done_bar[i & 7]); }
+                __syncwarp();
             } else if (variant == 6) {  // one wait per 2 stages (24 MMAs), 1 commit per 12
                 if ((i & 1) == 0) { mbar_wait(rb, 0); tc_fence_after(); }
                 if (elect_one()) { issue<0, 12>(d, a_lo, b_lo, idesc); umma_commit(&done_bar[i & 7]); }
@@ -101,8 +112,8 @@ int main() {
     const int iters = 4000;
     const char* names[] = {"pure MMA stream", "split issue + 2 probes + 2 commits (current)", "try_wait + fence + 12 MMA + commit",
                            "try_wait + fence + 12 MMA + 2 commits", "2 try_wait + fence + 12 MMA + 2 commits", "12 MMA + commit, no waits",
-                           "1 wait per 24 MMA, commit per 12"};
-    for (int v = 0; v < 7; ++v) {
+                           "1 wait per 24 MMA, commit per 12", "6 MMA, commit, 6 MMA, commit", "12 MMA | commit (separate elect)", "24 MMA + commit (per 2 stages)"};
+    for (int v = 0; v < 10; ++v) {
         bench<<<148, 128, 100 * 1024>>>(v, iters, d);
         long long c = 0;
         cudaError_t e = cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
