@@ -140,10 +140,11 @@ int resr_unique_count_u8(const float* image, int* counts_color, int* counts_gray
 int resr_poisson_rates(const float* image, float* rate_color, float* rate_gray, int b, int c, int h, int w,
                        void* workspace, size_t workspace_bytes, void* stream);
 /* random_add_poisson_noise_torch(clip, rounds) with its draws fed in: scale[b], gray[b],
- * samples_color = poisson(rate_color), samples_gray = poisson(rate_gray) or NULL. */
+ * samples_color = poisson(rate_color), samples_gray = poisson(rate_gray) or NULL. reuse_counts=1: the unique counts of
+ * this image are already in `workspace` (left there by resr_poisson_rates on the same image), skip recounting. */
 int resr_poisson_noise_apply(const float* image, float* out, const float* scale, const float* gray,
                              const float* samples_color, const float* samples_gray, int b, int c, int h, int w, int clip,
-                             int rounds, void* workspace, size_t workspace_bytes, void* stream);
+                             int rounds, void* workspace, size_t workspace_bytes, int reuse_counts, void* stream);
 
 /* imgproc.DiffJPEG(differentiable=False).forward(image, quality[b]) (imgproc.py:1462-1494). quality is NOT modified;
  * the factor the reference writes back in place (imgproc.py:1478-1479) is returned in factor_out[b] (may be NULL).

@@ -21,11 +21,38 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {  // ATen reflection_p
 }
 
 // ===================================================================================== filter2d (a8)
-// One block = 32 x 32 output tile of one (sample, channel) plane; 256 threads, each owns 4 consecutive rows of one
-// column. The reflect-padded (32+k-1)^2 input tile and the k x k taps live in shared memory; zero rows/columns
-// at the border of the (zero-padded 7..21 -> 21) kernel are trimmed per sample.
-static constexpr int kF2dTile = 32;
-static constexpr int kF2dRows = 4;
+// One block = 64 x 64 output tile of one (sample, channel) plane; 256 threads = 32 columns x 8 row groups, each thread
+// owns 8 consecutive rows of 2 columns (x and x+32). The reflect-padded halo tile and the taps live in shared memory.
+// The kernels of the degradation model are 7..21 supports zero-padded to 21 (dataset.py:102-103): the block finds
+// the centred square support KS of its sample and runs the KS-specialised body, whose (row, output) loops are fully
+// unrolled with the current tap column in registers: 16*KS FMAs per (2*(KS+7) + KS) shared loads.
+static constexpr int kF2dTile = 64;
+static constexpr int kF2dRows = 8;
+
+template <int KS>
+__device__ __forceinline__ void filter2d_body(const float* __restrict__ tile, int tpitch, const float* __restrict__ taps, int k,
+                                              int off, int tx, int ty0, float (&acc)[2][kF2dRows]) {
+    // taps: full k x k array; the KS x KS centred window starts at (off, off). tile row 0 / col 0 correspond to output
+    // (0,0) shifted by -(k/2); the window adds `off` again.
+    for (int kx = 0; kx < KS; ++kx) {
+        float w[KS];
+#pragma unroll
+        for (int ky = 0; ky < KS; ++ky) w[ky] = taps[(off + ky) * k + off + kx];
+        const float* col = tile + (ty0 + off) * tpitch + tx + off + kx;
+#pragma unroll
+        for (int rr = 0; rr < KS + kF2dRows - 1; ++rr) {
+            const float v0 = col[rr * tpitch], v1 = col[rr * tpitch + 32];
+#pragma unroll
+            for (int j = 0; j < kF2dRows; ++j) {
+                const int ky = rr - j;
+                if (ky >= 0 && ky < KS) {
+                    acc[0][j] = fmaf(v0, w[ky], acc[0][j]);
+                    acc[1][j] = fmaf(v1, w[ky], acc[1][j]);
+                }
+            }
+        }
+    }
+}
 
 __global__ void __launch_bounds__(256) filter2d_kernel(const float* __restrict__ in, const float* __restrict__ kern,
                                                        float* __restrict__ out, int B, int C, int H, int W, int k,
@@ -33,57 +60,76 @@ __global__ void __launch_bounds__(256) filter2d_kernel(const float* __restrict__
     extern __shared__ float sm[];
     const int r = k / 2;
     const int tw = kF2dTile + k - 1;
-    float* tile = sm;                 // [tw][tw + 1]
-    float* taps = sm + tw * (tw + 1);  // [k][k]
-    __shared__ int s_lo_y, s_hi_y, s_lo_x, s_hi_x;
-    const int plane = blockIdx.z;     // b * C + c
+    const int tpitch = tw + 1;
+    float* tile = sm;                  // [tw][tw + 1]
+    float* taps = sm + tw * tpitch;    // [k][k]
+    __shared__ int s_ext;              // max |offset from centre| of a non-zero tap
+    const int plane = blockIdx.z;      // b * C + c
     const int b = plane / C;
     const int x0 = blockIdx.x * kF2dTile, y0 = blockIdx.y * kF2dTile;
     const float* src = in + static_cast<size_t>(plane) * H * W;
     const float* kp = kern + (kern_batched ? static_cast<size_t>(b) * k * k : 0);
-    if (threadIdx.x == 0) { s_lo_y = k; s_hi_y = -1; s_lo_x = k; s_hi_x = -1; }
+    if (threadIdx.x == 0) s_ext = 0;
     __syncthreads();
     for (int i = threadIdx.x; i < k * k; i += blockDim.x) {
         const float v = kp[i];
         taps[i] = v;
-        if (v != 0.f) {
-            atomicMin(&s_lo_y, i / k); atomicMax(&s_hi_y, i / k);
-            atomicMin(&s_lo_x, i % k); atomicMax(&s_hi_x, i % k);
-        }
+        if (v != 0.f) atomicMax(&s_ext, max(abs(i / k - r), abs(i % k - r)));
     }
     for (int i = threadIdx.x; i < tw * tw; i += blockDim.x) {
         const int ty = i / tw, tx = i % tw;
         const int gy = reflect_idx(y0 + ty - r, H), gx = reflect_idx(x0 + tx - r, W);
-        // rows/cols beyond the image that the tile overhang would touch are clamped: their outputs are never stored
+        // positions the tile overhang would touch beyond the image are clamped: their outputs are never stored
         const int cy = min(max(gy, 0), H - 1), cx = min(max(gx, 0), W - 1);
-        tile[ty * (tw + 1) + tx] = src[static_cast<size_t>(cy) * W + cx];
+        tile[ty * tpitch + tx] = src[static_cast<size_t>(cy) * W + cx];
     }
     __syncthreads();
-    const int lo_y = s_lo_y, hi_y = s_hi_y, lo_x = s_lo_x, hi_x = s_hi_x;
+    const int ext = s_ext;
+    const int off = r - ext;           // first row/col of the centred support inside the k x k array
     const int tx = threadIdx.x & 31;
     const int ty0 = (threadIdx.x >> 5) * kF2dRows;
-    float acc[kF2dRows];
+    float acc[2][kF2dRows];
 #pragma unroll
-    for (int j = 0; j < kF2dRows; ++j) acc[j] = 0.f;
-    if (hi_y >= lo_y) {
-        for (int kx = lo_x; kx <= hi_x; ++kx) {
-            // sliding window down the column: input row (ty0 + rr) feeds output j with tap ky = rr - j
-            for (int rr = lo_y; rr <= hi_y + kF2dRows - 1; ++rr) {
-                const float v = tile[(ty0 + rr) * (tw + 1) + tx + kx];
+    for (int j = 0; j < kF2dRows; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
+    switch (2 * ext + 1) {
+        case 1: filter2d_body<1>(tile, tpitch, taps, k, off, tx, ty0, acc); break;
+        case 3: filter2d_body<3>(tile, tpitch, taps, k, off, tx, ty0, acc); break;
+        case 5: filter2d_body<5>(tile, tpitch, taps, k, off, tx, ty0, acc); break;
+        case 7: filter2d_body<7>(tile, tpitch, taps, k, off, tx, ty0, acc); break;
+        case 9: filter2d_body<9>(tile, tpitch, taps, k, off, tx, ty0, acc); break;
+        case 11: filter2d_body<11>(tile, tpitch, taps, k, off, tx, ty0, acc); break;
+        case 13: filter2d_body<13>(tile, tpitch, taps, k, off, tx, ty0, acc); break;
+        case 15: filter2d_body<15>(tile, tpitch, taps, k, off, tx, ty0, acc); break;
+        case 17: filter2d_body<17>(tile, tpitch, taps, k, off, tx, ty0, acc); break;
+        case 19: filter2d_body<19>(tile, tpitch, taps, k, off, tx, ty0, acc); break;
+        case 21: filter2d_body<21>(tile, tpitch, taps, k, off, tx, ty0, acc); break;
+        default: {  // generic odd support (k <= 63): rolled loops
+            const int ks = 2 * ext + 1;
+            for (int kx = 0; kx < ks; ++kx)
+                for (int rr = 0; rr < ks + kF2dRows - 1; ++rr) {
+                    const float v0 = tile[(ty0 + off + rr) * tpitch + tx + off + kx];
+                    const float v1 = tile[(ty0 + off + rr) * tpitch + tx + 32 + off + kx];
 #pragma unroll
-                for (int j = 0; j < kF2dRows; ++j) {
-                    const int ky = rr - j;
-                    if (ky >= lo_y && ky <= hi_y) acc[j] = fmaf(v, taps[ky * k + kx], acc[j]);
+                    for (int j = 0; j < kF2dRows; ++j) {
+                        const int ky = rr - j;
+                        if (ky >= 0 && ky < ks) {
+                            const float wv = taps[(off + ky) * k + off + kx];
+                            acc[0][j] = fmaf(v0, wv, acc[0][j]);
+                            acc[1][j] = fmaf(v1, wv, acc[1][j]);
+                        }
+                    }
                 }
-            }
         }
     }
-    const int gx = x0 + tx;
-    if (gx < W) {
 #pragma unroll
-        for (int j = 0; j < kF2dRows; ++j) {
-            const int gy = y0 + ty0 + j;
-            if (gy < H) out[static_cast<size_t>(plane) * H * W + static_cast<size_t>(gy) * W + gx] = acc[j];
+    for (int c = 0; c < 2; ++c) {
+        const int gx = x0 + tx + 32 * c;
+        if (gx < W) {
+#pragma unroll
+            for (int j = 0; j < kF2dRows; ++j) {
+                const int gy = y0 + ty0 + j;
+                if (gy < H) out[static_cast<size_t>(plane) * H * W + static_cast<size_t>(gy) * W + gx] = acc[c][j];
+            }
         }
     }
 }
@@ -174,6 +220,87 @@ __global__ void __launch_bounds__(256) usm_vpass_kernel(const float* __restrict_
     }
 }
 
+// Fused separable blur for the 51-tap case the training loops use (USMSharp(50, 0)): one block = 64 x 64 outputs.
+// The reflect-padded (64+50)^2 input tile is loaded once; the horizontal pass writes a (64+50) x 64 intermediate into
+// shared memory, the vertical pass and the pointwise tail finish in registers. Each thread slides a register window
+// over 8 consecutive outputs (58 loads, 408 FMAs with the taps as constant-bank operands).
+static constexpr int kUsmK = 51, kUsmT = 64, kUsmIn = kUsmT + kUsmK - 1;  // 114
+static constexpr int kUsmPitchA = kUsmIn + 1, kUsmPitchB = kUsmT + 1;      // odd pitches: conflict-free columns
+
+__device__ __forceinline__ void usm_window8(const float* __restrict__ p, int stride, float (&acc)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int t = 0; t < kUsmK + 7; ++t) {
+        const float v = p[t * stride];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int tap = t - j;
+            if (tap >= 0 && tap < kUsmK) acc[j] = fmaf(v, c_usm_taps[tap], acc[j]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) usm_fused_kernel(const float* __restrict__ src, const float* __restrict__ x,
+                                                        float* __restrict__ res, float* __restrict__ mask_or_out, int H,
+                                                        int W, int stage, float weight, float threshold) {
+    extern __shared__ float usm_sm[];
+    float* A = usm_sm;                              // [114][115] input tile (x for stage 0, mask for stage 1)
+    float* Bm = usm_sm + kUsmIn * kUsmPitchA;       // [114][65] horizontally blurred rows
+    const int plane = blockIdx.z;
+    const int x0 = blockIdx.x * kUsmT, y0 = blockIdx.y * kUsmT;
+    const size_t pbase = static_cast<size_t>(plane) * H * W;
+    const int r = kUsmK / 2;
+    for (int i = threadIdx.x; i < kUsmIn * kUsmIn; i += 256) {
+        const int ty = i / kUsmIn, tx = i % kUsmIn;
+        const int gy = reflect_idx(y0 + ty - r, H), gx = reflect_idx(x0 + tx - r, W);
+        A[ty * kUsmPitchA + tx] = src[pbase + static_cast<size_t>(min(max(gy, 0), H - 1)) * W + min(max(gx, 0), W - 1)];
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    {   // horizontal pass: lane = row (within a group of 32 rows), 4 column groups of 8 per warp
+        const int row = (warp & 3) * 32 + lane;
+        if (row < kUsmIn) {
+#pragma unroll 1
+            for (int cgi = 0; cgi < 4; ++cgi) {
+                const int c0 = ((warp >> 2) * 4 + cgi) * 8;
+                float acc[8];
+                usm_window8(A + row * kUsmPitchA + c0, 1, acc);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) Bm[row * kUsmPitchB + c0 + j] = acc[j];
+            }
+        }
+    }
+    __syncthreads();
+    // vertical pass: thread = column x (0..63), two groups of 8 rows
+    const int cx = threadIdx.x & 63;
+#pragma unroll 1
+    for (int rgi = 0; rgi < 2; ++rgi) {
+        const int r0 = ((threadIdx.x >> 6) * 2 + rgi) * 8;
+        float acc[8];
+        usm_window8(Bm + r0 * kUsmPitchB + cx, kUsmPitchB, acc);
+        const int gx = x0 + cx;
+        if (gx >= W) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int gy = y0 + r0 + j;
+            if (gy >= H) break;
+            const size_t o = pbase + static_cast<size_t>(gy) * W + gx;
+            if (stage == 0) {
+                const float xv = A[(r0 + j + r) * kUsmPitchA + cx + r];
+                const float rv = xv - acc[j];                                         // imgproc.py:1528
+                res[o] = rv;
+                mask_or_out[o] = (fabsf(rv) * 255.f > threshold) ? 1.f : 0.f;         // imgproc.py:1530-1531
+            } else {
+                const float xv = x[o], rv = res[o];
+                float sh = __fadd_rn(xv, __fmul_rn(weight, rv));                      // imgproc.py:1533
+                sh = fminf(fmaxf(sh, 0.f), 1.f);                                      // imgproc.py:1534
+                mask_or_out[o] = __fadd_rn(__fmul_rn(acc[j], sh), __fmul_rn(1.f - acc[j], xv));  // imgproc.py:1535
+            }
+        }
+    }
+}
+
 static int usm_set_taps(int radius, int sigma, int* k_out) {
     if (radius % 2 == 0) radius += 1;  // imgproc.py:1518-1519
     if (radius > kUsmMaxTaps) return set_error(RESR_E_INVALID, "USM radius %d too large", radius);
@@ -210,10 +337,22 @@ static int usm_impl(const float* x, float* out, float* ws, int B, int C, int H, 
     float* mask = ws + 2 * E;
     const dim3 gh((W + 255) / 256, H, B * C), gv((W + 31) / 32, (H + 63) / 64, B * C);
     const size_t sh = (256 + k - 1) * sizeof(float), sv = static_cast<size_t>(64 + k - 1) * 32 * sizeof(float);
-    usm_hpass_kernel<<<gh, 256, sh, s>>>(x, tmp, H, W, k);
-    usm_vpass_kernel<<<gv, 256, sv, s>>>(tmp, x, res, mask, H, W, k, 0, weight, threshold);
-    usm_hpass_kernel<<<gh, 256, sh, s>>>(mask, tmp, H, W, k);
-    usm_vpass_kernel<<<gv, 256, sv, s>>>(tmp, x, res, out, H, W, k, 1, weight, threshold);
+    if (k == kUsmK) {
+        const size_t smem = (static_cast<size_t>(kUsmIn) * kUsmPitchA + static_cast<size_t>(kUsmIn) * kUsmPitchB) * sizeof(float);
+        static bool attr = false;
+        if (!attr) {
+            cudaFuncSetAttribute(usm_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+            attr = true;
+        }
+        const dim3 gf((W + kUsmT - 1) / kUsmT, (H + kUsmT - 1) / kUsmT, B * C);
+        usm_fused_kernel<<<gf, 256, smem, s>>>(x, x, res, mask, H, W, 0, weight, threshold);
+        usm_fused_kernel<<<gf, 256, smem, s>>>(mask, x, res, out, H, W, 1, weight, threshold);
+    } else {
+        usm_hpass_kernel<<<gh, 256, sh, s>>>(x, tmp, H, W, k);
+        usm_vpass_kernel<<<gv, 256, sv, s>>>(tmp, x, res, mask, H, W, k, 0, weight, threshold);
+        usm_hpass_kernel<<<gh, 256, sh, s>>>(mask, tmp, H, W, k);
+        usm_vpass_kernel<<<gv, 256, sv, s>>>(tmp, x, res, out, H, W, k, 1, weight, threshold);
+    }
     RESR_LAUNCH_CHECK("usm");
     return RESR_OK;
 }
@@ -629,12 +768,13 @@ int resr_gaussian_noise_apply(const float* image, float* out, const float* sigma
 size_t resr_poisson_workspace_bytes(int b) { return static_cast<size_t>(b) * (16 * 4 + 2 * 4 + 2 * 4); }
 
 static int poisson_prepare(const float* image, int b, int c, int h, int w, int want_gray, void* workspace, size_t wsb,
-                           cudaStream_t s, unsigned** bm, int** counts, float** vals) {
+                           cudaStream_t s, unsigned** bm, int** counts, float** vals, bool reuse = false) {
     if (c != 3) return set_error(RESR_E_INVALID, "Poisson noise expects RGB images");
     if (wsb < resr_poisson_workspace_bytes(b)) return set_error(RESR_E_NOMEM, "Poisson workspace too small");
     *bm = static_cast<unsigned*>(workspace);
     *counts = reinterpret_cast<int*>(*bm + static_cast<size_t>(b) * 16);
     *vals = reinterpret_cast<float*>(*counts + 2 * b);
+    if (reuse) return RESR_OK;  // counts / vals of this image are already in the workspace (resr_poisson_rates)
     cudaMemsetAsync(*bm, 0, static_cast<size_t>(b) * 16 * 4, s);
     const int HW = h * w;
     int gx = (HW + 255) / 256;
@@ -672,12 +812,13 @@ int resr_poisson_rates(const float* image, float* rate_color, float* rate_gray, 
 
 int resr_poisson_noise_apply(const float* image, float* out, const float* scale, const float* gray, const float* samples_color,
                              const float* samples_gray, int b, int c, int h, int w, int clip, int rounds, void* workspace,
-                             size_t workspace_bytes, void* stream) {
+                             size_t workspace_bytes, int reuse_counts, void* stream) {
     if (!image || !out || !scale || !samples_color || !workspace) return set_error(RESR_E_INVALID, "null argument");
     if (samples_gray && !gray) return set_error(RESR_E_INVALID, "samples_gray needs gray flags");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     unsigned* bm; int* counts; float* vals;
-    const int rc = poisson_prepare(image, b, c, h, w, samples_gray != nullptr, workspace, workspace_bytes, s, &bm, &counts, &vals);
+    const int rc = poisson_prepare(image, b, c, h, w, samples_gray != nullptr, workspace, workspace_bytes, s, &bm, &counts, &vals,
+                                   reuse_counts != 0);
     if (rc != RESR_OK) return rc;
     poisson_noise_kernel<<<grid1d(static_cast<size_t>(b) * h * w), 256, 0, s>>>(image, out, scale, gray, samples_color,
                                                                               samples_gray, vals, b, h * w, clip, rounds);
@@ -698,6 +839,11 @@ int resr_crop(const float* image, float* out, int planes, int h_in, int w_in, in
     if (!image || !out) return set_error(RESR_E_INVALID, "null argument");
     if (top < 0 || left < 0 || top + h_out > h_in || left + w_out > w_in) return set_error(RESR_E_INVALID, "crop window out of range");
     const size_t total = static_cast<size_t>(planes) * h_out * w_out;
+    if (!round_to_u8 && h_out == h_in && w_out == w_in) {  // the window is the whole image (cfg2: HR is already 256^2)
+        if (cudaMemcpyAsync(out, image, total * sizeof(float), cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)) != cudaSuccess)
+            return set_error(RESR_E_CUDA, "crop copy failed");
+        return RESR_OK;
+    }
     crop_kernel<<<grid1d(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(image, out, planes, h_in, w_in, top, left, h_out,
                                                                             w_out, round_to_u8);
     RESR_LAUNCH_CHECK("crop");

@@ -21,7 +21,8 @@ from torch import nn
 from . import _lib
 
 __all__ = ["filter2d_torch", "USMSharp", "DiffJPEG", "random_add_gaussian_noise_torch",
-           "random_add_poisson_noise_torch", "random_crop", "interpolate", "degrade_batch"]
+           "random_add_poisson_noise_torch", "random_crop", "interpolate", "degrade_batch", "DegradePipeline",
+           "plan_to_device"]
 
 _MODES = {"area": 0, "bilinear": 1, "bicubic": 2}
 
@@ -154,6 +155,20 @@ def random_add_gaussian_noise_torch(image: torch.Tensor, sigma_range: tuple = (0
     return gaussian_noise_apply(image, sigma, gray, noise_color, noise_gray, clip, rounds)
 
 
+_pws_cache = {}
+
+
+def _poisson_workspace(b: int, device) -> torch.Tensor:
+    """Small persistent buffer holding the per-sample level bitmaps / counts / vals between the two Poisson calls."""
+    key = (device.type, device.index)
+    ws = _pws_cache.get(key)
+    need = _lib.lib().resr_poisson_workspace_bytes(b)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(max(need, 4096), dtype=torch.uint8, device=device)
+        _pws_cache[key] = ws
+    return ws
+
+
 def unique_count_u8(image: torch.Tensor, with_gray: bool = True):
     """Per-sample number of distinct u8 levels of the colour image and of its luma (reference imgproc.py:892, 903),
     computed on the device without host syncs. Returns int32 tensors (colour, gray)."""
@@ -161,7 +176,7 @@ def unique_count_u8(image: torch.Tensor, with_gray: bool = True):
     x = _prep(image)
     cc = torch.empty(b, dtype=torch.int32, device=x.device)
     cg = torch.empty(b, dtype=torch.int32, device=x.device) if with_gray else None
-    ws = _workspace(_lib.lib().resr_poisson_workspace_bytes(b), x.device)
+    ws = _poisson_workspace(b, x.device)
     _lib.check(_lib.lib().resr_unique_count_u8(_lib.ptr(x), _lib.ptr(cc), _lib.ptr(cg), b, c, h, w, _lib.ptr(ws),
                                                ws.numel(), _lib.stream_ptr()))
     return cc, cg
@@ -172,22 +187,23 @@ def poisson_rates(image: torch.Tensor, with_gray: bool):
     x = _prep(image)
     rc = torch.empty_like(x)
     rg = torch.empty(b, 1, h, w, device=x.device) if with_gray else None
-    ws = _workspace(_lib.lib().resr_poisson_workspace_bytes(b), x.device)
+    ws = _poisson_workspace(b, x.device)
     _lib.check(_lib.lib().resr_poisson_rates(_lib.ptr(x), _lib.ptr(rc), _lib.ptr(rg), b, c, h, w, _lib.ptr(ws),
                                              ws.numel(), _lib.stream_ptr()))
     return rc, rg
 
 
-def poisson_noise_apply(image, scale, gray, samples_color, samples_gray, clip=True, rounds=False):
-    """Deterministic core of random_add_poisson_noise_torch: all draws are arguments."""
+def poisson_noise_apply(image, scale, gray, samples_color, samples_gray, clip=True, rounds=False, reuse_counts=False):
+    """Deterministic core of random_add_poisson_noise_torch: all draws are arguments. reuse_counts=True: the unique
+    counts of `image` were just computed by poisson_rates(image, ...) (same gray setting) and are reused."""
     b, c, h, w = image.size()
     x = _prep(image)
     out = torch.empty_like(x)
-    ws = _workspace(_lib.lib().resr_poisson_workspace_bytes(b), x.device)
+    ws = _poisson_workspace(b, x.device)
     _lib.check(_lib.lib().resr_poisson_noise_apply(
         _lib.ptr(x), _lib.ptr(out), _lib.ptr(_prep(scale)), _lib.ptr(None if gray is None else _prep(gray)),
         _lib.ptr(_prep(samples_color)), _lib.ptr(None if samples_gray is None else _prep(samples_gray)), b, c, h, w,
-        int(bool(clip)), int(bool(rounds)), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+        int(bool(clip)), int(bool(rounds)), _lib.ptr(ws), ws.numel(), int(bool(reuse_counts)), _lib.stream_ptr()))
     return out
 
 
@@ -202,7 +218,7 @@ def random_add_poisson_noise_torch(image: torch.Tensor, scale_range: tuple = (0,
     rate_c, rate_g = poisson_rates(image, with_gray)
     samples_gray = torch.poisson(rate_g) if with_gray else None
     samples_color = torch.poisson(rate_c)
-    return poisson_noise_apply(image, scale, gray, samples_color, samples_gray, clip, rounds)
+    return poisson_noise_apply(image, scale, gray, samples_color, samples_gray, clip, rounds, reuse_counts=True)
 
 
 def _crop(image, top, left, h_out, w_out, round_to_u8=False):
@@ -265,11 +281,71 @@ def _noise(x, p):
     sc, sg = p.get("samples_color"), p.get("samples_gray")
     gray = _dev(p["gray"], dev)
     if sc is None:  # plan without recorded draws: sample from the rates with the torch generator
-        with_gray = bool(gray.sum() > 0)
+        g_any = p.get("gray_any")  # host-side decision recorded by plan_to_device (no device sync)
+        with_gray = bool(gray.sum() > 0) if g_any is None else bool(g_any)
         rc, rg = poisson_rates(x, with_gray)
         sg = torch.poisson(rg) if with_gray else None
         sc = torch.poisson(rc)
+        return poisson_noise_apply(x, _dev(p["scale"], dev), gray, sc, sg, reuse_counts=True)
     return poisson_noise_apply(x, _dev(p["scale"], dev), gray, _dev(sc, dev), _dev(sg, dev))
+
+
+def plan_to_device(plan: dict, device) -> dict:
+    """Copy of `plan` with every array moved to `device` once (so that replaying it launches no H2D copies) and the
+    host-side `gray_any` decisions recorded (so that no step has to synchronise on a device flag)."""
+    import numpy as np
+    out = {}
+    for k, v in plan.items():
+        if isinstance(v, dict):
+            d = {}
+            for kk, vv in v.items():
+                if isinstance(vv, np.ndarray):
+                    d[kk] = torch.from_numpy(np.ascontiguousarray(vv)).to(device=device, dtype=torch.float32)
+                else:
+                    d[kk] = vv
+            if "gray" in v:
+                g = v["gray"]
+                d["gray_any"] = bool(g.sum() > 0) if not torch.is_tensor(g) else bool(g.sum().item() > 0)
+            out[k] = d
+        elif isinstance(v, np.ndarray):
+            out[k] = torch.from_numpy(np.ascontiguousarray(v)).to(device=device, dtype=torch.float32)
+        else:
+            out[k] = v
+    return out
+
+
+class DegradePipeline:
+    """The degradation block for a fixed plan signature (branches, resize modes and sizes) with its whole launch
+    sequence captured in ONE CUDA graph: replaying a batch costs a single graph launch instead of ~25 kernel launches.
+    Inputs live in static device buffers (`hr`, `kernel1`, `kernel2`, `sinc_kernel` and the tensors inside `plan`);
+    update them in place (``pipe.hr.copy_(new_hr)``) and call the pipeline again."""
+
+    def __init__(self, hr, kernel1, kernel2, sinc_kernel, plan, use_graph: bool = True):
+        dev = hr.device
+        self.hr, self.kernel1, self.kernel2, self.sinc_kernel = (t.detach().clone().float().contiguous()
+                                                                 for t in (hr, kernel1, kernel2, sinc_kernel))
+        self.plan = plan_to_device(plan, dev)
+        self.graph = None
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):  # warm-up outside the capture: constant-table uploads, function attributes, workspaces
+                self.lr, self.hr_crop = degrade_batch(self.hr, self.kernel1, self.kernel2, self.sinc_kernel, self.plan)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        if use_graph:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.lr, self.hr_crop = degrade_batch(self.hr, self.kernel1, self.kernel2, self.sinc_kernel, self.plan)
+            self.graph = g
+        self.launches = None
+
+    def __call__(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.lr, self.hr_crop = degrade_batch(self.hr, self.kernel1, self.kernel2, self.sinc_kernel, self.plan)
+        return self.lr, self.hr_crop
 
 
 def degrade_batch(hr: torch.Tensor, kernel1: torch.Tensor, kernel2: torch.Tensor, sinc_kernel: torch.Tensor, plan: dict,

@@ -17,15 +17,17 @@ for i in range(B):
     k[i] = kk / kk.sum()
 k1 = k.to(dev); k2 = k.flip(0).contiguous().to(dev)
 sk = torch.zeros(B, 21, 21); sk[:, 10, 10] = 1; sk = sk.to(dev)
-for key in ("noise1", "noise2"):
-    for kk_, v in list(plan[key].items()):
-        if isinstance(v, np.ndarray): plan[key][kk_] = torch.from_numpy(v).to(dev)
-plan["jpeg1_quality"] = torch.from_numpy(plan["jpeg1_quality"]).to(dev)
-plan["jpeg2_quality"] = torch.from_numpy(plan["jpeg2_quality"]).to(dev)
-for _ in range(3): ip.degrade_batch(hr, k1, k2, sk, plan)
-torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(20): ip.degrade_batch(hr, k1, k2, sk, plan)
-e1.record(); torch.cuda.synchronize()
-print(f"degrade_batch 16x3x256x256 S0: {e0.elapsed_time(e1)/20*1e3:.1f} us/batch")
+plan_d = ip.plan_to_device(plan, dev)
+for name, fn in (("direct", None), ("graph", True)):
+    if fn is None:
+        run = lambda: ip.degrade_batch(hr, k1, k2, sk, plan_d)
+    else:
+        pipe = ip.DegradePipeline(hr, k1, k2, sk, plan)
+        run = pipe
+    for _ in range(3): run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(50): run()
+    e1.record(); torch.cuda.synchronize()
+    print(f"degrade_batch 16x3x256x256 S0 [{name}]: {e0.elapsed_time(e1)/50*1e3:.1f} us/batch")
