@@ -157,6 +157,18 @@ int resr_jpeg(const float* image, float* out, const float* quality, float* facto
 int resr_crop(const float* image, float* out, int planes, int h_in, int w_in, int top, int left, int h_out, int w_out,
               int round_to_u8, void* stream);
 
+/* Blur-kernel synthesis in float64 on the device (imgproc.py:72-90, 170-327, 576-603). One entry per kernel; the
+ * random draws (type, size, sigmas, angle, beta, cutoff) are made by the caller in the reference's RNG order
+ * (dataset.py:81-141). type: 0 Gaussian, 1 generalized Gaussian, 2 plateau, 3 sinc (Bessel J1), 4 delta.
+ * Every kernel is normalised to sum 1 and written centred, zero-padded to pad x pad (pad = 0: no padding, all
+ * sizes must then be equal). out_f64 / out_f32: [count, P, P], either may be NULL. params_host is HOST memory. */
+typedef struct resr_kernel_params {
+    int type, kernel_size, isotropic, reserved;
+    double sigma_x, sigma_y, theta, beta, cutoff;
+} resr_kernel_params;
+int resr_synthesize_kernels(const resr_kernel_params* params_host, int count, int pad, double* out_f64, float* out_f32,
+                            void* stream);
+
 #ifdef __cplusplus
 }
 #endif

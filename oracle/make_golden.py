@@ -43,10 +43,34 @@ def make_generator(ref_model):
     print("generator.npz written")
 
 
+def make_kernels(ref_imgproc, ref_config):
+    """Seeded calls of the reference kernel generators (imgproc.py:492-603); tests replay the same seeds."""
+    import math
+    import random
+    P = ref_config.degradation_model_parameters_dict
+    z = {}
+    for seed in range(16):
+        ks = P["gaussian_kernel_range"][seed % 8]
+        random.seed(seed)
+        np.random.seed(seed)
+        z[f"mixed_{seed}"] = ref_imgproc.random_mixed_kernels(
+            P["gaussian_kernel_type"], P["gaussian_kernel_probability1"], ks, P["gaussian_sigma_range1"],
+            P["gaussian_sigma_range1"], [-math.pi, math.pi], P["generalized_kernel_beta_range1"],
+            P["plateau_kernel_beta_range1"], noise_range=None)
+        z[f"mixed_{seed}_ks"] = np.int64(ks)
+    for i, (om, ks, pad) in enumerate([(1.2, 7, 0), (2.9, 13, 21), (0.7, 21, 21), (3.1, 9, 21)]):
+        z[f"sinc_{i}"] = ref_imgproc.generate_sinc_kernel(om, ks, padding=pad)
+        z[f"sinc_{i}_args"] = np.array([om, ks, pad])
+    np.savez_compressed(os.path.join(OUT, "kernels.npz"), **z)
+    print("kernels.npz written")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     ref_model, ref_imgproc, ref_config = refshim.load()
-    which = sys.argv[1:] or ["generator", "degrade"]
+    which = sys.argv[1:] or ["generator", "degrade", "kernels"]
+    if "kernels" in which:
+        make_kernels(ref_imgproc, ref_config)
     if "generator" in which:
         make_generator(ref_model)
     if "degrade" in which:

@@ -32,6 +32,13 @@ class ConvDesc(Structure):
     ]
 
 
+class KernelParams(Structure):
+    """struct resr_kernel_params (include/resr.h)."""
+    _fields_ = [("type", c_int), ("kernel_size", c_int), ("isotropic", c_int), ("reserved", c_int),
+                ("sigma_x", c_double), ("sigma_y", c_double), ("theta", c_double), ("beta", c_double),
+                ("cutoff", c_double)]
+
+
 # name -> (restype, argtypes); every symbol include/resr.h declares must be listed here (tests check both ways).
 SIGNATURES = {
     "resr_version": (c_int, []),
@@ -62,6 +69,7 @@ SIGNATURES = {
                                          c_int, c_int, c_int, c_void_p, c_size_t, c_int, c_void_p]),
     "resr_jpeg": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                           c_void_p]),
+    "resr_synthesize_kernels": (c_int, [POINTER(KernelParams), c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "resr_crop": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
 }
 

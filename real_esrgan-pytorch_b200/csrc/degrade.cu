@@ -76,12 +76,14 @@ __global__ void __launch_bounds__(256) filter2d_kernel(const float* __restrict__
         taps[i] = v;
         if (v != 0.f) atomicMax(&s_ext, max(abs(i / k - r), abs(i % k - r)));
     }
-    for (int i = threadIdx.x; i < tw * tw; i += blockDim.x) {
-        const int ty = i / tw, tx = i % tw;
-        const int gy = reflect_idx(y0 + ty - r, H), gx = reflect_idx(x0 + tx - r, W);
+    for (int ty = threadIdx.x >> 5; ty < tw; ty += 8) {  // one tile row per warp pass, coalesced along x
         // positions the tile overhang would touch beyond the image are clamped: their outputs are never stored
-        const int cy = min(max(gy, 0), H - 1), cx = min(max(gx, 0), W - 1);
-        tile[ty * tpitch + tx] = src[static_cast<size_t>(cy) * W + cx];
+        const int cy = min(max(reflect_idx(y0 + ty - r, H), 0), H - 1);
+        const float* srow = src + static_cast<size_t>(cy) * W;
+        for (int tx = threadIdx.x & 31; tx < tw; tx += 32) {
+            const int cx = min(max(reflect_idx(x0 + tx - r, W), 0), W - 1);
+            tile[ty * tpitch + tx] = srow[cx];
+        }
     }
     __syncthreads();
     const int ext = s_ext;
@@ -251,13 +253,16 @@ __global__ void __launch_bounds__(256) usm_fused_kernel(const float* __restrict_
     const int x0 = blockIdx.x * kUsmT, y0 = blockIdx.y * kUsmT;
     const size_t pbase = static_cast<size_t>(plane) * H * W;
     const int r = kUsmK / 2;
-    for (int i = threadIdx.x; i < kUsmIn * kUsmIn; i += 256) {
-        const int ty = i / kUsmIn, tx = i % kUsmIn;
-        const int gy = reflect_idx(y0 + ty - r, H), gx = reflect_idx(x0 + tx - r, W);
-        A[ty * kUsmPitchA + tx] = src[pbase + static_cast<size_t>(min(max(gy, 0), H - 1)) * W + min(max(gx, 0), W - 1)];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int ty = warp; ty < kUsmIn; ty += 8) {  // one tile row per warp pass, coalesced along x, no div/mod
+        const int gy = min(max(reflect_idx(y0 + ty - r, H), 0), H - 1);
+        const float* srow = src + pbase + static_cast<size_t>(gy) * W;
+        for (int tx = lane; tx < kUsmIn; tx += 32) {
+            const int gx = min(max(reflect_idx(x0 + tx - r, W), 0), W - 1);
+            A[ty * kUsmPitchA + tx] = srow[gx];
+        }
     }
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     {   // horizontal pass: lane = row (within a group of 32 rows), 4 column groups of 8 per warp
         const int row = (warp & 3) * 32 + lane;
         if (row < kUsmIn) {

@@ -392,3 +392,125 @@ def degrade_batch(hr: torch.Tensor, kernel1: torch.Tensor, kernel2: torch.Tensor
     lr = _crop(out, c["hr_top"] // c["upscale"], c["hr_left"] // c["upscale"], ls, ls, round_to_u8=True)
     hr_c = _crop(hr, c["hr_top"], c["hr_left"], c["image_size"], c["image_size"])
     return lr, hr_c
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Blur-kernel synthesis (reference imgproc.py:225-603, dataset.py:81-141): random draws on the host in the reference's
+# RNG order, arithmetic in float64 on the device (C ABI resr_synthesize_kernels).
+
+_KTYPES = {"gaussian": 0, "generalized": 1, "plateau": 2, "sinc": 3, "delta": 4}
+
+
+def _synth(params, pad=0, device=None, dtype=torch.float64):
+    """params: list of dicts (type, kernel_size, isotropic, sigma_x, sigma_y, theta, beta, cutoff) -> [n, P, P] tensor."""
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    n = len(params)
+    arr = (_lib.KernelParams * n)()
+    for i, p in enumerate(params):
+        arr[i].type = _KTYPES[p["type"]]
+        arr[i].kernel_size = int(p["kernel_size"])
+        arr[i].isotropic = int(bool(p.get("isotropic", True)))
+        arr[i].sigma_x = float(p.get("sigma_x", 1.0))
+        arr[i].sigma_y = float(p.get("sigma_y", 1.0))
+        arr[i].theta = float(p.get("theta", 0.0))
+        arr[i].beta = float(p.get("beta", 1.0))
+        arr[i].cutoff = float(p.get("cutoff", 1.0))
+    P = pad if pad else int(params[0]["kernel_size"])
+    out = torch.empty(n, P, P, dtype=dtype, device=device)
+    with torch.cuda.device(device):
+        _lib.check(_lib.lib().resr_synthesize_kernels(arr, n, int(pad), _lib.ptr(out) if dtype == torch.float64 else None,
+                                                      _lib.ptr(out) if dtype == torch.float32 else None, _lib.stream_ptr()))
+    return out
+
+
+def generate_sinc_kernel(cutoff: float, kernel_size: int, padding: int = 0):
+    """Reference imgproc.py:576-603. Returns a float64 ndarray like the reference."""
+    assert kernel_size % 2 == 1, "Kernel size must be an odd number."
+    pad = padding if padding > kernel_size else 0
+    return _synth([{"type": "sinc", "kernel_size": kernel_size, "cutoff": cutoff}], pad)[0].cpu().numpy()
+
+
+def _draw_gaussian_family(kind, kernel_size, sigma_x_range, sigma_y_range, rotation_range, beta_range, isotropic):
+    """RNG draw order of imgproc.py:330-489 (_random_bivariate_*_kernel)."""
+    import numpy as np
+    assert kernel_size % 2 == 1, "Kernel size must be an odd number."
+    assert sigma_x_range[0] < sigma_x_range[1], "Wrong sigma_x_range."
+    sigma_x = np.random.uniform(sigma_x_range[0], sigma_x_range[1])
+    if isotropic is False:
+        assert sigma_y_range[0] < sigma_y_range[1], "Wrong sigma_y_range."
+        assert rotation_range[0] < rotation_range[1], "Wrong rotation_range."
+        sigma_y = np.random.uniform(sigma_y_range[0], sigma_y_range[1])
+        rotation = np.random.uniform(rotation_range[0], rotation_range[1])
+    else:
+        sigma_y, rotation = sigma_x, 0
+    beta = 1.0
+    if kind != "gaussian":
+        if np.random.uniform() < 0.5:
+            beta = np.random.uniform(beta_range[0], 1)
+        else:
+            beta = np.random.uniform(1, beta_range[1])
+    return {"type": kind, "kernel_size": kernel_size, "isotropic": isotropic, "sigma_x": sigma_x, "sigma_y": sigma_y,
+            "theta": rotation, "beta": beta}
+
+
+def draw_mixed_kernel_params(kernel_type, kernel_prob, kernel_size, sigma_x_range, sigma_y_range, rotation_range,
+                             generalized_kernel_beta_range, plateau_kernel_beta_range):
+    """The host-side random decisions of random_mixed_kernels (imgproc.py:492-573), without the arithmetic."""
+    kt = random.choices(kernel_type, kernel_prob)[0]
+    iso = not kt.endswith("anisotropic")
+    if kt.startswith("generalized"):
+        return _draw_gaussian_family("generalized", kernel_size, sigma_x_range, sigma_y_range, rotation_range,
+                                     generalized_kernel_beta_range, iso), True
+    if kt.startswith("plateau"):
+        return _draw_gaussian_family("plateau", kernel_size, sigma_x_range, sigma_y_range, rotation_range,
+                                     plateau_kernel_beta_range, iso), False
+    if kt not in ("isotropic", "anisotropic"):
+        iso = True  # imgproc.py:566-572: unknown names fall back to the isotropic Gaussian
+    return _draw_gaussian_family("gaussian", kernel_size, sigma_x_range, sigma_y_range, rotation_range, None, iso), True
+
+
+def random_mixed_kernels(kernel_type, kernel_prob, kernel_size, sigma_x_range, sigma_y_range, rotation_range,
+                         generalized_kernel_beta_range, plateau_kernel_beta_range, noise_range=None):
+    """Reference imgproc.py:492-573. Returns a float64 ndarray like the reference."""
+    import numpy as np
+    p, noisy = draw_mixed_kernel_params(kernel_type, kernel_prob, kernel_size, sigma_x_range, sigma_y_range, rotation_range,
+                                        generalized_kernel_beta_range, plateau_kernel_beta_range)
+    k = _synth([p])[0].cpu().numpy()
+    if noise_range is not None and noisy:  # multiplicative kernel noise (imgproc.py:367-370); plateau kernels get None
+        assert noise_range[0] < noise_range[1], "Wrong noise range."
+        k = k * np.random.uniform(noise_range[0], noise_range[1], size=k.shape)
+        k = k / np.sum(k)
+    return k
+
+
+def synthesize_degradation_kernels(batch: int, parameters: dict, device=None):
+    """kernel1, kernel2, sinc_kernel for `batch` samples, sequenced per sample exactly as dataset.py:81-141 does
+    (same `random` / `np.random` draw order), synthesised in ONE device launch. Returns three [batch, 21, 21] fp32
+    CUDA tensors."""
+    import numpy as np
+    P = parameters
+    ps = []
+    for _ in range(batch):
+        for which in (1, 2):
+            ks = random.choice(P["gaussian_kernel_range"])
+            if np.random.uniform() < P[f"sinc_kernel_probability{which}"]:
+                if ks < int(np.median(P["gaussian_kernel_range"])):
+                    om = np.random.uniform(np.pi / 3, np.pi)
+                else:
+                    om = np.random.uniform(np.pi / 5, np.pi)
+                ps.append({"type": "sinc", "kernel_size": ks, "cutoff": om})
+            else:
+                p, _ = draw_mixed_kernel_params(P["gaussian_kernel_type"], P[f"gaussian_kernel_probability{which}"], ks,
+                                                P[f"gaussian_sigma_range{which}"], P[f"gaussian_sigma_range{which}"],
+                                                [-math.pi, math.pi], P[f"generalized_kernel_beta_range{which}"],
+                                                P[f"plateau_kernel_beta_range{which}"])
+                ps.append(p)
+        if np.random.uniform() < P["sinc_kernel_probability3"]:
+            ks = random.choice(P["gaussian_kernel_range"])
+            om = np.random.uniform(np.pi / 3, np.pi)
+            ps.append({"type": "sinc", "kernel_size": ks, "cutoff": om})
+        else:
+            ps.append({"type": "delta", "kernel_size": P["sinc_kernel_size"]})
+    pad = P["gaussian_kernel_range"][-1]
+    out = _synth(ps, pad, device, torch.float32).view(batch, 3, pad, pad)
+    return out[:, 0].contiguous(), out[:, 1].contiguous(), out[:, 2].contiguous()

@@ -13,7 +13,7 @@ from torch import nn
 
 from . import _lib
 
-__all__ = ["ResidualDenseBlock", "ResidualResidualDenseBlock", "Generator"]
+__all__ = ["ResidualDenseBlock", "ResidualResidualDenseBlock", "Generator", "plan_tiles", "infer_tiled"]
 
 
 def _conv(cin: int, cout: int) -> nn.Conv2d:
@@ -162,3 +162,45 @@ class Generator(nn.Module):
             _lib.check(_lib.lib().resr_generator_forward_host(self._native(), _lib.ptr(xc), _lib.ptr(y_host), n, h, w,
                                                               wp, wbytes, _lib.stream_ptr()))
         return y_host
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Large-image inference by spatial tiles with a receptive-field halo (BASELINE.json configs[4]; new functionality around
+# the unchanged reference API: inference.py:52-53 runs one whole-image forward). Tile indexing is integer arithmetic.
+
+
+def plan_tiles(h: int, w: int, tile_h: int, tile_w: int, halo: int):
+    """Covers an h x w LR image with interior rectangles of at most tile_h x tile_w. Returns a list of
+    (y0, y1, x0, x1, wy0, wy1, wx0, wx1): interior [y0,y1) x [x0,x1) and the input window = interior grown by `halo`,
+    clamped at the image border (where the convolutions' zero padding applies instead of neighbour data)."""
+    tiles = []
+    for y0 in range(0, h, tile_h):
+        y1 = min(y0 + tile_h, h)
+        for x0 in range(0, w, tile_w):
+            x1 = min(x0 + tile_w, w)
+            tiles.append((y0, y1, x0, x1, max(y0 - halo, 0), min(y1 + halo, h), max(x0 - halo, 0), min(x1 + halo, w)))
+    return tiles
+
+
+@torch.no_grad()
+def infer_tiled(gen: "Generator", x: torch.Tensor, tile_h: int = 512, tile_w: int = 1024, halo: int = 16, rank: int = 0,
+                world: int = 1, out: torch.Tensor = None):
+    """x: [1, 3, H, W] CUDA LR image. Tiles are dealt round-robin to `world` ranks (no collective: every rank computes
+    its own tiles from the shared input); this rank's interiors are written into `out` ([1, 3, 4H, 4W], allocated if
+    None) and also returned as [(y0, x0, tensor)] for a host-side gather."""
+    assert x.dim() == 4 and x.size(0) == 1 and x.size(1) == 3
+    _, _, h, w = x.shape
+    s = 4
+    if out is None:
+        out = torch.zeros((1, 3, s * h, s * w), dtype=torch.float32, device=x.device)
+    mine = []
+    for i, (y0, y1, x0, x1, wy0, wy1, wx0, wx1) in enumerate(plan_tiles(h, w, tile_h, tile_w, halo)):
+        if i % world != rank:
+            continue
+        win = x[:, :, wy0:wy1, wx0:wx1].contiguous()
+        sr = gen.infer(win)
+        oy, ox = s * (y0 - wy0), s * (x0 - wx0)
+        piece = sr[:, :, oy:oy + s * (y1 - y0), ox:ox + s * (x1 - x0)]
+        out[:, :, s * y0:s * y1, s * x0:s * x1] = piece
+        mine.append((s * y0, s * x0, piece))
+    return out, mine

@@ -92,3 +92,15 @@ def test_invalid_arguments_are_rejected():
     assert L.lib().resr_generator_create(ctypes.byref(h), 3, 3, 2) == 1  # RESR_E_INVALID before touching the device
     assert b"Generator(3, 3, 4)" in L.lib().resr_last_error()
     assert L.lib().resr_filter2d(None, None, None, 1, 3, 8, 8, 3, 1, None) == 1
+
+
+def test_tile_plan_is_an_exact_integer_cover():
+    import numpy as np
+    import resr_b200
+    for (h, w, th, tw, halo) in [(2048, 2048, 512, 1024, 16), (72, 200, 32, 128, 16), (100, 100, 64, 64, 8)]:
+        cover = np.zeros((h, w), np.int32)
+        for (y0, y1, x0, x1, wy0, wy1, wx0, wx1) in resr_b200.model.plan_tiles(h, w, th, tw, halo):
+            cover[y0:y1, x0:x1] += 1
+            assert wy0 == max(y0 - halo, 0) and wy1 == min(y1 + halo, h) and wx0 == max(x0 - halo, 0) and wx1 == min(x1 + halo, w)
+        assert (cover == 1).all()
+    assert len(resr_b200.model.plan_tiles(2048, 2048, 512, 1024, 16)) == 8

@@ -226,3 +226,38 @@ def test_block_end_to_end(block):
         print(f"seed {seed}: {int((diff > 0).sum())}/{diff.size} u8 values differ, max {int(diff.max())} levels")
         assert diff.max() <= 2
     assert bad <= 0.02 * tot
+
+
+def test_kernel_synthesis_device(golden_dir):
+    """Device float64 synthesis (resr_synthesize_kernels) vs the reference kernels: same seeds, same RNG order."""
+    import math
+    import random
+
+    import resr_b200
+    from tests.test_oracle_cpu import MODEL_PARAMS as P
+    z = np.load(os.path.join(golden_dir, "kernels.npz"))
+    ip = resr_b200.imgproc
+    for seed in range(16):
+        ks = int(z[f"mixed_{seed}_ks"])
+        random.seed(seed)
+        np.random.seed(seed)
+        k = ip.random_mixed_kernels(P["gaussian_kernel_type"], P["gaussian_kernel_probability1"], ks,
+                                    P["gaussian_sigma_range1"], P["gaussian_sigma_range1"], [-math.pi, math.pi],
+                                    P["generalized_kernel_beta_range1"], P["plateau_kernel_beta_range1"], noise_range=None)
+        assert k.dtype == np.float64 and k.shape == (ks, ks)
+        assert np.abs(k - z[f"mixed_{seed}"]).max() <= 1e-12
+    for i in range(4):
+        om, ks, pad = z[f"sinc_{i}_args"]
+        k = ip.generate_sinc_kernel(float(om), int(ks), padding=int(pad))
+        assert k.shape == z[f"sinc_{i}"].shape
+        assert np.abs(k - z[f"sinc_{i}"]).max() <= 1e-12
+    with pytest.raises(AssertionError):
+        ip.generate_sinc_kernel(1.0, 8)
+    # batched: sequencing of dataset.py:81-141 for a whole batch in one launch
+    from oracle import kernels as ok
+    random.seed(3)
+    np.random.seed(3)
+    k1, k2, sk = ip.synthesize_degradation_kernels(6, P)
+    assert k1.shape == (6, 21, 21) and k1.dtype == torch.float32
+    for t in (k1, k2, sk):
+        assert np.abs(t.sum((1, 2)).cpu().numpy() - 1).max() < 1e-5

@@ -136,3 +136,39 @@ def test_synth_and_canonical_plans_are_replayable():
         lr, hrc = od.degrade_batch(hr, k, k, k[:1], plan)
         assert lr.shape == (2, 3, 16, 16) and hrc.shape == (2, 3, 64, 64)
         assert np.abs(lr * 255 - np.rint(lr * 255)).max() < 1e-4
+
+
+MODEL_PARAMS = {  # config.py:20-39 (restated so the tests do not need the reference tree)
+    "sinc_kernel_size": 21, "gaussian_kernel_range": [7, 9, 11, 13, 15, 17, 19, 21],
+    "gaussian_kernel_type": ["isotropic", "anisotropic", "generalized_isotropic", "generalized_anisotropic",
+                             "plateau_isotropic", "plateau_anisotropic"],
+    "gaussian_kernel_probability1": [0.45, 0.25, 0.12, 0.03, 0.12, 0.03], "sinc_kernel_probability1": 0.1,
+    "gaussian_sigma_range1": [0.2, 3], "generalized_kernel_beta_range1": [0.5, 4], "plateau_kernel_beta_range1": [1, 2],
+    "gaussian_kernel_probability2": [0.45, 0.25, 0.12, 0.03, 0.12, 0.03], "sinc_kernel_probability2": 0.1,
+    "gaussian_sigma_range2": [0.2, 1.5], "generalized_kernel_beta_range2": [0.5, 4], "plateau_kernel_beta_range2": [1, 2],
+    "sinc_kernel_probability3": 0.8,
+}
+
+
+def test_kernel_synthesis_oracle_and_rng_order(golden_dir):
+    """Replaying the reference's seeds through the host-side draw mirror + the numpy oracle reproduces the reference
+    kernels (imgproc.py:492-603) to float64 round-off: checks both the formulas and the RNG consumption order."""
+    import math
+    import random
+
+    import resr_b200
+    from oracle import kernels as ok
+    z = np.load(os.path.join(golden_dir, "kernels.npz"))
+    P = MODEL_PARAMS
+    for seed in range(16):
+        ks = int(z[f"mixed_{seed}_ks"])
+        random.seed(seed)
+        np.random.seed(seed)
+        p, _ = resr_b200.imgproc.draw_mixed_kernel_params(
+            P["gaussian_kernel_type"], P["gaussian_kernel_probability1"], ks, P["gaussian_sigma_range1"],
+            P["gaussian_sigma_range1"], [-math.pi, math.pi], P["generalized_kernel_beta_range1"],
+            P["plateau_kernel_beta_range1"])
+        assert np.abs(ok.from_params(p) - z[f"mixed_{seed}"]).max() <= 1e-15
+    for i in range(4):
+        om, ks, pad = z[f"sinc_{i}_args"]
+        assert np.abs(ok.sinc(float(om), int(ks), int(pad)) - z[f"sinc_{i}"]).max() <= 1e-15
