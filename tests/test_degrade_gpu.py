@@ -234,7 +234,7 @@ def test_kernel_synthesis_device(golden_dir):
     import random
 
     import resr_b200
-    from tests.test_oracle_cpu import MODEL_PARAMS as P
+    from oracle.plan import DEGRADATION_MODEL_PARAMETERS as P
     z = np.load(os.path.join(golden_dir, "kernels.npz"))
     ip = resr_b200.imgproc
     for seed in range(16):

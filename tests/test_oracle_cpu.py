@@ -138,16 +138,7 @@ def test_synth_and_canonical_plans_are_replayable():
         assert np.abs(lr * 255 - np.rint(lr * 255)).max() < 1e-4
 
 
-MODEL_PARAMS = {  # config.py:20-39 (restated so the tests do not need the reference tree)
-    "sinc_kernel_size": 21, "gaussian_kernel_range": [7, 9, 11, 13, 15, 17, 19, 21],
-    "gaussian_kernel_type": ["isotropic", "anisotropic", "generalized_isotropic", "generalized_anisotropic",
-                             "plateau_isotropic", "plateau_anisotropic"],
-    "gaussian_kernel_probability1": [0.45, 0.25, 0.12, 0.03, 0.12, 0.03], "sinc_kernel_probability1": 0.1,
-    "gaussian_sigma_range1": [0.2, 3], "generalized_kernel_beta_range1": [0.5, 4], "plateau_kernel_beta_range1": [1, 2],
-    "gaussian_kernel_probability2": [0.45, 0.25, 0.12, 0.03, 0.12, 0.03], "sinc_kernel_probability2": 0.1,
-    "gaussian_sigma_range2": [0.2, 1.5], "generalized_kernel_beta_range2": [0.5, 4], "plateau_kernel_beta_range2": [1, 2],
-    "sinc_kernel_probability3": 0.8,
-}
+from oracle.plan import DEGRADATION_MODEL_PARAMETERS as MODEL_PARAMS  # noqa: E402
 
 
 def test_kernel_synthesis_oracle_and_rng_order(golden_dir):
