@@ -169,6 +169,31 @@ typedef struct resr_kernel_params {
 int resr_synthesize_kernels(const resr_kernel_params* params_host, int count, int pad, double* out_f64, float* out_f32,
                             void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Hot path 1, training: forward that keeps activations, fused L1 loss, full backward.
+ * Replaces `sr = model(lr); loss = L1(sr, hr); loss.backward()` (train_realesrnet.py:383-388) for the generator.
+ * grads_flat: fp32 [resr_generator_num_params()] in state_dict order (layout of resr_generator_tensor_span); every
+ * element is overwritten. The flat parameter vector given to resr_generator_load_params must stay alive (the
+ * transposed weight packs of the data-gradient convolutions are built from it on the first backward). w % 8 == 0.
+ * ---------------------------------------------------------------------------------------------------------- */
+size_t resr_generator_train_workspace_bytes(int n, int h, int w);
+int resr_generator_forward_train(resr_generator_t* g, const float* x, float* y, int n, int h, int w, void* workspace,
+                                 size_t workspace_bytes, void* stream);
+/* loss = mean |y - hr| (nn.L1Loss, train_realesrnet.py:190-194), written to loss_out (device float, may be NULL),
+ * followed by the backward pass of the forward_train call that last used `workspace`. hr: fp32 NCHW [n,3,4h,4w]. */
+int resr_generator_backward_l1(resr_generator_t* g, const float* hr, float* grads_flat, float* loss_out, int n, int h,
+                               int w, void* workspace, size_t workspace_bytes, void* stream);
+/* Backward from an upstream gradient dL/dy (fp32 NCHW [n,3,4h,4w]); the clamp of model.py:270 is applied inside. */
+int resr_generator_backward(resr_generator_t* g, const float* dy, float* grads_flat, int n, int h, int w, void* workspace,
+                            size_t workspace_bytes, void* stream);
+
+/* Weight / bias gradient of one 3x3 convolution through the tensor-core wgrad kernel (test / building block).
+ * x16: NHWC 16-bit input [n,h,w,x_cstride] (first cin channels; fmt_x 0 fp16 / 1 bf16); dy16_bf16: NHWC bf16 output
+ * gradient [n,h,w,64] (first cout channels, cout <= 64). dw: OIHW fp32 [cout,cin,3,3]; db: [cout] or NULL. */
+size_t resr_conv3x3_wgrad_workspace_bytes(int n, int h, int w, int cin, int cout);
+int resr_conv3x3_wgrad(const void* x16, int x_cstride, int fmt_x, const void* dy16_bf16, int n, int h, int w, int cin,
+                       int cout, float* dw, float* db, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

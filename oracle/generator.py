@@ -33,6 +33,21 @@ def rrdb_forward(x, sd, prefix):
 def generator_forward(x: torch.Tensor, sd: dict, num_rrdb: int = 23) -> torch.Tensor:
     """x: [N,3,H,W] fp32 in [0,1] -> [N,3,4H,4W] fp32 in [0,1]."""
     sd = {k: v.detach().to(torch.float32) for k, v in sd.items()}
+    return _forward(x, sd, num_rrdb)
+
+
+def l1_loss_and_grads(x: torch.Tensor, hr: torch.Tensor, sd: dict):
+    """Reference training-step core under fp32 autograd (train_realesrnet.py:383-388 without AMP): returns
+    (loss, {name: grad}) of loss = nn.L1Loss()(G(x), hr)."""
+    params = {k: v.detach().clone().to(torch.float32).requires_grad_(True) for k, v in sd.items()}
+    with torch.enable_grad():
+        sr = _forward(x, params, 23)
+        loss = torch.nn.functional.l1_loss(sr, hr)
+        loss.backward()
+    return loss.detach(), {k: p.grad for k, p in params.items()}, sr.detach()
+
+
+def _forward(x, sd, num_rrdb=23):
     out1 = _conv(x, sd, "conv1")  # model.py:258 (PixelUnshuffle(1) is the identity at x4, model.py:257)
     out = out1
     for i in range(num_rrdb):  # model.py:259
@@ -42,7 +57,7 @@ def generator_forward(x: torch.Tensor, sd: dict, num_rrdb: int = 23) -> torch.Te
     out = F.leaky_relu(_conv(F.interpolate(out, scale_factor=2, mode="nearest"), sd, "upsampling2.0"), 0.2)  # :265
     out = F.leaky_relu(_conv(out, sd, "conv3.0"), 0.2)  # :267
     out = _conv(out, sd, "conv4")  # :268
-    return out.clamp_(0.0, 1.0)  # :270
+    return torch.clamp(out, 0.0, 1.0)  # :270 (clamp_ in the reference)
 
 
 def random_state_dict(seed: int) -> dict:

@@ -7,7 +7,8 @@ Everything dispatches through ctypes into the C ABI of lib/libresr.so (include/r
 fallback: importing works anywhere, computing needs the built library and a B200.
 """
 from . import _lib  # noqa: F401
+from . import autograd  # noqa: F401
 from . import imgproc  # noqa: F401
 from . import model  # noqa: F401
 
-__all__ = ["_lib", "imgproc", "model"]
+__all__ = ["_lib", "autograd", "imgproc", "model"]

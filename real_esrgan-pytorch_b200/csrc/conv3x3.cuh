@@ -12,6 +12,7 @@ enum EpMode : int {
     EP_RDB = 1,    // v = (acc + b) * 0.2 + res1         (model.py:94-96)
     EP_RRDB = 2,   // v = ((acc + b) * 0.2 + res1) * 0.2 + res2   (model.py:94-96 then :129-130)
     EP_SKIP = 3,   // v = res1 + (acc + b)               (model.py:261-262)
+    EP_ADD2 = 4,   // v = (acc + b) [+ res1] + res2_scale * res2   (backward: gradient accumulation)
 };
 
 struct ConvArgs {
@@ -43,6 +44,15 @@ struct ConvArgs {
     int res2_cstride;
     float* out_nchw;       // NCHW fp32 output with out_nchw_c channels (or null)
     int out_nchw_c;
+    // ---- backward (data-gradient) extensions; all zero in the forward pass
+    unsigned slice_nores_mask;  // bit s: Cout slice s does not read res1
+    unsigned slice_noutf_mask;  // bit s: slice s does not write the fp32 output
+    unsigned slice_no16_mask;   // bit s: slice s does not write the 16-bit output
+    int out16_slice_fixed;      // 1: every writing slice stores at out16_choff (instead of out16_choff + slice * cout_slice)
+    const void* mask16;         // LeakyReLU' mask source: NHWC 16-bit activations; v *= (act > 0 ? 1 : 0.2) before out16
+    int mask16_cstride, mask16_choff;
+    float res2_scale;           // EP_ADD2
+    float* out_nchw_raw;        // pre-clamp copy of the NCHW output (training: clamp backward needs it)
     int dbg_flags;            // experiments only: 1 = skip output stores, 2 = producer re-reads row 0, 4 = issue 1/4 of the MMAs
     unsigned long long* dbg;  // optional: CTA (0,0) writes phase timestamps (globaltimer ns) here, 16 slots
 };

@@ -305,7 +305,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         const int q = warp & 3;        // TMEM lane quadrant this warp may access
         const int m = q * 32 + lane;   // M row == TMEM lane == pixel of the tile
         const bool lead_warp = ((warp - 4) & 3) == 0;  // first warp of the group issues its TMA traffic
-        const bool staged = a.has_out16 || a.has_outf || a.has_res1;
+        // per-slice output selection (backward: only the top slice produces the masked 16-bit dY, the others
+        // accumulate into the fp32 gradient buffer)
+        const bool use_res1 = a.has_res1 && !((a.slice_nores_mask >> slice) & 1u);
+        const bool use_outf = a.has_outf && !((a.slice_noutf_mask >> slice) & 1u);
+        const bool use_o16 = a.has_out16 && !((a.slice_no16_mask >> slice) & 1u);
+        const bool staged = use_o16 || use_outf || use_res1;
         uint8_t* tileR = epi + gi * epi_bytes;                       // fp32 residual tile (TMA load)
         uint8_t* tileF = tileR + (a.has_res1 ? kTileFBytes : 0);     // fp32 output tile (TMA store)
         uint8_t* tile16 = tileF + (a.has_outf ? kTileFBytes : 0);    // 16-bit output tile (TMA store)
@@ -343,7 +348,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
                 const int y = ra - 1 + j;
                 const bool emit = (y >= ya) && (y < yb);
                 const uint32_t slot = slot_of(v);
-                if (emit && a.has_res1 && !res_inflight) {  // first row of a strip for this group: nothing prefetched
+                if (emit && use_res1 && !res_inflight) {  // first row of a strip for this group: nothing prefetched
                     if (lead_warp) {
                         if (elect_one()) {
                             mbar_expect_tx(rbar, 128 * 128);
@@ -366,7 +371,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
 #pragma unroll
                 for (int i = 0; i < NOUT; ++i) val[i] = __fadd_rn(val[i], bias_s[i]);
                 float4 resv[NOUT / 4];
-                if (a.has_res1) {
+                if (use_res1) {
                     mbar_wait(rbar, res_phase);
                     res_phase ^= 1;
 #pragma unroll
@@ -379,7 +384,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
                     if (lead_warp) tma_store_wait_read();
                     named_bar_sync(1 + gi, 128);
                     res_inflight = false;
-                    if (a.has_res1 && y + a.nepi < yb) {
+                    if (use_res1 && y + a.nepi < yb) {
                         res_inflight = true;
                         if (lead_warp) {
                             if (elect_one()) {
@@ -390,11 +395,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
                         }
                     }
                 }
-                if (a.has_res1) {
+                if (use_res1) {
 #pragma unroll
                     for (int i = 0; i < NOUT / 4; ++i) {
                         const float4 r4 = resv[i];
-                        if (a.ep_mode == EP_SKIP) {
+                        if (a.ep_mode == EP_SKIP || a.ep_mode == EP_ADD2) {
                             val[4 * i + 0] = __fadd_rn(r4.x, val[4 * i + 0]);
                             val[4 * i + 1] = __fadd_rn(r4.y, val[4 * i + 1]);
                             val[4 * i + 2] = __fadd_rn(r4.z, val[4 * i + 2]);
@@ -419,21 +424,58 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
                         val[4 * i + 3] = __fadd_rn(__fmul_rn(val[4 * i + 3], 0.2f), r4.w);
                     }
                 }
+                if (a.ep_mode == EP_ADD2 && a.res2) {
+                    const size_t pix = (static_cast<size_t>(valid ? n : 0) * a.H + y) * a.W + (valid ? x : 0);
+                    const float4* r2 = reinterpret_cast<const float4*>(a.res2 + pix * a.res2_cstride + a.res_choff + slice * NOUT);
+#pragma unroll
+                    for (int i = 0; i < NOUT / 4; ++i) {
+                        const float4 r4 = __ldg(r2 + i);
+                        val[4 * i + 0] = fmaf(a.res2_scale, r4.x, val[4 * i + 0]);
+                        val[4 * i + 1] = fmaf(a.res2_scale, r4.y, val[4 * i + 1]);
+                        val[4 * i + 2] = fmaf(a.res2_scale, r4.z, val[4 * i + 2]);
+                        val[4 * i + 3] = fmaf(a.res2_scale, r4.w, val[4 * i + 3]);
+                    }
+                }
                 if (a.lrelu) {
 #pragma unroll
                     for (int i = 0; i < NOUT; ++i) val[i] = val[i] > 0.f ? val[i] : __fmul_rn(val[i], 0.2f);
+                }
+                if (a.out_nchw_raw && valid) {
+                    const size_t plane = static_cast<size_t>(a.H) * a.W;
+                    float* o = a.out_nchw_raw + static_cast<size_t>(n) * a.out_nchw_c * plane + static_cast<size_t>(y) * a.W + x;
+#pragma unroll
+                    for (int c = 0; c < NOUT; ++c) {
+                        const int cc = slice * NOUT + c;
+                        if (cc < a.out_nchw_c) o[static_cast<size_t>(cc) * plane] = val[c];
+                    }
                 }
                 if (a.clamp01) {
 #pragma unroll
                     for (int i = 0; i < NOUT; ++i) val[i] = fminf(fmaxf(val[i], 0.f), 1.f);
                 }
-                if (a.has_outf) {
+                if (use_outf) {
 #pragma unroll
                     for (int i = 0; i < NOUT / 4; ++i)
                         *reinterpret_cast<float4*>(tileF + m * 128 + ((i ^ (m & 7)) << 4)) =
                             make_float4(val[4 * i], val[4 * i + 1], val[4 * i + 2], val[4 * i + 3]);
                 }
-                if (a.has_out16) {
+                if (use_o16 && a.mask16) {  // LeakyReLU backward: slope 1 where the saved activation is > 0, else 0.2
+                    const size_t pix = (static_cast<size_t>(valid ? n : 0) * a.H + y) * a.W + (valid ? x : 0);
+                    const uint4* mk = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(a.mask16) + pix * a.mask16_cstride +
+                                                                     a.mask16_choff + slice * NOUT);
+#pragma unroll
+                    for (int i = 0; i < NOUT / 8; ++i) {
+                        const uint4 q4 = __ldg(mk + i);
+                        const uint32_t w4[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const uint32_t h16 = (w4[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu;
+                            const bool pos = ((h16 & 0x8000u) == 0) && ((h16 & 0x7FFFu) != 0);
+                            if (!pos) val[8 * i + e] = __fmul_rn(val[8 * i + e], 0.2f);
+                        }
+                    }
+                }
+                if (use_o16) {
                     uint32_t pk[NOUT / 2];
 #pragma unroll
                     for (int i = 0; i < NOUT / 2; ++i) {
@@ -455,9 +497,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
                     named_bar_sync(1 + gi, 128);
                     if (lead_warp) {
                       if (elect_one()) {
-                        if (a.has_outf) tma_store_4d(&tmapOF, tileF, a.outf_choff + slice * NOUT, x0, y, n0);
-                        if (a.has_out16) {
-                            const int c0 = a.out16_choff + slice * NOUT;
+                        if (use_outf) tma_store_4d(&tmapOF, tileF, a.outf_choff + slice * NOUT, x0, y, n0);
+                        if (use_o16) {
+                            const int c0 = a.out16_choff + (a.out16_slice_fixed ? 0 : slice * NOUT);
                             if (!a.out16_up2) {
                                 tma_store_4d(&tmapO16, tile16, c0, x0, y, n0);
                             } else {

@@ -11,73 +11,17 @@
 #include "../../include/resr.h"
 #include "conv3x3.cuh"
 #include "errors.h"
+#include "gen_internal.cuh"
 
 namespace resr {
-
-// ------------------------------------------------------------------------------------------- layer table
-struct ConvSpec {
-    int cin, cout;
-    int nout;      // channels per CTA slice (32, or 16 for the 3-channel output conv)
-    int nslices;
-    int nchunks;   // ceil(cin / 64)
-    int fmt;       // operand format: 0 fp16, 1 bf16
-    size_t p_off;  // offset of weight in the flat fp32 parameter vector (bias follows the weight)
-    size_t w_off;  // byte offset of the packed weights
-    size_t b_off;  // float offset of the padded bias
-};
-
-static const int kNumConvs = 351;
-static const int kNumRRDB = 23;
-
-struct Table {
-    ConvSpec c[kNumConvs];
-    size_t n_params, pack_bytes, bias_floats;
-    Table() {
-        int i = 0;
-        auto add = [&](int cin, int cout, int fmt) {
-            ConvSpec& s = c[i++];
-            s.cin = cin;
-            s.cout = cout;
-            s.nout = cout >= 32 ? 32 : 16;
-            s.nslices = (cout + s.nout - 1) / s.nout;
-            s.nchunks = (cin + 63) / 64;
-            s.fmt = fmt;
-        };
-        add(3, 64, 0);  // conv1 (input image kept in fp16: 11 significant bits for [0,1] pixels)
-        for (int r = 0; r < kNumRRDB * 3; ++r) {
-            for (int k = 0; k < 4; ++k) add(64 + 32 * k, 32, 1);
-            add(192, 64, 1);
-        }
-        add(64, 64, 1);  // conv2 reads the bf16 trunk output
-        add(64, 64, 0);  // upsampling1.0   (tail runs with fp16 operands)
-        add(64, 64, 0);  // upsampling2.0
-        add(64, 64, 0);  // conv3.0
-        add(64, 3, 0);   // conv4
-        size_t p = 0, w = 0, b = 0;
-        for (int k = 0; k < kNumConvs; ++k) {
-            c[k].p_off = p;
-            p += static_cast<size_t>(c[k].cout) * c[k].cin * 9 + c[k].cout;
-            c[k].w_off = w;
-            w += static_cast<size_t>(c[k].nslices) * c[k].nchunks * 3 * (3 * c[k].nout) * 128;
-            c[k].b_off = b;
-            b += static_cast<size_t>(c[k].nslices) * c[k].nout;
-        }
-        n_params = p;
-        pack_bytes = w;
-        bias_floats = b;
-    }
-};
-static const Table& table() {
-    static Table t;
-    return t;
-}
 
 // ------------------------------------------------------------------------------------------- small kernels
 
 // OIHW fp32 -> [slice][chunk][dx][n = dy*NOUT + co][64 ch] 16-bit with the 128B shared-memory swizzle applied, so a
 // plain bulk copy drops a ready-to-use UMMA B operand into shared memory.
 __global__ void pack_conv_kernel(const float* __restrict__ w, const float* __restrict__ bias, uint16_t* __restrict__ wp,
-                                 float* __restrict__ bp, int cin, int cout, int nout, int nslices, int nchunks, int fmt) {
+                                 float* __restrict__ bp, int cin, int cout, int nout, int nslices, int nchunks, int fmt,
+                                 int transposed) {
     const int NT = 3 * nout;
     const size_t total = static_cast<size_t>(nslices) * nchunks * 3 * NT * 64;
     for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
@@ -94,7 +38,13 @@ __global__ void pack_conv_kernel(const float* __restrict__ w, const float* __res
         const int dy = n / nout;
         const int ci = chunk * 64 + k;
         float v = 0.f;
-        if (co < cout && ci < cin) v = w[((static_cast<size_t>(co) * cin + ci) * 3 + dy) * 3 + dx];
+        if (!transposed) {
+            if (co < cout && ci < cin) v = w[((static_cast<size_t>(co) * cin + ci) * 3 + dy) * 3 + dx];
+        } else {
+            // data-gradient convolution: its output channel `co` is a forward INPUT channel, its input channel `ci` a
+            // forward OUTPUT channel, taps flipped
+            if (co < cin && ci < cout) v = w[((static_cast<size_t>(ci) * cin + co) * 3 + (2 - dy)) * 3 + (2 - dx)];
+        }
         uint16_t bits;
         if (fmt == 1) {
             __nv_bfloat16 h = __float2bfloat16_rn(v);
@@ -108,8 +58,9 @@ __global__ void pack_conv_kernel(const float* __restrict__ w, const float* __res
         wp[off] = bits;
     }
     const int nb = nslices * nout;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nb; i += gridDim.x * blockDim.x)
-        bp[i] = (i < cout && bias) ? bias[i] : 0.f;
+    if (bp)
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nb; i += gridDim.x * blockDim.x)
+            bp[i] = (i < cout && bias) ? bias[i] : 0.f;
 }
 
 // NCHW fp32 -> NHWC 16-bit with channels zero-padded to c_pad (multiple of 8).
@@ -145,40 +96,18 @@ __global__ void nchw_to_nhwc16_kernel(const float* __restrict__ x, uint16_t* __r
     }
 }
 
-static int grid_for(size_t total, int block) {
+int grid_for(size_t total, int block) {
     size_t g = (total + block - 1) / block;
     if (g > 148 * 16) g = 148 * 16;
     if (g < 1) g = 1;
     return static_cast<int>(g);
 }
 
-// ------------------------------------------------------------------------------------------- generator object
-struct Step {
-    int conv;   // index into the layer table
-    ConvMaps maps;
-    ConvArgs a;
-};
-
-struct Plan {
-    int N = 0, H = 0, W = 0;
-    void* ws = nullptr;
-    std::vector<Step> steps;
-    uint16_t* xin = nullptr;
-    bool valid = false;
-};
-
-}  // namespace resr
-
-struct resr_generator {
-    uint8_t* wpack = nullptr;
-    float* bias = nullptr;
-    bool loaded = false;
-    int num_sms = 148;
-    int force_mode = -1;
-    resr::Plan plan;
-};
-
-namespace resr {
+void launch_pack_conv(const float* w, const float* bias, uint16_t* wp, float* bp, int cin, int cout, int nout, int nslices,
+                      int nchunks, int fmt, int transposed, cudaStream_t s) {
+    const size_t total = static_cast<size_t>(nslices) * nchunks * 3 * (3 * nout) * 64;
+    pack_conv_kernel<<<grid_for(total, 256), 256, 0, s>>>(w, bias, wp, bp, cin, cout, nout, nslices, nchunks, fmt, transposed);
+}
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -403,6 +332,8 @@ void resr_generator_destroy(resr_generator_t* g) {
     if (!g) return;
     cudaFree(g->wpack);
     cudaFree(g->bias);
+    cudaFree(g->wpack_t);
+    cudaFree(g->zero_bias);
     delete g;
 }
 
@@ -415,13 +346,15 @@ int resr_generator_load_params(resr_generator_t* g, const float* flat, void* str
         const size_t total = static_cast<size_t>(c.nslices) * c.nchunks * 3 * (3 * c.nout) * 64;
         const float* w = flat + c.p_off;
         const float* b = w + static_cast<size_t>(c.cout) * c.cin * 9;
-        pack_conv_kernel<<<grid_for(total, 256), 256, 0, s>>>(w, b, reinterpret_cast<uint16_t*>(g->wpack + c.w_off),
-                                                             g->bias + c.b_off, c.cin, c.cout, c.nout, c.nslices,
-                                                             c.nchunks, c.fmt);
+        (void)total;
+        launch_pack_conv(w, b, reinterpret_cast<uint16_t*>(g->wpack + c.w_off), g->bias + c.b_off, c.cin, c.cout, c.nout,
+                         c.nslices, c.nchunks, c.fmt, 0, s);
     }
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(RESR_E_CUDA, "pack kernels: %s", cudaGetErrorString(e));
     g->loaded = true;
+    g->packed_t = false;
+    g->flat_params = flat;
     return RESR_OK;
 }
 
@@ -502,8 +435,8 @@ int resr_conv3x3(const resr_conv_desc* d, void* stream) {
     float* bp = nullptr;
     if (cudaMalloc(&wp, pack_bytes) != cudaSuccess || cudaMalloc(&bp, nslices * nout * 4) != cudaSuccess)
         return set_error(RESR_E_CUDA, "cudaMalloc failed");
-    pack_conv_kernel<<<grid_for(pack_bytes / 2, 256), 256, 0, s>>>(d->weight, d->bias, reinterpret_cast<uint16_t*>(wp), bp,
-                                                                 d->cin, d->cout, nout, nslices, nchunks, d->fmt_in);
+    launch_pack_conv(d->weight, d->bias, reinterpret_cast<uint16_t*>(wp), bp, d->cin, d->cout, nout, nslices, nchunks,
+                     d->fmt_in, 0, s);
     cudaStreamSynchronize(s);  // the conv prefetches its weights before the programmatic grid dependency resolves
     ConvArgs a;
     ConvMaps maps;

@@ -1,0 +1,637 @@
+// Training path of the generator: forward that keeps every activation, L1 loss, and the full backward pass
+// (data gradients through the same tcgen05 convolution kernel with transposed weights, weight gradients through
+// wgrad_tc.cu). Reference: autograd of /root/reference/model.py:64-132, 206-275 and nn.L1Loss
+// (train_realesrnet.py:190-194, 383-388). See DESIGN.md §6.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "../../include/resr.h"
+#include "conv3x3.cuh"
+#include "errors.h"
+#include "gen_internal.cuh"
+#include "wgrad.cuh"
+
+namespace resr {
+
+// ================================================================================================ small kernels
+
+// NHWC 16-bit [P][cstride], channels [c0, c0 + C) -> channels-first bf16 [Cpad][P]; rows C..Cpad-1 are zero-filled.
+__global__ void __launch_bounds__(256) nhwc16_to_cf_kernel(const uint16_t* __restrict__ in, int cstride, int c0, int C, int Cpad,
+                                                          size_t P, int fmt_in, uint16_t* __restrict__ out) {
+    __shared__ uint16_t tile[32][34];
+    const size_t p0 = static_cast<size_t>(blockIdx.x) * 32;
+    const int cb = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 row groups
+    for (int i = ty; i < 32; i += 8) {  // i = pixel within tile, tx = channel
+        const size_t p = p0 + i;
+        const int c = cb + tx;
+        uint16_t v = 0;
+        if (p < P && c < C) {
+            v = in[p * cstride + c0 + c];
+            if (fmt_in == 0) {  // fp16 -> bf16
+                const __half h = *reinterpret_cast<const __half*>(&v);
+                const __nv_bfloat16 b = __float2bfloat16_rn(__half2float(h));
+                v = *reinterpret_cast<const uint16_t*>(&b);
+            }
+        }
+        tile[i][tx] = v;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {  // i = channel within tile, tx = pixel
+        const size_t p = p0 + tx;
+        const int c = cb + i;
+        if (p < P && c < Cpad) out[static_cast<size_t>(c) * P + p] = tile[tx][i];
+    }
+}
+
+// Same transpose, but writes THREE channels-first copies shifted by one pixel along x (zero at the row ends):
+//     out[dx][c][n][y][x] = in[n][y][x - dx + 1][c]   (dx = 0, 1, 2; zero when x - dx + 1 is outside [0, W))
+// The weight-gradient kernel pairs X[.., x + dx - 1] with dY[.., x]; TMA cannot start a box at an odd 2-byte offset of
+// the innermost (pixel) dimension, so the horizontal tap shift is materialised here instead.
+__global__ void __launch_bounds__(256) nhwc16_to_cf_shift3_kernel(const uint16_t* __restrict__ in, int cstride, int C, int Cpad,
+                                                                 size_t P, int W, uint16_t* __restrict__ out) {
+    __shared__ uint16_t tile[32][34];
+    const size_t p0 = static_cast<size_t>(blockIdx.x) * 32;
+    const int cb = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = ty; i < 32; i += 8) {
+        const size_t p = p0 + i;
+        const int c = cb + tx;
+        tile[i][tx] = (p < P && c < C) ? in[p * cstride + c] : static_cast<uint16_t>(0);
+    }
+    __syncthreads();
+    const size_t plane = static_cast<size_t>(Cpad) * P;
+    for (int i = ty; i < 32; i += 8) {
+        const size_t p = p0 + tx;
+        const int c = cb + i;
+        if (p < P && c < Cpad) {
+            const uint16_t v = tile[tx][i];
+            const int x = static_cast<int>(p % W);
+            uint16_t* row = out + static_cast<size_t>(c) * P;
+            row[plane + p] = v;                       // dx = 1
+            if (x > 0) row[p - 1] = v;                // dx = 0: out[x - 1] = in[x]
+            if (x == W - 1) row[p] = 0;
+            if (x < W - 1) row[2 * plane + p + 1] = v;  // dx = 2: out[x + 1] = in[x]
+            if (x == 0) row[2 * plane + p] = 0;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) scale_f32_to_bf16_kernel(const float* __restrict__ a, float sa, const float* __restrict__ b,
+                                                               float sb, uint16_t* __restrict__ out, size_t n) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        float v = sa * a[i];
+        if (b) v += sb * b[i];
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        out[i] = *reinterpret_cast<const uint16_t*>(&h);
+    }
+}
+
+__global__ void __launch_bounds__(256) axpby_f32_kernel(const float* __restrict__ a, float sa, const float* __restrict__ b, float sb,
+                                                       float* __restrict__ out, size_t n) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+        out[i] = sa * a[i] + sb * b[i];
+}
+
+// Backward of nearest x2 upsampling (model.py:264-265): out[n,y,x,c] = sum of the 2x2 block of in[n,2y+a,2x+b,c].
+// in: bf16 [N,2H,2W,64]; outputs (either may be null): fp32 and bf16 [N,H,W,64].
+__global__ void __launch_bounds__(256) sum2x2_kernel(const uint16_t* __restrict__ in, float* __restrict__ outf,
+                                                    uint16_t* __restrict__ out16, int N, int H, int W) {
+    const size_t total = static_cast<size_t>(N) * H * W * 32;  // one thread per channel pair
+    for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int cp = idx % 32;
+        const size_t pix = idx / 32;
+        const int x = pix % W;
+        const int y = (pix / W) % H;
+        const size_t n = pix / (static_cast<size_t>(W) * H);
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const size_t pi = (n * 2 * H + 2 * y + (k >> 1)) * (2 * W) + 2 * x + (k & 1);
+            const uint32_t v = reinterpret_cast<const uint32_t*>(in + pi * 64)[cp];
+            s0 += __uint_as_float(v << 16);
+            s1 += __uint_as_float(v & 0xFFFF0000u);
+        }
+        if (outf) { outf[pix * 64 + 2 * cp] = s0; outf[pix * 64 + 2 * cp + 1] = s1; }
+        if (out16) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(s0, s1);
+            reinterpret_cast<uint32_t*>(out16 + pix * 64)[cp] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+    }
+}
+
+// Gradient of the network output. mode 0: L1 loss vs hr (train_realesrnet.py:190-194, 385): g = sign(clamp(v) - hr) / numel,
+// loss accumulated in double; mode 1: g = upstream gradient `ref`. Both are gated by the clamp (model.py:270): the
+// gradient passes where 0 <= v <= 1. Writes the NHWC bf16 operand of conv4's backward ([pixels][64], channels >= 3 zero).
+__global__ void __launch_bounds__(256) out_grad_kernel(const float* __restrict__ raw, const float* __restrict__ ref,
+                                                      uint16_t* __restrict__ dy, double* __restrict__ loss_sum, int N, size_t HW,
+                                                      float inv_numel, int mode) {
+    __shared__ double red[8];
+    const size_t total = static_cast<size_t>(N) * HW;
+    double local = 0.0;
+    for (size_t pix = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; pix < total; pix += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const size_t n = pix / HW, r = pix % HW;
+        float g[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const size_t o = (n * 3 + c) * HW + r;
+            const float v = raw[o];
+            float gv;
+            if (mode == 0) {
+                const float d = fminf(fmaxf(v, 0.f), 1.f) - ref[o];
+                local += fabs(static_cast<double>(d));
+                gv = d > 0.f ? inv_numel : (d < 0.f ? -inv_numel : 0.f);
+            } else {
+                gv = ref[o];
+            }
+            g[c] = (v < 0.f || v > 1.f) ? 0.f : gv;
+        }
+        uint4* dst = reinterpret_cast<uint4*>(dy + pix * 64);
+        const __nv_bfloat162 h01 = __floats2bfloat162_rn(g[0], g[1]);
+        const __nv_bfloat162 h23 = __floats2bfloat162_rn(g[2], 0.f);
+        dst[0] = make_uint4(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23), 0u, 0u);
+#pragma unroll
+        for (int i = 1; i < 8; ++i) dst[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (mode == 0) {
+        for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s = 0;
+            for (int i = 0; i < 8; ++i) s += red[i];
+            atomicAdd(loss_sum, s);
+        }
+    }
+}
+
+__global__ void finish_loss_kernel(const double* __restrict__ sum, float* __restrict__ loss, double inv_numel) {
+    *loss = static_cast<float>(*sum * inv_numel);
+}
+
+static int egrid(size_t total) {
+    size_t g = (total + 255) / 256;
+    if (g > 148 * 32) g = 148 * 32;
+    return static_cast<int>(g < 1 ? 1 : g);
+}
+
+// ================================================================================================ conv launcher
+
+struct Geo { int H, W, BW, BN, mode; };
+
+static Geo make_geo(const resr_generator* g, int H, int W) {
+    Geo q;
+    q.H = H; q.W = W;
+    conv3x3_pick_tile(W, &q.BW, &q.BN);
+    q.mode = q.BN == 1 ? 0 : 1;
+    if (g->force_mode >= 0 && q.BN == 1) q.mode = g->force_mode;
+    return q;
+}
+
+struct ConvIO {
+    const void* in16 = nullptr; int in_c = 64;
+    const uint8_t* wpack = nullptr; const float* bias = nullptr;
+    int nout = 32, nslices = 1, nchunks = 1, fmt = 1;
+    void* out16 = nullptr; int out16_c = 64, out16_choff = 0, out16_fmt = 1, out16_up2 = 0, out16_fixed = 0; unsigned no16_mask = 0;
+    float* outf = nullptr; int outf_c = 64, outf_choff = 0; unsigned noutf_mask = 0;
+    const float* res1 = nullptr; int res1_c = 64, res_choff = 0; unsigned nores_mask = 0;
+    const float* res2 = nullptr; int res2_c = 64; float res2_scale = 1.f;
+    const void* mask16 = nullptr; int mask16_c = 64, mask16_choff = 0;
+    int ep_mode = EP_PLAIN, lrelu = 0, clamp01 = 0;
+    float* out_nchw = nullptr; float* out_nchw_raw = nullptr; int out_nchw_c = 3;
+};
+
+static int launch_conv_io(const resr_generator* g, const Geo& q, int N, const ConvIO& io, cudaStream_t s) {
+    ConvArgs a;
+    ConvMaps m;
+    memset(&a, 0, sizeof(a));
+    memset(&m, 0, sizeof(m));
+    a.N = N; a.H = q.H; a.W = q.W; a.BW = q.BW; a.BN = q.BN;
+    a.nxs = (q.W + q.BW - 1) / q.BW;
+    a.ncg = ((N + q.BN - 1) / q.BN) * a.nxs;
+    a.nchunks = io.nchunks;
+    a.mode = q.mode;
+    a.fmt_in = io.fmt;
+    a.rows_total = static_cast<long long>(a.ncg) * q.H;
+    a.wpack = io.wpack; a.bias = io.bias;
+    a.ep_mode = io.ep_mode; a.lrelu = io.lrelu; a.clamp01 = io.clamp01;
+    int rc = conv3x3_make_tmap_act(&m.a, io.in16, N, q.H, q.W, io.in_c, q.mode, q.BW, q.BN);
+    if (io.out16) {
+        a.has_out16 = 1; a.out16_fmt = io.out16_fmt; a.out16_choff = io.out16_choff; a.out16_up2 = io.out16_up2;
+        a.out16_slice_fixed = io.out16_fixed; a.slice_no16_mask = io.no16_mask;
+        rc |= conv3x3_make_tmap_out16(&m.o16, io.out16, N, q.H, q.W, io.out16_c, io.nout, q.BW, q.BN, io.out16_up2);
+    }
+    if (io.outf) {
+        a.has_outf = 1; a.outf_choff = io.outf_choff; a.slice_noutf_mask = io.noutf_mask;
+        rc |= conv3x3_make_tmap_f32(&m.of, io.outf, N, q.H, q.W, io.outf_c, q.BW, q.BN);
+    }
+    if (io.res1) {
+        a.has_res1 = 1; a.res_choff = io.res_choff; a.slice_nores_mask = io.nores_mask;
+        rc |= conv3x3_make_tmap_f32(&m.r1, io.res1, N, q.H, q.W, io.res1_c, q.BW, q.BN);
+    }
+    a.res2 = io.res2; a.res2_cstride = io.res2_c; a.res2_scale = io.res2_scale;
+    a.mask16 = io.mask16; a.mask16_cstride = io.mask16_c; a.mask16_choff = io.mask16_choff;
+    a.out_nchw = io.out_nchw; a.out_nchw_raw = io.out_nchw_raw; a.out_nchw_c = io.out_nchw_c;
+    if (!conv3x3_plan_smem(&a, io.nout)) rc |= 1 << 20;
+    if (rc != 0) return set_error(RESR_E_CUDA, "conv planning failed (%d)", rc);
+    const cudaError_t e = conv3x3_launch(m, a, io.nout, io.nslices, g->num_sms, s);
+    if (e != cudaSuccess) return set_error(RESR_E_CUDA, "conv launch: %s", cudaGetErrorString(e));
+    return RESR_OK;
+}
+
+// ================================================================================================ workspace
+
+static size_t up1k(size_t v) { return (v + 1023) / 1024 * 1024; }
+
+struct TrainWs {
+    size_t xin, c[70], f[4], t1, t2, t3, t4, yraw;       // forward
+    size_t g, dya, dyb, dx[3], dskip, biga, bigb, mida, midb, xt, dyt, partial, loss;  // backward
+    size_t total;
+};
+
+static TrainWs train_layout(size_t N, size_t H, size_t W, int num_sms) {
+    const size_t P = N * H * W;
+    TrainWs L;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { const size_t at = o; o = up1k(o + bytes); return at; };
+    L.xin = take(P * 64 * 2);
+    for (int i = 0; i < 70; ++i) L.c[i] = take(P * 192 * 2);
+    for (int i = 0; i < 4; ++i) L.f[i] = take(P * 64 * 4);
+    L.t1 = take(4 * P * 64 * 2);
+    L.t2 = take(16 * P * 64 * 2);
+    L.t3 = take(16 * P * 64 * 2);
+    L.t4 = take(16 * P * 64 * 2);
+    L.yraw = take(16 * P * 3 * 4);
+    L.g = take(P * 192 * 4);
+    L.dya = take(P * 64 * 2);
+    L.dyb = take(P * 64 * 2);
+    for (int i = 0; i < 3; ++i) L.dx[i] = take(P * 64 * 4);
+    L.dskip = take(P * 64 * 4);
+    L.biga = take(16 * P * 64 * 2);
+    L.bigb = take(16 * P * 64 * 2);
+    L.mida = take(4 * P * 64 * 2);
+    L.midb = take(4 * P * 64 * 2);
+    L.xt = take(16 * P * 64 * 2 > P * 192 * 2 ? 16 * P * 64 * 2 : P * 192 * 2);
+    L.dyt = take(3 * 16 * P * 64 * 2);
+    L.partial = take(wgrad_partial_bytes(num_sms));
+    L.loss = take(64);
+    L.total = o;
+    return L;
+}
+
+static void ensure_transposed_packs(resr_generator* g, cudaStream_t s) {
+    const Table& T = table();
+    if (!g->wpack_t) {
+        cudaMalloc(&g->wpack_t, T.packt_bytes);
+        cudaMalloc(&g->zero_bias, 256 * sizeof(float));
+        cudaMemsetAsync(g->zero_bias, 0, 256 * sizeof(float), s);
+    }
+    if (g->packed_t) return;
+    for (int k = 1; k < kNumConvs; ++k) {  // conv 0 (3 -> 64) never needs its input gradient
+        const ConvSpec& c = T.c[k];
+        launch_pack_conv(g->flat_params + c.p_off, nullptr, reinterpret_cast<uint16_t*>(g->wpack_t + c.wt_off), nullptr, c.cin, c.cout,
+                         32, c.t_nslices, c.t_nchunks, 1, 1, s);
+    }
+    g->packed_t = true;
+}
+
+}  // namespace resr
+
+using namespace resr;
+
+namespace {
+
+struct Bufs {
+    uint16_t *xin, *c[70], *t1, *t2, *t3, *t4, *dya, *dyb, *biga, *bigb, *mida, *midb, *xt, *dyt;
+    float *f[4], *yraw, *g, *dx[3], *dskip, *partial;
+    double* loss;
+};
+
+Bufs carve(void* ws, const TrainWs& L) {
+    uint8_t* b = static_cast<uint8_t*>(ws);
+    Bufs B;
+    B.xin = reinterpret_cast<uint16_t*>(b + L.xin);
+    for (int i = 0; i < 70; ++i) B.c[i] = reinterpret_cast<uint16_t*>(b + L.c[i]);
+    for (int i = 0; i < 4; ++i) B.f[i] = reinterpret_cast<float*>(b + L.f[i]);
+    B.t1 = reinterpret_cast<uint16_t*>(b + L.t1); B.t2 = reinterpret_cast<uint16_t*>(b + L.t2);
+    B.t3 = reinterpret_cast<uint16_t*>(b + L.t3); B.t4 = reinterpret_cast<uint16_t*>(b + L.t4);
+    B.yraw = reinterpret_cast<float*>(b + L.yraw);
+    B.g = reinterpret_cast<float*>(b + L.g);
+    B.dya = reinterpret_cast<uint16_t*>(b + L.dya); B.dyb = reinterpret_cast<uint16_t*>(b + L.dyb);
+    for (int i = 0; i < 3; ++i) B.dx[i] = reinterpret_cast<float*>(b + L.dx[i]);
+    B.dskip = reinterpret_cast<float*>(b + L.dskip);
+    B.biga = reinterpret_cast<uint16_t*>(b + L.biga); B.bigb = reinterpret_cast<uint16_t*>(b + L.bigb);
+    B.mida = reinterpret_cast<uint16_t*>(b + L.mida); B.midb = reinterpret_cast<uint16_t*>(b + L.midb);
+    B.xt = reinterpret_cast<uint16_t*>(b + L.xt); B.dyt = reinterpret_cast<uint16_t*>(b + L.dyt);
+    B.partial = reinterpret_cast<float*>(b + L.partial);
+    B.loss = reinterpret_cast<double*>(b + L.loss);
+    return B;
+}
+
+#define RESR_TRY(expr) do { const int rc__ = (expr); if (rc__ != RESR_OK) return rc__; } while (0)
+
+// forward conv of layer `k` with the inference packs
+ConvIO fwd_io(const resr_generator* g, int k) {
+    const ConvSpec& c = table().c[k];
+    ConvIO io;
+    io.wpack = g->wpack + c.w_off; io.bias = g->bias + c.b_off;
+    io.nout = c.nout; io.nslices = c.nslices; io.nchunks = c.nchunks; io.fmt = c.fmt;
+    return io;
+}
+
+int forward_train(resr_generator* g, const float* x, float* y, int N, int H, int W, const Bufs& B, cudaStream_t s) {
+    const Geo g0 = make_geo(g, H, W), g1 = make_geo(g, 2 * H, 2 * W), g2 = make_geo(g, 4 * H, 4 * W);
+    const size_t P = static_cast<size_t>(N) * H * W;
+    // growth channels of every concat buffer must be finite before the zero-padded K chunks read them
+    for (int i = 0; i < 70; ++i) cudaMemsetAsync(B.c[i], 0, P * 192 * 2, s);
+    RESR_TRY(resr_nchw_to_nhwc16(x, B.xin, N, 3, H, W, 64, 0, s));
+    int k = 0;
+    {
+        ConvIO io = fwd_io(g, k++);
+        io.in16 = B.xin; io.in_c = 64;
+        io.outf = B.f[0]; io.out16 = B.c[0]; io.out16_c = 192;
+        RESR_TRY(launch_conv_io(g, g0, N, io, s));
+    }
+    for (int i = 0; i < kNumRRDB; ++i) {
+        float* X0 = (i == 0) ? B.f[0] : B.f[3];
+        for (int j = 0; j < 3; ++j) {
+            const int r = 3 * i + j;
+            float* xm = (j == 0) ? X0 : B.f[j];
+            for (int q = 0; q < 4; ++q) {
+                ConvIO io = fwd_io(g, k++);
+                io.in16 = B.c[r]; io.in_c = 192; io.lrelu = 1;
+                io.out16 = B.c[r]; io.out16_c = 192; io.out16_choff = 64 + 32 * q;
+                RESR_TRY(launch_conv_io(g, g0, N, io, s));
+            }
+            ConvIO io = fwd_io(g, k++);
+            io.in16 = B.c[r]; io.in_c = 192;
+            io.res1 = xm;
+            if (j < 2) { io.ep_mode = EP_RDB; io.outf = B.f[j + 1]; }
+            else { io.ep_mode = EP_RRDB; io.res2 = X0; io.res2_c = 64; io.outf = B.f[3]; }
+            io.out16 = B.c[r + 1]; io.out16_c = 192;
+            RESR_TRY(launch_conv_io(g, g0, N, io, s));
+        }
+    }
+    {   // conv2 + skip, stored nearest-upsampled x2 (fp16)
+        ConvIO io = fwd_io(g, k++);
+        io.in16 = B.c[69]; io.in_c = 192; io.ep_mode = EP_SKIP; io.res1 = B.f[0];
+        io.out16 = B.t1; io.out16_c = 64; io.out16_fmt = 0; io.out16_up2 = 1;
+        RESR_TRY(launch_conv_io(g, g0, N, io, s));
+    }
+    {
+        ConvIO io = fwd_io(g, k++);
+        io.in16 = B.t1; io.lrelu = 1; io.out16 = B.t2; io.out16_fmt = 0; io.out16_up2 = 1;
+        RESR_TRY(launch_conv_io(g, g1, N, io, s));
+    }
+    {
+        ConvIO io = fwd_io(g, k++);
+        io.in16 = B.t2; io.lrelu = 1; io.out16 = B.t3; io.out16_fmt = 0;
+        RESR_TRY(launch_conv_io(g, g2, N, io, s));
+    }
+    {
+        ConvIO io = fwd_io(g, k++);
+        io.in16 = B.t3; io.lrelu = 1; io.out16 = B.t4; io.out16_fmt = 0;
+        RESR_TRY(launch_conv_io(g, g2, N, io, s));
+    }
+    {
+        ConvIO io = fwd_io(g, k++);
+        io.in16 = B.t4; io.clamp01 = 1; io.out_nchw = y; io.out_nchw_raw = B.yraw; io.out_nchw_c = 3;
+        RESR_TRY(launch_conv_io(g, g2, N, io, s));
+    }
+    return RESR_OK;
+}
+
+// weight + bias gradient of layer k. x16: NHWC input activations of the layer (first cin channels of a c_stride-wide
+// tensor, format fmt_x); dy16: NHWC bf16 output gradient (64-channel buffer). Both are transposed to channels-first.
+int layer_wgrad(resr_generator* g, int k, const uint16_t* x16, int x_cstride, int fmt_x, bool x_already_transposed, int xt_rows,
+                const uint16_t* dy16, int N, const Geo& q, const Bufs& B, float* grads, cudaStream_t s) {
+    const ConvSpec& c = table().c[k];
+    const size_t P = static_cast<size_t>(N) * q.H * q.W;
+    if (!x_already_transposed) {
+        xt_rows = (c.cin + 31) / 32 * 32;
+        nhwc16_to_cf_kernel<<<dim3(static_cast<unsigned>((P + 31) / 32), xt_rows / 32), 256, 0, s>>>(x16, x_cstride, 0, c.cin, xt_rows, P,
+                                                                                                       fmt_x, B.xt);
+    }
+    const int dy_rows = (c.cout + 31) / 32 * 32;
+    nhwc16_to_cf_shift3_kernel<<<dim3(static_cast<unsigned>((P + 31) / 32), dy_rows / 32), 256, 0, s>>>(dy16, 64, c.cout, dy_rows, P, q.W, B.dyt);
+    float* dw = grads + c.p_off;
+    float* db = dw + static_cast<size_t>(c.cout) * c.cin * 9;
+    const int rc = wgrad_launch(B.xt, xt_rows, B.dyt, dy_rows, N, q.H, q.W, c.cin, c.cout, B.partial, dw, db, g->num_sms, s);
+    if (rc != 0) return set_error(RESR_E_CUDA, "wgrad of layer %d failed (%d)", k, rc);
+    return RESR_OK;
+}
+
+// data-gradient convolution of layer k: ConvIO preset with the transposed packs
+ConvIO bwd_io(const resr_generator* g, int k) {
+    const ConvSpec& c = table().c[k];
+    ConvIO io;
+    io.wpack = g->wpack_t + c.wt_off; io.bias = g->zero_bias;
+    io.nout = 32; io.nslices = c.t_nslices; io.nchunks = c.t_nchunks; io.fmt = 1;
+    return io;
+}
+
+// Common backward: B.biga holds conv4's output gradient (NHWC bf16 [16P][64], 3 channels used).
+int backward_common(resr_generator* g, float* grads, int N, int H, int W, const Bufs& B, cudaStream_t s) {
+    const Geo g0 = make_geo(g, H, W), g1 = make_geo(g, 2 * H, 2 * W), g2 = make_geo(g, 4 * H, 4 * W);
+    const size_t P = static_cast<size_t>(N) * H * W;
+    ensure_transposed_packs(g, s);
+    cudaMemsetAsync(B.dya, 0, P * 64 * 2, s);
+    cudaMemsetAsync(B.dyb, 0, P * 64 * 2, s);
+    const int kConv2 = 346, kUp1 = 347, kUp2 = 348, kConv3 = 349, kConv4 = 350;
+
+    // ---- tail (model.py:264-270 backwards)
+    RESR_TRY(layer_wgrad(g, kConv4, B.t4, 64, 0, false, 0, B.biga, N, g2, B, grads, s));
+    {   // d(T4) masked by LeakyReLU'(conv3 out) -> conv3's dY
+        ConvIO io = bwd_io(g, kConv4);
+        io.in16 = B.biga; io.out16 = B.bigb; io.mask16 = B.t4;
+        RESR_TRY(launch_conv_io(g, g2, N, io, s));
+    }
+    RESR_TRY(layer_wgrad(g, kConv3, B.t3, 64, 0, false, 0, B.bigb, N, g2, B, grads, s));
+    {
+        ConvIO io = bwd_io(g, kConv3);
+        io.in16 = B.bigb; io.out16 = B.biga; io.mask16 = B.t3;
+        RESR_TRY(launch_conv_io(g, g2, N, io, s));
+    }
+    RESR_TRY(layer_wgrad(g, kUp2, B.t2, 64, 0, false, 0, B.biga, N, g2, B, grads, s));
+    {   // d(T2) at 4x, masked by LeakyReLU'(up1 out) (T2 holds its upsampled copy), then the 2x2 sum of nearest x2
+        ConvIO io = bwd_io(g, kUp2);
+        io.in16 = B.biga; io.out16 = B.bigb; io.mask16 = B.t2;
+        RESR_TRY(launch_conv_io(g, g2, N, io, s));
+        sum2x2_kernel<<<egrid(4 * P * 32), 256, 0, s>>>(B.bigb, nullptr, B.mida, N, 2 * H, 2 * W);
+    }
+    RESR_TRY(layer_wgrad(g, kUp1, B.t1, 64, 0, false, 0, B.mida, N, g1, B, grads, s));
+    {   // d(T1) at 2x (no activation on the skip sum), 2x2 sum -> d(out) at LR: fp32 (skip branch) + bf16 (conv2's dY)
+        ConvIO io = bwd_io(g, kUp1);
+        io.in16 = B.mida; io.out16 = B.midb;
+        RESR_TRY(launch_conv_io(g, g1, N, io, s));
+        sum2x2_kernel<<<egrid(P * 32), 256, 0, s>>>(B.midb, B.dskip, B.dya, N, H, W);
+    }
+    RESR_TRY(layer_wgrad(g, kConv2, B.c[69], 192, 1, false, 0, B.dya, N, g0, B, grads, s));
+    {   // d(trunk output), fp32
+        ConvIO io = bwd_io(g, kConv2);
+        io.in16 = B.dya; io.outf = B.dx[0];
+        RESR_TRY(launch_conv_io(g, g0, N, io, s));
+    }
+
+    // ---- trunk, RRDB 22 .. 0 (model.py:123-132 and 87-98 backwards)
+    for (int i = kNumRRDB - 1; i >= 0; --i) {
+        // d(out) of this RRDB is in dx[0]; rdb3 sees 0.2 * d(out)
+        const float* dbuf[3] = {B.dx[0], B.dx[1], B.dx[2]};
+        float* dxin[3] = {B.dx[1], B.dx[2], B.dx[1]};
+        const float dscale[3] = {0.2f, 1.f, 1.f};
+        for (int jj = 0; jj < 3; ++jj) {
+            const int j = 2 - jj;          // rdb3, rdb2, rdb1
+            const int r = 3 * i + j;       // concat buffer / RDB index
+            const int k5 = 1 + 5 * r + 4;  // layer index of this RDB's conv5
+            const float* D = dbuf[jj];
+            // channels-first copy of the whole concat buffer: the X operand of all five weight gradients
+            nhwc16_to_cf_kernel<<<dim3(static_cast<unsigned>((P + 31) / 32), 6), 256, 0, s>>>(B.c[r], 192, 0, 192, 192, P, 1, B.xt);
+            // conv5: dY5 = 0.2 * d(xout)
+            scale_f32_to_bf16_kernel<<<egrid(P * 64), 256, 0, s>>>(D, 0.2f * dscale[jj], nullptr, 0.f, B.dya, P * 64);
+            RESR_TRY(layer_wgrad(g, k5, nullptr, 0, 1, true, 192, B.dya, N, g0, B, grads, s));
+            {
+                ConvIO io = bwd_io(g, k5);  // 6 output slices: 0..4 -> G (first writer), 5 -> masked dY of conv4
+                io.in16 = B.dya;
+                io.outf = B.g; io.outf_c = 192; io.noutf_mask = 1u << 5;
+                io.out16 = B.dyb; io.out16_fixed = 1; io.no16_mask = 0x1Fu;
+                io.mask16 = B.c[r]; io.mask16_c = 192;
+                RESR_TRY(launch_conv_io(g, g0, N, io, s));
+            }
+            uint16_t* cur = B.dyb;
+            uint16_t* nxt = B.dya;
+            for (int q = 3; q >= 1; --q) {  // conv4, conv3, conv2: accumulate into G, top slice -> masked dY of conv(q)
+                const int kq = 1 + 5 * r + q;
+                RESR_TRY(layer_wgrad(g, kq, nullptr, 0, 1, true, 192, cur, N, g0, B, grads, s));
+                const int nsl = table().c[kq].t_nslices;  // 5, 4, 3
+                ConvIO io = bwd_io(g, kq);
+                io.in16 = cur; io.ep_mode = EP_ADD2;
+                io.res1 = B.g; io.res1_c = 192;
+                io.outf = B.g; io.outf_c = 192; io.noutf_mask = 1u << (nsl - 1);
+                io.out16 = nxt; io.out16_fixed = 1; io.no16_mask = (1u << (nsl - 1)) - 1u;
+                io.mask16 = B.c[r]; io.mask16_c = 192;
+                RESR_TRY(launch_conv_io(g, g0, N, io, s));
+                uint16_t* t = cur; cur = nxt; nxt = t;
+            }
+            {   // conv1: d(xin) = conv1's data gradient + G[0:64] + d(xout)
+                const int k1 = 1 + 5 * r;
+                RESR_TRY(layer_wgrad(g, k1, nullptr, 0, 1, true, 192, cur, N, g0, B, grads, s));
+                ConvIO io = bwd_io(g, k1);
+                io.in16 = cur; io.ep_mode = EP_ADD2;
+                io.res1 = B.g; io.res1_c = 192;
+                io.res2 = D; io.res2_c = 64; io.res2_scale = dscale[jj];
+                io.outf = dxin[jj]; io.outf_c = 64;
+                RESR_TRY(launch_conv_io(g, g0, N, io, s));
+            }
+        }
+        // d(x0) = d(rdb1 input) + d(out)   (model.py:129-130)
+        axpby_f32_kernel<<<egrid(P * 64), 256, 0, s>>>(B.dx[1], 1.f, B.dx[0], 1.f, B.dx[0], P * 64);
+    }
+    // ---- conv1 (model.py:258): dY = d(trunk input) + d(skip)
+    scale_f32_to_bf16_kernel<<<egrid(P * 64), 256, 0, s>>>(B.dx[0], 1.f, B.dskip, 1.f, B.dya, P * 64);
+    RESR_TRY(layer_wgrad(g, 0, B.xin, 64, 0, false, 0, B.dya, N, g0, B, grads, s));
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(RESR_E_CUDA, "backward: %s", cudaGetErrorString(e));
+    return RESR_OK;
+}
+
+int check_train_args(resr_generator_t* g, int n, int h, int w, void* ws, size_t ws_bytes) {
+    if (!g || !ws) return set_error(RESR_E_INVALID, "null argument");
+    if (n <= 0 || h <= 0 || w <= 0) return set_error(RESR_E_INVALID, "bad shape");
+    if (w % 8 != 0) return set_error(RESR_E_INVALID, "training path needs W %% 8 == 0 (channels-first TMA strides), got %d", w);
+    if (!g->loaded || !g->flat_params) return set_error(RESR_E_INVALID, "resr_generator_load_params has not been called");
+    if (ws_bytes < resr_generator_train_workspace_bytes(n, h, w)) return set_error(RESR_E_NOMEM, "training workspace too small");
+    if ((reinterpret_cast<uintptr_t>(ws) & 1023) != 0) return set_error(RESR_E_INVALID, "workspace must be 1024-byte aligned");
+    return RESR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t resr_generator_train_workspace_bytes(int n, int h, int w) {
+    if (n <= 0 || h <= 0 || w <= 0) return 0;
+    return train_layout(n, h, w, 160).total;
+}
+
+int resr_generator_forward_train(resr_generator_t* g, const float* x, float* y, int n, int h, int w, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+    RESR_TRY(check_train_args(g, n, h, w, workspace, workspace_bytes));
+    if (!x || !y) return set_error(RESR_E_INVALID, "null argument");
+    const Bufs B = carve(workspace, train_layout(n, h, w, 160));
+    return forward_train(g, x, y, n, h, w, B, static_cast<cudaStream_t>(stream));
+}
+
+int resr_generator_backward_l1(resr_generator_t* g, const float* hr, float* grads_flat, float* loss_out, int n, int h, int w,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+    RESR_TRY(check_train_args(g, n, h, w, workspace, workspace_bytes));
+    if (!hr || !grads_flat) return set_error(RESR_E_INVALID, "null argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const Bufs B = carve(workspace, train_layout(n, h, w, 160));
+    const size_t HW = static_cast<size_t>(16) * h * w;
+    const double numel = static_cast<double>(n) * 3 * HW;
+    cudaMemsetAsync(B.loss, 0, sizeof(double), s);
+    out_grad_kernel<<<egrid(static_cast<size_t>(n) * HW), 256, 0, s>>>(B.yraw, hr, B.biga, B.loss, n, HW, static_cast<float>(1.0 / numel), 0);
+    if (loss_out) finish_loss_kernel<<<1, 1, 0, s>>>(B.loss, loss_out, 1.0 / numel);
+    return backward_common(g, grads_flat, n, h, w, B, s);
+}
+
+int resr_generator_backward(resr_generator_t* g, const float* dy, float* grads_flat, int n, int h, int w, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+    RESR_TRY(check_train_args(g, n, h, w, workspace, workspace_bytes));
+    if (!dy || !grads_flat) return set_error(RESR_E_INVALID, "null argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const Bufs B = carve(workspace, train_layout(n, h, w, 160));
+    const size_t HW = static_cast<size_t>(16) * h * w;
+    out_grad_kernel<<<egrid(static_cast<size_t>(n) * HW), 256, 0, s>>>(B.yraw, dy, B.biga, nullptr, n, HW, 0.f, 1);
+    return backward_common(g, grads_flat, n, h, w, B, s);
+}
+
+int resr_conv3x3_wgrad(const void* x16, int x_cstride, int fmt_x, const void* dy16_bf16, int n, int h, int w, int cin, int cout,
+                       float* dw, float* db, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!x16 || !dy16_bf16 || !dw || !workspace) return set_error(RESR_E_INVALID, "null argument");
+    if (w % 8 != 0 || cout > 64 || cin > x_cstride) return set_error(RESR_E_INVALID, "unsupported wgrad shape");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t P = static_cast<size_t>(n) * h * w;
+    const int xr = (cin + 31) / 32 * 32, yr = (cout + 31) / 32 * 32;
+    const size_t need = up1k(P * xr * 2) + up1k(3 * P * yr * 2) + wgrad_partial_bytes(160);
+    if (workspace_bytes < need) return set_error(RESR_E_NOMEM, "wgrad workspace too small (need %zu)", need);
+    uint16_t* xt = static_cast<uint16_t*>(workspace);
+    uint16_t* dyt = reinterpret_cast<uint16_t*>(static_cast<uint8_t*>(workspace) + up1k(P * xr * 2));
+    float* partial = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(dyt) + up1k(3 * P * yr * 2));
+    nhwc16_to_cf_kernel<<<dim3(static_cast<unsigned>((P + 31) / 32), xr / 32), 256, 0, s>>>(static_cast<const uint16_t*>(x16), x_cstride, 0, cin, xr, P, fmt_x, xt);
+    nhwc16_to_cf_shift3_kernel<<<dim3(static_cast<unsigned>((P + 31) / 32), yr / 32), 256, 0, s>>>(static_cast<const uint16_t*>(dy16_bf16), 64, cout, yr, P, w, dyt);
+    if (getenv("RESR_DEBUG_SYNC")) {
+        const cudaError_t e = cudaStreamSynchronize(s);
+        fprintf(stderr, "[resr] transposes: %s\n", cudaGetErrorString(e));
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    static unsigned long long* hang_host = nullptr;
+    if (getenv("RESR_DEBUG_SYNC") && !hang_host) {
+        cudaHostAlloc(&hang_host, 8, cudaHostAllocMapped);
+        *hang_host = 0;
+        unsigned long long* dptr = nullptr;
+        cudaHostGetDevicePointer(&dptr, hang_host, 0);
+        g_wgrad_hang_slot = dptr;
+    }
+    const int rc = wgrad_launch(xt, xr, dyt, yr, n, h, w, cin, cout, partial, dw, db, sms, s);
+    if (getenv("RESR_DEBUG_SYNC")) {
+        const cudaError_t e = cudaStreamSynchronize(s);
+        fprintf(stderr, "[resr] wgrad: rc=%d %s hang=%llx\n", rc, cudaGetErrorString(e), hang_host ? *hang_host : 0ull);
+    }
+    if (rc != 0) return set_error(RESR_E_CUDA, "wgrad failed (%d)", rc);
+    return RESR_OK;
+}
+
+size_t resr_conv3x3_wgrad_workspace_bytes(int n, int h, int w, int cin, int cout) {
+    const size_t P = static_cast<size_t>(n) * h * w;
+    const int xr = (cin + 31) / 32 * 32, yr = (cout + 31) / 32 * 32;
+    return up1k(P * xr * 2) + up1k(3 * P * yr * 2) + wgrad_partial_bytes(160);
+}
+
+}  // extern "C"

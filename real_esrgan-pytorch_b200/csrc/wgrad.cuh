@@ -1,0 +1,31 @@
+// Internal interface of the tensor-core weight-gradient kernel (wgrad_tc.cu).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace resr {
+
+struct WgradArgs {
+    int N, H, W;
+    int cin, cout;
+    int n_mb;             // input-channel blocks of 128
+    int n_cs;             // output-channel slices of 32
+    int segs_per_row;     // ceil(W / 64)
+    long long kstages_total;  // N * H * segs_per_row (one stage = 64 pixels of one row)
+    float* partial;       // [nsplit][n_mb][n_cs][3 dy][128 ci][96 = (dx, co)] fp32
+    int nstages;
+    int dy_rows;          // channel rows of one shifted copy of dY^T
+    int dbg_mode;         // experiments: 1 skip dY loads, 2 skip MMAs, 4 skip X load
+    volatile unsigned long long* hang;  // optional host-mapped debug slot: written before a barrier-timeout trap
+};
+
+size_t wgrad_partial_bytes(int num_sms);
+
+// xt: channels-first bf16 activations [x_channels][N][H][W]; dyt: three x-shifted channels-first bf16 copies of the
+// output gradient [3][dy_channels][N][H][W] (dy_channels >= ceil(cout/32)*32; copy dx holds dY[.., x - dx + 1]). dw: OIHW fp32 [cout][cin][3][3]; db: [cout] or null.
+int wgrad_launch(const uint16_t* xt, int x_channels, const uint16_t* dyt, int dy_channels, int N, int H, int W, int cin, int cout,
+                 float* partial, float* dw, float* db, int num_sms, cudaStream_t s);
+extern volatile unsigned long long* g_wgrad_hang_slot;  // set by tests (host-mapped), see train.cu
+
+}  // namespace resr

@@ -1,0 +1,257 @@
+// Weight gradient of a 3x3 convolution on the tensor cores (tcgen05 + TMEM):
+//     dW[co][ci][dy][dx] = sum_{n,y,x} dY[n,y,x,co] * X[n, y+dy-1, x+dx-1, ci]        (autograd of model.py:75-79)
+// as a K-major GEMM over pixels. Both operands are read from CHANNELS-FIRST bf16 copies (X^T [ci][n][y][x],
+// dY^T [co][n][y][x]) so that a TMA box of 64 pixels x 128 (or 32) channels lands in shared memory as a standard
+// K-major, 128B-swizzled operand tile (rows = channels, K = pixels). One pipeline stage = one 64-pixel segment of one
+// image row:
+//     A  = X^T tile            [128 ci x 64 px]                        (M = 128)
+//     B  = 9 shifted dY^T tiles [(dx, co) x 64 px] for dy = 0..2         (N = 96 per dy, zero-filled outside the image;
+//          the dx shift comes from three pre-shifted channels-first copies of dY: TMA cannot start a box at an odd
+//          2-byte offset of its innermost dimension, the dy shift is a plain coordinate offset)
+//     D[dy] (TMEM, 128 x 96 fp32) += A * B[dy]^T
+// A CTA owns one (ci block, co slice) pair and a contiguous range of pixel segments (split-K); partial sums go to a
+// workspace and a second kernel reduces the splits into the OIHW gradient.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "conv3x3.cuh"
+#include "ptx.cuh"
+#include "wgrad.cuh"
+
+namespace resr {
+
+static constexpr int kWgStageBytes = 16384 + 9 * 4096;  // 53,248 = 52 KB
+static constexpr int kWgMaxStages = 4;
+static constexpr uint32_t kWgDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint64_t wg_desc(uint32_t lo) { return (static_cast<uint64_t>(kWgDescHi) << 32) | lo; }
+
+volatile unsigned long long* g_wgrad_hang_slot = nullptr;
+
+__device__ __forceinline__ void wg_wait(uint64_t* bar, uint32_t parity, const WgradArgs& a, unsigned code) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 255u) == 0 && clock64() - t0 > 2000000000ll) {
+            if (a.hang) { *a.hang = (static_cast<unsigned long long>(code) << 32) | (blockIdx.y << 16) | threadIdx.x; __threadfence_system(); }
+            __trap();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUtensorMap tmapDY, const WgradArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* misc = smem + a.nstages * kWgStageBytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(misc);
+    uint64_t* empty = full + kWgMaxStages;
+    uint64_t* done = empty + kWgMaxStages;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(done + 1);
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int lane = threadIdx.x & 31;
+    const int unit = blockIdx.x;               // (mb, cs)
+    const int mb = unit / a.n_cs, cs = unit % a.n_cs;
+    const int split = blockIdx.y;
+    const long long k0 = a.kstages_total * split / gridDim.y;
+    const long long k1 = a.kstages_total * (split + 1) / gridDim.y;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tmapX);
+        prefetch_tmap(&tmapDY);
+        for (int i = 0; i < a.nstages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+        mbar_init(done, 1);
+        fence_mbar_init();
+    }
+    if (warp == 2) { tmem_alloc(tmem_ptr, 512); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = *tmem_ptr;
+    const int segs = a.segs_per_row;
+
+    if (warp == 0) {
+        int stage = 0; uint32_t phase = 0;
+        for (long long k = k0; k < k1; ++k) {
+            const int xs = static_cast<int>(k % segs);
+            const int y = static_cast<int>((k / segs) % a.H);
+            const int n = static_cast<int>(k / (static_cast<long long>(segs) * a.H));
+            wg_wait(empty + stage, phase ^ 1, a, 1);
+            if (elect_one()) {
+                uint8_t* st = smem + stage * kWgStageBytes;
+                const uint32_t tx = ((a.dbg_mode & 4) ? 0 : 16384) + ((a.dbg_mode & 1) ? 0 : 9 * 4096);
+                if (tx) mbar_expect_tx(full + stage, tx); else mbar_arrive(full + stage);
+                if (!(a.dbg_mode & 4)) tma_load_4d(st, &tmapX, full + stage, xs * 64, y, n, mb * 128);
+                if (!(a.dbg_mode & 1))
+                for (int dy = 0; dy < 3; ++dy)
+                    for (int dx = 0; dx < 3; ++dx)
+                        tma_load_4d(st + 16384 + (dy * 3 + dx) * 4096, &tmapDY, full + stage, xs * 64, y - dy + 1, n, dx * a.dy_rows + cs * 32);
+            }
+            __syncwarp();
+            if (++stage == a.nstages) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc = make_idesc_f16(1, 128, 96);
+        const uint32_t s_lo = (smem_u32(smem) & 0x3FFFFu) >> 4;
+        int stage = 0; uint32_t phase = 0;
+        uint32_t acc = 0;
+        for (long long k = k0; k < k1; ++k) {
+            wg_wait(full + stage, phase, a, 2);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t a_lo = s_lo + stage * (kWgStageBytes >> 4);
+                const uint32_t b_lo = a_lo + (16384 >> 4);
+                if (!(a.dbg_mode & 2))
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        umma_f16(tbase + dy * 96, wg_desc(a_lo + ks * 2), wg_desc(b_lo + dy * (12288 >> 4) + ks * 2), idesc,
+                                 (acc | ks) ? 1u : 0u);
+                }
+                umma_commit(empty + stage);
+            }
+            __syncwarp();
+            acc = 1;
+            if (++stage == a.nstages) { stage = 0; phase ^= 1; }
+        }
+        if (elect_one()) umma_commit(done);
+        __syncwarp();
+    } else if (warp >= 4) {
+        const int q = warp & 3;
+        const int m = q * 32 + lane;  // ci row within the block
+        wg_wait(done, 0, a, 3);
+        tc_fence_after();
+        float* dst = a.partial + ((((static_cast<size_t>(split) * a.n_mb + mb) * a.n_cs + cs) * 3) * 128 + m) * 96;
+        const bool any = k1 > k0;
+#pragma unroll 1
+        for (int dy = 0; dy < 3; ++dy) {
+            float* row = dst + static_cast<size_t>(dy) * 128 * 96;
+#pragma unroll 1
+            for (int c = 0; c < 3; ++c) {
+                float v[32];
+                tmem_ld32(tbase + (static_cast<uint32_t>(q * 32) << 16) + dy * 96 + c * 32, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    reinterpret_cast<float4*>(row + c * 32)[i] =
+                        any ? make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tbase, 512);
+}
+
+// dW[co][ci][dy][dx] = sum over splits of partial[split][mb][cs][dy][ci % 128][dx * 32 + co % 32]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int cin, int cout, int n_mb,
+                                    int n_cs, int nsplit) {
+    const int total = cout * cin * 9;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int dx = idx % 3, dy = (idx / 3) % 3;
+        const int ci = (idx / 9) % cin, co = idx / (9 * cin);
+        const int mb = ci >> 7, cs = co >> 5;
+        const size_t off = ((((static_cast<size_t>(mb) * n_cs + cs) * 3 + dy) * 128) + (ci & 127)) * 96 + dx * 32 + (co & 31);
+        const size_t stride = static_cast<size_t>(n_mb) * n_cs * 3 * 128 * 96;
+        float s = 0.f;
+        for (int sp = 0; sp < nsplit; ++sp) s += partial[sp * stride + off];
+        dw[idx] = s;
+    }
+}
+
+// db[co] = sum_p dY^T[co][p]  (channels-first bf16)
+__global__ void bias_grad_kernel(const uint16_t* __restrict__ dyt, size_t P, int cout, float* __restrict__ db) {
+    __shared__ float red[32];
+    const int co = blockIdx.x;
+    if (co >= cout) return;
+    const uint16_t* row = dyt + static_cast<size_t>(co) * P;
+    float s = 0.f;
+    for (size_t p = threadIdx.x; p < P; p += blockDim.x) s += __uint_as_float(static_cast<uint32_t>(row[p]) << 16);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float w = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        for (int o = 16; o > 0; o >>= 1) w += __shfl_down_sync(0xffffffffu, w, o);
+        if (threadIdx.x == 0) db[co] = w;
+    }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled wg_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+// channels-first bf16 tensor [C][N][H][W]; box = 64 px x rows channels
+static int make_cf_map(CUtensorMap* out, const void* base, int C, int N, int H, int W, int rows) {
+    PFN_encodeTiled enc = wg_encode_fn();
+    if (!enc) return -1;
+    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N), static_cast<cuuint64_t>(C)};
+    const cuuint64_t strides[3] = {static_cast<cuuint64_t>(W) * 2, static_cast<cuuint64_t>(H) * W * 2, static_cast<cuuint64_t>(N) * H * W * 2};
+    const cuuint32_t box[4] = {64, 1, 1, static_cast<cuuint32_t>(rows)};
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
+}
+
+size_t wgrad_partial_bytes(int num_sms) {
+    // worst case: 4 units (cin 192, cout 64) x (num_sms / 4) splits, or 1 unit x num_sms splits
+    return static_cast<size_t>(num_sms + 8) * 3 * 128 * 96 * sizeof(float);
+}
+
+int wgrad_launch(const uint16_t* xt, int x_channels, const uint16_t* dyt, int dy_channels, int N, int H, int W, int cin, int cout,
+                 float* partial, float* dw, float* db, int num_sms, cudaStream_t s) {
+    if (W % 8 != 0) return -2;  // TMA global strides must be multiples of 16 bytes
+    WgradArgs a;
+    memset(&a, 0, sizeof(a));
+    a.N = N; a.H = H; a.W = W; a.cin = cin; a.cout = cout;
+    a.n_mb = (cin + 127) / 128;
+    a.n_cs = (cout + 31) / 32;
+    a.segs_per_row = (W + 63) / 64;
+    a.kstages_total = static_cast<long long>(N) * H * a.segs_per_row;
+    a.partial = partial;
+    a.nstages = kWgMaxStages;
+    a.hang = g_wgrad_hang_slot;
+    a.dbg_mode = getenv("RESR_WG_DBG") ? atoi(getenv("RESR_WG_DBG")) : 0;
+    const int units = a.n_mb * a.n_cs;
+    long long nsplit = num_sms / units;
+    if (nsplit > a.kstages_total) nsplit = a.kstages_total;
+    if (nsplit < 1) nsplit = 1;
+    CUtensorMap mx, my;
+    int rc = make_cf_map(&mx, xt, x_channels, N, H, W, 128);
+    rc |= make_cf_map(&my, dyt, 3 * dy_channels, N, H, W, 32);
+    a.dy_rows = dy_channels;
+    if (rc != 0) return rc;
+    const int smem = 1024 + kWgMaxStages * kWgStageBytes + 256;
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -3;
+        attr = true;
+    }
+    wgrad_tc_kernel<<<dim3(units, static_cast<unsigned>(nsplit)), 256, smem, s>>>(mx, my, a);
+    if (getenv("RESR_DEBUG_SYNC")) {
+        const cudaError_t e = cudaStreamSynchronize(s);
+        fprintf(stderr, "[resr] wgrad_tc_kernel grid (%d,%lld) smem %d: %s\n", units, nsplit, smem, cudaGetErrorString(e));
+    }
+    const int total = cout * cin * 9;
+    wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, s>>>(partial, dw, cin, cout, a.n_mb, a.n_cs, static_cast<int>(nsplit));
+    if (db)  // the unshifted copy (dx = 1)
+        bias_grad_kernel<<<cout, 256, 0, s>>>(dyt + static_cast<size_t>(dy_channels) * N * H * W, static_cast<size_t>(N) * H * W, cout, db);
+    return cudaGetLastError() == cudaSuccess ? 0 : -4;
+}
+
+}  // namespace resr
