@@ -183,6 +183,13 @@ int resr_generator_forward_train(resr_generator_t* g, const float* x, float* y, 
  * followed by the backward pass of the forward_train call that last used `workspace`. hr: fp32 NCHW [n,3,4h,4w]. */
 int resr_generator_backward_l1(resr_generator_t* g, const float* hr, float* grads_flat, float* loss_out, int n, int h,
                                int w, void* workspace, size_t workspace_bytes, void* stream);
+/* forward_train + L1 + backward in one call. The first call with a given argument set runs eagerly and captures the
+ * launch sequence (~2,400 kernels) into a CUDA graph; later calls with the SAME pointers and shape replay it, so keep
+ * x / hr / y / grads_flat / loss_out in persistent buffers. resr_generator_step_is_graph() tells whether a graph is live. */
+int resr_generator_train_step_l1(resr_generator_t* g, const float* x, const float* hr, float* y, float* grads_flat,
+                                 float* loss_out, int n, int h, int w, void* workspace, size_t workspace_bytes,
+                                 void* stream);
+int resr_generator_step_is_graph(resr_generator_t* g);
 /* Backward from an upstream gradient dL/dy (fp32 NCHW [n,3,4h,4w]); the clamp of model.py:270 is applied inside. */
 int resr_generator_backward(resr_generator_t* g, const float* dy, float* grads_flat, int n, int h, int w, void* workspace,
                             size_t workspace_bytes, void* stream);

@@ -92,3 +92,61 @@ def l1_loss_backward(gen, lr: torch.Tensor, hr: torch.Tensor, accumulate: bool =
                                               _lib.stream_ptr()))
     _scatter_grads(gen, flat, accumulate)
     return loss, sr, flat
+
+
+class TrainStep:
+    """Persistent-buffer training-step core for a fixed (N, H, W): `step(lr, hr)` copies the batch into static device
+    buffers and runs forward + L1 + backward as ONE CUDA-graph replay (C ABI resr_generator_train_step_l1).
+    Gradients land in `self.flat` (fp32, state_dict order); with a process group they are averaged over ranks with a
+    single NCCL all-reduce (data parallel, reference has none: SURVEY.md §2.1) before being scattered to param.grad."""
+
+    def __init__(self, gen, n: int, h: int, w: int, device=None, process_group=None, world_size: int = 1):
+        if w % 8 != 0:
+            raise _lib.ResrError(f"the training path needs W % 8 == 0 (got {w})")
+        self.gen, self.shape = gen, (n, h, w)
+        dev = device or next(gen.parameters()).device
+        self.lr = torch.zeros((n, 3, h, w), dtype=torch.float32, device=dev)
+        self.hr = torch.zeros((n, 3, 4 * h, 4 * w), dtype=torch.float32, device=dev)
+        self.sr = torch.empty_like(self.hr)
+        self.flat = torch.zeros(_lib.lib().resr_generator_num_params(), dtype=torch.float32, device=dev)
+        self.loss = torch.zeros((), dtype=torch.float32, device=dev)
+        self.group, self.world = process_group, world_size
+        # CUDA graphs cannot be captured on the legacy default stream: the step runs on its own stream, ordered
+        # against the caller's current stream on both sides
+        self.stream = torch.cuda.Stream(device=dev)
+
+    def step(self, lr: torch.Tensor = None, hr: torch.Tensor = None, scatter: bool = True):
+        n, h, w = self.shape
+        gen = self.gen
+        cur = torch.cuda.current_stream(self.lr.device)
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            if lr is not None:
+                self.lr.copy_(lr, non_blocking=True)
+            if hr is not None:
+                self.hr.copy_(hr, non_blocking=True)
+            gen._ensure_packed()
+            wp, wbytes = _train_workspace(gen, n, h, w, self.lr.device)
+            _lib.check(_lib.lib().resr_generator_train_step_l1(
+                gen._native(), _lib.ptr(self.lr), _lib.ptr(self.hr), _lib.ptr(self.sr), _lib.ptr(self.flat), _lib.ptr(self.loss), n, h,
+                w, wp, wbytes, _lib.stream_ptr()))
+            if self.world > 1:
+                allreduce_mean_(self.flat, self.group, self.world)
+        cur.wait_stream(self.stream)
+        if scatter:
+            _scatter_grads(gen, self.flat, accumulate=False)
+        return self.loss, self.sr, self.flat
+
+    @property
+    def is_graph(self) -> bool:
+        return bool(_lib.lib().resr_generator_step_is_graph(self.gen._native()))
+
+
+def allreduce_mean_(flat: torch.Tensor, group=None, world_size: int = None):
+    """The one collective of data-parallel training: sum the flat gradient vector over ranks (NCCL over NVLink on the
+    GPU box, gloo in the CPU tests) and divide by the world size."""
+    import torch.distributed as dist
+    world_size = world_size or dist.get_world_size(group)
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat.div_(world_size)
+    return flat

@@ -93,6 +93,11 @@ struct Plan {
 }  // namespace resr
 
 struct resr_generator {
+    // training-step CUDA graph (train.cu): one cached instantiation per argument set
+    cudaGraphExec_t step_exec = nullptr;
+    const void* step_key[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int step_shape[3] = {0, 0, 0};
+    bool step_graph_failed = false;
     uint8_t* wpack_t = nullptr;   // transposed packs for the backward data-gradient convolutions (lazily allocated)
     float* zero_bias = nullptr;
     bool packed_t = false;
@@ -110,6 +115,8 @@ namespace resr {
 int grid_for(size_t total, int block);
 // OIHW fp32 -> packed 16-bit tiles (generator.cu). transposed=1 packs the data-gradient convolution
 // W'[ci][co][dy][dx] = W[co][ci][2-dy][2-dx] (cin/cout are the FORWARD channel counts; bias ignored).
+// (re)builds the transposed packs if the handle has them allocated or `force` is set (train.cu)
+void ensure_transposed_packs(resr_generator* g, cudaStream_t s, bool force);
 void launch_pack_conv(const float* w, const float* bias, uint16_t* wp, float* bp, int cin, int cout, int nout, int nslices,
                       int nchunks, int fmt, int transposed, cudaStream_t s);
 }  // namespace resr

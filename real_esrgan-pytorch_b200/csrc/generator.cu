@@ -334,6 +334,7 @@ void resr_generator_destroy(resr_generator_t* g) {
     cudaFree(g->bias);
     cudaFree(g->wpack_t);
     cudaFree(g->zero_bias);
+    if (g->step_exec) cudaGraphExecDestroy(g->step_exec);
     delete g;
 }
 
@@ -355,6 +356,7 @@ int resr_generator_load_params(resr_generator_t* g, const float* flat, void* str
     g->loaded = true;
     g->packed_t = false;
     g->flat_params = flat;
+    ensure_transposed_packs(g, s, false);  // training handles keep the data-gradient packs in step with the weights
     return RESR_OK;
 }
 

@@ -283,14 +283,15 @@ static TrainWs train_layout(size_t N, size_t H, size_t W, int num_sms) {
     return L;
 }
 
-static void ensure_transposed_packs(resr_generator* g, cudaStream_t s) {
+void ensure_transposed_packs(resr_generator* g, cudaStream_t s, bool force) {
     const Table& T = table();
     if (!g->wpack_t) {
+        if (!force) return;  // inference-only handle
         cudaMalloc(&g->wpack_t, T.packt_bytes);
         cudaMalloc(&g->zero_bias, 256 * sizeof(float));
         cudaMemsetAsync(g->zero_bias, 0, 256 * sizeof(float), s);
     }
-    if (g->packed_t) return;
+    if (g->packed_t || !g->flat_params) return;
     for (int k = 1; k < kNumConvs; ++k) {  // conv 0 (3 -> 64) never needs its input gradient
         const ConvSpec& c = T.c[k];
         launch_pack_conv(g->flat_params + c.p_off, nullptr, reinterpret_cast<uint16_t*>(g->wpack_t + c.wt_off), nullptr, c.cin, c.cout,
@@ -438,7 +439,7 @@ ConvIO bwd_io(const resr_generator* g, int k) {
 int backward_common(resr_generator* g, float* grads, int N, int H, int W, const Bufs& B, cudaStream_t s) {
     const Geo g0 = make_geo(g, H, W), g1 = make_geo(g, 2 * H, 2 * W), g2 = make_geo(g, 4 * H, 4 * W);
     const size_t P = static_cast<size_t>(N) * H * W;
-    ensure_transposed_packs(g, s);
+    ensure_transposed_packs(g, s, true);
     cudaMemsetAsync(B.dya, 0, P * 64 * 2, s);
     cudaMemsetAsync(B.dyb, 0, P * 64 * 2, s);
     const int kConv2 = 346, kUp1 = 347, kUp2 = 348, kConv3 = 349, kConv4 = 350;
@@ -589,6 +590,49 @@ int resr_generator_backward(resr_generator_t* g, const float* dy, float* grads_f
     out_grad_kernel<<<egrid(static_cast<size_t>(n) * HW), 256, 0, s>>>(B.yraw, dy, B.biga, nullptr, n, HW, 0.f, 1);
     return backward_common(g, grads_flat, n, h, w, B, s);
 }
+
+int resr_generator_train_step_l1(resr_generator_t* g, const float* x, const float* hr, float* y, float* grads_flat, float* loss_out,
+                                 int n, int h, int w, void* workspace, size_t workspace_bytes, void* stream) {
+    RESR_TRY(check_train_args(g, n, h, w, workspace, workspace_bytes));
+    if (!x || !hr || !y || !grads_flat) return set_error(RESR_E_INVALID, "null argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const void* key[6] = {x, hr, y, grads_flat, loss_out, workspace};
+    const bool same = g->step_exec && memcmp(key, g->step_key, sizeof(key)) == 0 && g->step_shape[0] == n && g->step_shape[1] == h &&
+                      g->step_shape[2] == w;
+    if (same) {
+        const cudaError_t e = cudaGraphLaunch(g->step_exec, s);
+        if (e != cudaSuccess) return set_error(RESR_E_CUDA, "cudaGraphLaunch: %s", cudaGetErrorString(e));
+        return RESR_OK;
+    }
+    auto eager = [&]() -> int {
+        RESR_TRY(resr_generator_forward_train(g, x, y, n, h, w, workspace, workspace_bytes, stream));
+        return resr_generator_backward_l1(g, hr, grads_flat, loss_out, n, h, w, workspace, workspace_bytes, stream);
+    };
+    // first call with these arguments: run once eagerly (allocations, function attributes, transposed packs), then
+    // capture the identical launch sequence (~2400 kernels) into a graph that later calls replay
+    RESR_TRY(eager());
+    if (g->step_graph_failed || getenv("RESR_NO_GRAPH")) return RESR_OK;
+    if (cudaStreamSynchronize(s) != cudaSuccess) return set_error(RESR_E_CUDA, "train step failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (g->step_exec) { cudaGraphExecDestroy(g->step_exec); g->step_exec = nullptr; }
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); g->step_graph_failed = true; return RESR_OK; }
+    const int rc = eager();
+    const cudaError_t ec = cudaStreamEndCapture(s, &graph);
+    if (rc != RESR_OK || ec != cudaSuccess || !graph) {
+        cudaGetLastError();
+        if (graph) cudaGraphDestroy(graph);
+        g->step_graph_failed = true;  // keep running eagerly (the eager result above is already valid)
+        return RESR_OK;
+    }
+    const cudaError_t ei = cudaGraphInstantiate(&g->step_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ei != cudaSuccess) { cudaGetLastError(); g->step_exec = nullptr; g->step_graph_failed = true; return RESR_OK; }
+    memcpy(g->step_key, key, sizeof(key));
+    g->step_shape[0] = n; g->step_shape[1] = h; g->step_shape[2] = w;
+    return RESR_OK;
+}
+
+int resr_generator_step_is_graph(resr_generator_t* g) { return g && g->step_exec ? 1 : 0; }
 
 int resr_conv3x3_wgrad(const void* x16, int x_cstride, int fmt_x, const void* dy16_bf16, int n, int h, int w, int cin, int cout,
                        float* dw, float* db, void* workspace, size_t workspace_bytes, void* stream) {

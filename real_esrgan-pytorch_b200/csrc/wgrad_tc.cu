@@ -146,37 +146,41 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constant
     if (warp == 2) tmem_dealloc(tbase, 512);
 }
 
-// dW[co][ci][dy][dx] = sum over splits of partial[split][mb][cs][dy][ci % 128][dx * 32 + co % 32]
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int cin, int cout, int n_mb,
-                                    int n_cs, int nsplit) {
-    const int total = cout * cin * 9;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-        const int dx = idx % 3, dy = (idx / 3) % 3;
-        const int ci = (idx / 9) % cin, co = idx / (9 * cin);
-        const int mb = ci >> 7, cs = co >> 5;
-        const size_t off = ((((static_cast<size_t>(mb) * n_cs + cs) * 3 + dy) * 128) + (ci & 127)) * 96 + dx * 32 + (co & 31);
-        const size_t stride = static_cast<size_t>(n_mb) * n_cs * 3 * 128 * 96;
+// dW[co][ci][dy][dx] = sum over splits of partial[split][mb][cs][dy][ci % 128][dx * 32 + co % 32]. One thread per partial
+// element: the split-strided reads are coalesced, the OIHW write happens once.
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int cin, int cout,
+                                                          int n_mb, int n_cs, int nsplit) {
+    const size_t stride = static_cast<size_t>(n_mb) * n_cs * 3 * 128 * 96;
+    for (size_t e = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; e < stride; e += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int col = e % 96;
+        size_t t = e / 96;
+        const int cil = t % 128; t /= 128;
+        const int dy = t % 3; t /= 3;
+        const int cs = t % n_cs;
+        const int mb = static_cast<int>(t / n_cs);
+        const int ci = mb * 128 + cil, co = cs * 32 + (col & 31), dx = col >> 5;
+        if (ci >= cin || co >= cout) continue;
         float s = 0.f;
-        for (int sp = 0; sp < nsplit; ++sp) s += partial[sp * stride + off];
-        dw[idx] = s;
+        for (int sp = 0; sp < nsplit; ++sp) s += partial[sp * stride + e];
+        dw[((static_cast<size_t>(co) * cin + ci) * 3 + dy) * 3 + dx] = s;
     }
 }
 
-// db[co] = sum_p dY^T[co][p]  (channels-first bf16)
-__global__ void bias_grad_kernel(const uint16_t* __restrict__ dyt, size_t P, int cout, float* __restrict__ db) {
-    __shared__ float red[32];
+// db[co] += sum_p dY^T[co][p]  (channels-first bf16); grid (cout, chunks), db must be zero-initialised.
+__global__ void __launch_bounds__(256) bias_grad_kernel(const uint16_t* __restrict__ dyt, size_t P, int cout, float* __restrict__ db) {
+    __shared__ float red[8];
     const int co = blockIdx.x;
-    if (co >= cout) return;
     const uint16_t* row = dyt + static_cast<size_t>(co) * P;
     float s = 0.f;
-    for (size_t p = threadIdx.x; p < P; p += blockDim.x) s += __uint_as_float(static_cast<uint32_t>(row[p]) << 16);
+    for (size_t p = blockIdx.y * static_cast<size_t>(blockDim.x) + threadIdx.x; p < P; p += static_cast<size_t>(gridDim.y) * blockDim.x)
+        s += __uint_as_float(static_cast<uint32_t>(row[p]) << 16);
     for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
     __syncthreads();
-    if (threadIdx.x < 32) {
-        float w = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
-        for (int o = 16; o > 0; o >>= 1) w += __shfl_down_sync(0xffffffffu, w, o);
-        if (threadIdx.x == 0) db[co] = w;
+    if (threadIdx.x == 0) {
+        float w = 0.f;
+        for (int i = 0; i < 8; ++i) w += red[i];
+        atomicAdd(db + co, w);
     }
 }
 
@@ -228,8 +232,9 @@ int wgrad_launch(const uint16_t* xt, int x_channels, const uint16_t* dyt, int dy
     a.hang = g_wgrad_hang_slot;
     a.dbg_mode = getenv("RESR_WG_DBG") ? atoi(getenv("RESR_WG_DBG")) : 0;
     const int units = a.n_mb * a.n_cs;
+    // split-K over pixels: at least ~16 pipeline steps per CTA (every split writes a 147 KB partial tile)
     long long nsplit = num_sms / units;
-    if (nsplit > a.kstages_total) nsplit = a.kstages_total;
+    if (nsplit > a.kstages_total / 16) nsplit = a.kstages_total / 16;
     if (nsplit < 1) nsplit = 1;
     CUtensorMap mx, my;
     int rc = make_cf_map(&mx, xt, x_channels, N, H, W, 128);
@@ -247,10 +252,16 @@ int wgrad_launch(const uint16_t* xt, int x_channels, const uint16_t* dyt, int dy
         const cudaError_t e = cudaStreamSynchronize(s);
         fprintf(stderr, "[resr] wgrad_tc_kernel grid (%d,%lld) smem %d: %s\n", units, nsplit, smem, cudaGetErrorString(e));
     }
-    const int total = cout * cin * 9;
-    wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, s>>>(partial, dw, cin, cout, a.n_mb, a.n_cs, static_cast<int>(nsplit));
-    if (db)  // the unshifted copy (dx = 1)
-        bias_grad_kernel<<<cout, 256, 0, s>>>(dyt + static_cast<size_t>(dy_channels) * N * H * W, static_cast<size_t>(N) * H * W, cout, db);
+    const size_t pstride = static_cast<size_t>(a.n_mb) * a.n_cs * 3 * 128 * 96;
+    wgrad_reduce_kernel<<<static_cast<unsigned>((pstride + 255) / 256), 256, 0, s>>>(partial, dw, cin, cout, a.n_mb, a.n_cs,
+                                                                                    static_cast<int>(nsplit));
+    if (db) {  // from the unshifted copy (dx = 1); accumulates with atomics into a zeroed db
+        const size_t P = static_cast<size_t>(N) * H * W;
+        int chunks = static_cast<int>((P + 8191) / 8192);
+        if (chunks > 64) chunks = 64;
+        cudaMemsetAsync(db, 0, cout * sizeof(float), s);
+        bias_grad_kernel<<<dim3(cout, chunks), 256, 0, s>>>(dyt + static_cast<size_t>(dy_channels) * P, P, cout, db);
+    }
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 

@@ -97,3 +97,26 @@ def test_autograd_function_matches_fused_path():
     loss.backward()
     got = torch.cat([p.grad.reshape(-1) for p in g.parameters()])
     assert _cos(got, flat) >= 0.99999
+
+
+def test_train_step_graph_replay_matches_eager():
+    """The CUDA-graph training step (persistent buffers) reproduces the eager fused call, also after a weight update."""
+    import resr_b200
+    from oracle import generator as og
+    g = resr_b200.model.Generator(3, 3, 4)
+    g.load_state_dict(og.random_state_dict(2))
+    g = g.cuda().train()
+    torch.manual_seed(11)
+    lr = torch.rand(2, 3, 16, 32, device="cuda")
+    hr = torch.rand(2, 3, 64, 128, device="cuda")
+    ts = resr_b200.autograd.TrainStep(g, 2, 16, 32)
+    for it in range(3):
+        loss_e, _, flat_e = resr_b200.autograd.l1_loss_backward(g, lr, hr)
+        loss_g, _, flat_g = ts.step(lr, hr)
+        torch.cuda.synchronize()
+        assert abs(loss_e.item() - loss_g.item()) <= 1e-6
+        assert _cos(flat_e.cpu(), flat_g.cpu()) >= 0.999999
+        with torch.no_grad():  # SGD-like update: the packed (and transposed) weights must follow
+            for p in g.parameters():
+                p.add_(p.grad, alpha=-1e-3)
+    assert ts.is_graph
