@@ -42,21 +42,37 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    """SM clock and throttle reasons DURING the timed region (NVML, 20 ms period; nvidia-smi fallback)."""
 
     def __init__(self, index):
         self.rows, self.stop, self.index = [], threading.Event(), index
         self.t = threading.Thread(target=self.run, daemon=True)
+        self.max_mhz = None
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            while not self.stop.is_set():
+                mhz = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                r = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)) if hasattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.rows.append((mhz, r))
+                self.stop.wait(0.02)
+            return
+        except Exception:
+            pass
+        q = "clocks.sm,clocks.max.sm"
         while not self.stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                    a, b = (float(v) for v in out.split(","))
+                    self.max_mhz = b
+                    self.rows.append((a, 0))
             except Exception:
                 pass
             self.stop.wait(0.2)
@@ -71,11 +87,15 @@ class ClockSampler:
 
     def summary(self):
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(float(r[0]) for r in self.rows)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons, "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        sm = sorted(r[0] for r in self.rows)
+        bits = 0
+        for r in self.rows:
+            bits |= r[1]
+        # NVML clocks-event-reason bits
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        reasons = [n for b, n in names.items() if bits & b]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm)}
 
 
 def cpu_generator_baseline(seconds_budget=20.0, max_iters=5):
@@ -152,6 +172,59 @@ def degradation_bench(device, steps, warmup, peaks):
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
                          "traffic": None, "algorithmic_bytes_per_step": stage_bytes,
                          "note": "stage-sum bytes / whole-pipeline time; blur stencils are FMA-bound (SURVEY.md §8d caveat)"}}
+
+
+# ------------------------------------------------------------------------------------------------- training step
+
+
+def training_bench(device, steps, warmup, peaks, world):
+    """configs[3]: RealESRNet training-step core per GPU — plan-driven degradation of 16 HR crops (256^2 -> LR 64^2),
+    generator forward + L1 + backward, and (world > 1) the NCCL all-reduce of the flat gradient vector. Optimizer / EMA
+    are outside the north-star path."""
+    import torch.distributed as dist
+
+    import resr_b200
+    from oracle import plan as oplan
+    ip = resr_b200.imgproc
+    B, H, W = 16, 256, 256
+    plan = oplan.canonical_plan_s0(B, H, W, seed=1)
+    g = torch.Generator(device="cpu").manual_seed(2)
+    hr = torch.rand(B, 3, H, W, generator=g).to(device)
+    k = torch.zeros(B, 21, 21)
+    k[:, 8:13, 8:13] = 1 / 25
+    k = k.to(device)
+    pipe = ip.DegradePipeline(hr, k, k, k, plan)
+    torch.manual_seed(0)
+    gen = resr_b200.model.Generator(3, 3, 4).to(device).train()
+    ts = resr_b200.autograd.TrainStep(gen, B, H // 4, W // 4, device, None, world)
+
+    def step():
+        lr, hr_c = pipe()
+        return ts.step(lr, hr_c, scatter=False)
+
+    for _ in range(max(3, warmup)):
+        loss, _, _ = step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss, _, _ = step()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    tflops = 3 * FLOP_PER_LR_PIXEL * B * (H // 4) * (W // 4) / (ms * 1e-3) / 1e12
+    return {"metric": "training pairs/s", "value": world * B / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms, "n_gpus": world,
+            "loss": float(loss.item()), "cuda_graph": bool(ts.is_graph),
+            "config": {"workload": "per GPU: degradation (plan S0, CUDA graph) of 16x3x256x256 HR + RRDBNet x4 forward/L1/backward "
+                                   "on 16x3x64x64 LR (one CUDA graph), flat-gradient NCCL all-reduce when n_gpus > 1; no optimizer"},
+            "roofline": {"bound": "tensor", "achieved": tflops, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                         "frac": tflops / peaks["tf_sustained"], "traffic": None,
+                         "note": "algorithmic FLOPs = 3 x forward (SURVEY.md §8d): 7.05 TFLOP per GPU-step"}}
 
 
 # ------------------------------------------------------------------------------------------------- arms
@@ -276,6 +349,14 @@ def run_ours(args):
                 line["degradation"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_generator_baseline()
+    train = None
+    if not args.no_train:  # every rank takes part (all-reduce)
+        try:
+            train = training_bench(device, max(5, min(args.steps, 20)), args.warmup, peaks, world)
+        except Exception as e:
+            train = {"error": repr(e)}
+    if rank == 0:
+        line["training"] = train
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -291,6 +372,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="LR images per GPU (64 = BASELINE configs[2])")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-degrade", action="store_true", help="skip the secondary degradation leg")
+    ap.add_argument("--no-train", action="store_true", help="skip the secondary training-step leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
