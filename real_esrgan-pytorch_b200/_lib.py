@@ -4,7 +4,7 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libresr.so")
+LIB_PATH = os.environ.get("RESR_LIB_PATH") or os.path.join(_HERE, "lib", "libresr.so")  # override: A/B builds in development
 
 
 class ResrError(RuntimeError):

@@ -22,6 +22,7 @@ struct ConvArgs {
     int nxs;        // x segments per image row = ceil(W / BW)
     int ncg;        // column groups = ceil(N / BN) * nxs
     int nchunks;    // input channels / 64 (zero-padded weights cover the remainder)
+    int tail_ksteps;  // K16 steps of the LAST chunk that carry real channels (1..4); the zero-weight rest is not issued
     int mode;       // 0: one TMA load of BW+2 px per (row, chunk), dx taken by shifting the smem descriptor
                     // 1: three TMA loads per (row, chunk), one per dx (any BW x BN split)
     int nstages;    // activation ring depth
@@ -36,8 +37,10 @@ struct ConvArgs {
     int out16_fmt;         // 0 fp16, 1 bf16
     int out16_choff;       // first destination channel of slice 0
     int out16_up2;         // 1: destination is [N,2H,2W,*]; every pixel is written to its 2x2 nearest-upsampled sites
-    int has_outf;          // fp32 NHWC output through tmapOF
+    int has_outf;          // fp32 NHWC output: each epilogue thread stores its pixel's 128 contiguous bytes directly
     int outf_choff;
+    float* outf;           // base of the fp32 NHWC output, outf_cstride channels per pixel
+    int outf_cstride;
     int has_res1;          // fp32 NHWC residual through tmapR1 (TMA load into the fp32 staging tile)
     int res_choff;
     const float* res2;     // second residual (EP_RRDB only): plain global loads
@@ -56,6 +59,17 @@ struct ConvArgs {
     int dbg_flags;            // experiments only: 1 = skip output stores, 2 = producer re-reads row 0, 4 = issue 1/4 of the MMAs
     unsigned long long* dbg;  // optional: CTA (0,0) writes phase timestamps (globaltimer ns) here, 16 slots
 };
+
+// K16 steps of the last 64-channel chunk that hold real input channels.
+inline int conv3x3_tail_ksteps(int cin) {
+#ifdef RESR_NO_TAILSKIP
+    (void)cin;
+    return 4;
+#else
+    const int r = cin % 64;
+    return r == 0 || r > 32 ? 4 : (r > 16 ? 2 : 1);
+#endif
+}
 
 struct ConvMaps {
     CUtensorMap a;    // activations (load)

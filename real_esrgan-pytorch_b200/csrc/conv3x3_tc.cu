@@ -30,6 +30,13 @@
 #include "conv3x3.cuh"
 #include "ptx.cuh"
 
+// Kernel perturbation flags for bottleneck experiments (tools/power_probe.py); compiled out of the product build.
+#ifdef RESR_EXPERIMENTS
+#define DBGF(x) ((a.dbg_flags & (x)) != 0)
+#else
+#define DBGF(x) false
+#endif
+
 namespace resr {
 
 static constexpr int kStageBytes = 17408;  // 136 rows x 128 B (mode 0 uses 130 rows, mode 1 uses 128)
@@ -60,7 +67,7 @@ __device__ __forceinline__ unsigned long long gtimer() {
 __device__ __forceinline__ uint32_t slot_of(long long v) { return static_cast<uint32_t>((16 - (v & 15)) & 15); }
 
 __host__ __device__ inline int epi_group_bytes(const ConvArgs& a, int nout) {
-    const int f = (a.has_outf ? kTileFBytes : 0) + (a.has_res1 ? kTileFBytes : 0);
+    const int f = (a.has_res1 || a.has_outf) ? kTileFBytes : 0;  // one fp32 tile: residual in, result out (in place)
     const int h = a.has_out16 ? 128 * nout * 2 : 0;
     return f + (h + 1023) / 1024 * 1024;
 }
@@ -73,14 +80,14 @@ __device__ __forceinline__ uint64_t desc_of(uint32_t lo) { return (static_cast<u
 // All MMAs of one pipeline stage, straight-line. SPLIT: 0 = one N=3*NOUT MMA at d0; 1 / 2 = ring seam (slot 14 / 15),
 // the (dy=0,1 | dy=2) resp. (dy=0 | dy=1,2) column blocks go to d0 and to the start of the ring. NDX: horizontal taps
 // served by this stage (3 in mode 0: descriptor shifted by dx pixels; 1 in mode 1).
-template <int NOUT, int SPLIT, int I0, int I1>
+template <int NOUT, int SPLIT, int KS, int I0, int I1>
 __device__ __forceinline__ void issue_range(uint32_t d0, uint32_t ring0, uint32_t a_lo, uint32_t b_lo, uint32_t idesc3,
                                             uint32_t idesc2, uint32_t idesc1) {
     constexpr uint32_t WT = (3 * NOUT * 128) >> 4;   // one (chunk, dx) weight tile, in 16-byte units
     constexpr uint32_t ROWS = (NOUT * 128) >> 4;     // NOUT weight rows
 #pragma unroll
-    for (int i = I0; i < I1; ++i) {                  // i = dx * 4 + ks
-        const int dx = i >> 2, ks = i & 3;
+    for (int i = I0; i < I1; ++i) {                  // i = dx * KS + ks; KS = K16 steps that carry real channels
+        const int dx = i / KS, ks = i % KS;
         const uint64_t ad = desc_of(a_lo + dx * 8 + ks * 2);
         const uint32_t bl = b_lo + dx * WT + ks * 2;
         if (SPLIT == 0) {
@@ -95,14 +102,28 @@ __device__ __forceinline__ void issue_range(uint32_t d0, uint32_t ring0, uint32_
     }
 }
 // MMAs [I0, I1) of a stage, dispatching on the ring-seam case (uniform per output row).
-template <int NOUT, int I0, int I1>
+template <int NOUT, int KS, int I0, int I1>
 __device__ __forceinline__ void issue_part(uint32_t s0, uint32_t d0, uint32_t ring0, uint32_t a_lo, uint32_t b_lo,
                                            uint32_t idesc3, uint32_t idesc2, uint32_t idesc1) {
-    if (s0 <= 13) issue_range<NOUT, 0, I0, I1>(d0, ring0, a_lo, b_lo, idesc3, idesc2, idesc1);
-    else if (s0 == 14) issue_range<NOUT, 1, I0, I1>(d0, ring0, a_lo, b_lo, idesc3, idesc2, idesc1);
-    else issue_range<NOUT, 2, I0, I1>(d0, ring0, a_lo, b_lo, idesc3, idesc2, idesc1);
+    if (s0 <= 13) issue_range<NOUT, 0, KS, I0, I1>(d0, ring0, a_lo, b_lo, idesc3, idesc2, idesc1);
+    else if (s0 == 14) issue_range<NOUT, 1, KS, I0, I1>(d0, ring0, a_lo, b_lo, idesc3, idesc2, idesc1);
+    else issue_range<NOUT, 2, KS, I0, I1>(d0, ring0, a_lo, b_lo, idesc3, idesc2, idesc1);
 }
 
+
+// First (HALF = 0) or second (HALF = 1) half of the MMAs of one pipeline step whose chunk carries `ks` K16 steps of real
+// channels (4 for a full 64-channel chunk; fewer for the zero-padded tail chunk of Cin = 96 / 160 / 3).
+template <int NOUT, int NDX, int HALF>
+__device__ __forceinline__ void issue_half(int ks, uint32_t s0, uint32_t d0, uint32_t ring0, uint32_t a_lo, uint32_t b_lo,
+                                           uint32_t idesc3, uint32_t idesc2, uint32_t idesc1) {
+#define RESR_HALF(KS)                                                                                              \
+    if (HALF == 0) issue_part<NOUT, KS, 0, (NDX * KS) / 2>(s0, d0, ring0, a_lo, b_lo, idesc3, idesc2, idesc1);       \
+    else issue_part<NOUT, KS, (NDX * KS) / 2, NDX * KS>(s0, d0, ring0, a_lo, b_lo, idesc3, idesc2, idesc1)
+    if (ks == 2) { RESR_HALF(2); }
+    else if (ks == 1) { RESR_HALF(1); }
+    else { RESR_HALF(4); }
+#undef RESR_HALF
+}
 
 // The MMA-issuing warp. The tensor core is fed by ONE instruction stream with a shallow queue, so every non-MMA
 // instruction of this warp is tensor-pipe idle time (tools/mma_bench3.cu): the loop keeps 32-bit incremental
@@ -113,7 +134,6 @@ template <int NOUT, int MODE>
 __device__ __forceinline__ void mma_role(const ConvArgs& a, const RowRange rr, const uint32_t tbase, const uint32_t wsm_addr,
                                          const uint32_t stg_addr, const uint32_t full_a, const uint32_t empty_a,
                                          const uint32_t accfull_a, const uint32_t slotfree_a) {
-    constexpr int NMMA = MODE == 0 ? 12 : 4;  // MMAs per pipeline step
     constexpr uint32_t WT = (3 * NOUT * 128) >> 4;
     const uint32_t idesc3 = make_idesc_f16(a.fmt_in, 128, 3 * NOUT);
     const uint32_t idesc2 = make_idesc_f16(a.fmt_in, 128, 2 * NOUT);
@@ -124,6 +144,7 @@ __device__ __forceinline__ void mma_role(const ConvArgs& a, const RowRange rr, c
     const uint32_t b_step = (MODE == 0 ? 3 : 1) * WT;
     const int nstages = a.nstages;
     const int H = a.H;
+    const bool dbg_quarter = DBGF(4), dbg_nomma = DBGF(16);
     int stage = 0;
     uint32_t phase = 0;
     uint32_t a_lo = s_lo;
@@ -155,8 +176,9 @@ __device__ __forceinline__ void mma_role(const ConvArgs& a, const RowRange rr, c
                 if (!full_ready) mbar_wait_a(full_a + (stage << 3), phase);
                 tc_fence_after();
                 const bool last = (st == nsteps - 1);
+                const int ks = dbg_quarter ? 1 : ((st >= nsteps - (MODE == 0 ? 1 : 3)) ? a.tail_ksteps : 4);  // steps of the last K chunk
                 if (elect_one()) {
-                    issue_part<NOUT, 0, NMMA / 2>(s0, d0, tbase, a_lo, b_lo, idesc3, idesc2, idesc1);
+                    if (!dbg_nomma) issue_half<NOUT, MODE == 0 ? 3 : 1, 0>(ks, s0, d0, tbase, a_lo, b_lo, idesc3, idesc2, idesc1);
                     if (pending_empty >= 0) umma_commit_a(empty_a + (pending_empty << 3));
                 }
                 __syncwarp();
@@ -167,7 +189,7 @@ __device__ __forceinline__ void mma_role(const ConvArgs& a, const RowRange rr, c
                 full_ready = mbar_test_wait_a(full_a + (stage << 3), phase);
                 if (last && r < rb) slot_ready = mbar_test_wait_a(slotfree_a + (((0u - (vnew + 1)) & 15u) << 3), ((vnew + 1) >> 4) & 1u);
                 if (elect_one()) {
-                    issue_part<NOUT, NMMA / 2, NMMA>(s0, d0, tbase, a_cur, b_lo, idesc3, idesc2, idesc1);
+                    if (!dbg_nomma) issue_half<NOUT, MODE == 0 ? 3 : 1, 1>(ks, s0, d0, tbase, a_cur, b_lo, idesc3, idesc2, idesc1);
                     if (last) {
                         umma_commit_a(accfull_a + (((s0 + 2) & 15u) << 3));      // row r-1 has its last contribution
                         if (r == rb) {                                            // strip end: rows rb, rb+1 get no more
@@ -280,9 +302,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
                     for (int dx = 0; dx < ndx; ++dx) {
                         mbar_wait(empty + stage, phase ^ 1);
                         if (elect_one()) {
-                            mbar_expect_tx(full + stage, tx_bytes);
-                            tma_load_4d(stg + stage * kStageBytes, &tmapA, full + stage, c * 64,
-                                        a.mode == 0 ? x0 - 1 : x0 + dx - 1, r, n0);
+                            if (DBGF(32)) {
+                                mbar_arrive(full + stage);
+                            } else {
+                                mbar_expect_tx(full + stage, tx_bytes);
+                                tma_load_4d(stg + stage * kStageBytes, &tmapA, full + stage, c * 64,
+                                            a.mode == 0 ? x0 - 1 : x0 + dx - 1, DBGF(2) ? 0 : r, DBGF(2) ? 0 : n0);
+                            }
                         }
                         __syncwarp();
                         if (++stage == a.nstages) { stage = 0; phase ^= 1; }
@@ -311,12 +337,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         const bool use_outf = a.has_outf && !((a.slice_noutf_mask >> slice) & 1u);
         const bool use_o16 = a.has_out16 && !((a.slice_no16_mask >> slice) & 1u);
         const bool staged = use_o16 || use_outf || use_res1;
-        uint8_t* tileR = epi + gi * epi_bytes;                       // fp32 residual tile (TMA load)
-        uint8_t* tileF = tileR + (a.has_res1 ? kTileFBytes : 0);     // fp32 output tile (TMA store)
-        uint8_t* tile16 = tileF + (a.has_outf ? kTileFBytes : 0);    // 16-bit output tile (TMA store)
+        uint8_t* tileR = epi + gi * epi_bytes;                       // fp32 tile: residual (TMA load), then result (TMA store)
+        uint8_t* tile16 = tileR + ((a.has_res1 || a.has_outf) ? kTileFBytes : 0);  // 16-bit output tile (TMA store)
         uint64_t* rbar = res_full + gi;
         uint32_t res_phase = 0;
-        bool res_inflight = false;  // the residual tile of the row about to be processed was prefetched
         const uint32_t lane_base = tbase + (static_cast<uint32_t>(q * 32) << 16);
         const int img_in_tile = m / a.BW;
         const int x_in_tile = m % a.BW;
@@ -346,10 +370,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
                 const long long v = v0 + j;
                 if (static_cast<int>(v % a.nepi) != gi) continue;
                 const int y = ra - 1 + j;
-                const bool emit = (y >= ya) && (y < yb);
+                const bool emit = (y >= ya) && (y < yb) && !DBGF(8);
                 const uint32_t slot = slot_of(v);
-                if (emit && use_res1 && !res_inflight) {  // first row of a strip for this group: nothing prefetched
+                if (emit && use_res1) {
+                    // this row's fp32 residual streams into the group's fp32 tile behind the wait for the accumulator;
+                    // the tile is free once the previous row's TMA store (issued by the same thread) has read it
                     if (lead_warp) {
+                        tma_store_wait_read();
                         if (elect_one()) {
                             mbar_expect_tx(rbar, 128 * 128);
                             tma_load_4d(tileR, &tmapR1, rbar, a.res_choff + slice * NOUT, x0, y, n0);
@@ -377,25 +404,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
 #pragma unroll
                     for (int i = 0; i < NOUT / 4; ++i)
                         resv[i] = *reinterpret_cast<const float4*>(tileR + m * 128 + ((i ^ (m & 7)) << 4));
-                }
-                if (staged) {
-                    // tiles are free once the previous TMA stores have read them and (residual tile) everyone has
-                    // copied its row to registers; then the NEXT row's residual is fetched behind this row's math
-                    if (lead_warp) tma_store_wait_read();
-                    named_bar_sync(1 + gi, 128);
-                    res_inflight = false;
-                    if (use_res1 && y + a.nepi < yb) {
-                        res_inflight = true;
-                        if (lead_warp) {
-                            if (elect_one()) {
-                                mbar_expect_tx(rbar, 128 * 128);
-                                tma_load_4d(tileR, &tmapR1, rbar, a.res_choff + slice * NOUT, x0, y + a.nepi, n0);
-                            }
-                            __syncwarp();
-                        }
-                    }
-                }
-                if (use_res1) {
 #pragma unroll
                     for (int i = 0; i < NOUT / 4; ++i) {
                         const float4 r4 = resv[i];
@@ -411,6 +419,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
                             val[4 * i + 3] = __fadd_rn(__fmul_rn(val[4 * i + 3], 0.2f), r4.w);
                         }
                     }
+                }
+                if (staged && !use_res1) {
+                    // the output tiles are free once the previous TMA stores have read them (with a residual, the
+                    // completed load above already implies that: it was issued behind the same wait)
+                    if (lead_warp) tma_store_wait_read();
+                    named_bar_sync(1 + gi, 128);
                 }
                 if (a.ep_mode == EP_RRDB) {
                     const size_t pix = (static_cast<size_t>(valid ? n : 0) * a.H + y) * a.W + (valid ? x : 0);
@@ -453,10 +467,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
 #pragma unroll
                     for (int i = 0; i < NOUT; ++i) val[i] = fminf(fmaxf(val[i], 0.f), 1.f);
                 }
-                if (use_outf) {
+                if (use_outf) {  // fp32 master, written over this thread's own (already consumed) residual row
 #pragma unroll
                     for (int i = 0; i < NOUT / 4; ++i)
-                        *reinterpret_cast<float4*>(tileF + m * 128 + ((i ^ (m & 7)) << 4)) =
+                        *reinterpret_cast<float4*>(tileR + m * 128 + ((i ^ (m & 7)) << 4)) =
                             make_float4(val[4 * i], val[4 * i + 1], val[4 * i + 2], val[4 * i + 3]);
                 }
                 if (use_o16 && a.mask16) {  // LeakyReLU backward: slope 1 where the saved activation is > 0, else 0.2
@@ -497,8 +511,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
                     named_bar_sync(1 + gi, 128);
                     if (lead_warp) {
                       if (elect_one()) {
-                        if (use_outf) tma_store_4d(&tmapOF, tileF, a.outf_choff + slice * NOUT, x0, y, n0);
-                        if (use_o16) {
+                        if (use_outf && !DBGF(1)) tma_store_4d(&tmapOF, tileR, a.outf_choff + slice * NOUT, x0, y, n0);
+                        if (use_o16 && !DBGF(1)) {
                             const int c0 = a.out16_choff + (a.out16_slice_fixed ? 0 : slice * NOUT);
                             if (!a.out16_up2) {
                                 tma_store_4d(&tmapO16, tile16, c0, x0, y, n0);
@@ -678,6 +692,17 @@ cudaError_t conv3x3_launch(const ConvMaps& maps, const ConvArgs& args, int cout_
     if (gx < 1) gx = 1;
     const dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(nslices), 1);
     const int threads = 128 + 128 * args.nepi;
+    static const int env_flags = getenv("RESR_CONV_DBGFLAGS") ? atoi(getenv("RESR_CONV_DBGFLAGS")) : 0;  // experiments only
+    if (env_flags && !(args.dbg_flags & 0x40000000)) {
+        ConvArgs fixed = args;
+        fixed.dbg_flags |= env_flags | 0x40000000;
+        return conv3x3_launch(maps, fixed, cout_slice, nslices, num_sms, stream);
+    }
+    if (args.tail_ksteps != 1 && args.tail_ksteps != 2 && args.tail_ksteps != 4) {
+        ConvArgs fixed = args;
+        fixed.tail_ksteps = 4;
+        return conv3x3_launch(maps, fixed, cout_slice, nslices, num_sms, stream);
+    }
     if (cout_slice == 32) return launch_t<32>(maps, args, grid, threads, stream);
     if (cout_slice == 16) return launch_t<16>(maps, args, grid, threads, stream);
     return cudaErrorInvalidValue;

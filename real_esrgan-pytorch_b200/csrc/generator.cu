@@ -180,6 +180,7 @@ static int build_plan(resr_generator* g, int N, int H, int W, void* ws) {
         a.nxs = (q.W + q.BW - 1) / q.BW;
         a.ncg = ((N + q.BN - 1) / q.BN) * a.nxs;
         a.nchunks = cs.nchunks;
+        a.tail_ksteps = conv3x3_tail_ksteps(cs.cin);
         a.mode = q.mode;
         a.fmt_in = cs.fmt;
         a.rows_total = static_cast<long long>(a.ncg) * q.H;
@@ -194,7 +195,7 @@ static int build_plan(resr_generator* g, int N, int H, int W, void* ws) {
         map_rc |= conv3x3_make_tmap_out16(&st.maps.o16, dst, N, q.H, q.W, c_total, T.c[st.conv].nout, q.BW, q.BN, up2);
     };
     auto set_outf = [&](Step& st, float* dst) {
-        st.a.has_outf = 1; st.a.outf_choff = 0;
+        st.a.has_outf = 1; st.a.outf_choff = 0; st.a.outf = static_cast<float*>(dst); st.a.outf_cstride = 64;
         map_rc |= conv3x3_make_tmap_f32(&st.maps.of, dst, N, geo[0].H, geo[0].W, 64, geo[0].BW, geo[0].BN);
     };
     auto set_res1 = [&](Step& st, const float* src) {
@@ -451,6 +452,7 @@ int resr_conv3x3(const resr_conv_desc* d, void* stream) {
     a.nxs = (d->w + a.BW - 1) / a.BW;
     a.ncg = ((d->n + a.BN - 1) / a.BN) * a.nxs;
     a.nchunks = nchunks;
+    a.tail_ksteps = conv3x3_tail_ksteps(d->cin);
     a.fmt_in = d->fmt_in;
     a.rows_total = static_cast<long long>(a.ncg) * d->h;
     a.wpack = wp; a.bias = bp;
@@ -461,7 +463,7 @@ int resr_conv3x3(const resr_conv_desc* d, void* stream) {
         rc |= conv3x3_make_tmap_out16(&maps.o16, d->out16, d->n, d->h, d->w, d->out16_cstride, nout, a.BW, a.BN, d->out16_up2);
     }
     if (d->outf) {
-        a.has_outf = 1; a.outf_choff = d->outf_choff;
+        a.has_outf = 1; a.outf_choff = d->outf_choff; a.outf = static_cast<float*>(d->outf); a.outf_cstride = d->outf_cstride;
         rc |= conv3x3_make_tmap_f32(&maps.of, d->outf, d->n, d->h, d->w, d->outf_cstride, a.BW, a.BN);
     }
     if (d->res1) {

@@ -196,6 +196,7 @@ struct ConvIO {
     const void* in16 = nullptr; int in_c = 64;
     const uint8_t* wpack = nullptr; const float* bias = nullptr;
     int nout = 32, nslices = 1, nchunks = 1, fmt = 1;
+    int kvalid = 0;  // real input channels (0: every chunk is full)
     void* out16 = nullptr; int out16_c = 64, out16_choff = 0, out16_fmt = 1, out16_up2 = 0, out16_fixed = 0; unsigned no16_mask = 0;
     float* outf = nullptr; int outf_c = 64, outf_choff = 0; unsigned noutf_mask = 0;
     const float* res1 = nullptr; int res1_c = 64, res_choff = 0; unsigned nores_mask = 0;
@@ -214,6 +215,7 @@ static int launch_conv_io(const resr_generator* g, const Geo& q, int N, const Co
     a.nxs = (q.W + q.BW - 1) / q.BW;
     a.ncg = ((N + q.BN - 1) / q.BN) * a.nxs;
     a.nchunks = io.nchunks;
+    a.tail_ksteps = io.kvalid ? conv3x3_tail_ksteps(io.kvalid) : 4;
     a.mode = q.mode;
     a.fmt_in = io.fmt;
     a.rows_total = static_cast<long long>(a.ncg) * q.H;
@@ -227,6 +229,7 @@ static int launch_conv_io(const resr_generator* g, const Geo& q, int N, const Co
     }
     if (io.outf) {
         a.has_outf = 1; a.outf_choff = io.outf_choff; a.slice_noutf_mask = io.noutf_mask;
+        a.outf = io.outf; a.outf_cstride = io.outf_c;
         rc |= conv3x3_make_tmap_f32(&m.of, io.outf, N, q.H, q.W, io.outf_c, q.BW, q.BN);
     }
     if (io.res1) {
@@ -340,7 +343,7 @@ ConvIO fwd_io(const resr_generator* g, int k) {
     const ConvSpec& c = table().c[k];
     ConvIO io;
     io.wpack = g->wpack + c.w_off; io.bias = g->bias + c.b_off;
-    io.nout = c.nout; io.nslices = c.nslices; io.nchunks = c.nchunks; io.fmt = c.fmt;
+    io.nout = c.nout; io.nslices = c.nslices; io.nchunks = c.nchunks; io.fmt = c.fmt; io.kvalid = c.cin;
     return io;
 }
 
@@ -431,7 +434,7 @@ ConvIO bwd_io(const resr_generator* g, int k) {
     const ConvSpec& c = table().c[k];
     ConvIO io;
     io.wpack = g->wpack_t + c.wt_off; io.bias = g->zero_bias;
-    io.nout = 32; io.nslices = c.t_nslices; io.nchunks = c.t_nchunks; io.fmt = 1;
+    io.nout = 32; io.nslices = c.t_nslices; io.nchunks = c.t_nchunks; io.fmt = 1; io.kvalid = c.cout;
     return io;
 }
 

@@ -8,7 +8,7 @@ dev = "cuda"
 n, h, w = 64, 128, 128
 x16 = torch.randn(n, h, w, 192, device=dev).bfloat16()
 names = ["entry", "setup", "depwait", "weights", "first_stage", "mma_done", "epi_done", "cta_done"]
-for cin, cout, mode, ct, fl in [(64, 32, "o16", 192, 0), (128, 32, "o16", 192, 0), (192, 32, "o16", 192, 0), (192, 64, "rdb", 192, 0)]:
+for cin, cout, mode, ct, fl in [(64, 32, "o16", 192, 0), (64, 32, "o16", 64, 0), (64, 32, "o16dense", 192, 0), (64, 32, "o16dense", 64, 0), (64, 32, "o16dense", 64, 1), (64, 32, "o16", 192, 1), (128, 32, "o16", 192, 0), (128, 32, "o16dense", 128, 0), (128, 32, "o16dense", 128, 1)]:
     x16 = torch.randn(n, h, w, ct, device=dev).bfloat16()
     wt = (torch.randn(cout, cin, 3, 3, device=dev) * 0.05)
     b = torch.randn(cout, device=dev)
@@ -34,4 +34,4 @@ for cin, cout, mode, ct, fl in [(64, 32, "o16", 192, 0), (128, 32, "o16", 192, 0
         L.check(L.lib().resr_conv3x3(ctypes.byref(d), L.stream_ptr()))
     t = dbg.cpu().tolist()
     base = t[0]
-    print(f"cin={cin} cout={cout} {mode} flags={fl}: " + "  ".join(f"{nm}={(t[i]-base)/1e3:.1f}us" for i, nm in enumerate(names)))
+    print(f"ct={ct} cin={cin} cout={cout} {mode} flags={fl}: " + "  ".join(f"{nm}={(t[i]-base)/1e3:.1f}us" for i, nm in enumerate(names)))
