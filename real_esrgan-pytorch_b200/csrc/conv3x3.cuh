@@ -86,7 +86,8 @@ cudaError_t conv3x3_launch(const ConvMaps& maps, const ConvArgs& args, int cout_
 bool conv3x3_plan_smem(ConvArgs* args, int cout_slice);
 
 // Tensor maps. base: NHWC tensor [N,H,W,C].
-int conv3x3_make_tmap_act(CUtensorMap* out, const void* base, int N, int H, int W, int C, int mode, int BW, int BN);
+int conv3x3_make_tmap_act(CUtensorMap* out, const void* base, int N, int H, int W, int C, int mode, int BW, int BN,
+                          int cvalid = 0);  // cvalid: channels the convolution reads (0 = all C)
 int conv3x3_make_tmap_out16(CUtensorMap* out, const void* base, int N, int H, int W, int C, int nout, int BW, int BN,
                             int up2);  // N,H,W = geometry of the CONVOLUTION (destination is 2H x 2W when up2)
 int conv3x3_make_tmap_f32(CUtensorMap* out, const void* base, int N, int H, int W, int C, int BW, int BN);

@@ -599,10 +599,15 @@ static PFN_encodeTiled get_encode_fn() {
     return fn;
 }
 
-int conv3x3_make_tmap_act(CUtensorMap* out, const void* base, int N, int H, int W, int C, int mode, int BW, int BN) {
+int conv3x3_make_tmap_act(CUtensorMap* out, const void* base, int N, int H, int W, int C, int mode, int BW, int BN,
+                          int cvalid) {
     PFN_encodeTiled enc = get_encode_fn();
     if (!enc) return -1;
-    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+    // Channels at and beyond `cvalid` are out of bounds for the map: the 64-channel box of the tail chunk is zero-filled
+    // there instead of fetching the neighbouring (zero-weight) channels of the concat buffer from DRAM.
+    int cdim = cvalid > 0 ? (cvalid + 7) / 8 * 8 : C;
+    if (cdim > C) cdim = C;
+    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(cdim), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
                                 static_cast<cuuint64_t>(N)};
     const cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(W) * C * 2,
                                    static_cast<cuuint64_t>(H) * W * C * 2};

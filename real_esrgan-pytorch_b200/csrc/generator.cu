@@ -186,7 +186,7 @@ static int build_plan(resr_generator* g, int N, int H, int W, void* ws) {
         a.rows_total = static_cast<long long>(a.ncg) * q.H;
         a.wpack = g->wpack + cs.w_off;
         a.bias = g->bias + cs.b_off;
-        map_rc |= conv3x3_make_tmap_act(&st.maps.a, in16, N, q.H, q.W, cin_total, q.mode, q.BW, q.BN);
+        map_rc |= conv3x3_make_tmap_act(&st.maps.a, in16, N, q.H, q.W, cin_total, q.mode, q.BW, q.BN, cs.cin);
         return st;
     };
     auto set_out16 = [&](Step& st, int s, void* dst, int c_total, int choff, int fmt, int up2) {
@@ -457,7 +457,7 @@ int resr_conv3x3(const resr_conv_desc* d, void* stream) {
     a.rows_total = static_cast<long long>(a.ncg) * d->h;
     a.wpack = wp; a.bias = bp;
     a.ep_mode = d->ep_mode; a.lrelu = d->lrelu; a.clamp01 = d->clamp01;
-    int rc = conv3x3_make_tmap_act(&maps.a, d->in16, d->n, d->h, d->w, d->c_total, a.mode, a.BW, a.BN);
+    int rc = conv3x3_make_tmap_act(&maps.a, d->in16, d->n, d->h, d->w, d->c_total, a.mode, a.BW, a.BN, d->cin);
     if (d->out16) {
         a.has_out16 = 1; a.out16_fmt = d->out16_fmt; a.out16_choff = d->out16_choff; a.out16_up2 = d->out16_up2;
         rc |= conv3x3_make_tmap_out16(&maps.o16, d->out16, d->n, d->h, d->w, d->out16_cstride, nout, a.BW, a.BN, d->out16_up2);

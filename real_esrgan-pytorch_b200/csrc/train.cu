@@ -221,7 +221,7 @@ static int launch_conv_io(const resr_generator* g, const Geo& q, int N, const Co
     a.rows_total = static_cast<long long>(a.ncg) * q.H;
     a.wpack = io.wpack; a.bias = io.bias;
     a.ep_mode = io.ep_mode; a.lrelu = io.lrelu; a.clamp01 = io.clamp01;
-    int rc = conv3x3_make_tmap_act(&m.a, io.in16, N, q.H, q.W, io.in_c, q.mode, q.BW, q.BN);
+    int rc = conv3x3_make_tmap_act(&m.a, io.in16, N, q.H, q.W, io.in_c, q.mode, q.BW, q.BN, io.kvalid);
     if (io.out16) {
         a.has_out16 = 1; a.out16_fmt = io.out16_fmt; a.out16_choff = io.out16_choff; a.out16_up2 = io.out16_up2;
         a.out16_slice_fixed = io.out16_fixed; a.slice_no16_mask = io.no16_mask;
