@@ -98,6 +98,9 @@ struct resr_generator {
     const void* step_key[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int step_shape[3] = {0, 0, 0};
     bool step_graph_failed = false;
+    // second stream of the backward pass: the weight-gradient chain of a layer runs beside the data-gradient chain
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_dy = nullptr, ev_join = nullptr;
     uint8_t* wpack_t = nullptr;   // transposed packs for the backward data-gradient convolutions (lazily allocated)
     float* zero_bias = nullptr;
     bool packed_t = false;

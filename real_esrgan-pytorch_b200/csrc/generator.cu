@@ -336,6 +336,10 @@ void resr_generator_destroy(resr_generator_t* g) {
     cudaFree(g->wpack_t);
     cudaFree(g->zero_bias);
     if (g->step_exec) cudaGraphExecDestroy(g->step_exec);
+    if (g->side_stream) cudaStreamDestroy(g->side_stream);
+    if (g->ev_fork) cudaEventDestroy(g->ev_fork);
+    if (g->ev_dy) cudaEventDestroy(g->ev_dy);
+    if (g->ev_join) cudaEventDestroy(g->ev_join);
     delete g;
 }
 

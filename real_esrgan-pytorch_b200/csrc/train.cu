@@ -20,63 +20,80 @@ namespace resr {
 // ================================================================================================ small kernels
 
 // NHWC 16-bit [P][cstride], channels [c0, c0 + C) -> channels-first bf16 [Cpad][P]; rows C..Cpad-1 are zero-filled.
+// SHIFT3 additionally writes the copies shifted by one pixel along x (zero at the row ends),
+//     out[dx][c][n][y][x] = in[n][y][x - dx + 1][c]   (dx = 0, 1, 2; zero when x - dx + 1 is outside [0, W)),
+// because the weight-gradient kernel pairs X[.., x + dx - 1] with dY[.., x] and TMA cannot start a box at an odd 2-byte
+// offset of the innermost (pixel) dimension; and, when db is given, accumulates the bias gradient
+// db[c] += sum_p in[p][c] in the same pass (db zeroed by the caller).
+// One block = 32 channels x 256 pixels; all global traffic is 16-byte vectors (requires W % 8 == 0, c0 % 8 == 0,
+// cstride % 8 == 0).
+template <bool SHIFT3>
 __global__ void __launch_bounds__(256) nhwc16_to_cf_kernel(const uint16_t* __restrict__ in, int cstride, int c0, int C, int Cpad,
-                                                          size_t P, int fmt_in, uint16_t* __restrict__ out) {
-    __shared__ uint16_t tile[32][34];
-    const size_t p0 = static_cast<size_t>(blockIdx.x) * 32;
+                                                          size_t P, int W, int fmt_in, uint16_t* __restrict__ out,
+                                                          float* __restrict__ db) {
+    constexpr int kRow = 272;                   // halo pixel -1 at index 7, pixels 0..255 at 8..263, halo 256 at 264
+    __shared__ __align__(16) uint16_t tile[32][kRow];
     const int cb = blockIdx.y * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 row groups
-    for (int i = ty; i < 32; i += 8) {  // i = pixel within tile, tx = channel
-        const size_t p = p0 + i;
-        const int c = cb + tx;
-        uint16_t v = 0;
-        if (p < P && c < C) {
-            v = in[p * cstride + c0 + c];
+    const long long p0 = static_cast<long long>(blockIdx.x) * 256;
+    for (int idx = threadIdx.x; idx < 258 * 4; idx += 256) {
+        const int px = idx >> 2, q = idx & 3;   // px 0..257 <-> pixel p0 - 1 + px
+        const long long p = p0 - 1 + px;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (p >= 0 && p < static_cast<long long>(P) && cb + q * 8 < C)
+            v = *reinterpret_cast<const uint4*>(in + static_cast<size_t>(p) * cstride + c0 + cb + q * 8);
+        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            uint16_t e = static_cast<uint16_t>(w4[j >> 1] >> ((j & 1) * 16));
             if (fmt_in == 0) {  // fp16 -> bf16
-                const __half h = *reinterpret_cast<const __half*>(&v);
-                const __nv_bfloat16 b = __float2bfloat16_rn(__half2float(h));
-                v = *reinterpret_cast<const uint16_t*>(&b);
+                const __half h = *reinterpret_cast<const __half*>(&e);
+                const __nv_bfloat16 bb = __float2bfloat16_rn(__half2float(h));
+                e = *reinterpret_cast<const uint16_t*>(&bb);
+            }
+            if (cb + q * 8 + j >= C) e = 0;
+            tile[q * 8 + j][7 + px] = e;
+        }
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t plane = static_cast<size_t>(Cpad) * P;
+    for (int c = warp; c < 32; c += 8) {
+        if (cb + c >= Cpad) break;
+        const long long p = p0 + 8 * lane;      // this lane's 8 pixels (never straddle an image row: W % 8 == 0)
+        const uint4 cur = *reinterpret_cast<const uint4*>(&tile[c][8 + 8 * lane]);
+        float bs = 0.f;
+        if (p < static_cast<long long>(P)) {
+            uint16_t* row = out + static_cast<size_t>(cb + c) * P + p;
+            if (!SHIFT3) {
+                *reinterpret_cast<uint4*>(row) = cur;
+            } else {
+                const uint32_t prev = *reinterpret_cast<const uint32_t*>(&tile[c][6 + 8 * lane]);   // pixels -2, -1
+                const uint32_t next = *reinterpret_cast<const uint32_t*>(&tile[c][16 + 8 * lane]);  // pixels 8, 9
+                const int x = static_cast<int>(p % W);
+                uint4 lo, hi;  // lo: out[dx=0][p + i] = in[p + i + 1];  hi: out[dx=2][p + i] = in[p + i - 1]
+                lo.x = __funnelshift_r(cur.x, cur.y, 16);
+                lo.y = __funnelshift_r(cur.y, cur.z, 16);
+                lo.z = __funnelshift_r(cur.z, cur.w, 16);
+                lo.w = __funnelshift_r(cur.w, next, 16);
+                hi.x = __funnelshift_r(prev, cur.x, 16);
+                hi.y = __funnelshift_r(cur.x, cur.y, 16);
+                hi.z = __funnelshift_r(cur.y, cur.z, 16);
+                hi.w = __funnelshift_r(cur.z, cur.w, 16);
+                if (x + 8 == W) lo.w &= 0x0000FFFFu;  // last pixel of an image row has no right neighbour
+                if (x == 0) hi.x &= 0xFFFF0000u;      // first pixel has no left neighbour
+                *reinterpret_cast<uint4*>(row) = lo;
+                *reinterpret_cast<uint4*>(row + plane) = cur;
+                *reinterpret_cast<uint4*>(row + 2 * plane) = hi;
+            }
+            if (SHIFT3 && db) {
+                const uint32_t w4[4] = {cur.x, cur.y, cur.z, cur.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) bs += __uint_as_float(w4[j] << 16) + __uint_as_float(w4[j] & 0xFFFF0000u);
             }
         }
-        tile[i][tx] = v;
-    }
-    __syncthreads();
-    for (int i = ty; i < 32; i += 8) {  // i = channel within tile, tx = pixel
-        const size_t p = p0 + tx;
-        const int c = cb + i;
-        if (p < P && c < Cpad) out[static_cast<size_t>(c) * P + p] = tile[tx][i];
-    }
-}
-
-// Same transpose, but writes THREE channels-first copies shifted by one pixel along x (zero at the row ends):
-//     out[dx][c][n][y][x] = in[n][y][x - dx + 1][c]   (dx = 0, 1, 2; zero when x - dx + 1 is outside [0, W))
-// The weight-gradient kernel pairs X[.., x + dx - 1] with dY[.., x]; TMA cannot start a box at an odd 2-byte offset of
-// the innermost (pixel) dimension, so the horizontal tap shift is materialised here instead.
-__global__ void __launch_bounds__(256) nhwc16_to_cf_shift3_kernel(const uint16_t* __restrict__ in, int cstride, int C, int Cpad,
-                                                                 size_t P, int W, uint16_t* __restrict__ out) {
-    __shared__ uint16_t tile[32][34];
-    const size_t p0 = static_cast<size_t>(blockIdx.x) * 32;
-    const int cb = blockIdx.y * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    for (int i = ty; i < 32; i += 8) {
-        const size_t p = p0 + i;
-        const int c = cb + tx;
-        tile[i][tx] = (p < P && c < C) ? in[p * cstride + c] : static_cast<uint16_t>(0);
-    }
-    __syncthreads();
-    const size_t plane = static_cast<size_t>(Cpad) * P;
-    for (int i = ty; i < 32; i += 8) {
-        const size_t p = p0 + tx;
-        const int c = cb + i;
-        if (p < P && c < Cpad) {
-            const uint16_t v = tile[tx][i];
-            const int x = static_cast<int>(p % W);
-            uint16_t* row = out + static_cast<size_t>(c) * P;
-            row[plane + p] = v;                       // dx = 1
-            if (x > 0) row[p - 1] = v;                // dx = 0: out[x - 1] = in[x]
-            if (x == W - 1) row[p] = 0;
-            if (x < W - 1) row[2 * plane + p + 1] = v;  // dx = 2: out[x + 1] = in[x]
-            if (x == 0) row[2 * plane + p] = 0;
+        if (SHIFT3 && db) {
+            for (int o = 16; o > 0; o >>= 1) bs += __shfl_down_sync(0xffffffffu, bs, o);
+            if (lane == 0 && cb + c < C) atomicAdd(db + cb + c, bs);
         }
     }
 }
@@ -350,8 +367,8 @@ ConvIO fwd_io(const resr_generator* g, int k) {
 int forward_train(resr_generator* g, const float* x, float* y, int N, int H, int W, const Bufs& B, cudaStream_t s) {
     const Geo g0 = make_geo(g, H, W), g1 = make_geo(g, 2 * H, 2 * W), g2 = make_geo(g, 4 * H, 4 * W);
     const size_t P = static_cast<size_t>(N) * H * W;
-    // growth channels of every concat buffer must be finite before the zero-padded K chunks read them
-    for (int i = 0; i < 70; ++i) cudaMemsetAsync(B.c[i], 0, P * 192 * 2, s);
+    // (no clearing of the concat buffers: a layer's activation tensor map ends at its last input channel, the rest of
+    // the tail chunk is zero-filled by TMA, so never-written growth channels are never read)
     RESR_TRY(resr_nchw_to_nhwc16(x, B.xin, N, 3, H, W, 64, 0, s));
     int k = 0;
     {
@@ -411,20 +428,47 @@ int forward_train(resr_generator* g, const float* x, float* y, int N, int H, int
 
 // weight + bias gradient of layer k. x16: NHWC input activations of the layer (first cin channels of a c_stride-wide
 // tensor, format fmt_x); dy16: NHWC bf16 output gradient (64-channel buffer). Both are transposed to channels-first.
+// The weight-gradient chain (transposes, split-K GEMM, reduction) of a layer only consumes the layer's dY and saved
+// input, nothing downstream on the data-gradient chain waits for it: it runs on a second stream (a parallel branch of
+// the captured graph) and fills the SMs the short data-gradient kernels leave idle. RESR_TRAIN_ONE_STREAM=1 disables it.
+cudaStream_t wgrad_stream(resr_generator* g, cudaStream_t s) {
+    static const bool one = getenv("RESR_TRAIN_ONE_STREAM") != nullptr;
+    if (one) return s;
+    if (!g->side_stream) {
+        if (cudaStreamCreateWithFlags(&g->side_stream, cudaStreamNonBlocking) != cudaSuccess) { g->side_stream = nullptr; return s; }
+        cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&g->ev_dy, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&g->ev_join, cudaEventDisableTiming);
+    }
+    return g->side_stream;
+}
+// side stream continues from the current point of the main stream
+void fork_to(resr_generator* g, cudaStream_t s, cudaStream_t w) {
+    if (w == s) return;
+    cudaEventRecord(g->ev_fork, s);
+    cudaStreamWaitEvent(w, g->ev_fork, 0);
+}
+
 int layer_wgrad(resr_generator* g, int k, const uint16_t* x16, int x_cstride, int fmt_x, bool x_already_transposed, int xt_rows,
                 const uint16_t* dy16, int N, const Geo& q, const Bufs& B, float* grads, cudaStream_t s) {
     const ConvSpec& c = table().c[k];
     const size_t P = static_cast<size_t>(N) * q.H * q.W;
+    cudaStream_t w = wgrad_stream(g, s);
+    fork_to(g, s, w);  // dY of this layer (and everything before it) is complete on the main stream
     if (!x_already_transposed) {
         xt_rows = (c.cin + 31) / 32 * 32;
-        nhwc16_to_cf_kernel<<<dim3(static_cast<unsigned>((P + 31) / 32), xt_rows / 32), 256, 0, s>>>(x16, x_cstride, 0, c.cin, xt_rows, P,
-                                                                                                       fmt_x, B.xt);
+        nhwc16_to_cf_kernel<false><<<dim3(static_cast<unsigned>((P + 255) / 256), xt_rows / 32), 256, 0, w>>>(x16, x_cstride, 0, c.cin, xt_rows, P, q.W,
+                                                                                                               fmt_x, B.xt, nullptr);
     }
     const int dy_rows = (c.cout + 31) / 32 * 32;
-    nhwc16_to_cf_shift3_kernel<<<dim3(static_cast<unsigned>((P + 31) / 32), dy_rows / 32), 256, 0, s>>>(dy16, 64, c.cout, dy_rows, P, q.W, B.dyt);
     float* dw = grads + c.p_off;
-    float* db = dw + static_cast<size_t>(c.cout) * c.cin * 9;
-    const int rc = wgrad_launch(B.xt, xt_rows, B.dyt, dy_rows, N, q.H, q.W, c.cin, c.cout, B.partial, dw, db, g->num_sms, s);
+    float* db = dw + static_cast<size_t>(c.cout) * c.cin * 9;  // zeroed with the whole gradient vector at the start of the backward
+    nhwc16_to_cf_kernel<true><<<dim3(static_cast<unsigned>((P + 255) / 256), dy_rows / 32), 256, 0, w>>>(dy16, 64, 0, c.cout, dy_rows, P, q.W, 1, B.dyt, db);
+    if (w != s) {  // the main stream may overwrite the dY buffer once its channels-first copies exist
+        cudaEventRecord(g->ev_dy, w);
+        cudaStreamWaitEvent(s, g->ev_dy, 0);
+    }
+    const int rc = wgrad_launch(B.xt, xt_rows, B.dyt, dy_rows, N, q.H, q.W, c.cin, c.cout, B.partial, dw, nullptr, g->num_sms, w);
     if (rc != 0) return set_error(RESR_E_CUDA, "wgrad of layer %d failed (%d)", k, rc);
     return RESR_OK;
 }
@@ -443,6 +487,7 @@ int backward_common(resr_generator* g, float* grads, int N, int H, int W, const 
     const Geo g0 = make_geo(g, H, W), g1 = make_geo(g, 2 * H, 2 * W), g2 = make_geo(g, 4 * H, 4 * W);
     const size_t P = static_cast<size_t>(N) * H * W;
     ensure_transposed_packs(g, s, true);
+    cudaMemsetAsync(grads, 0, table().n_params * sizeof(float), s);  // bias gradients are accumulated with atomics
     cudaMemsetAsync(B.dya, 0, P * 64 * 2, s);
     cudaMemsetAsync(B.dyb, 0, P * 64 * 2, s);
     const int kConv2 = 346, kUp1 = 347, kUp2 = 348, kConv3 = 349, kConv4 = 350;
@@ -493,7 +538,11 @@ int backward_common(resr_generator* g, float* grads, int N, int H, int W, const 
             const int k5 = 1 + 5 * r + 4;  // layer index of this RDB's conv5
             const float* D = dbuf[jj];
             // channels-first copy of the whole concat buffer: the X operand of all five weight gradients
-            nhwc16_to_cf_kernel<<<dim3(static_cast<unsigned>((P + 31) / 32), 6), 256, 0, s>>>(B.c[r], 192, 0, 192, 192, P, 1, B.xt);
+            {
+                cudaStream_t wst = wgrad_stream(g, s);
+                fork_to(g, s, wst);
+                nhwc16_to_cf_kernel<false><<<dim3(static_cast<unsigned>((P + 255) / 256), 6), 256, 0, wst>>>(B.c[r], 192, 0, 192, 192, P, W, 1, B.xt, nullptr);
+            }
             // conv5: dY5 = 0.2 * d(xout)
             scale_f32_to_bf16_kernel<<<egrid(P * 64), 256, 0, s>>>(D, 0.2f * dscale[jj], nullptr, 0.f, B.dya, P * 64);
             RESR_TRY(layer_wgrad(g, k5, nullptr, 0, 1, true, 192, B.dya, N, g0, B, grads, s));
@@ -537,6 +586,10 @@ int backward_common(resr_generator* g, float* grads, int N, int H, int W, const 
     // ---- conv1 (model.py:258): dY = d(trunk input) + d(skip)
     scale_f32_to_bf16_kernel<<<egrid(P * 64), 256, 0, s>>>(B.dx[0], 1.f, B.dskip, 1.f, B.dya, P * 64);
     RESR_TRY(layer_wgrad(g, 0, B.xin, 64, 0, false, 0, B.dya, N, g0, B, grads, s));
+    if (g->side_stream && wgrad_stream(g, s) != s) {  // join: the gradient vector is complete when the main stream continues
+        cudaEventRecord(g->ev_join, g->side_stream);
+        cudaStreamWaitEvent(s, g->ev_join, 0);
+    }
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(RESR_E_CUDA, "backward: %s", cudaGetErrorString(e));
     return RESR_OK;
@@ -649,8 +702,9 @@ int resr_conv3x3_wgrad(const void* x16, int x_cstride, int fmt_x, const void* dy
     uint16_t* xt = static_cast<uint16_t*>(workspace);
     uint16_t* dyt = reinterpret_cast<uint16_t*>(static_cast<uint8_t*>(workspace) + up1k(P * xr * 2));
     float* partial = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(dyt) + up1k(3 * P * yr * 2));
-    nhwc16_to_cf_kernel<<<dim3(static_cast<unsigned>((P + 31) / 32), xr / 32), 256, 0, s>>>(static_cast<const uint16_t*>(x16), x_cstride, 0, cin, xr, P, fmt_x, xt);
-    nhwc16_to_cf_shift3_kernel<<<dim3(static_cast<unsigned>((P + 31) / 32), yr / 32), 256, 0, s>>>(static_cast<const uint16_t*>(dy16_bf16), 64, cout, yr, P, w, dyt);
+    nhwc16_to_cf_kernel<false><<<dim3(static_cast<unsigned>((P + 255) / 256), xr / 32), 256, 0, s>>>(static_cast<const uint16_t*>(x16), x_cstride, 0, cin, xr, P, w, fmt_x, xt, nullptr);
+    if (db) cudaMemsetAsync(db, 0, cout * sizeof(float), s);
+    nhwc16_to_cf_kernel<true><<<dim3(static_cast<unsigned>((P + 255) / 256), yr / 32), 256, 0, s>>>(static_cast<const uint16_t*>(dy16_bf16), 64, 0, cout, yr, P, w, 1, dyt, db);
     if (getenv("RESR_DEBUG_SYNC")) {
         const cudaError_t e = cudaStreamSynchronize(s);
         fprintf(stderr, "[resr] transposes: %s\n", cudaGetErrorString(e));
@@ -666,7 +720,7 @@ int resr_conv3x3_wgrad(const void* x16, int x_cstride, int fmt_x, const void* dy
         cudaHostGetDevicePointer(&dptr, hang_host, 0);
         g_wgrad_hang_slot = dptr;
     }
-    const int rc = wgrad_launch(xt, xr, dyt, yr, n, h, w, cin, cout, partial, dw, db, sms, s);
+    const int rc = wgrad_launch(xt, xr, dyt, yr, n, h, w, cin, cout, partial, dw, nullptr, sms, s);
     if (getenv("RESR_DEBUG_SYNC")) {
         const cudaError_t e = cudaStreamSynchronize(s);
         fprintf(stderr, "[resr] wgrad: rc=%d %s hang=%llx\n", rc, cudaGetErrorString(e), hang_host ? *hang_host : 0ull);
