@@ -86,9 +86,10 @@ typedef struct resr_conv_desc {
     int out16_fmt, out16_cstride, out16_choff, out16_up2;
     float* outf;
     int outf_cstride, outf_choff;
-    const float* res1;
-    const float* res2;
+    const void* res1;        /* fp32 NHWC, or 16-bit NHWC when res16 != 0 */
+    const void* res2;
     int res_cstride, res_choff;
+    int res16, res16_fmt;    /* res16 = 1: res1 / res2 are 16-bit tensors of format res16_fmt (0 fp16, 1 bf16) */
     float* out_nchw;
     int out_nchw_c;
     int dbg_flags;           /* experiments only (0 in production) */

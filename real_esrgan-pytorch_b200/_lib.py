@@ -25,6 +25,7 @@ class ConvDesc(Structure):
         ("outf_cstride", c_int), ("outf_choff", c_int),
         ("res1", c_void_p), ("res2", c_void_p),
         ("res_cstride", c_int), ("res_choff", c_int),
+        ("res16", c_int), ("res16_fmt", c_int),
         ("out_nchw", c_void_p),
         ("out_nchw_c", c_int),
         ("dbg_flags", c_int),

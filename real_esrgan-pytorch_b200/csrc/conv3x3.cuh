@@ -41,9 +41,13 @@ struct ConvArgs {
     int outf_choff;
     float* outf;           // base of the fp32 NHWC output, outf_cstride channels per pixel
     int outf_cstride;
-    int has_res1;          // fp32 NHWC residual through tmapR1 (TMA load into the fp32 staging tile)
-    int res_choff;
-    const float* res2;     // second residual (EP_RRDB only): plain global loads
+    int has_res1;          // fp32 NHWC residual: each epilogue thread loads its pixel's channels straight into registers
+    int res_choff;         //   before it waits for the accumulator (no shared-memory tile, no dependency on the TMA queue)
+    const void* res1;
+    int res1_cstride;
+    int res16;             // 0: res1 / res2 are fp32; 1: both are 16-bit NHWC tensors in format res16_fmt (the residual
+    int res16_fmt;         //    stream of the inference trunk IS the fp16 conv input: no fp32 master is kept)
+    const void* res2;      // second residual (EP_RRDB / EP_ADD2): plain global loads
     int res2_cstride;
     float* out_nchw;       // NCHW fp32 output with out_nchw_c channels (or null)
     int out_nchw_c;
@@ -75,7 +79,6 @@ struct ConvMaps {
     CUtensorMap a;    // activations (load)
     CUtensorMap o16;  // 16-bit output (store), 4-D or 5-D (up2)
     CUtensorMap of;   // fp32 output (store)
-    CUtensorMap r1;   // fp32 residual (load)
 };
 
 // Launch one convolution. `cout_slice` is 32 or 16 (channels per CTA slice), `nslices` slices cover Cout.

@@ -67,7 +67,7 @@ __device__ __forceinline__ unsigned long long gtimer() {
 __device__ __forceinline__ uint32_t slot_of(long long v) { return static_cast<uint32_t>((16 - (v & 15)) & 15); }
 
 __host__ __device__ inline int epi_group_bytes(const ConvArgs& a, int nout) {
-    const int f = (a.has_res1 || a.has_outf) ? kTileFBytes : 0;  // one fp32 tile: residual in, result out (in place)
+    const int f = a.has_outf ? kTileFBytes : 0;  // fp32 output tile (TMA store)
     const int h = a.has_out16 ? 128 * nout * 2 : 0;
     return f + (h + 1023) / 1024 * 1024;
 }
@@ -123,6 +123,22 @@ __device__ __forceinline__ void issue_half(int ks, uint32_t s0, uint32_t d0, uin
     else if (ks == 1) { RESR_HALF(1); }
     else { RESR_HALF(4); }
 #undef RESR_HALF
+}
+
+// eight 16-bit values (fp16 or bf16) of a uint4 -> fp32
+__device__ __forceinline__ void unpack16x8(const uint4 q, int fmt, float (&f)[8]) {
+    const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (fmt == 1) {
+            f[2 * i] = __uint_as_float(w4[i] << 16);
+            f[2 * i + 1] = __uint_as_float(w4[i] & 0xFFFF0000u);
+        } else {
+            const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&w4[i]));
+            f[2 * i] = h.x;
+            f[2 * i + 1] = h.y;
+        }
+    }
 }
 
 // The MMA-issuing warp. The tensor core is fed by ONE instruction stream with a shallow queue, so every non-MMA
@@ -213,7 +229,7 @@ __device__ __forceinline__ void mma_role(const ConvArgs& a, const RowRange rr, c
 template <int NOUT>
 __global__ void __launch_bounds__(512, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapO16,
-                  const __grid_constant__ CUtensorMap tmapOF, const __grid_constant__ CUtensorMap tmapR1,
+                  const __grid_constant__ CUtensorMap tmapOF,
                   const ConvArgs a) {
     constexpr int NT = 3 * NOUT;     // MMA N: (dy, co)
     constexpr int WTILE = NT * 128;  // bytes of one (chunk, dx) weight tile: NT rows x 64 ch x 2 B
@@ -237,15 +253,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     uint64_t* acc_full = empty + kMaxStages;
     uint64_t* slot_free = acc_full + kSlots;
     uint64_t* wbar = slot_free + kSlots;
-    uint64_t* res_full = wbar + 1;  // [4]
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full + 4);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(wbar + 1);
     float* bias_s = reinterpret_cast<float*>(misc + 512);
 
     if (threadIdx.x == 0) {
         prefetch_tmap(&tmapA);
         if (a.has_out16) prefetch_tmap(&tmapO16);
         if (a.has_outf) prefetch_tmap(&tmapOF);
-        if (a.has_res1) prefetch_tmap(&tmapR1);
         for (int i = 0; i < a.nstages; ++i) {
             mbar_init(full + i, 1);
             mbar_init(empty + i, 1);
@@ -255,7 +269,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
             mbar_init(slot_free + i, 128);
         }
         mbar_init(wbar, 1);
-        for (int i = 0; i < 4; ++i) mbar_init(res_full + i, 1);
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -336,11 +349,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         const bool use_res1 = a.has_res1 && !((a.slice_nores_mask >> slice) & 1u);
         const bool use_outf = a.has_outf && !((a.slice_noutf_mask >> slice) & 1u);
         const bool use_o16 = a.has_out16 && !((a.slice_no16_mask >> slice) & 1u);
-        const bool staged = use_o16 || use_outf || use_res1;
-        uint8_t* tileR = epi + gi * epi_bytes;                       // fp32 tile: residual (TMA load), then result (TMA store)
-        uint8_t* tile16 = tileR + ((a.has_res1 || a.has_outf) ? kTileFBytes : 0);  // 16-bit output tile (TMA store)
-        uint64_t* rbar = res_full + gi;
-        uint32_t res_phase = 0;
+        const bool staged = use_o16 || use_outf;
+        uint8_t* tileR = epi + gi * epi_bytes;                       // fp32 output tile (TMA store)
+        uint8_t* tile16 = tileR + (a.has_outf ? kTileFBytes : 0);  // 16-bit output tile (TMA store)
         const uint32_t lane_base = tbase + (static_cast<uint32_t>(q * 32) << 16);
         const int img_in_tile = m / a.BW;
         const int x_in_tile = m % a.BW;
@@ -372,16 +383,24 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
                 const int y = ra - 1 + j;
                 const bool emit = (y >= ya) && (y < yb) && !DBGF(8);
                 const uint32_t slot = slot_of(v);
+                float4 resv[NOUT / 4];   // fp32 residual, or (res16) NOUT 16-bit values in the first NOUT / 8 entries
                 if (emit && use_res1) {
-                    // this row's fp32 residual streams into the group's fp32 tile behind the wait for the accumulator;
-                    // the tile is free once the previous row's TMA store (issued by the same thread) has read it
-                    if (lead_warp) {
-                        tma_store_wait_read();
-                        if (elect_one()) {
-                            mbar_expect_tx(rbar, 128 * 128);
-                            tma_load_4d(tileR, &tmapR1, rbar, a.res_choff + slice * NOUT, x0, y, n0);
+                    // this row's residual: contiguous bytes per thread, requested before the wait for the accumulator so
+                    // the latency hides behind the row's MMAs
+                    const size_t pix = (static_cast<size_t>(valid ? n : 0) * a.H + y) * a.W + (valid ? x : 0);
+                    if (a.res16) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(a.res1) + pix * a.res1_cstride +
+                                                                         a.res_choff + slice * NOUT);
+#pragma unroll
+                        for (int i = 0; i < NOUT / 8; ++i) {
+                            const uint4 q4 = rp[i];
+                            resv[i] = make_float4(__uint_as_float(q4.x), __uint_as_float(q4.y), __uint_as_float(q4.z), __uint_as_float(q4.w));
                         }
-                        __syncwarp();
+                    } else {
+                        const float4* rp = reinterpret_cast<const float4*>(static_cast<const float*>(a.res1) + pix * a.res1_cstride +
+                                                                           a.res_choff + slice * NOUT);
+#pragma unroll
+                        for (int i = 0; i < NOUT / 4; ++i) resv[i] = rp[i];
                     }
                 }
                 mbar_wait(acc_full + slot, static_cast<uint32_t>(v >> 4) & 1);
@@ -397,13 +416,20 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
 
 #pragma unroll
                 for (int i = 0; i < NOUT; ++i) val[i] = __fadd_rn(val[i], bias_s[i]);
-                float4 resv[NOUT / 4];
-                if (use_res1) {
-                    mbar_wait(rbar, res_phase);
-                    res_phase ^= 1;
+                if (use_res1 && a.res16) {  // widen the 16-bit residual in place (consumed below as fp32)
+                    float wide[NOUT];
 #pragma unroll
-                    for (int i = 0; i < NOUT / 4; ++i)
-                        resv[i] = *reinterpret_cast<const float4*>(tileR + m * 128 + ((i ^ (m & 7)) << 4));
+                    for (int i = 0; i < NOUT / 8; ++i) {
+                        float f8[8];
+                        unpack16x8(make_uint4(__float_as_uint(resv[i].x), __float_as_uint(resv[i].y), __float_as_uint(resv[i].z),
+                                              __float_as_uint(resv[i].w)), a.res16_fmt, f8);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) wide[8 * i + e] = f8[e];
+                    }
+#pragma unroll
+                    for (int i = 0; i < NOUT / 4; ++i) resv[i] = make_float4(wide[4 * i], wide[4 * i + 1], wide[4 * i + 2], wide[4 * i + 3]);
+                }
+                if (use_res1) {
 #pragma unroll
                     for (int i = 0; i < NOUT / 4; ++i) {
                         const float4 r4 = resv[i];
@@ -420,27 +446,40 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
                         }
                     }
                 }
-                if (staged && !use_res1) {
-                    // the output tiles are free once the previous TMA stores have read them (with a residual, the
-                    // completed load above already implies that: it was issued behind the same wait)
+                if (staged) {  // the output tiles are free once the previous row's TMA stores have read them
                     if (lead_warp) tma_store_wait_read();
                     named_bar_sync(1 + gi, 128);
                 }
                 if (a.ep_mode == EP_RRDB) {
                     const size_t pix = (static_cast<size_t>(valid ? n : 0) * a.H + y) * a.W + (valid ? x : 0);
-                    const float4* r2 = reinterpret_cast<const float4*>(a.res2 + pix * a.res2_cstride + a.res_choff + slice * NOUT);
+                    if (a.res16) {
+                        // plain (coherent) loads: in the inference trunk res2 is the RRDB input held in the very buffer
+                        // this launch overwrites -- each element is read by the thread that later stores its replacement
+                        const uint4* r2 = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(a.res2) + pix * a.res2_cstride +
+                                                                         a.res_choff + slice * NOUT);
 #pragma unroll
-                    for (int i = 0; i < NOUT / 4; ++i) {
-                        const float4 r4 = __ldg(r2 + i);
-                        val[4 * i + 0] = __fadd_rn(__fmul_rn(val[4 * i + 0], 0.2f), r4.x);
-                        val[4 * i + 1] = __fadd_rn(__fmul_rn(val[4 * i + 1], 0.2f), r4.y);
-                        val[4 * i + 2] = __fadd_rn(__fmul_rn(val[4 * i + 2], 0.2f), r4.z);
-                        val[4 * i + 3] = __fadd_rn(__fmul_rn(val[4 * i + 3], 0.2f), r4.w);
+                        for (int i = 0; i < NOUT / 8; ++i) {
+                            float f8[8];
+                            unpack16x8(r2[i], a.res16_fmt, f8);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) val[8 * i + e] = __fadd_rn(__fmul_rn(val[8 * i + e], 0.2f), f8[e]);
+                        }
+                    } else {
+                        const float4* r2 = reinterpret_cast<const float4*>(static_cast<const float*>(a.res2) + pix * a.res2_cstride +
+                                                                           a.res_choff + slice * NOUT);
+#pragma unroll
+                        for (int i = 0; i < NOUT / 4; ++i) {
+                            const float4 r4 = __ldg(r2 + i);
+                            val[4 * i + 0] = __fadd_rn(__fmul_rn(val[4 * i + 0], 0.2f), r4.x);
+                            val[4 * i + 1] = __fadd_rn(__fmul_rn(val[4 * i + 1], 0.2f), r4.y);
+                            val[4 * i + 2] = __fadd_rn(__fmul_rn(val[4 * i + 2], 0.2f), r4.z);
+                            val[4 * i + 3] = __fadd_rn(__fmul_rn(val[4 * i + 3], 0.2f), r4.w);
+                        }
                     }
                 }
                 if (a.ep_mode == EP_ADD2 && a.res2) {
                     const size_t pix = (static_cast<size_t>(valid ? n : 0) * a.H + y) * a.W + (valid ? x : 0);
-                    const float4* r2 = reinterpret_cast<const float4*>(a.res2 + pix * a.res2_cstride + a.res_choff + slice * NOUT);
+                    const float4* r2 = reinterpret_cast<const float4*>(static_cast<const float*>(a.res2) + pix * a.res2_cstride + a.res_choff + slice * NOUT);
 #pragma unroll
                     for (int i = 0; i < NOUT / 4; ++i) {
                         const float4 r4 = __ldg(r2 + i);
@@ -467,7 +506,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
 #pragma unroll
                     for (int i = 0; i < NOUT; ++i) val[i] = fminf(fmaxf(val[i], 0.f), 1.f);
                 }
-                if (use_outf) {  // fp32 master, written over this thread's own (already consumed) residual row
+                if (use_outf) {  // fp32 master
 #pragma unroll
                     for (int i = 0; i < NOUT / 4; ++i)
                         *reinterpret_cast<float4*>(tileR + m * 128 + ((i ^ (m & 7)) << 4)) =
@@ -497,7 +536,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
                             __nv_bfloat162 h = __floats2bfloat162_rn(val[2 * i], val[2 * i + 1]);
                             pk[i] = *reinterpret_cast<uint32_t*>(&h);
                         } else {
-                            __half2 h = __floats2half2_rn(val[2 * i], val[2 * i + 1]);
+                            __half2 h = __floats2half2_rn(fminf(fmaxf(val[2 * i], -65504.f), 65504.f),
+                                                          fminf(fmaxf(val[2 * i + 1], -65504.f), 65504.f));  // saturate, never inf
                             pk[i] = *reinterpret_cast<uint32_t*>(&h);
                         }
                     }
@@ -511,8 +551,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
                     named_bar_sync(1 + gi, 128);
                     if (lead_warp) {
                       if (elect_one()) {
-                        if (use_outf && !DBGF(1)) tma_store_4d(&tmapOF, tileR, a.outf_choff + slice * NOUT, x0, y, n0);
-                        if (use_o16 && !DBGF(1)) {
+                        if (use_outf && !DBGF(1) && !DBGF(64)) tma_store_4d(&tmapOF, tileR, a.outf_choff + slice * NOUT, x0, y, n0);
+                        if (use_o16 && !DBGF(1) && !(DBGF(128) && a.has_res1)) {
                             const int c0 = a.out16_choff + (a.out16_slice_fixed ? 0 : slice * NOUT);
                             if (!a.out16_up2) {
                                 tma_store_4d(&tmapO16, tile16, c0, x0, y, n0);
@@ -682,7 +722,7 @@ static cudaError_t launch_t(const ConvMaps& maps, const ConvArgs& args, dim3 gri
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<NOUT>, maps.a, maps.o16, maps.of, maps.r1, args);
+    return cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<NOUT>, maps.a, maps.o16, maps.of, args);
 }
 
 cudaError_t conv3x3_launch(const ConvMaps& maps, const ConvArgs& args, int cout_slice, int nslices, int num_sms,

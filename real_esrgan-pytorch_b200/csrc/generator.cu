@@ -112,7 +112,7 @@ void launch_pack_conv(const float* w, const float* bias, uint16_t* wp, float* bp
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct WsLayout {
-    size_t xin, ca, cb, f[4], t1, t2, t3, t4, total;
+    size_t xin, c[3], f0, t1, t2, t3, t4, total;
 };
 static WsLayout ws_layout(size_t N, size_t H, size_t W) {
     const size_t P = N * H * W;
@@ -124,9 +124,8 @@ static WsLayout ws_layout(size_t N, size_t H, size_t W) {
         return at;
     };
     L.xin = take(P * 64 * 2);
-    L.ca = take(P * 192 * 2);
-    L.cb = take(P * 192 * 2);
-    for (int i = 0; i < 4; ++i) L.f[i] = take(P * 64 * 4);
+    for (int i = 0; i < 3; ++i) L.c[i] = take(P * 192 * 2);
+    L.f0 = take(P * 64 * 4);
     L.t1 = take(4 * P * 64 * 2);
     L.t2 = take(16 * P * 64 * 2);
     L.t3 = take(16 * P * 64 * 2);
@@ -143,9 +142,11 @@ static int build_plan(resr_generator* g, int N, int H, int W, void* ws) {
     const WsLayout L = ws_layout(N, H, W);
     uint8_t* base = static_cast<uint8_t*>(ws);
     uint16_t* xin = reinterpret_cast<uint16_t*>(base + L.xin);
-    uint16_t* cbuf[2] = {reinterpret_cast<uint16_t*>(base + L.ca), reinterpret_cast<uint16_t*>(base + L.cb)};
-    float* F[4];
-    for (int i = 0; i < 4; ++i) F[i] = reinterpret_cast<float*>(base + L.f[i]);
+    // three 192-channel concat buffers: [0] holds the RRDB input (and receives the RRDB output in place), [1] / [2] the
+    // inputs of its second / third dense block; F0 = fp32 copy of conv1's output for the global skip (model.py:261-262)
+    uint16_t* cbuf[3];
+    for (int i = 0; i < 3; ++i) cbuf[i] = reinterpret_cast<uint16_t*>(base + L.c[i]);
+    float* F0 = reinterpret_cast<float*>(base + L.f0);
     uint16_t* t1 = reinterpret_cast<uint16_t*>(base + L.t1);
     uint16_t* t2 = reinterpret_cast<uint16_t*>(base + L.t2);
     uint16_t* t3 = reinterpret_cast<uint16_t*>(base + L.t3);
@@ -161,10 +162,8 @@ static int build_plan(resr_generator* g, int N, int H, int W, void* ws) {
         geo[s].mode = geo[s].BN == 1 ? 0 : 1;
         if (g->force_mode >= 0) geo[s].mode = (geo[s].BN == 1) ? g->force_mode : 1;
     }
-    // The zero-padded K chunks of conv2/conv4 of each RDB read growth channels that the current RDB has not written
-    // yet: they are multiplied by zero weights, so they only have to be finite.
-    cudaMemsetAsync(cbuf[0], 0, static_cast<size_t>(N) * H * W * 192 * 2, 0);
-    cudaMemsetAsync(cbuf[1], 0, static_cast<size_t>(N) * H * W * 192 * 2, 0);
+    // (one-time hygiene: no layer reads a channel that has not been written, the activation tensor maps end at Cin)
+    for (int i = 0; i < 3; ++i) cudaMemsetAsync(cbuf[i], 0, static_cast<size_t>(N) * H * W * 192 * 2, 0);
 
     const Table& T = table();
     int map_rc = 0;
@@ -199,55 +198,54 @@ static int build_plan(resr_generator* g, int N, int H, int W, void* ws) {
         map_rc |= conv3x3_make_tmap_f32(&st.maps.of, dst, N, geo[0].H, geo[0].W, 64, geo[0].BW, geo[0].BN);
     };
     auto set_res1 = [&](Step& st, const float* src) {
-        st.a.has_res1 = 1; st.a.res_choff = 0;
-        map_rc |= conv3x3_make_tmap_f32(&st.maps.r1, src, N, geo[0].H, geo[0].W, 64, geo[0].BW, geo[0].BN);
+        st.a.has_res1 = 1; st.a.res_choff = 0; st.a.res1 = src; st.a.res1_cstride = 64;
     };
     auto push = [&](Step& st) {
         if (!conv3x3_plan_smem(&st.a, T.c[st.conv].nout)) map_rc |= 1 << 20;
         p.steps.push_back(st);
     };
 
+    // 16-bit residual: the trunk's residual stream is the fp16 conv input itself (channels [0, 64) of a concat buffer)
+    auto set_res16 = [&](Step& st, const uint16_t* src) {
+        st.a.has_res1 = 1; st.a.res_choff = 0; st.a.res1 = src; st.a.res1_cstride = 192;
+        st.a.res16 = 1; st.a.res16_fmt = 0;
+    };
     int conv = 0;
     {   // conv1: model.py:258
         Step st = make_step(conv, 0, xin, 64);
         st.a.ep_mode = EP_PLAIN;
-        set_outf(st, F[0]);
-        set_out16(st, 0, cbuf[0], 192, 0, 1, 0);
+        set_outf(st, F0);
+        set_out16(st, 0, cbuf[0], 192, 0, 0, 0);
         push(st);
         ++conv;
     }
-    int cur = 0;  // concat buffer holding the current RDB input
     for (int i = 0; i < kNumRRDB; ++i) {
-        float* X0 = (i == 0) ? F[0] : F[3];
         for (int j = 0; j < 3; ++j) {
-            float* xin_master = (j == 0) ? X0 : F[j];
+            uint16_t* cin_buf = cbuf[j];
             for (int k = 0; k < 4; ++k) {  // model.py:90-93
-                Step st = make_step(conv, 0, cbuf[cur], 192);
+                Step st = make_step(conv, 0, cin_buf, 192);
                 st.a.ep_mode = EP_PLAIN; st.a.lrelu = 1;
-                set_out16(st, 0, cbuf[cur], 192, 64 + 32 * k, 1, 0);
+                set_out16(st, 0, cin_buf, 192, 64 + 32 * k, 0, 0);
                 push(st);
                 ++conv;
             }
-            Step st = make_step(conv, 0, cbuf[cur], 192);  // model.py:94-96 (+ :129-130 for the third RDB)
-            set_res1(st, xin_master);
+            Step st = make_step(conv, 0, cin_buf, 192);  // model.py:94-96 (+ :129-130 for the third RDB)
+            set_res16(st, cin_buf);
             if (j < 2) {
                 st.a.ep_mode = EP_RDB;
-                set_outf(st, F[j + 1]);
             } else {
                 st.a.ep_mode = EP_RRDB;
-                st.a.res2 = X0; st.a.res2_cstride = 64;
-                set_outf(st, F[3]);
+                st.a.res2 = cbuf[0]; st.a.res2_cstride = 192;
             }
-            set_out16(st, 0, cbuf[cur ^ 1], 192, 0, 1, 0);
+            set_out16(st, 0, cbuf[(j + 1) % 3], 192, 0, 0, 0);
             push(st);
             ++conv;
-            cur ^= 1;
         }
     }
     {   // conv2 + skip (model.py:260-262), written nearest-upsampled x2 (model.py:264) in fp16
-        Step st = make_step(conv, 0, cbuf[cur], 192);
+        Step st = make_step(conv, 0, cbuf[0], 192);
         st.a.ep_mode = EP_SKIP;
-        set_res1(st, F[0]);
+        set_res1(st, F0);
         set_out16(st, 0, t1, 64, 0, 0, 1);
         push(st);
         ++conv;
@@ -471,8 +469,8 @@ int resr_conv3x3(const resr_conv_desc* d, void* stream) {
         rc |= conv3x3_make_tmap_f32(&maps.of, d->outf, d->n, d->h, d->w, d->outf_cstride, a.BW, a.BN);
     }
     if (d->res1) {
-        a.has_res1 = 1; a.res_choff = d->res_choff;
-        rc |= conv3x3_make_tmap_f32(&maps.r1, d->res1, d->n, d->h, d->w, d->res_cstride, a.BW, a.BN);
+        a.has_res1 = 1; a.res_choff = d->res_choff; a.res1 = d->res1; a.res1_cstride = d->res_cstride;
+        a.res16 = d->res16; a.res16_fmt = d->res16_fmt;
     }
     a.res2 = d->res2; a.res2_cstride = d->res_cstride;
     a.out_nchw = d->out_nchw; a.out_nchw_c = d->out_nchw_c;

@@ -251,7 +251,7 @@ static int launch_conv_io(const resr_generator* g, const Geo& q, int N, const Co
     }
     if (io.res1) {
         a.has_res1 = 1; a.res_choff = io.res_choff; a.slice_nores_mask = io.nores_mask;
-        rc |= conv3x3_make_tmap_f32(&m.r1, io.res1, N, q.H, q.W, io.res1_c, q.BW, q.BN);
+        a.res1 = io.res1; a.res1_cstride = io.res1_c;
     }
     a.res2 = io.res2; a.res2_cstride = io.res2_c; a.res2_scale = io.res2_scale;
     a.mask16 = io.mask16; a.mask16_cstride = io.mask16_c; a.mask16_choff = io.mask16_choff;
@@ -361,6 +361,7 @@ ConvIO fwd_io(const resr_generator* g, int k) {
     ConvIO io;
     io.wpack = g->wpack + c.w_off; io.bias = g->bias + c.b_off;
     io.nout = c.nout; io.nslices = c.nslices; io.nchunks = c.nchunks; io.fmt = c.fmt; io.kvalid = c.cin;
+    io.out16_fmt = 0;  // forward activations are fp16 (the operand format of every consumer)
     return io;
 }
 
@@ -519,7 +520,7 @@ int backward_common(resr_generator* g, float* grads, int N, int H, int W, const 
         RESR_TRY(launch_conv_io(g, g1, N, io, s));
         sum2x2_kernel<<<egrid(P * 32), 256, 0, s>>>(B.midb, B.dskip, B.dya, N, H, W);
     }
-    RESR_TRY(layer_wgrad(g, kConv2, B.c[69], 192, 1, false, 0, B.dya, N, g0, B, grads, s));
+    RESR_TRY(layer_wgrad(g, kConv2, B.c[69], 192, 0, false, 0, B.dya, N, g0, B, grads, s));
     {   // d(trunk output), fp32
         ConvIO io = bwd_io(g, kConv2);
         io.in16 = B.dya; io.outf = B.dx[0];
@@ -541,7 +542,7 @@ int backward_common(resr_generator* g, float* grads, int N, int H, int W, const 
             {
                 cudaStream_t wst = wgrad_stream(g, s);
                 fork_to(g, s, wst);
-                nhwc16_to_cf_kernel<false><<<dim3(static_cast<unsigned>((P + 255) / 256), 6), 256, 0, wst>>>(B.c[r], 192, 0, 192, 192, P, W, 1, B.xt, nullptr);
+                nhwc16_to_cf_kernel<false><<<dim3(static_cast<unsigned>((P + 255) / 256), 6), 256, 0, wst>>>(B.c[r], 192, 0, 192, 192, P, W, 0, B.xt, nullptr);
             }
             // conv5: dY5 = 0.2 * d(xout)
             scale_f32_to_bf16_kernel<<<egrid(P * 64), 256, 0, s>>>(D, 0.2f * dscale[jj], nullptr, 0.f, B.dya, P * 64);

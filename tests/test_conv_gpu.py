@@ -17,7 +17,7 @@ def _nhwc16(x, c_total, dtype):
 
 
 def _run_conv(x16, cin, weight, bias, *, fmt, mode=-1, ep_mode=0, lrelu=0, clamp01=0, out16=None, out16_fmt=1,
-              out16_choff=0, out16_up2=0, outf=None, outf_choff=0, res1=None, res2=None, out_nchw=None):
+              out16_choff=0, out16_up2=0, outf=None, outf_choff=0, res1=None, res2=None, out_nchw=None, res16_fmt=None):
     import resr_b200
     L = resr_b200._lib
     n, h, w, c_total = x16.shape
@@ -37,6 +37,8 @@ def _run_conv(x16, cin, weight, bias, *, fmt, mode=-1, ep_mode=0, lrelu=0, clamp
         d.res1, d.res_cstride, d.res_choff = res1.data_ptr(), res1.shape[-1], 0
     if res2 is not None:
         d.res2 = res2.data_ptr()
+    if res16_fmt is not None:
+        d.res16, d.res16_fmt = 1, res16_fmt
     if out_nchw is not None:
         d.out_nchw, d.out_nchw_c = out_nchw.data_ptr(), out_nchw.shape[1]
     L.check(L.lib().resr_conv3x3(ctypes.byref(d), L.stream_ptr()))
@@ -110,6 +112,35 @@ def test_conv_epilogues():
     outf.zero_()
     _run_conv(x16, cin, wt, b, fmt=1, lrelu=1, outf=outf)
     assert (outf - F.leaky_relu(conv, 0.2)).abs().max().item() < 2e-4
+
+
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_conv_16bit_residual_stream_in_place(fmt):
+    """Inference trunk epilogues: the residuals are 16-bit NHWC tensors (the conv inputs themselves) and the RRDB output
+    overwrites the buffer that holds res2 (model.py:94-96, 129-130)."""
+    torch.manual_seed(11 + fmt)
+    dev = "cuda"
+    dt = torch.float16 if fmt == 0 else torch.bfloat16
+    n, h, w, cin, cout = 2, 37, 128, 192, 64
+    x = torch.randn(n, cin, h, w, device=dev).to(dt).float()
+    wt = (torch.randn(cout, cin, 3, 3, device=dev) * 0.03).to(dt).float()
+    b = torch.randn(cout, device=dev) * 0.1
+    x16 = _nhwc16(x, cin, dt)
+    conv = F.conv2d(x, wt, b, padding=1).permute(0, 2, 3, 1).contiguous()
+    r1 = torch.randn(n, h, w, 192, device=dev).to(dt)
+    r2buf = torch.randn(n, h, w, 192, device=dev).to(dt)
+    r2 = r2buf.clone()
+    # rdb: 0.2 * v + r1[..., :64]
+    o16 = torch.zeros(n, h, w, 192, device=dev, dtype=dt)
+    _run_conv(x16, cin, wt, b, fmt=fmt, ep_mode=1, res1=r1, out16=o16, out16_fmt=fmt, res16_fmt=fmt)
+    ref = conv * 0.2 + r1[..., :64].float()
+    assert torch.equal(o16[..., :64], ref.to(dt)) or (o16[..., :64].float() - ref).abs().max().item() < 2e-2
+    assert ((o16[..., :64].float() - ref).abs() <= ref.abs() * 2.0 ** (-8 if fmt else -11) + 2e-4).all()
+    # rrdb, output written over the res2 buffer
+    _run_conv(x16, cin, wt, b, fmt=fmt, ep_mode=2, res1=r1, res2=r2buf, out16=r2buf, out16_fmt=fmt, res16_fmt=fmt)
+    ref = (conv * 0.2 + r1[..., :64].float()) * 0.2 + r2[..., :64].float()
+    assert ((r2buf[..., :64].float() - ref).abs() <= ref.abs() * 2.0 ** (-8 if fmt else -11) + 2e-4).all()
+    assert torch.equal(r2buf[..., 64:], r2[..., 64:])
 
 
 def test_conv_rgb_out_clamped():
