@@ -39,7 +39,9 @@ def test_abi_constants():
     assert lib.resr_generator_tensor_span(701, ctypes.byref(off), ctypes.byref(cnt)) == 0
     assert off.value + cnt.value == 16697987 and cnt.value == 3
     assert lib.resr_generator_tensor_span(702, ctypes.byref(off), ctypes.byref(cnt)) != 0
-    assert lib.resr_generator_workspace_bytes(64, 128, 128) > 8 * 2 ** 30
+    # cfg3 workspace: fp16 input + 3 concat buffers (192 ch) + fp32 skip copy + 2x / 4x tail activations
+    px = 64 * 128 * 128
+    assert lib.resr_generator_workspace_bytes(64, 128, 128) == px * (64 * 2 + 3 * 192 * 2 + 64 * 4 + 4 * 64 * 2 + 3 * 16 * 64 * 2)
     assert lib.resr_generator_workspace_bytes(0, 1, 1) == 0
 
 
