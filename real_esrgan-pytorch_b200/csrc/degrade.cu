@@ -76,18 +76,27 @@ __global__ void __launch_bounds__(256) filter2d_kernel(const float* __restrict__
         taps[i] = v;
         if (v != 0.f) atomicMax(&s_ext, max(abs(i / k - r), abs(i % k - r)));
     }
-    for (int ty = threadIdx.x >> 5; ty < tw; ty += 8) {  // one tile row per warp pass, coalesced along x
-        // positions the tile overhang would touch beyond the image are clamped: their outputs are never stored
-        const int cy = min(max(reflect_idx(y0 + ty - r, H), 0), H - 1);
-        const float* srow = src + static_cast<size_t>(cy) * W;
-        for (int tx = threadIdx.x & 31; tx < tw; tx += 32) {
-            const int cx = min(max(reflect_idx(x0 + tx - r, W), 0), W - 1);
-            tile[ty * tpitch + tx] = srow[cx];
-        }
-    }
     __syncthreads();
     const int ext = s_ext;
     const int off = r - ext;           // first row/col of the centred support inside the k x k array
+    {   // only the halo the trimmed support needs is fetched: tile rows / columns [off, tw - off). One tile row per warp
+        // pass, coalesced along x; the reflected columns of this lane are computed once. Positions the tile overhang
+        // would touch beyond the image are clamped: their outputs are never stored.
+        const int lane = threadIdx.x & 31;
+        int cxk[4];          // tw <= 64 + 62
+#pragma unroll
+        for (int q = 0; q < 4; ++q) cxk[q] = min(max(reflect_idx(x0 + off + lane + 32 * q - r, W), 0), W - 1);
+        const int span = tw - 2 * off;
+        for (int ty = off + (threadIdx.x >> 5); ty < tw - off; ty += 8) {
+            const int cy = min(max(reflect_idx(y0 + ty - r, H), 0), H - 1);
+            const float* srow = src + static_cast<size_t>(cy) * W;
+            float* trow = tile + ty * tpitch + off;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (lane + 32 * q < span) trow[lane + 32 * q] = srow[cxk[q]];
+        }
+    }
+    __syncthreads();
     const int tx = threadIdx.x & 31;
     const int ty0 = (threadIdx.x >> 5) * kF2dRows;
     float acc[2][kF2dRows];
@@ -254,12 +263,31 @@ __global__ void __launch_bounds__(256) usm_fused_kernel(const float* __restrict_
     const size_t pbase = static_cast<size_t>(plane) * H * W;
     const int r = kUsmK / 2;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int ty = warp; ty < kUsmIn; ty += 8) {  // one tile row per warp pass, coalesced along x, no div/mod
-        const int gy = min(max(reflect_idx(y0 + ty - r, H), 0), H - 1);
-        const float* srow = src + pbase + static_cast<size_t>(gy) * W;
-        for (int tx = lane; tx < kUsmIn; tx += 32) {
-            const int gx = min(max(reflect_idx(x0 + tx - r, W), 0), W - 1);
-            A[ty * kUsmPitchA + tx] = srow[gx];
+    {   // one tile row per warp pass, coalesced along x; the reflected column of each of this lane's 4 tile columns is
+        // computed once, the rows are issued four at a time so that 16 loads are in flight per thread
+        int gxk[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) gxk[k] = min(max(reflect_idx(x0 + lane + 32 * k - r, W), 0), W - 1);
+        const bool last_ok = lane + 96 < kUsmIn;
+        for (int ty = warp; ty < kUsmIn; ty += 32) {
+            float v[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int t = ty + 8 * u;
+                const int gy = min(max(reflect_idx(y0 + min(t, kUsmIn - 1) - r, H), 0), H - 1);
+                const float* srow = src + pbase + static_cast<size_t>(gy) * W;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[u][k] = srow[gxk[k]];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int t = ty + 8 * u;
+                if (t < kUsmIn) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) A[t * kUsmPitchA + lane + 32 * k] = v[u][k];
+                    if (last_ok) A[t * kUsmPitchA + lane + 96] = v[u][3];
+                }
+            }
         }
     }
     __syncthreads();
