@@ -120,13 +120,13 @@ def cpu_generator_baseline(seconds_budget=20.0, max_iters=5):
 # ------------------------------------------------------------------------------------------------- degradation
 
 
-def degradation_bench(device, steps, warmup, peaks):
-    """configs[1]: 16 x 3 x 256 x 256 HR crops through the canonical plan S0; device-timed with resident inputs."""
+def degradation_bench(device, steps, warmup, peaks, B=16):
+    """configs[1]: B x 3 x 256 x 256 HR crops (B = 16) through the canonical plan S0; device-timed with resident inputs.
+    B = 256 is the large-batch variant SURVEY.md §8d asks for (launch latencies amortised)."""
     import resr_b200
-    from oracle import plan as oplan
     ip = resr_b200.imgproc
-    B, H, W = 16, 256, 256
-    plan = oplan.canonical_plan_s0(B, H, W, seed=0)
+    H, W = 256, 256
+    plan = resr_b200.plan.canonical_plan_s0(B, H, W, seed=0)
     g = torch.Generator(device="cpu").manual_seed(0)
     hr = torch.rand(B, 3, H, W, generator=g).to(device)
     k = torch.zeros(B, 21, 21)
@@ -165,7 +165,7 @@ def degradation_bench(device, steps, warmup, peaks):
                        + 2 * e2_ + 2 * e2_ + 2 * e2_ + 2 * e2_)
     gbs = stage_bytes / (ms * 1e-3) / 1e9
     return {"metric": "degraded pairs/s", "value": B / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms,
-            "config": {"workload": "second-order degradation, 16x3x256x256 HR -> 16x3x64x64 LR, canonical plan S0 "
+            "config": {"workload": f"second-order degradation, {B}x3x256x256 HR -> {B}x3x64x64 LR, canonical plan S0 "
                                    "(SURVEY.md §8d): Gaussian noise tensors host-fed and resident, Poisson draws by "
                                    "torch.poisson inside the timed region; one CUDA-graph replay per batch"},
             "gpu_launches_per_step": 18,
@@ -184,10 +184,9 @@ def training_bench(device, steps, warmup, peaks, world):
     import torch.distributed as dist
 
     import resr_b200
-    from oracle import plan as oplan
     ip = resr_b200.imgproc
     B, H, W = 16, 256, 256
-    plan = oplan.canonical_plan_s0(B, H, W, seed=1)
+    plan = resr_b200.plan.canonical_plan_s0(B, H, W, seed=1)
     g = torch.Generator(device="cpu").manual_seed(2)
     hr = torch.rand(B, 3, H, W, generator=g).to(device)
     k = torch.zeros(B, 21, 21)
@@ -345,6 +344,9 @@ def run_ours(args):
         if not args.no_degrade:
             try:
                 line["degradation"] = degradation_bench(device, max(10, args.steps), args.warmup, peaks)
+                big = degradation_bench(device, 10, 3, peaks, B=256)  # large-batch regime
+                line["degradation"]["large_batch"] = {"batch": 256, "value": big["value"], "unit": big["unit"],
+                                                      "ms_per_step": big["ms_per_step"], "roofline_frac": big["roofline"]["frac"]}
             except Exception as e:  # keep the headline even if the secondary leg breaks
                 line["degradation"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu:

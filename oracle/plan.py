@@ -6,9 +6,7 @@ degradation ("the same blur kernels and noise tensors fed from the host", BASELI
 
   record_reference_plan(...)  runs the UNMODIFIED reference block (build container only) and records the plan,
                               every intermediate image and the final (lr, hr).
-  synth_plan(...)             draws a plan with the reference's distributions WITHOUT the reference (for the GPU
-                              box / benchmarks): same decision structure, numpy RNG.
-  canonical_plan_s0(...)      the canonical plan S0 of SURVEY.md §8d used for roofline accounting.
+  synth_plan / canonical_plan_s0 are re-exported from the product's host module (real_esrgan-pytorch_b200/plan.py).
 Plan layout (dict): blur1, resize1{mode,out_h,out_w,scale}, noise1{type,sigma|scale,gray,noise_color|samples_color,
 noise_gray|samples_gray}, jpeg1_quality, blur2, resize2{...}, noise2{...}, final_order (0: resize->sinc->jpeg,
 1: jpeg->resize->sinc), resize3{...}, jpeg2_quality, crop{hr_top,hr_left,image_size,upscale}.
@@ -199,72 +197,14 @@ def record_reference_plan(hr, kernel1, kernel2, sinc_kernel, seed):
 # ------------------------------------------------------------------------------------------------------------------
 
 
-def _resize_decision(rng, probs, lo, hi):
-    t = rng.choice(3, p=probs)
-    if t == 0:
-        return float(rng.uniform(1, hi))
-    if t == 1:
-        return float(rng.uniform(lo, 1))
-    return 1.0
+# Plan synthesis without the reference is host logic of the product (resr_b200.plan); the oracle re-exports it so the
+# tests can keep one import.
+import importlib.util as _ilu
+import os as _os
 
-
-def synth_plan(batch, hr_h, hr_w, seed, image_size=256, upscale=4):
-    """Draws a plan with the reference's probabilities/ranges (config.py:41-62, train_realesrnet.py:275-371) from a
-    numpy Generator. Noise tensors are drawn here too (numpy), so a plan is self-contained."""
-    rng = np.random.default_rng(seed)
-    plan = {"blur1": int(rng.uniform() <= 1.0)}
-    s = _resize_decision(rng, [0.2, 0.7, 0.1], 0.15, 1.5)
-    h1, w1 = od.interp_out_size(hr_h, s), od.interp_out_size(hr_w, s)
-    plan["resize1"] = {"mode": int(rng.integers(3)), "out_h": h1, "out_w": w1, "scale": s}
-
-    def noise(h, w, sig_rng, sc_rng):
-        gray = (rng.uniform(size=batch) < 0.4).astype(np.float32)
-        if rng.uniform() < 0.5:
-            p = {"type": "gaussian", "sigma": rng.uniform(*sig_rng, size=batch).astype(np.float32), "gray": gray,
-                 "noise_color": rng.standard_normal((batch, 3, h, w), dtype=np.float32)}
-            if gray.sum() > 0:
-                p["noise_gray"] = rng.standard_normal((h, w), dtype=np.float32)
-        else:
-            p = {"type": "poisson", "scale": rng.uniform(*sc_rng, size=batch).astype(np.float32), "gray": gray,
-                 "samples_color": None}  # Poisson draws depend on the image: filled in by fill_poisson_samples
-        return p
-
-    plan["noise1"] = noise(h1, w1, (1, 30), (0.05, 3))
-    plan["jpeg1_quality"] = rng.uniform(30, 95, size=batch).astype(np.float32)
-    plan["blur2"] = int(rng.uniform() < 0.8)
-    s2 = _resize_decision(rng, [0.3, 0.4, 0.3], 0.3, 1.2)
-    h2, w2 = int(hr_h / upscale * s2), int(hr_w / upscale * s2)
-    plan["resize2"] = {"mode": int(rng.integers(3)), "out_h": h2, "out_w": w2, "scale": None}
-    plan["noise2"] = noise(h2, w2, (1, 25), (0.05, 2.5))
-    plan["final_order"] = int(not (rng.uniform() < 0.5))
-    plan["resize3"] = {"mode": int(rng.integers(3)), "out_h": hr_h // upscale, "out_w": hr_w // upscale, "scale": None}
-    plan["jpeg2_quality"] = rng.uniform(30, 95, size=batch).astype(np.float32)
-    plan["crop"] = {"hr_top": int(rng.integers(0, hr_h - image_size + 1)),
-                    "hr_left": int(rng.integers(0, hr_w - image_size + 1)), "image_size": image_size, "upscale": upscale}
-    return plan
-
-
-def canonical_plan_s0(batch, hr_h=256, hr_w=256, seed=0):
-    """SURVEY.md §8d canonical plan S0: blur1; bicubic x0.5; Gaussian noise with a gray mix; JPEG; blur2; bilinear ->
-    H/4; Poisson noise; branch A (area resize (identity), sinc, JPEG); round; crop offset 0."""
-    rng = np.random.default_rng(seed)
-    h1, w1 = hr_h // 2, hr_w // 2
-    h2, w2 = hr_h // 4, hr_w // 4
-    gray = np.zeros(batch, np.float32)
-    gray[::3] = 1
-    return {
-        "blur1": 1,
-        "resize1": {"mode": od.BICUBIC, "out_h": h1, "out_w": w1, "scale": 0.5},
-        "noise1": {"type": "gaussian", "sigma": rng.uniform(1, 30, size=batch).astype(np.float32), "gray": gray,
-                   "noise_color": rng.standard_normal((batch, 3, h1, w1), dtype=np.float32),
-                   "noise_gray": rng.standard_normal((h1, w1), dtype=np.float32)},
-        "jpeg1_quality": rng.uniform(30, 95, size=batch).astype(np.float32),
-        "blur2": 1,
-        "resize2": {"mode": od.BILINEAR, "out_h": h2, "out_w": w2, "scale": None},
-        "noise2": {"type": "poisson", "scale": rng.uniform(0.05, 2.5, size=batch).astype(np.float32), "gray": gray,
-                   "samples_color": None},
-        "final_order": 0,
-        "resize3": {"mode": od.AREA, "out_h": h2, "out_w": w2, "scale": None},
-        "jpeg2_quality": rng.uniform(30, 95, size=batch).astype(np.float32),
-        "crop": {"hr_top": 0, "hr_left": 0, "image_size": min(256, hr_h), "upscale": 4},
-    }
+_spec = _ilu.spec_from_file_location("_resr_plan", _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))),
+                                                                   "real_esrgan-pytorch_b200", "plan.py"))
+_plan = _ilu.module_from_spec(_spec)
+_spec.loader.exec_module(_plan)
+synth_plan = _plan.synth_plan
+canonical_plan_s0 = _plan.canonical_plan_s0

@@ -3,6 +3,7 @@
 Host-side mirror of the reference's Python API for those paths (same names, arguments and error behaviour):
   model.Generator / ResidualDenseBlock / ResidualResidualDenseBlock      (/root/reference/model.py)
   imgproc.filter2d_torch / USMSharp / DiffJPEG / random_add_*_noise_torch / random_crop (/root/reference/imgproc.py)
+  plan.synth_plan / canonical_plan_s0: host decisions + host-drawn tensors of train_realesrnet.py:267-377
 Everything dispatches through ctypes into the C ABI of lib/libresr.so (include/resr.h). There is no CPU
 fallback: importing works anywhere, computing needs the built library and a B200.
 """
@@ -10,5 +11,6 @@ from . import _lib  # noqa: F401
 from . import autograd  # noqa: F401
 from . import imgproc  # noqa: F401
 from . import model  # noqa: F401
+from . import plan  # noqa: F401
 
-__all__ = ["_lib", "autograd", "imgproc", "model"]
+__all__ = ["_lib", "autograd", "imgproc", "model", "plan"]

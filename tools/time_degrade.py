@@ -3,11 +3,10 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import resr_b200
-from oracle import plan as oplan
 ip = resr_b200.imgproc
 B, H, W = 16, 256, 256
 dev = torch.device("cuda")
-plan = oplan.canonical_plan_s0(B, H, W, seed=0)
+plan = resr_b200.plan.canonical_plan_s0(B, H, W, seed=0)
 hr = torch.rand(B, 3, H, W, device=dev)
 k = torch.zeros(B, 21, 21); ax = torch.arange(21) - 10.0
 for i in range(B):
