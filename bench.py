@@ -337,7 +337,12 @@ def run_ours(args):
             "gpu_launches": launches * args.steps,
             "clocks": clocks.summary(),
             "roofline": {"bound": "tensor", "achieved": tflops, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                         "frac": tflops / peaks["tf_sustained"], "traffic": None,
+                         "frac": tflops / peaks["tf_sustained"],
+                         # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the five launches of one
+                         # dense block (345 of the 351 launches are such blocks) at cfg3: ncu --set full capture in
+                         # profiles/r01_v5_rdb_ncu_full.csv (182 / 323 / 328 / 470 / 525 MB; algorithmic 201 / 268 / 335 /
+                         # 402 / 671 MB -- conv5's residual and second slice hit L2)
+                         "traffic": 365.7e6 if (N, H, W) == (64, 128, 128) else None,
                          "kernel": "conv3x3_tc_kernel (351 launches per forward; algorithmic FLOPs 35,853,696 per LR pixel)",
                          "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)"},
         }
