@@ -67,6 +67,16 @@ int resr_generator_forward(resr_generator_t* g, const float* x, float* y, int n,
 int resr_generator_forward_host(resr_generator_t* g, const float* x_host, float* y_host, int n, int h, int w,
                                 void* workspace, size_t workspace_bytes, void* stream);
 
+/* Pipelined serving variant of forward_host: returns as soon as the work is queued. Two staging slots rotate, the
+ * H2D copy of call k+1 and the D2H copy of call k-1 run on the handle's own copy streams while call k computes on
+ * `stream`. y_host of a call is complete after resr_generator_host_sync (or after the second following call returned
+ * from its internal wait). The workspace must hold resr_generator_workspace_bytes + 2 x (1 KB-aligned input + output).
+ * Use ONE stream and ONE workspace per handle for all async calls. */
+int resr_generator_forward_host_async(resr_generator_t* g, const float* x_host, float* y_host, int n, int h, int w,
+                                      void* workspace, size_t workspace_bytes, void* stream);
+/* Waits for every queued async call of this handle (copies included). */
+int resr_generator_host_sync(resr_generator_t* g);
+
 /* Number of kernels of this library that one resr_generator_forward launches (for bench accounting). */
 int resr_generator_launches_per_forward(void);
 

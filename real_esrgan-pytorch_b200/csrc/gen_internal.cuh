@@ -100,6 +100,10 @@ struct resr_generator {
     const void* step_key[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int step_shape[3] = {0, 0, 0};
     bool step_graph_failed = false;
+    // pipelined host path (generator.cu): copy streams, per-slot events, call counter
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_fwd[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+    unsigned long long host_calls = 0;
     // second stream of the backward pass: the weight-gradient chain of a layer runs beside the data-gradient chain
     cudaStream_t side_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_dy = nullptr, ev_join = nullptr;

@@ -334,6 +334,13 @@ void resr_generator_destroy(resr_generator_t* g) {
     cudaFree(g->wpack_t);
     cudaFree(g->zero_bias);
     if (g->step_exec) cudaGraphExecDestroy(g->step_exec);
+    if (g->h2d_stream) cudaStreamDestroy(g->h2d_stream);
+    if (g->d2h_stream) cudaStreamDestroy(g->d2h_stream);
+    for (int i = 0; i < 2; ++i) {
+        if (g->ev_h2d[i]) cudaEventDestroy(g->ev_h2d[i]);
+        if (g->ev_fwd[i]) cudaEventDestroy(g->ev_fwd[i]);
+        if (g->ev_d2h[i]) cudaEventDestroy(g->ev_d2h[i]);
+    }
     if (g->side_stream) cudaStreamDestroy(g->side_stream);
     if (g->ev_fork) cudaEventDestroy(g->ev_fork);
     if (g->ev_dy) cudaEventDestroy(g->ev_dy);
@@ -411,6 +418,57 @@ int resr_generator_forward_host(resr_generator_t* g, const float* x_host, float*
     if (cudaMemcpyAsync(y_host, yd, out_bytes, cudaMemcpyDeviceToHost, s) != cudaSuccess) return set_error(RESR_E_CUDA, "D2H failed");
     const cudaError_t e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) return set_error(RESR_E_CUDA, "forward_host: %s", cudaGetErrorString(e));
+    return RESR_OK;
+}
+
+int resr_generator_forward_host_async(resr_generator_t* g, const float* x_host, float* y_host, int n, int h, int w,
+                                      void* workspace, size_t workspace_bytes, void* stream) {
+    if (!g || !x_host || !y_host) return set_error(RESR_E_INVALID, "null argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t in_bytes = static_cast<size_t>(n) * 3 * h * w * 4, out_bytes = in_bytes * 16;
+    const size_t need = resr_generator_workspace_bytes(n, h, w);
+    const size_t in_al = (in_bytes + 1023) / 1024 * 1024, out_al = (out_bytes + 1023) / 1024 * 1024;
+    const size_t off0 = (need + 1023) / 1024 * 1024;
+    if (workspace_bytes < off0 + 2 * (in_al + out_al))
+        return set_error(RESR_E_NOMEM, "workspace too small for two host staging slots (need %zu)", off0 + 2 * (in_al + out_al));
+    if (!g->h2d_stream) {
+        if (cudaStreamCreateWithFlags(&g->h2d_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&g->d2h_stream, cudaStreamNonBlocking) != cudaSuccess)
+            return set_error(RESR_E_CUDA, "cannot create copy streams");
+        for (int i = 0; i < 2; ++i) {
+            cudaEventCreateWithFlags(&g->ev_h2d[i], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&g->ev_fwd[i], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&g->ev_d2h[i], cudaEventDisableTiming);
+        }
+    }
+    const int slot = static_cast<int>(g->host_calls & 1);
+    const bool reused = g->host_calls >= 2;  // this slot has been through a full cycle before
+    uint8_t* base = static_cast<uint8_t*>(workspace) + off0 + static_cast<size_t>(slot) * (in_al + out_al);
+    float* xd = reinterpret_cast<float*>(base);
+    float* yd = reinterpret_cast<float*>(base + in_al);
+    // H2D into the slot once the forward that last read it is done
+    if (reused) cudaStreamWaitEvent(g->h2d_stream, g->ev_fwd[slot], 0);
+    if (cudaMemcpyAsync(xd, x_host, in_bytes, cudaMemcpyHostToDevice, g->h2d_stream) != cudaSuccess) return set_error(RESR_E_CUDA, "H2D failed");
+    cudaEventRecord(g->ev_h2d[slot], g->h2d_stream);
+    // forward once the input has landed and the slot's previous result has left the device
+    cudaStreamWaitEvent(s, g->ev_h2d[slot], 0);
+    if (reused) cudaStreamWaitEvent(s, g->ev_d2h[slot], 0);
+    const int rc = resr_generator_forward(g, xd, yd, n, h, w, workspace, need, stream);
+    if (rc != RESR_OK) return rc;
+    cudaEventRecord(g->ev_fwd[slot], s);
+    cudaStreamWaitEvent(g->d2h_stream, g->ev_fwd[slot], 0);
+    if (cudaMemcpyAsync(y_host, yd, out_bytes, cudaMemcpyDeviceToHost, g->d2h_stream) != cudaSuccess) return set_error(RESR_E_CUDA, "D2H failed");
+    cudaEventRecord(g->ev_d2h[slot], g->d2h_stream);
+    ++g->host_calls;
+    return RESR_OK;
+}
+
+int resr_generator_host_sync(resr_generator_t* g) {
+    if (!g) return set_error(RESR_E_INVALID, "null argument");
+    if (!g->d2h_stream) return RESR_OK;
+    cudaError_t e = cudaStreamSynchronize(g->h2d_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g->d2h_stream);
+    if (e != cudaSuccess) return set_error(RESR_E_CUDA, "host_sync: %s", cudaGetErrorString(e));
     return RESR_OK;
 }
 

@@ -164,6 +164,28 @@ class Generator(nn.Module):
         return y_host
 
 
+    @torch.no_grad()
+    def infer_host_async(self, x_host: torch.Tensor, y_host: torch.Tensor, device=None) -> torch.Tensor:
+        """Pipelined serving call: queues H2D + forward + D2H and returns; copies of neighbouring calls overlap this call's
+        compute (two staging slots inside the workspace). `x_host` / `y_host` must be pinned fp32 tensors that stay alive
+        and untouched until `host_sync()` (or two further calls) — alternate between two `y_host` buffers."""
+        device = device or next(self.parameters()).device
+        n, _, h, w = x_host.shape
+        if not (x_host.is_pinned() and y_host.is_pinned()) or x_host.dtype != torch.float32 or not x_host.is_contiguous():
+            raise _lib.ResrError("infer_host_async needs pinned contiguous fp32 host tensors")
+        self._ensure_packed()
+        extra = 2 * (x_host.numel() * 4 * 17 + 4096)
+        ws = self._get_workspace(n, h, w, device, extra)
+        wp, wbytes = self._aligned(ws)
+        with torch.cuda.device(device):
+            _lib.check(_lib.lib().resr_generator_forward_host_async(self._native(), _lib.ptr(x_host), _lib.ptr(y_host), n, h,
+                                                                    w, wp, wbytes, _lib.stream_ptr()))
+        return y_host
+
+    def host_sync(self):
+        _lib.check(_lib.lib().resr_generator_host_sync(self._native()))
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # Large-image inference by spatial tiles with a receptive-field halo (BASELINE.json configs[4]; new functionality around
 # the unchanged reference API: inference.py:52-53 runs one whole-image forward). Tile indexing is integer arithmetic.

@@ -94,3 +94,22 @@ def test_tiled_inference_matches_whole_image():
     for r in range(2):
         resr_b200.model.infer_tiled(g, x, 32, 128, 16, rank=r, world=2, out=out)
     assert torch.equal(out, tiled)
+
+
+@pytest.mark.gpu
+def test_pipelined_host_calls_match_blocking_call():
+    """resr_generator_forward_host_async: rotating staging slots, copies overlapping compute; results equal the blocking
+    host call bit for bit, in order."""
+    import resr_b200
+    g, _ = _make(5)
+    torch.manual_seed(3)
+    xs = [torch.rand(2, 3, 24, 136).pin_memory() for _ in range(5)]
+    ref = [g.infer_host(x).clone() for x in xs]
+    outs = [torch.empty(2, 3, 96, 544).pin_memory() for _ in range(5)]
+    for x, o in zip(xs, outs):
+        g.infer_host_async(x, o)
+    g.host_sync()
+    for r, o in zip(ref, outs):
+        assert torch.equal(r, o)
+    with pytest.raises(resr_b200._lib.ResrError):
+        g.infer_host_async(torch.rand(1, 3, 8, 8), torch.empty(1, 3, 32, 32))  # not pinned
