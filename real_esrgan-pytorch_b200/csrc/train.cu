@@ -214,6 +214,7 @@ struct ConvIO {
     const uint8_t* wpack = nullptr; const float* bias = nullptr;
     int nout = 32, nslices = 1, nchunks = 1, fmt = 1;
     int kvalid = 0;  // real input channels (0: every chunk is full)
+    bool backward = false;
     void* out16 = nullptr; int out16_c = 64, out16_choff = 0, out16_fmt = 1, out16_up2 = 0, out16_fixed = 0; unsigned no16_mask = 0;
     float* outf = nullptr; int outf_c = 64, outf_choff = 0; unsigned noutf_mask = 0;
     const float* res1 = nullptr; int res1_c = 64, res_choff = 0; unsigned nores_mask = 0;
@@ -258,7 +259,10 @@ static int launch_conv_io(const resr_generator* g, const Geo& q, int N, const Co
     a.out_nchw = io.out_nchw; a.out_nchw_raw = io.out_nchw_raw; a.out_nchw_c = io.out_nchw_c;
     if (!conv3x3_plan_smem(&a, io.nout)) rc |= 1 << 20;
     if (rc != 0) return set_error(RESR_E_CUDA, "conv planning failed (%d)", rc);
-    const cudaError_t e = conv3x3_launch(m, a, io.nout, io.nslices, g->num_sms, s);
+    // the data-gradient convolutions leave some SMs to the weight-gradient chain running on the side stream
+    static const int bwd_sms = getenv("RESR_TRAIN_BWD_SMS") ? atoi(getenv("RESR_TRAIN_BWD_SMS")) : 0;
+    const int sms = (io.backward && bwd_sms > 0 && bwd_sms < g->num_sms) ? bwd_sms : g->num_sms;
+    const cudaError_t e = conv3x3_launch(m, a, io.nout, io.nslices, sms, s);
     if (e != cudaSuccess) return set_error(RESR_E_CUDA, "conv launch: %s", cudaGetErrorString(e));
     return RESR_OK;
 }
@@ -479,7 +483,7 @@ ConvIO bwd_io(const resr_generator* g, int k) {
     const ConvSpec& c = table().c[k];
     ConvIO io;
     io.wpack = g->wpack_t + c.wt_off; io.bias = g->zero_bias;
-    io.nout = 32; io.nslices = c.t_nslices; io.nchunks = c.t_nchunks; io.fmt = 1; io.kvalid = c.cout;
+    io.nout = 32; io.nslices = c.t_nslices; io.nchunks = c.t_nchunks; io.fmt = 1; io.kvalid = c.cout; io.backward = true;
     return io;
 }
 
