@@ -166,9 +166,9 @@ def degradation_bench(device, steps, warmup, peaks, B=16):
     gbs = stage_bytes / (ms * 1e-3) / 1e9
     return {"metric": "degraded pairs/s", "value": B / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms,
             "config": {"workload": f"second-order degradation, {B}x3x256x256 HR -> {B}x3x64x64 LR, canonical plan S0 "
-                                   "(SURVEY.md §8d): Gaussian noise tensors host-fed and resident, Poisson draws by "
-                                   "torch.poisson inside the timed region; one CUDA-graph replay per batch"},
-            "gpu_launches_per_step": 18,
+                                   "(SURVEY.md §8d): Gaussian noise tensors host-fed and resident, Poisson draws made "
+                                   "inside the fused noise kernel (Philox) in the timed region; one CUDA-graph replay per batch"},
+            "gpu_launches_per_step": 14,
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
                          "traffic": None, "algorithmic_bytes_per_step": stage_bytes,
                          "note": "stage-sum bytes / whole-pipeline time; blur stencils are FMA-bound (SURVEY.md §8d caveat)"}}

@@ -157,6 +157,15 @@ int resr_poisson_noise_apply(const float* image, float* out, const float* scale,
                              const float* samples_color, const float* samples_gray, int b, int c, int h, int w, int clip,
                              int rounds, void* workspace, size_t workspace_bytes, int reuse_counts, void* stream);
 
+/* Production variant of resr_poisson_noise_apply: the Poisson draws are made inside the kernel (Philox4x32-10 counter RNG,
+ * one subsequence per draw; exact samplers: Hoermann's PTRS rejection for rate >= 10, multiplication method below), so no
+ * rate tensors and no sampler launches are needed: memset + presence bitmap + one fused kernel. gray == NULL: no sample uses
+ * the luma branch (imgproc.py:886). `call_counter`: one persistent device u64 owned by the caller; every call (and every
+ * replay of a captured CUDA graph) increments it and draws from a fresh Philox offset. */
+int resr_poisson_noise_sampled(const float* image, float* out, const float* scale, const float* gray, int b, int c, int h, int w,
+                               int clip, int rounds, unsigned long long seed, unsigned long long* call_counter,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
 /* imgproc.DiffJPEG(differentiable=False).forward(image, quality[b]) (imgproc.py:1462-1494). quality is NOT modified;
  * the factor the reference writes back in place (imgproc.py:1478-1479) is returned in factor_out[b] (may be NULL).
  * clamp_input=1 fuses the torch.clamp(out, 0, 1) of train_realesrnet.py:308. q_y/q_cb/q_cr (all or none): dump of the

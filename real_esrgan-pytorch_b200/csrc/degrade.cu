@@ -1,6 +1,7 @@
 // Hot path 2: second-order degradation ops as CUDA kernels for sm_100a (fp32 NCHW images, as the reference holds
 // them). Reference: /root/reference/imgproc.py (filter2d_torch :1089, USMSharp :1514, noise :829-1086, DiffJPEG
 // :1124-1494, random_crop :1894) and the sequencing in train_realesrnet.py:267-377. See DESIGN.md §5.
+#include <curand_kernel.h>
 #include <cmath>
 #include <cstring>
 
@@ -502,7 +503,8 @@ __global__ void __launch_bounds__(256) gaussian_noise_kernel(const float* __rest
 // Presence bitmap of the 256 u8 levels per sample, colour image (all channels) and luma: replaces the per-sample
 // torch.unique host syncs of imgproc.py:892, 903. bitmaps: [B][2][8] uint32 (0 = colour, 1 = gray), pre-zeroed.
 __global__ void __launch_bounds__(256) u8_presence_kernel(const float* __restrict__ x, unsigned* __restrict__ bitmaps, int C,
-                                                          int HW, int want_gray) {
+                                                          int HW, int want_gray, unsigned long long* __restrict__ call_counter) {
+    if (call_counter && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *call_counter += 1;  // sampled mode
     __shared__ unsigned sbits[16];
     if (threadIdx.x < 16) sbits[threadIdx.x] = 0;
     __syncthreads();
@@ -566,6 +568,97 @@ __global__ void __launch_bounds__(256) poisson_noise_kernel(const float* __restr
             n = __fmul_rn(n, sc);                                               // imgproc.py:914
             out[o] = noise_post(__fadd_rn(in3[c], n), clip, rounds);
         }
+    }
+}
+
+// Same arithmetic with the Poisson draws made in the kernel (production mode of the plan-driven pipeline: no rate tensors,
+// no library sampler launches): Philox4x32-10 counter RNG, one subsequence per pixel, `*counter` advances once per call
+// (bumped by the presence kernel that runs before), exact rejection / multiplication samplers on top of it (poisson_draw;
+// cuRAND's header-only Philox generator supplies the uniforms). vals = 2 ** ceil(log2(#unique)) come straight from the 256-bit presence bitmaps.
+__device__ __forceinline__ float vals_of(const unsigned* __restrict__ bm8) {
+    int n = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) n += __popc(bm8[w]);
+    int v = 1;
+    while (v < n) v <<= 1;
+    return static_cast<float>(v);
+}
+
+// Poisson(lam) from a Philox stream. lam >= 10: PTRS, Hoermann's transformed rejection with squeeze (the algorithm NumPy and
+// torch's CPU sampler use; ~1.1 iterations, two uniforms each). lam < 10:
+// multiplication method (lam + 1 uniforms on average). Both are exact samplers.
+__device__ __forceinline__ float poisson_draw(curandStatePhilox4_32_10_t* st, float lam) {
+    if (lam <= 0.f) return 0.f;
+    if (lam < 10.f) {
+        const float enlam = __expf(-lam);
+        float prod = curand_uniform(st);
+        int k = 0;
+        while (prod > enlam) {
+            prod *= curand_uniform(st);
+            ++k;
+        }
+        return static_cast<float>(k);
+    }
+    const float slam = sqrtf(lam), loglam = logf(lam);
+    const float b = 0.931f + 2.53f * slam;
+    const float a = -0.059f + 0.02483f * b;
+    const float invalpha = 1.1239f + 1.1328f / (b - 3.4f);
+    const float vr = 0.9277f - 3.6224f / (b - 2.f);
+    while (true) {
+        const float U = curand_uniform(st) - 0.5f;
+        const float V = curand_uniform(st);
+        const float us = 0.5f - fabsf(U);
+        const float k = floorf((2.f * a / us + b) * U + lam + 0.43f);
+        if (us >= 0.07f && V <= vr) return k;
+        if (k < 0.f || (us < 0.013f && V > us)) continue;
+        // exact test, reached by ~10 % of the proposals; fp32 logs / lgammaf put an absolute error of ~1e-4 on a log
+        // acceptance ratio, i.e. a relative bias of the acceptance probability far below the sampling noise
+        const float lhs = logf(V * invalpha / (a / (us * us) + b));
+        const float rhs = -lam + k * loglam - lgammaf(k + 1.f);
+        if (lhs <= rhs) return k;
+    }
+}
+
+__global__ void __launch_bounds__(256) poisson_noise_sampled_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                                                    const float* __restrict__ scale, const float* __restrict__ gray,
+                                                                    const unsigned* __restrict__ bitmaps,
+                                                                    const unsigned long long* __restrict__ counter,
+                                                                    unsigned long long seed, int with_gray, int B, int HW, int clip,
+                                                                    int rounds) {
+    // four threads per pixel: lanes 0..2 of a quad draw the colour channels, lane 3 the luma sample (the sampler's loop
+    // count grows with the rate, so the draws are spread over threads instead of being made one after the other)
+    const size_t total = static_cast<size_t>(B) * HW;
+    const unsigned long long call = *counter;
+    const size_t tid = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    const size_t idx = tid >> 2;
+    const int k = static_cast<int>(tid & 3);
+    const bool live = idx < total;
+    const size_t pi = live ? idx : 0;
+    const int b = pi / HW;
+    const int p = pi % HW;
+    const size_t base = static_cast<size_t>(b) * 3 * HW + p;
+    const float r = x[base], g = x[base + HW], bl = x[base + 2 * static_cast<size_t>(HW)];
+    const float vc = vals_of(bitmaps + b * 16);
+    const float vg = with_gray ? vals_of(bitmaps + b * 16 + 8) : 1.f;
+    const float qg = round_u8(gray_of(r, g, bl));
+    const float mine = k == 0 ? r : (k == 1 ? g : bl);
+    const float q = k < 3 ? round_u8(mine) : qg;                                 // imgproc.py:888-889, 901
+    const float v = k < 3 ? vc : vg;
+    float draw = 0.f;
+    if (live && (k < 3 || with_gray)) {
+        curandStatePhilox4_32_10_t st;
+        curand_init(seed, tid, call * 64ull, &st);
+        draw = poisson_draw(&st, __fmul_rn(q, v));                               // imgproc.py:895, 906
+    }
+    float n = __fsub_rn(__fdiv_rn(draw, v), q);                                  // imgproc.py:896-897, 906-907
+    const float ng = __shfl_sync(0xffffffffu, n, (threadIdx.x & 31) | 3);       // the quad's luma noise
+    if (live && k < 3) {
+        if (with_gray) {
+            const float gm = gray[b];
+            n = __fadd_rn(__fmul_rn(n, 1.f - gm), __fmul_rn(ng, gm));           // imgproc.py:910
+        }
+        n = __fmul_rn(n, scale[b]);                                             // imgproc.py:914
+        out[base + static_cast<size_t>(k) * HW] = noise_post(__fadd_rn(mine, n), clip, rounds);
     }
 }
 
@@ -812,7 +905,7 @@ static int poisson_prepare(const float* image, int b, int c, int h, int w, int w
     const int HW = h * w;
     int gx = (HW + 255) / 256;
     if (gx > 64) gx = 64;
-    u8_presence_kernel<<<dim3(gx, b), 256, 0, s>>>(image, *bm, c, HW, want_gray);
+    u8_presence_kernel<<<dim3(gx, b), 256, 0, s>>>(image, *bm, c, HW, want_gray, nullptr);
     unique_counts_kernel<<<(2 * b + 127) / 128, 128, 0, s>>>(*bm, *counts, *vals, b);
     RESR_LAUNCH_CHECK("poisson_prepare");
     return RESR_OK;
@@ -856,6 +949,26 @@ int resr_poisson_noise_apply(const float* image, float* out, const float* scale,
     poisson_noise_kernel<<<grid1d(static_cast<size_t>(b) * h * w), 256, 0, s>>>(image, out, scale, gray, samples_color,
                                                                               samples_gray, vals, b, h * w, clip, rounds);
     RESR_LAUNCH_CHECK("poisson_noise");
+    return RESR_OK;
+}
+
+int resr_poisson_noise_sampled(const float* image, float* out, const float* scale, const float* gray, int b, int c, int h, int w,
+                               int clip, int rounds, unsigned long long seed, unsigned long long* call_counter, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+    if (!image || !out || !scale || !workspace || !call_counter) return set_error(RESR_E_INVALID, "null argument");
+    if (c != 3) return set_error(RESR_E_INVALID, "Poisson noise expects RGB images");
+    if (workspace_bytes < resr_poisson_workspace_bytes(b)) return set_error(RESR_E_NOMEM, "Poisson workspace too small");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    unsigned* bm = static_cast<unsigned*>(workspace);
+    unsigned long long* counter = call_counter;  // advances on every call / CUDA-graph replay: fresh Philox offsets
+    cudaMemsetAsync(bm, 0, static_cast<size_t>(b) * 16 * 4, s);
+    const int HW = h * w;
+    int gx = (HW + 255) / 256;
+    if (gx > 64) gx = 64;
+    u8_presence_kernel<<<dim3(gx, b), 256, 0, s>>>(image, bm, c, HW, gray != nullptr, counter);
+    poisson_noise_sampled_kernel<<<static_cast<unsigned>((static_cast<size_t>(b) * HW * 4 + 255) / 256), 256, 0, s>>>(image, out, scale, gray, bm, counter, seed,
+                                                                                  gray != nullptr, b, HW, clip, rounds);
+    RESR_LAUNCH_CHECK("poisson_noise_sampled");
     return RESR_OK;
 }
 

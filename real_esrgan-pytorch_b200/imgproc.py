@@ -207,6 +207,30 @@ def poisson_noise_apply(image, scale, gray, samples_color, samples_gray, clip=Tr
     return out
 
 
+_pctr_cache = {}
+
+
+def poisson_noise_sampled(image, scale, gray, seed: int, clip=True, rounds=False):
+    """Production form of the Poisson stage for the plan-driven pipeline: draws are made inside the kernel (Philox
+    counter RNG + exact PTRS / multiplication samplers), so the stage is a memset, the
+    presence-bitmap kernel and ONE fused kernel. `gray=None`: no sample takes the luma branch. Every call (and every CUDA
+    graph replay) advances a per-device call counter, i.e. draws fresh samples for a fixed `seed`."""
+    b, c, h, w = image.size()
+    x = _prep(image)
+    out = torch.empty_like(x)
+    ws = _poisson_workspace(b, x.device)
+    key = (x.device.type, x.device.index)
+    ctr = _pctr_cache.get(key)
+    if ctr is None:
+        ctr = torch.zeros(1, dtype=torch.int64, device=x.device)
+        _pctr_cache[key] = ctr
+    _lib.check(_lib.lib().resr_poisson_noise_sampled(
+        _lib.ptr(x), _lib.ptr(out), _lib.ptr(_prep(scale)), _lib.ptr(None if gray is None else _prep(gray)), b, c, h, w,
+        int(bool(clip)), int(bool(rounds)), int(seed) & (2 ** 64 - 1), _lib.ptr(ctr), _lib.ptr(ws), ws.numel(),
+        _lib.stream_ptr()))
+    return out
+
+
 def random_add_poisson_noise_torch(image: torch.Tensor, scale_range: tuple = (0, 1.0), gray_prob: int = 0,
                                    clip: bool = True, rounds: bool = False) -> torch.Tensor:
     """Reference imgproc.py:1060-1086; draws in the reference order: scale, gray flags, [gray Poisson], colour Poisson."""
@@ -280,9 +304,12 @@ def _noise(x, p):
                                     _dev(p.get("noise_gray"), dev))
     sc, sg = p.get("samples_color"), p.get("samples_gray")
     gray = _dev(p["gray"], dev)
-    if sc is None:  # plan without recorded draws: sample from the rates with the torch generator
+    if sc is None:  # plan without recorded draws
         g_any = p.get("gray_any")  # host-side decision recorded by plan_to_device (no device sync)
         with_gray = bool(gray.sum() > 0) if g_any is None else bool(g_any)
+        if p.get("sampler", "device") == "device":  # draws inside the fused kernel
+            return poisson_noise_sampled(x, _dev(p["scale"], dev), gray if with_gray else None, int(p.get("seed", 0)))
+        # "torch": sample from the rates with the torch generator (same sampler, three more launches)
         rc, rg = poisson_rates(x, with_gray)
         sg = torch.poisson(rg) if with_gray else None
         sc = torch.poisson(rc)

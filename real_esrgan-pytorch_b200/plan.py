@@ -60,8 +60,10 @@ def synth_plan(batch, hr_h, hr_w, seed, image_size=256, upscale=4):
             if gray.sum() > 0:
                 p["noise_gray"] = rng.standard_normal((h, w), dtype=np.float32)
         else:
+            # Poisson draws depend on the image: made on the device (sampler "device": inside the fused noise kernel,
+            # Philox seed below; "torch": torch.poisson on the rate tensors), or host-fed through samples_color / _gray
             p = {"type": "poisson", "scale": rng.uniform(*sc_rng, size=batch).astype(np.float32), "gray": gray,
-                 "samples_color": None}  # Poisson draws depend on the image: filled in by fill_poisson_samples
+                 "samples_color": None, "sampler": "device", "seed": int(rng.integers(1, 2 ** 31))}
         return p
 
     plan["noise1"] = noise(h1, w1, (1, 30), (0.05, 3))
@@ -97,7 +99,7 @@ def canonical_plan_s0(batch, hr_h=256, hr_w=256, seed=0):
         "blur2": 1,
         "resize2": {"mode": BILINEAR, "out_h": h2, "out_w": w2, "scale": None},
         "noise2": {"type": "poisson", "scale": rng.uniform(0.05, 2.5, size=batch).astype(np.float32), "gray": gray,
-                   "samples_color": None},
+                   "samples_color": None, "sampler": "device", "seed": int(rng.integers(1, 2 ** 31))},
         "final_order": 0,
         "resize3": {"mode": AREA, "out_h": h2, "out_w": w2, "scale": None},
         "jpeg2_quality": rng.uniform(30, 95, size=batch).astype(np.float32),

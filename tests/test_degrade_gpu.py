@@ -261,3 +261,47 @@ def test_kernel_synthesis_device(golden_dir):
     assert k1.shape == (6, 21, 21) and k1.dtype == torch.float32
     for t in (k1, k2, sk):
         assert np.abs(t.sum((1, 2)).cpu().numpy() - 1).max() < 1e-5
+
+
+@pytest.mark.gpu
+def test_poisson_sampled_in_kernel_statistics():
+    """resr_poisson_noise_sampled: the draws made inside the fused kernel are Poisson(q * vals) (imgproc.py:895, 906) in
+    the small-rate and in the large-rate regime of the sampler, the luma branch is shared by the three channels, and
+    consecutive calls draw fresh samples."""
+    import scipy.stats as st
+    import resr_b200
+    ip = resr_b200.imgproc
+    dev = "cuda"
+    b, h, w = 2, 160, 256
+    levels = torch.empty(b, 3, h, w)
+    levels[:, :, :40] = 3.0
+    levels[:, :, 40:80] = 10.0
+    levels[:, :, 80:] = 200.0
+    levels[:, :, 0, :256] = torch.arange(256.0)          # all 256 levels present -> vals = 256 (colour and luma)
+    x = (levels / 255.0).to(dev)
+    scale = torch.ones(b, device=dev)
+    out = ip.poisson_noise_sampled(x, scale, None, seed=1234, clip=False)
+    draws = ((out - x) + x) * 256.0                        # n = draw / vals - q, scale = 1, q = x on the u8 grid
+    for lv, rows in ((3.0, slice(1, 40)), (10.0, slice(40, 80)), (200.0, slice(80, 160))):
+        lam = lv / 255.0 * 256.0
+        d = draws[:, :, rows].reshape(-1).double().cpu().numpy()
+        assert abs(d - d.round()).max() < 2e-2            # integers up to fp32 rounding of the affine map
+        d = d.round()
+        n = d.size
+        assert abs(d.mean() - lam) < 5 * (lam / n) ** 0.5
+        assert abs(d.var() - lam) < 0.05 * lam
+        ks = st.kstest(d + np.random.default_rng(0).uniform(-0.5, 0.5, n), lambda t: _pois_cont_cdf(t, lam, st)).statistic
+        assert ks < 0.02, ks
+    out2 = ip.poisson_noise_sampled(x, scale, None, seed=1234, clip=False)
+    assert not torch.equal(out, out2)                     # the call counter advanced
+    gray = torch.ones(b, device=dev)
+    og = ip.poisson_noise_sampled(x, scale, gray, seed=7, clip=False)
+    nz = og - x
+    assert (nz[:, 0] - nz[:, 1]).abs().max().item() < 1e-6 and (nz[:, 0] - nz[:, 2]).abs().max().item() < 1e-6
+
+
+def _pois_cont_cdf(t, lam, st):
+    """CDF of Poisson(lam) + Uniform(-0.5, 0.5) (continuity-smoothed, so the KS statistic is meaningful)."""
+    k = np.floor(t + 0.5)
+    frac = t + 0.5 - k
+    return st.poisson.cdf(k - 1, lam) + frac * st.poisson.pmf(k, lam)
