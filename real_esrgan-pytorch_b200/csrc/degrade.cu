@@ -253,7 +253,7 @@ __device__ __forceinline__ void usm_window8(const float* __restrict__ p, int str
     }
 }
 
-__global__ void __launch_bounds__(256) usm_fused_kernel(const float* __restrict__ src, const float* __restrict__ x,
+__global__ void __launch_bounds__(512) usm_fused_kernel(const float* __restrict__ src, const float* __restrict__ x,
                                                         float* __restrict__ res, float* __restrict__ mask_or_out, int H,
                                                         int W, int stage, float weight, float threshold) {
     extern __shared__ float usm_sm[];
@@ -270,11 +270,11 @@ __global__ void __launch_bounds__(256) usm_fused_kernel(const float* __restrict_
 #pragma unroll
         for (int k = 0; k < 4; ++k) gxk[k] = min(max(reflect_idx(x0 + lane + 32 * k - r, W), 0), W - 1);
         const bool last_ok = lane + 96 < kUsmIn;
-        for (int ty = warp; ty < kUsmIn; ty += 32) {
+        for (int ty = warp; ty < kUsmIn; ty += 64) {
             float v[4][4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int t = ty + 8 * u;
+                const int t = ty + 16 * u;
                 const int gy = min(max(reflect_idx(y0 + min(t, kUsmIn - 1) - r, H), 0), H - 1);
                 const float* srow = src + pbase + static_cast<size_t>(gy) * W;
 #pragma unroll
@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(256) usm_fused_kernel(const float* __restrict_
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int t = ty + 8 * u;
+                const int t = ty + 16 * u;
                 if (t < kUsmIn) {
 #pragma unroll
                     for (int k = 0; k < 3; ++k) A[t * kUsmPitchA + lane + 32 * k] = v[u][k];
@@ -292,12 +292,12 @@ __global__ void __launch_bounds__(256) usm_fused_kernel(const float* __restrict_
         }
     }
     __syncthreads();
-    {   // horizontal pass: lane = row (within a group of 32 rows), 4 column groups of 8 per warp
+    {   // horizontal pass: lane = row (within a group of 32 rows), 2 column groups of 8 per warp (16 warps)
         const int row = (warp & 3) * 32 + lane;
         if (row < kUsmIn) {
 #pragma unroll 1
-            for (int cgi = 0; cgi < 4; ++cgi) {
-                const int c0 = ((warp >> 2) * 4 + cgi) * 8;
+            for (int cgi = 0; cgi < 2; ++cgi) {
+                const int c0 = ((warp >> 2) * 2 + cgi) * 8;
                 float acc[8];
                 usm_window8(A + row * kUsmPitchA + c0, 1, acc);
 #pragma unroll
@@ -306,11 +306,11 @@ __global__ void __launch_bounds__(256) usm_fused_kernel(const float* __restrict_
         }
     }
     __syncthreads();
-    // vertical pass: thread = column x (0..63), two groups of 8 rows
+    // vertical pass: thread = column x (0..63), one group of 8 rows each (8 groups)
     const int cx = threadIdx.x & 63;
 #pragma unroll 1
-    for (int rgi = 0; rgi < 2; ++rgi) {
-        const int r0 = ((threadIdx.x >> 6) * 2 + rgi) * 8;
+    for (int rgi = 0; rgi < 1; ++rgi) {
+        const int r0 = (threadIdx.x >> 6) * 8;
         float acc[8];
         usm_window8(Bm + r0 * kUsmPitchB + cx, kUsmPitchB, acc);
         const int gx = x0 + cx;
@@ -379,8 +379,8 @@ static int usm_impl(const float* x, float* out, float* ws, int B, int C, int H, 
             attr = true;
         }
         const dim3 gf((W + kUsmT - 1) / kUsmT, (H + kUsmT - 1) / kUsmT, B * C);
-        usm_fused_kernel<<<gf, 256, smem, s>>>(x, x, res, mask, H, W, 0, weight, threshold);
-        usm_fused_kernel<<<gf, 256, smem, s>>>(mask, x, res, out, H, W, 1, weight, threshold);
+        usm_fused_kernel<<<gf, 512, smem, s>>>(x, x, res, mask, H, W, 0, weight, threshold);
+        usm_fused_kernel<<<gf, 512, smem, s>>>(mask, x, res, out, H, W, 1, weight, threshold);
     } else {
         usm_hpass_kernel<<<gh, 256, sh, s>>>(x, tmp, H, W, k);
         usm_vpass_kernel<<<gv, 256, sv, s>>>(tmp, x, res, mask, H, W, k, 0, weight, threshold);
