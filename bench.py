@@ -328,6 +328,32 @@ def run_ours(args):
     ms_e2e = timed_e2e(lambda k: gen.infer_host_async(x_host, y_hosts[k & 1], device), gen.host_sync)
     checksum = float(y_host[0, :, ::64, ::64].double().sum())
 
+    # ---- degradation leg: every rank degrades its own batches (no collective on the path); aggregate = world x B / max time
+    deg = None
+    if not args.no_degrade:
+        big, err = None, None
+        try:
+            deg = degradation_bench(device, max(10, args.steps), args.warmup, peaks)
+            big = degradation_bench(device, 10, 3, peaks, B=256)  # large-batch regime
+        except Exception as e:  # keep the headline even if the secondary leg breaks
+            err = repr(e)
+        # the collective runs on every rank whatever happened above (a failed rank contributes +inf)
+        tt = torch.tensor([deg["ms_per_step"] if err is None else float("inf"),
+                           big["ms_per_step"] if err is None else float("inf")], device=device)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        m16, m256 = float(tt[0].item()), float(tt[1].item())
+        if err is not None or m16 == float("inf"):
+            deg = {"error": err or "another rank failed"}
+        else:
+            deg["ms_per_step"] = m16
+            deg["value"] = world * 16 / (m16 * 1e-3)
+            deg["n_gpus"] = world
+            deg["roofline"]["achieved"] = deg["roofline"]["algorithmic_bytes_per_step"] / (m16 * 1e-3) / 1e9
+            deg["roofline"]["frac"] = deg["roofline"]["achieved"] / peaks["hbm"]
+            deg["roofline"]["note"] += "; per GPU"
+            deg["large_batch"] = {"batch_per_gpu": 256, "value": world * 256 / (m256 * 1e-3), "unit": big["unit"], "ms_per_step": m256,
+                                  "roofline_frac": big["roofline"]["algorithmic_bytes_per_step"] / (m256 * 1e-3) / 1e9 / peaks["hbm"]}
     if rank == 0:
         px = N * H * W
         launches = L.lib().resr_generator_launches_per_forward()
@@ -358,14 +384,8 @@ def run_ours(args):
                          "kernel": "conv3x3_tc_kernel (351 launches per forward; algorithmic FLOPs 35,853,696 per LR pixel)",
                          "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)"},
         }
-        if not args.no_degrade:
-            try:
-                line["degradation"] = degradation_bench(device, max(10, args.steps), args.warmup, peaks)
-                big = degradation_bench(device, 10, 3, peaks, B=256)  # large-batch regime
-                line["degradation"]["large_batch"] = {"batch": 256, "value": big["value"], "unit": big["unit"],
-                                                      "ms_per_step": big["ms_per_step"], "roofline_frac": big["roofline"]["frac"]}
-            except Exception as e:  # keep the headline even if the secondary leg breaks
-                line["degradation"] = {"error": repr(e)}
+        if deg is not None:
+            line["degradation"] = deg
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_generator_baseline()
     train = None
