@@ -217,8 +217,29 @@ def training_bench(device, steps, warmup, peaks, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     tflops = 3 * FLOP_PER_LR_PIXEL * B * (H // 4) * (W // 4) / (ms * 1e-3) / 1e12
+    # optimizer side (outside the north-star metric): fused Adam + EMA over the flat vectors and the
+    # repack of the tensor-core weight tiles that the next forward needs
+    opt_info = None
+    try:
+        opt = resr_b200.optim.FlatAdamEMA(gen)
+        flat = ts.flat
+        for _ in range(2):
+            opt.step(flat)
+            gen._ensure_packed()
+        torch.cuda.synchronize()
+        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        o0.record()
+        for _ in range(5):
+            opt.step(flat)
+            gen._ensure_packed()
+        o1.record()
+        torch.cuda.synchronize()
+        oms = o0.elapsed_time(o1) / 5
+        opt_info = {"ms_per_step": oms, "what": "resr_adam_ema_step (36 B per parameter) + weight repack (702 pack launches)"}
+    except Exception as e:
+        opt_info = {"error": repr(e)}
     return {"metric": "training pairs/s", "value": world * B / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms, "n_gpus": world,
-            "loss": float(loss.item()), "cuda_graph": bool(ts.is_graph),
+            "loss": float(loss.item()), "cuda_graph": bool(ts.is_graph), "optimizer": opt_info,
             "config": {"workload": "per GPU: degradation (plan S0, CUDA graph) of 16x3x256x256 HR + RRDBNet x4 forward/L1/backward "
                                    "on 16x3x64x64 LR (one CUDA graph), flat-gradient NCCL all-reduce when n_gpus > 1; no optimizer"},
             "roofline": {"bound": "tensor", "achieved": tflops, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",

@@ -221,6 +221,17 @@ size_t resr_conv3x3_wgrad_workspace_bytes(int n, int h, int w, int cin, int cout
 int resr_conv3x3_wgrad(const void* x16, int x_cstride, int fmt_x, const void* dy16_bf16, int n, int h, int w, int cin,
                        int cout, float* dw, float* db, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- optimizer side of the training step ------------------------------------------------------
+ * One fused elementwise pass over flat fp32 vectors of n elements (resr_generator_num_params for the whole generator):
+ *   torch.optim.Adam(lr, betas=(beta1, beta2), eps) step number `step` (1-based; no weight decay, no amsgrad), arithmetic
+ *   order of torch's single-tensor implementation (train_realesrnet.py:197-200, 390), on grads * grad_scale
+ *   (grad_scale = 1 / loss_scale replaces GradScaler's unscale_, train_realesrnet.py:388-391), then
+ *   EMA.update(): shadow = (1 - ema_decay) * param + ema_decay * shadow (model.py:42-49); ema_shadow may be NULL.
+ * All pointers are device pointers; params / exp_avg / exp_avg_sq / ema_shadow are updated in place. */
+int resr_adam_ema_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* ema_shadow, size_t n,
+                       float lr, float beta1, float beta2, float eps, long long step, float ema_decay, float grad_scale,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,6 +11,7 @@ from . import _lib  # noqa: F401
 from . import autograd  # noqa: F401
 from . import imgproc  # noqa: F401
 from . import model  # noqa: F401
+from . import optim  # noqa: F401
 from . import plan  # noqa: F401
 
-__all__ = ["_lib", "autograd", "imgproc", "model", "plan"]
+__all__ = ["_lib", "autograd", "imgproc", "model", "optim", "plan"]

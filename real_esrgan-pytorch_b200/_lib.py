@@ -74,6 +74,8 @@ SIGNATURES = {
                                            ctypes.c_ulonglong, c_void_p, c_void_p, c_size_t, c_void_p]),
     "resr_jpeg": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                           c_void_p]),
+    "resr_adam_ema_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_float, c_float,
+                                   c_float, ctypes.c_longlong, c_float, c_float, c_void_p]),
     "resr_synthesize_kernels": (c_int, [POINTER(KernelParams), c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "resr_generator_train_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "resr_generator_forward_train": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),

@@ -102,7 +102,12 @@ class Generator(nn.Module):
     def _ensure_packed(self):
         ver = self._param_version()
         if self._packed_version != ver:
-            self._flat = self.flat_parameters()
+            master = getattr(self, "_flat_master", None)
+            first = next(self.parameters())
+            if master is not None and first.data_ptr() == master.data_ptr() and first.device == master.device:
+                self._flat = master  # parameters are views of one flat vector (optim.FlatAdamEMA): nothing to gather
+            else:
+                self._flat = self.flat_parameters()
             _lib.check(_lib.lib().resr_generator_load_params(self._native(), _lib.ptr(self._flat), _lib.stream_ptr()))
             self._packed_version = ver
 

@@ -120,3 +120,47 @@ def test_train_step_graph_replay_matches_eager():
             for p in g.parameters():
                 p.add_(p.grad, alpha=-1e-3)
     assert ts.is_graph
+
+
+@pytest.mark.gpu
+def test_flat_adam_ema_matches_torch_adam_and_reference_ema():
+    """resr_adam_ema_step vs torch.optim.Adam(lr, betas) (train_realesrnet.py:197-200) followed by the
+    reference EMA update (model.py:42-49), five steps on the generator's real parameter layout."""
+    import resr_b200
+    torch.manual_seed(0)
+    g = resr_b200.model.Generator(3, 3, 4).cuda()
+    keys = list(g.state_dict().keys())
+    ref_params = [p.detach().clone().requires_grad_(True) for p in g.parameters()]
+    ref_opt = torch.optim.Adam(ref_params, 2e-4, (0.9, 0.99))
+    shadow = [p.detach().clone() for p in ref_params]
+    opt = resr_b200.optim.FlatAdamEMA(g, lr=2e-4, betas=(0.9, 0.99), ema_decay=0.999)
+    assert list(g.state_dict().keys()) == keys and next(g.parameters()).data_ptr() == opt.flat.data_ptr()
+    x = torch.rand(1, 3, 16, 24, device="cuda")
+    with torch.no_grad():
+        y0 = g(x).clone()
+    n = opt.flat.numel()
+    for step in range(5):
+        grads = torch.randn(n, device="cuda") * (10.0 ** (step - 3))
+        pos = 0
+        for p in ref_params:
+            p.grad = grads[pos:pos + p.numel()].view_as(p).clone()
+            pos += p.numel()
+        ref_opt.step()
+        for s_, p in zip(shadow, ref_params):
+            s_.copy_((1.0 - 0.999) * p.data + 0.999 * s_)
+        opt.step(grads)
+    ref_flat = torch.cat([p.detach().reshape(-1) for p in ref_params])
+    ref_shadow = torch.cat([s_.reshape(-1) for s_ in shadow])
+    assert (opt.flat - ref_flat).abs().max().item() <= 2e-7
+    assert (opt.shadow - ref_shadow).abs().max().item() <= 2e-7
+    torch.testing.assert_close(torch.cat([p.detach().reshape(-1) for p in g.parameters()]), opt.flat, rtol=0, atol=0)
+    with torch.no_grad():
+        y1 = g(x)                                    # weights were repacked from the master copy
+    assert (y1 - y0).abs().max().item() > 0
+    opt.apply_shadow()
+    with torch.no_grad():
+        y2 = g(x)
+    opt.restore()
+    with torch.no_grad():
+        y3 = g(x)
+    assert torch.equal(y3, y1) and not torch.equal(y2, y1)
