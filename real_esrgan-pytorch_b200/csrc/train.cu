@@ -214,7 +214,6 @@ struct ConvIO {
     const uint8_t* wpack = nullptr; const float* bias = nullptr;
     int nout = 32, nslices = 1, nchunks = 1, fmt = 1;
     int kvalid = 0;  // real input channels (0: every chunk is full)
-    bool backward = false;
     void* out16 = nullptr; int out16_c = 64, out16_choff = 0, out16_fmt = 1, out16_up2 = 0, out16_fixed = 0; unsigned no16_mask = 0;
     float* outf = nullptr; int outf_c = 64, outf_choff = 0; unsigned noutf_mask = 0;
     const float* res1 = nullptr; int res1_c = 64, res_choff = 0; unsigned nores_mask = 0;
@@ -259,10 +258,7 @@ static int launch_conv_io(const resr_generator* g, const Geo& q, int N, const Co
     a.out_nchw = io.out_nchw; a.out_nchw_raw = io.out_nchw_raw; a.out_nchw_c = io.out_nchw_c;
     if (!conv3x3_plan_smem(&a, io.nout)) rc |= 1 << 20;
     if (rc != 0) return set_error(RESR_E_CUDA, "conv planning failed (%d)", rc);
-    // the data-gradient convolutions leave some SMs to the weight-gradient chain running on the side stream
-    static const int bwd_sms = getenv("RESR_TRAIN_BWD_SMS") ? atoi(getenv("RESR_TRAIN_BWD_SMS")) : 0;
-    const int sms = (io.backward && bwd_sms > 0 && bwd_sms < g->num_sms) ? bwd_sms : g->num_sms;
-    const cudaError_t e = conv3x3_launch(m, a, io.nout, io.nslices, sms, s);
+    const cudaError_t e = conv3x3_launch(m, a, io.nout, io.nslices, g->num_sms, s);
     if (e != cudaSuccess) return set_error(RESR_E_CUDA, "conv launch: %s", cudaGetErrorString(e));
     return RESR_OK;
 }
@@ -483,7 +479,7 @@ ConvIO bwd_io(const resr_generator* g, int k) {
     const ConvSpec& c = table().c[k];
     ConvIO io;
     io.wpack = g->wpack_t + c.wt_off; io.bias = g->zero_bias;
-    io.nout = 32; io.nslices = c.t_nslices; io.nchunks = c.t_nchunks; io.fmt = 1; io.kvalid = c.cout; io.backward = true;
+    io.nout = 32; io.nslices = c.t_nslices; io.nchunks = c.t_nchunks; io.fmt = 1; io.kvalid = c.cout;
     return io;
 }
 
@@ -710,26 +706,10 @@ int resr_conv3x3_wgrad(const void* x16, int x_cstride, int fmt_x, const void* dy
     nhwc16_to_cf_kernel<false><<<dim3(static_cast<unsigned>((P + 255) / 256), xr / 32), 256, 0, s>>>(static_cast<const uint16_t*>(x16), x_cstride, 0, cin, xr, P, w, fmt_x, xt, nullptr);
     if (db) cudaMemsetAsync(db, 0, cout * sizeof(float), s);
     nhwc16_to_cf_kernel<true><<<dim3(static_cast<unsigned>((P + 255) / 256), yr / 32), 256, 0, s>>>(static_cast<const uint16_t*>(dy16_bf16), 64, 0, cout, yr, P, w, 1, dyt, db);
-    if (getenv("RESR_DEBUG_SYNC")) {
-        const cudaError_t e = cudaStreamSynchronize(s);
-        fprintf(stderr, "[resr] transposes: %s\n", cudaGetErrorString(e));
-    }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    static unsigned long long* hang_host = nullptr;
-    if (getenv("RESR_DEBUG_SYNC") && !hang_host) {
-        cudaHostAlloc(&hang_host, 8, cudaHostAllocMapped);
-        *hang_host = 0;
-        unsigned long long* dptr = nullptr;
-        cudaHostGetDevicePointer(&dptr, hang_host, 0);
-        g_wgrad_hang_slot = dptr;
-    }
     const int rc = wgrad_launch(xt, xr, dyt, yr, n, h, w, cin, cout, partial, dw, nullptr, sms, s);
-    if (getenv("RESR_DEBUG_SYNC")) {
-        const cudaError_t e = cudaStreamSynchronize(s);
-        fprintf(stderr, "[resr] wgrad: rc=%d %s hang=%llx\n", rc, cudaGetErrorString(e), hang_host ? *hang_host : 0ull);
-    }
     if (rc != 0) return set_error(RESR_E_CUDA, "wgrad failed (%d)", rc);
     return RESR_OK;
 }

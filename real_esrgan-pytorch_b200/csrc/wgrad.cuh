@@ -16,8 +16,6 @@ struct WgradArgs {
     float* partial;       // [nsplit][n_mb][n_cs][3 dy][128 ci][96 = (dx, co)] fp32
     int nstages;
     int dy_rows;          // channel rows of one shifted copy of dY^T
-    int dbg_mode;         // experiments: 1 skip dY loads, 2 skip MMAs, 4 skip X load
-    volatile unsigned long long* hang;  // optional host-mapped debug slot: written before a barrier-timeout trap
 };
 
 size_t wgrad_partial_bytes(int num_sms);
@@ -26,6 +24,5 @@ size_t wgrad_partial_bytes(int num_sms);
 // output gradient [3][dy_channels][N][H][W] (dy_channels >= ceil(cout/32)*32; copy dx holds dY[.., x - dx + 1]). dw: OIHW fp32 [cout][cin][3][3]; db: [cout] or null.
 int wgrad_launch(const uint16_t* xt, int x_channels, const uint16_t* dyt, int dy_channels, int N, int H, int W, int cin, int cout,
                  float* partial, float* dw, float* db, int num_sms, cudaStream_t s);
-extern volatile unsigned long long* g_wgrad_hang_slot;  // set by tests (host-mapped), see train.cu
 
 }  // namespace resr

@@ -26,19 +26,7 @@ static constexpr int kWgMaxStages = 4;
 static constexpr uint32_t kWgDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
 __device__ __forceinline__ uint64_t wg_desc(uint32_t lo) { return (static_cast<uint64_t>(kWgDescHi) << 32) | lo; }
 
-volatile unsigned long long* g_wgrad_hang_slot = nullptr;
-
-__device__ __forceinline__ void wg_wait(uint64_t* bar, uint32_t parity, const WgradArgs& a, unsigned code) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 255u) == 0 && clock64() - t0 > 2000000000ll) {
-            if (a.hang) { *a.hang = (static_cast<unsigned long long>(code) << 32) | (blockIdx.y << 16) | threadIdx.x; __threadfence_system(); }
-            __trap();
-        }
-    }
-}
+__device__ __forceinline__ void wg_wait(uint64_t* bar, uint32_t parity, const WgradArgs&, unsigned) { mbar_wait(bar, parity); }
 
 __global__ void __launch_bounds__(256, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUtensorMap tmapDY, const WgradArgs a) {
@@ -81,10 +69,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constant
             wg_wait(empty + stage, phase ^ 1, a, 1);
             if (elect_one()) {
                 uint8_t* st = smem + stage * kWgStageBytes;
-                const uint32_t tx = ((a.dbg_mode & 4) ? 0 : 16384) + ((a.dbg_mode & 1) ? 0 : 9 * 4096);
-                if (tx) mbar_expect_tx(full + stage, tx); else mbar_arrive(full + stage);
-                if (!(a.dbg_mode & 4)) tma_load_4d(st, &tmapX, full + stage, xs * 64, y, n, mb * 128);
-                if (!(a.dbg_mode & 1))
+                mbar_expect_tx(full + stage, 16384 + 9 * 4096);
+                tma_load_4d(st, &tmapX, full + stage, xs * 64, y, n, mb * 128);
                 for (int dy = 0; dy < 3; ++dy)
                     for (int dx = 0; dx < 3; ++dx)
                         tma_load_4d(st + 16384 + (dy * 3 + dx) * 4096, &tmapDY, full + stage, xs * 64, y - dy + 1, n, dx * a.dy_rows + cs * 32);
@@ -103,7 +89,6 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constant
             if (elect_one()) {
                 const uint32_t a_lo = s_lo + stage * (kWgStageBytes >> 4);
                 const uint32_t b_lo = a_lo + (16384 >> 4);
-                if (!(a.dbg_mode & 2))
 #pragma unroll
                 for (int dy = 0; dy < 3; ++dy) {
 #pragma unroll
@@ -229,8 +214,6 @@ int wgrad_launch(const uint16_t* xt, int x_channels, const uint16_t* dyt, int dy
     a.kstages_total = static_cast<long long>(N) * H * a.segs_per_row;
     a.partial = partial;
     a.nstages = kWgMaxStages;
-    a.hang = g_wgrad_hang_slot;
-    a.dbg_mode = getenv("RESR_WG_DBG") ? atoi(getenv("RESR_WG_DBG")) : 0;
     const int units = a.n_mb * a.n_cs;
     // split-K over pixels: at least ~16 pipeline steps per CTA (every split writes a 147 KB partial tile)
     long long nsplit = num_sms / units;
@@ -248,10 +231,6 @@ int wgrad_launch(const uint16_t* xt, int x_channels, const uint16_t* dyt, int dy
         attr = true;
     }
     wgrad_tc_kernel<<<dim3(units, static_cast<unsigned>(nsplit)), 256, smem, s>>>(mx, my, a);
-    if (getenv("RESR_DEBUG_SYNC")) {
-        const cudaError_t e = cudaStreamSynchronize(s);
-        fprintf(stderr, "[resr] wgrad_tc_kernel grid (%d,%lld) smem %d: %s\n", units, nsplit, smem, cudaGetErrorString(e));
-    }
     const size_t pstride = static_cast<size_t>(a.n_mb) * a.n_cs * 3 * 128 * 96;
     wgrad_reduce_kernel<<<static_cast<unsigned>((pstride + 255) / 256), 256, 0, s>>>(partial, dw, cin, cout, a.n_mb, a.n_cs,
                                                                                     static_cast<int>(nsplit));
