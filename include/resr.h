@@ -157,6 +157,13 @@ int resr_poisson_noise_apply(const float* image, float* out, const float* scale,
                              const float* samples_color, const float* samples_gray, int b, int c, int h, int w, int clip,
                              int rounds, void* workspace, size_t workspace_bytes, int reuse_counts, void* stream);
 
+/* Production variant of resr_gaussian_noise_apply: the normal deviates are drawn inside the kernel (Philox4x32-10; the gray
+ * field is ONE H x W field shared by the batch, imgproc.py:853-856). gray == NULL: no sample uses the gray field.
+ * `call_state`: two persistent, zero-initialised device u64 owned by the caller ([0] call counter, [1] scratch): every
+ * call / CUDA-graph replay draws fresh noise for a fixed seed. */
+int resr_gaussian_noise_sampled(const float* image, float* out, const float* sigma, const float* gray, int b, int c, int h, int w,
+                                int clip, int rounds, unsigned long long seed, unsigned long long* call_state, void* stream);
+
 /* Production variant of resr_poisson_noise_apply: the Poisson draws are made inside the kernel (Philox4x32-10 counter RNG,
  * one subsequence per draw; exact samplers: Hoermann's PTRS rejection for rate >= 10, multiplication method below), so no
  * rate tensors and no sampler launches are needed: memset + presence bitmap + one fused kernel. gray == NULL: no sample uses

@@ -70,6 +70,8 @@ SIGNATURES = {
     "resr_poisson_rates": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "resr_poisson_noise_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                          c_int, c_int, c_int, c_void_p, c_size_t, c_int, c_void_p]),
+    "resr_gaussian_noise_sampled": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                            ctypes.c_ulonglong, c_void_p, c_void_p]),
     "resr_poisson_noise_sampled": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                            ctypes.c_ulonglong, c_void_p, c_void_p, c_size_t, c_void_p]),
     "resr_jpeg": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,

@@ -500,6 +500,42 @@ __global__ void __launch_bounds__(256) gaussian_noise_kernel(const float* __rest
     }
 }
 
+// Same arithmetic with the normal deviates drawn in the kernel (production mode of the plan-driven pipeline: no host-drawn
+// noise tensors): Philox4x32-10, subsequence = element index for the colour field, = pixel index (shared by all samples
+// and channels, imgproc.py:853-856: ONE H x W field) for the gray field with a different key. state[0] is the call counter
+// (advanced by the last block to finish, so every block of this launch reads the same value), state[1] the block ticket.
+__global__ void __launch_bounds__(256) gaussian_noise_sampled_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                                                     const float* __restrict__ sigma, const float* __restrict__ gray,
+                                                                     unsigned long long seed, unsigned long long* __restrict__ state,
+                                                                     int with_gray, int B, int C, int HW, int clip, int rounds) {
+    const size_t total = static_cast<size_t>(B) * C * HW;
+    const unsigned long long call = state[0];
+    for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int b = idx / (static_cast<size_t>(C) * HW);
+        const int p = idx % HW;
+        const float sg = sigma[b];
+        curandStatePhilox4_32_10_t st;
+        curand_init(seed, idx, call * 8ull, &st);
+        float n = __fdiv_rn(__fmul_rn(curand_normal(&st), sg), 255.f);  // imgproc.py:858
+        if (with_gray) {                                                 // imgproc.py:853-861
+            const float g = gray[b];
+            curand_init(seed ^ 0x9E3779B97F4A7C15ull, static_cast<unsigned long long>(p), call * 8ull, &st);
+            const float ng = __fdiv_rn(__fmul_rn(curand_normal(&st), sg), 255.f);
+            n = __fadd_rn(__fmul_rn(n, 1.f - g), __fmul_rn(ng, g));
+        }
+        out[idx] = noise_post(__fadd_rn(x[idx], n), clip, rounds);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&state[1], 1ull) == gridDim.x - 1) {
+            state[1] = 0;
+            state[0] = call + 1;
+        }
+    }
+}
+
 // Presence bitmap of the 256 u8 levels per sample, colour image (all channels) and luma: replaces the per-sample
 // torch.unique host syncs of imgproc.py:892, 903. bitmaps: [B][2][8] uint32 (0 = colour, 1 = gray), pre-zeroed.
 __global__ void __launch_bounds__(256) u8_presence_kernel(const float* __restrict__ x, unsigned* __restrict__ bitmaps, int C,
@@ -888,6 +924,16 @@ int resr_gaussian_noise_apply(const float* image, float* out, const float* sigma
     gaussian_noise_kernel<<<grid1d(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(image, out, sigma, gray, noise_color,
                                                                                        noise_gray, b, c, h * w, clip, rounds);
     RESR_LAUNCH_CHECK("gaussian_noise");
+    return RESR_OK;
+}
+
+int resr_gaussian_noise_sampled(const float* image, float* out, const float* sigma, const float* gray, int b, int c, int h, int w,
+                                int clip, int rounds, unsigned long long seed, unsigned long long* call_state, void* stream) {
+    if (!image || !out || !sigma || !call_state) return set_error(RESR_E_INVALID, "null argument");
+    const size_t total = static_cast<size_t>(b) * c * h * w;
+    gaussian_noise_sampled_kernel<<<grid1d(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(image, out, sigma, gray, seed, call_state,
+                                                                                               gray != nullptr, b, c, h * w, clip, rounds);
+    RESR_LAUNCH_CHECK("gaussian_noise_sampled");
     return RESR_OK;
 }
 

@@ -208,6 +208,25 @@ def poisson_noise_apply(image, scale, gray, samples_color, samples_gray, clip=Tr
 
 
 _pctr_cache = {}
+_gctr_cache = {}
+
+
+def gaussian_noise_sampled(image, sigma, gray, seed: int, clip=True, rounds=False):
+    """Production form of the Gaussian-noise stage for the plan-driven pipeline: the normal deviates are drawn inside the
+    kernel (Philox), the gray field is one H x W field shared by the batch (imgproc.py:853-856). `gray=None`: no sample uses
+    the gray field. Every call / CUDA-graph replay draws fresh noise for a fixed `seed`."""
+    b, c, h, w = image.size()
+    x = _prep(image)
+    out = torch.empty_like(x)
+    key = (x.device.type, x.device.index)
+    st = _gctr_cache.get(key)
+    if st is None:
+        st = torch.zeros(2, dtype=torch.int64, device=x.device)
+        _gctr_cache[key] = st
+    _lib.check(_lib.lib().resr_gaussian_noise_sampled(
+        _lib.ptr(x), _lib.ptr(out), _lib.ptr(_prep(sigma)), _lib.ptr(None if gray is None else _prep(gray)), b, c, h, w,
+        int(bool(clip)), int(bool(rounds)), int(seed) & (2 ** 64 - 1), _lib.ptr(st), _lib.stream_ptr()))
+    return out
 
 
 def poisson_noise_sampled(image, scale, gray, seed: int, clip=True, rounds=False):
@@ -300,6 +319,11 @@ def _dev(t, device):
 def _noise(x, p):
     dev = x.device
     if p["type"] == "gaussian":
+        if p.get("noise_color") is None:  # plan without host-drawn fields: draw inside the kernel
+            g_any = p.get("gray_any")
+            gray = _dev(p["gray"], dev)
+            with_gray = bool(gray.sum() > 0) if g_any is None else bool(g_any)
+            return gaussian_noise_sampled(x, _dev(p["sigma"], dev), gray if with_gray else None, int(p.get("seed", 0)))
         return gaussian_noise_apply(x, _dev(p["sigma"], dev), _dev(p["gray"], dev), _dev(p["noise_color"], dev),
                                     _dev(p.get("noise_gray"), dev))
     sc, sg = p.get("samples_color"), p.get("samples_gray")

@@ -43,9 +43,11 @@ def _resize_decision(rng, probs, lo, hi):
     return 1.0
 
 
-def synth_plan(batch, hr_h, hr_w, seed, image_size=256, upscale=4):
+def synth_plan(batch, hr_h, hr_w, seed, image_size=256, upscale=4, device_noise=False):
     """Draws a plan with the reference's probabilities/ranges (config.py:41-62, train_realesrnet.py:275-371) from a
-    numpy Generator. Noise tensors are drawn here too (numpy), so a plan is self-contained."""
+    numpy Generator. Gaussian noise fields are drawn here too (numpy) so that a plan is self-contained and replayable by
+    the oracle; `device_noise=True` leaves them out and the noise kernel draws them (Philox). Poisson draws depend on the
+    image and are always made on the device unless samples are attached to the plan."""
     rng = np.random.default_rng(seed)
     plan = {"blur1": int(rng.uniform() <= 1.0)}
     s = _resize_decision(rng, [0.2, 0.7, 0.1], 0.15, 1.5)
@@ -55,10 +57,13 @@ def synth_plan(batch, hr_h, hr_w, seed, image_size=256, upscale=4):
     def noise(h, w, sig_rng, sc_rng):
         gray = (rng.uniform(size=batch) < 0.4).astype(np.float32)
         if rng.uniform() < 0.5:
-            p = {"type": "gaussian", "sigma": rng.uniform(*sig_rng, size=batch).astype(np.float32), "gray": gray,
-                 "noise_color": rng.standard_normal((batch, 3, h, w), dtype=np.float32)}
-            if gray.sum() > 0:
-                p["noise_gray"] = rng.standard_normal((h, w), dtype=np.float32)
+            p = {"type": "gaussian", "sigma": rng.uniform(*sig_rng, size=batch).astype(np.float32), "gray": gray}
+            if device_noise:  # the normal deviates are drawn inside the noise kernel (Philox, seed below)
+                p["noise_color"], p["seed"] = None, int(rng.integers(1, 2 ** 31))
+            else:             # host-drawn fields travel with the plan (replayable by the oracle)
+                p["noise_color"] = rng.standard_normal((batch, 3, h, w), dtype=np.float32)
+                if gray.sum() > 0:
+                    p["noise_gray"] = rng.standard_normal((h, w), dtype=np.float32)
         else:
             # Poisson draws depend on the image: made on the device (sampler "device": inside the fused noise kernel,
             # Philox seed below; "torch": torch.poisson on the rate tensors), or host-fed through samples_color / _gray

@@ -305,3 +305,30 @@ def _pois_cont_cdf(t, lam, st):
     k = np.floor(t + 0.5)
     frac = t + 0.5 - k
     return st.poisson.cdf(k - 1, lam) + frac * st.poisson.pmf(k, lam)
+
+
+@pytest.mark.gpu
+def test_gaussian_noise_sampled_in_kernel_statistics():
+    """resr_gaussian_noise_sampled: N(0, (sigma/255)^2) colour noise per element, ONE gray field shared by the batch
+    (imgproc.py:853-861), fresh draws on every call."""
+    import scipy.stats as st
+    import resr_b200
+    ip = resr_b200.imgproc
+    dev = "cuda"
+    b, h, w = 3, 128, 192
+    x = torch.full((b, 3, h, w), 0.5, device=dev)
+    sigma = torch.tensor([5.0, 10.0, 20.0], device=dev)
+    out = ip.gaussian_noise_sampled(x, sigma, None, seed=99, clip=False)
+    for i in range(b):
+        z = ((out[i] - 0.5) * 255.0 / sigma[i]).reshape(-1).double().cpu().numpy()
+        assert abs(z.mean()) < 5 / np.sqrt(z.size) and abs(z.std() - 1) < 0.01
+        assert st.kstest(z, "norm").statistic < 0.01
+    c01 = np.corrcoef(((out[0, 0] - 0.5)).reshape(-1).cpu().numpy(), ((out[0, 1] - 0.5)).reshape(-1).cpu().numpy())[0, 1]
+    assert abs(c01) < 0.02                                        # channels are independent
+    assert not torch.equal(out, ip.gaussian_noise_sampled(x, sigma, None, seed=99, clip=False))
+    gray = torch.tensor([1.0, 1.0, 0.0], device=dev)
+    og = ip.gaussian_noise_sampled(x, sigma, gray, seed=5, clip=False)
+    n0, n1 = (og[0] - 0.5) / sigma[0], (og[1] - 0.5) / sigma[1]
+    assert (n0[0] - n0[1]).abs().max().item() < 1e-6              # gray: same field on the three channels ...
+    assert (n0 - n1).abs().max().item() < 1e-6                    # ... and on every gray sample of the batch
+    assert (og[2, 0] - og[2, 1]).abs().max().item() > 1e-3        # colour sample keeps independent channels
