@@ -235,7 +235,7 @@ def training_bench(device, steps, warmup, peaks, world):
         o1.record()
         torch.cuda.synchronize()
         oms = o0.elapsed_time(o1) / 5
-        opt_info = {"ms_per_step": oms, "what": "resr_adam_ema_step (36 B per parameter) + weight repack (702 pack launches)"}
+        opt_info = {"ms_per_step": oms, "what": "resr_adam_ema_step (36 B per parameter) + repack of all tensor-core weight tiles (2 launches)"}
     except Exception as e:
         opt_info = {"error": repr(e)}
     return {"metric": "training pairs/s", "value": world * B / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms, "n_gpus": world,

@@ -112,6 +112,8 @@ struct resr_generator {
     bool packed_t = false;
     const float* flat_params = nullptr;  // last parameter vector handed to load_params (device memory, caller-owned)
     uint8_t* wpack = nullptr;
+    void* pack_jobs = nullptr;    // device tables of the batched weight-pack kernel (forward / transposed)
+    void* pack_jobs_t = nullptr;
     float* bias = nullptr;
     bool loaded = false;
     int num_sms = 148;
@@ -126,6 +128,7 @@ int grid_for(size_t total, int block);
 // W'[ci][co][dy][dx] = W[co][ci][2-dy][2-dx] (cin/cout are the FORWARD channel counts; bias ignored).
 // (re)builds the transposed packs if the handle has them allocated or `force` is set (train.cu)
 void ensure_transposed_packs(resr_generator* g, cudaStream_t s, bool force);
+int launch_pack_all(resr_generator* g, const float* flat, int transposed, cudaStream_t s);
 void launch_pack_conv(const float* w, const float* bias, uint16_t* wp, float* bp, int cin, int cout, int nout, int nslices,
                       int nchunks, int fmt, int transposed, cudaStream_t s);
 }  // namespace resr

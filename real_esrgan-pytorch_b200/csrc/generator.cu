@@ -19,13 +19,12 @@ namespace resr {
 
 // OIHW fp32 -> [slice][chunk][dx][n = dy*NOUT + co][64 ch] 16-bit with the 128B shared-memory swizzle applied, so a
 // plain bulk copy drops a ready-to-use UMMA B operand into shared memory.
-__global__ void pack_conv_kernel(const float* __restrict__ w, const float* __restrict__ bias, uint16_t* __restrict__ wp,
-                                 float* __restrict__ bp, int cin, int cout, int nout, int nslices, int nchunks, int fmt,
-                                 int transposed) {
+__device__ __forceinline__ void pack_conv_body(const float* __restrict__ w, const float* __restrict__ bias, uint16_t* __restrict__ wp,
+                                               float* __restrict__ bp, int cin, int cout, int nout, int nslices, int nchunks, int fmt,
+                                               int transposed, size_t first, size_t stride) {
     const int NT = 3 * nout;
     const size_t total = static_cast<size_t>(nslices) * nchunks * 3 * NT * 64;
-    for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
-         idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    for (size_t idx = first; idx < total; idx += stride) {
         const int k = idx % 64;
         size_t t = idx / 64;
         const int n = t % NT;
@@ -59,8 +58,29 @@ __global__ void pack_conv_kernel(const float* __restrict__ w, const float* __res
     }
     const int nb = nslices * nout;
     if (bp)
-        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nb; i += gridDim.x * blockDim.x)
-            bp[i] = (i < cout && bias) ? bias[i] : 0.f;
+        for (size_t i = first; i < static_cast<size_t>(nb); i += stride) bp[i] = (i < static_cast<size_t>(cout) && bias) ? bias[i] : 0.f;
+}
+
+__global__ void pack_conv_kernel(const float* __restrict__ w, const float* __restrict__ bias, uint16_t* __restrict__ wp,
+                                 float* __restrict__ bp, int cin, int cout, int nout, int nslices, int nchunks, int fmt,
+                                 int transposed) {
+    pack_conv_body(w, bias, wp, bp, cin, cout, nout, nslices, nchunks, fmt, transposed,
+                   blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x, static_cast<size_t>(gridDim.x) * blockDim.x);
+}
+
+// All layers in one launch (blockIdx.y = layer): the repack after every optimizer step is 2 launches instead of 701.
+struct PackJob {
+    unsigned long long p_off, w_off, b_off;  // floats into the flat parameter vector, bytes into the pack, floats into the bias
+    int cin, cout, nout, nslices, nchunks, fmt;
+};
+__global__ void __launch_bounds__(256) pack_all_kernel(const float* __restrict__ flat, const PackJob* __restrict__ jobs,
+                                                       uint8_t* __restrict__ wpack, float* __restrict__ bias, int transposed) {
+    const PackJob j = jobs[blockIdx.y];
+    const float* w = flat + j.p_off;
+    const float* b = w + static_cast<size_t>(j.cout) * j.cin * 9;
+    pack_conv_body(w, transposed ? nullptr : b, reinterpret_cast<uint16_t*>(wpack + j.w_off), transposed ? nullptr : bias + j.b_off,
+                   j.cin, j.cout, j.nout, j.nslices, j.nchunks, j.fmt, transposed,
+                   blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x, static_cast<size_t>(gridDim.x) * blockDim.x);
 }
 
 // NCHW fp32 -> NHWC 16-bit with channels zero-padded to c_pad (multiple of 8).
@@ -101,6 +121,34 @@ int grid_for(size_t total, int block) {
     if (g > 148 * 16) g = 148 * 16;
     if (g < 1) g = 1;
     return static_cast<int>(g);
+}
+
+// Packs every layer from the flat parameter vector: forward packs (+ padded biases) or the transposed data-gradient packs.
+int launch_pack_all(resr_generator* g, const float* flat, int transposed, cudaStream_t s) {
+    const Table& T = table();
+    PackJob** slot = reinterpret_cast<PackJob**>(transposed ? &g->pack_jobs_t : &g->pack_jobs);
+    if (!*slot) {
+        std::vector<PackJob> h(kNumConvs);
+        for (int k = 0; k < kNumConvs; ++k) {
+            const ConvSpec& c = T.c[k];
+            PackJob& j = h[k];
+            j.p_off = c.p_off;
+            j.cin = c.cin; j.cout = c.cout;
+            if (!transposed) {
+                j.w_off = c.w_off; j.b_off = c.b_off; j.nout = c.nout; j.nslices = c.nslices; j.nchunks = c.nchunks; j.fmt = c.fmt;
+            } else {
+                j.w_off = c.wt_off; j.b_off = 0; j.nout = 32; j.nslices = c.t_nslices; j.nchunks = c.t_nchunks; j.fmt = 1;
+            }
+        }
+        if (cudaMalloc(slot, kNumConvs * sizeof(PackJob)) != cudaSuccess) return -1;
+        cudaMemcpyAsync(*slot, h.data(), kNumConvs * sizeof(PackJob), cudaMemcpyHostToDevice, s);
+        cudaStreamSynchronize(s);  // h is a local
+    }
+    // conv 0 (3 -> 64) never needs its input gradient: the transposed table is launched from layer 1
+    const int first = transposed ? 1 : 0;
+    pack_all_kernel<<<dim3(24, kNumConvs - first), 256, 0, s>>>(flat, *slot + first, transposed ? g->wpack_t : g->wpack, g->bias,
+                                                                transposed);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
 void launch_pack_conv(const float* w, const float* bias, uint16_t* wp, float* bp, int cin, int cout, int nout, int nslices,
@@ -332,6 +380,8 @@ void resr_generator_destroy(resr_generator_t* g) {
     cudaFree(g->wpack);
     cudaFree(g->bias);
     cudaFree(g->wpack_t);
+    cudaFree(g->pack_jobs);
+    cudaFree(g->pack_jobs_t);
     cudaFree(g->zero_bias);
     if (g->step_exec) cudaGraphExecDestroy(g->step_exec);
     if (g->h2d_stream) cudaStreamDestroy(g->h2d_stream);
@@ -352,15 +402,7 @@ int resr_generator_load_params(resr_generator_t* g, const float* flat, void* str
     if (!g || !flat) return set_error(RESR_E_INVALID, "null argument");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const Table& T = table();
-    for (int k = 0; k < kNumConvs; ++k) {
-        const ConvSpec& c = T.c[k];
-        const size_t total = static_cast<size_t>(c.nslices) * c.nchunks * 3 * (3 * c.nout) * 64;
-        const float* w = flat + c.p_off;
-        const float* b = w + static_cast<size_t>(c.cout) * c.cin * 9;
-        (void)total;
-        launch_pack_conv(w, b, reinterpret_cast<uint16_t*>(g->wpack + c.w_off), g->bias + c.b_off, c.cin, c.cout, c.nout,
-                         c.nslices, c.nchunks, c.fmt, 0, s);
-    }
+    if (launch_pack_all(g, flat, 0, s) != 0) return set_error(RESR_E_CUDA, "weight packing failed");
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(RESR_E_CUDA, "pack kernels: %s", cudaGetErrorString(e));
     g->loaded = true;

@@ -312,11 +312,7 @@ void ensure_transposed_packs(resr_generator* g, cudaStream_t s, bool force) {
         cudaMemsetAsync(g->zero_bias, 0, 256 * sizeof(float), s);
     }
     if (g->packed_t || !g->flat_params) return;
-    for (int k = 1; k < kNumConvs; ++k) {  // conv 0 (3 -> 64) never needs its input gradient
-        const ConvSpec& c = T.c[k];
-        launch_pack_conv(g->flat_params + c.p_off, nullptr, reinterpret_cast<uint16_t*>(g->wpack_t + c.wt_off), nullptr, c.cin, c.cout,
-                         32, c.t_nslices, c.t_nchunks, 1, 1, s);
-    }
+    launch_pack_all(g, g->flat_params, 1, s);
     g->packed_t = true;
 }
 
