@@ -180,6 +180,10 @@ class Generator(nn.Module):
             raise _lib.ResrError("infer_host_async needs pinned contiguous fp32 host tensors")
         self._ensure_packed()
         extra = 2 * (x_host.numel() * 4 * 17 + 4096)
+        cur = self._workspace
+        if cur is not None and (cur.device != device or cur.numel() < _lib.lib().resr_generator_workspace_bytes(n, h, w) + extra + 1024):
+            self.host_sync()  # queued copies still use the workspace that is about to be replaced
+            torch.cuda.synchronize(device)
         ws = self._get_workspace(n, h, w, device, extra)
         wp, wbytes = self._aligned(ws)
         with torch.cuda.device(device):
