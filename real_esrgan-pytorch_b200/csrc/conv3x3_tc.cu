@@ -593,10 +593,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
 
 bool conv3x3_plan_smem(ConvArgs* a, int cout_slice) {
     const int wbytes = a->nchunks * 3 * (3 * cout_slice) * 128;
-    // The per-row epilogue latency (TMEM drain, staging, TMA store; ~1.6k cycles, ~3.6k with the fp32 residual tile) is
-    // hidden by running several epilogue groups on consecutive rows; a row's MMAs take nchunks * 672 cycles.
-    const bool fp32_tiles = a->has_outf || a->has_res1;
-    int nepi = fp32_tiles ? 2 : (a->nchunks == 1 ? 3 : 2);
+    // The per-row epilogue latency (TMEM drain, staging, TMA store; ~1.6k cycles, more with an fp32 output tile) is hidden
+    // by running several epilogue groups on consecutive rows. Three groups whenever they fit beside at least four
+    // stages (8 KB of shared memory each without an fp32 tile); two with the 24 KB fp32 variant.
+    int nepi = a->has_outf ? 2 : 3;
     const char* env = getenv("RESR_CONV_NEPI");
     if (env) nepi = atoi(env);
     if (nepi < 1) nepi = 1;
