@@ -113,3 +113,21 @@ def test_pipelined_host_calls_match_blocking_call():
         assert torch.equal(r, o)
     with pytest.raises(resr_b200._lib.ResrError):
         g.infer_host_async(torch.rand(1, 3, 8, 8), torch.empty(1, 3, 32, 32))  # not pinned
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(1, 3, 1, 1), (1, 3, 2, 3), (1, 3, 5, 7), (2, 3, 9, 130), (1, 3, 3, 257), (5, 3, 8, 8),
+                                   (3, 3, 7, 16), (17, 3, 6, 64), (1, 3, 1, 128), (2, 3, 130, 9)])
+def test_generator_awkward_shapes(shape):
+    """Single-pixel images, one-row images, ragged widths (W = 130, 257: a 2 / 1 pixel last segment), every lane split
+    (W = 8, 16, 64 -> 16, 8, 2 images per M tile) with image counts that do not fill the last tile."""
+    from oracle import generator as og
+    g, sd = _make(7)
+    torch.manual_seed(sum(shape))
+    x = torch.rand(*shape)
+    with torch.no_grad():
+        y = g(x.cuda()).cpu()
+    ref = og.generator_forward(x, sd)
+    err = (y - ref).abs().max().item()
+    psnr = 10 * np.log10(1.0 / max(torch.mean((y - ref) ** 2).item(), 1e-20))
+    assert err <= 2e-2 and psnr >= 45.0, (err, psnr)
