@@ -44,7 +44,7 @@ def _cos(a, b):
     return float(torch.dot(a.double(), b.double()) / (a.double().norm() * b.double().norm() + 1e-300))
 
 
-@pytest.mark.parametrize("seed,shape", [(0, (1, 3, 16, 24)), (1, (2, 3, 16, 64))])
+@pytest.mark.parametrize("seed,shape", [(0, (1, 3, 16, 24)), (1, (2, 3, 16, 64)), (2, (3, 3, 5, 8)), (3, (1, 3, 9, 136))])
 def test_generator_loss_and_gradients_vs_oracle_autograd(seed, shape):
     import resr_b200
     from oracle import generator as og
