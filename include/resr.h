@@ -228,6 +228,43 @@ size_t resr_conv3x3_wgrad_workspace_bytes(int n, int h, int w, int cin, int cout
 int resr_conv3x3_wgrad(const void* x16, int x_cstride, int fmt_x, const void* dy16_bf16, int n, int h, int w, int cin,
                        int cout, float* dw, float* db, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- the whole degradation block in one call (train_realesrnet.py:267-377 == train_realesrgan.py:347-457) ---------------
+ * A POD plan holds every host decision of one execution of the block; per-sample parameters and host-fed random draws
+ * are DEVICE pointers owned by the caller. Stage order, kernels and arithmetic are those of the op-level entry points. */
+typedef struct resr_resize_spec {
+    int mode;        /* 0 area, 1 bilinear, 2 bicubic (random.choice, train:279, 317, 349) */
+    int out_h, out_w;/* used when scale <= 0: F.interpolate(size=...) (coordinate scale in/out) */
+    double scale;    /* > 0: F.interpolate(scale_factor=scale): out = floor(in * scale), coordinate scale 1/scale (train:288) */
+} resr_resize_spec;
+typedef struct resr_noise_spec {
+    int type;                 /* 0 Gaussian (imgproc.py:1029-1057), 1 Poisson (imgproc.py:1060-1086) */
+    const float* param;       /* [B] sigma (Gaussian) or scale (Poisson) */
+    const float* gray;        /* [B] gray flags */
+    int gray_any;             /* host-side: any gray flag set (imgproc.py:852, 884) */
+    const float* draws_color; /* host-fed draws: normal field / Poisson samples [B,3,h,w]; NULL: drawn inside the kernel */
+    const float* draws_gray;  /* normal field [h,w] / Poisson samples [B,1,h,w], read only when gray_any */
+    unsigned long long seed;  /* Philox seed of the in-kernel samplers */
+} resr_noise_spec;
+typedef struct resr_degrade_plan {
+    int batch, hr_h, hr_w;
+    int usm_radius, usm_sigma;            /* 50, 0 (train:232) */
+    float usm_weight, usm_threshold;      /* 0.5, 10 (imgproc.py:1525) */
+    int blur1, blur2, final_order;        /* blur flags (train:275, 313); 0: resize-sinc-jpeg, 1: jpeg-resize-sinc (train:347) */
+    int kernel_size, sinc_batched;        /* 21; 1 when sinc_kernel is [B,k,k], 0 when [1,k,k] */
+    resr_resize_spec resize1, resize2, resize3;
+    resr_noise_spec noise1, noise2;
+    const float* jpeg1_quality;           /* [B] (train:307, 356/361); not modified (the factor goes to the workspace) */
+    const float* jpeg2_quality;
+    int crop_top, crop_left, image_size, upscale;   /* HR crop window (imgproc.py:1894-1934), LR offsets = HR offsets / upscale */
+    unsigned long long* rng_state;        /* 8 persistent zero-initialised device u64 (in-kernel samplers), or NULL */
+} resr_degrade_plan;
+size_t resr_degrade_workspace_bytes(const resr_degrade_plan* plan);
+/* hr: [B,3,hr_h,hr_w]; kernel1 / kernel2: [B,k,k]; sinc_kernel: [B or 1,k,k]; lr_out: [B,3,image_size/upscale,..] on
+ * the u8 grid; hr_out: [B,3,image_size,image_size] (the unsharpened target, train:377). */
+int resr_degrade_batch(const resr_degrade_plan* plan, const float* hr, const float* kernel1, const float* kernel2,
+                       const float* sinc_kernel, float* lr_out, float* hr_out, void* workspace, size_t workspace_bytes,
+                       void* stream);
+
 /* ---- optimizer side of the training step ------------------------------------------------------
  * One fused elementwise pass over flat fp32 vectors of n elements (resr_generator_num_params for the whole generator):
  *   torch.optim.Adam(lr, betas=(beta1, beta2), eps) step number `step` (1-based; no weight decay, no amsgrad), arithmetic

@@ -33,6 +33,29 @@ class ConvDesc(Structure):
     ]
 
 
+class ResizeSpec(Structure):
+    """struct resr_resize_spec (include/resr.h)."""
+    _fields_ = [("mode", c_int), ("out_h", c_int), ("out_w", c_int), ("scale", c_double)]
+
+
+class NoiseSpec(Structure):
+    """struct resr_noise_spec (include/resr.h)."""
+    _fields_ = [("type", c_int), ("param", c_void_p), ("gray", c_void_p), ("gray_any", c_int), ("draws_color", c_void_p),
+                ("draws_gray", c_void_p), ("seed", ctypes.c_ulonglong)]
+
+
+class DegradePlan(Structure):
+    """struct resr_degrade_plan (include/resr.h)."""
+    _fields_ = [("batch", c_int), ("hr_h", c_int), ("hr_w", c_int),
+                ("usm_radius", c_int), ("usm_sigma", c_int), ("usm_weight", c_float), ("usm_threshold", c_float),
+                ("blur1", c_int), ("blur2", c_int), ("final_order", c_int), ("kernel_size", c_int), ("sinc_batched", c_int),
+                ("resize1", ResizeSpec), ("resize2", ResizeSpec), ("resize3", ResizeSpec),
+                ("noise1", NoiseSpec), ("noise2", NoiseSpec),
+                ("jpeg1_quality", c_void_p), ("jpeg2_quality", c_void_p),
+                ("crop_top", c_int), ("crop_left", c_int), ("image_size", c_int), ("upscale", c_int),
+                ("rng_state", c_void_p)]
+
+
 class KernelParams(Structure):
     """struct resr_kernel_params (include/resr.h)."""
     _fields_ = [("type", c_int), ("kernel_size", c_int), ("isotropic", c_int), ("reserved", c_int),
@@ -76,6 +99,9 @@ SIGNATURES = {
                                            ctypes.c_ulonglong, c_void_p, c_void_p, c_size_t, c_void_p]),
     "resr_jpeg": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                           c_void_p]),
+    "resr_degrade_workspace_bytes": (c_size_t, [POINTER(DegradePlan)]),
+    "resr_degrade_batch": (c_int, [POINTER(DegradePlan), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_size_t, c_void_p]),
     "resr_adam_ema_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_float, c_float,
                                    c_float, ctypes.c_longlong, c_float, c_float, c_void_p]),
     "resr_synthesize_kernels": (c_int, [POINTER(KernelParams), c_int, c_int, c_void_p, c_void_p, c_void_p]),

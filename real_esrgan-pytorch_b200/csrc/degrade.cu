@@ -1042,4 +1042,114 @@ int resr_crop(const float* image, float* out, int planes, int h_in, int w_in, in
     return RESR_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ whole block in one call
+// train_realesrnet.py:267-377 from a POD plan (every host decision of the block + device pointers to its per-sample
+// parameters and, optionally, host-fed random draws). Same kernels and same order as the op-level entry points above.
+static size_t degrade_max_elems(const resr_degrade_plan* p) {
+    auto out_hw = [](int h, int w, const resr_resize_spec& r, int* oh, int* ow) {
+        if (r.scale > 0) { *oh = static_cast<int>(floor(static_cast<double>(h) * r.scale)); *ow = static_cast<int>(floor(static_cast<double>(w) * r.scale)); }
+        else { *oh = r.out_h; *ow = r.out_w; }
+    };
+    int h = p->hr_h, w = p->hr_w, h1, w1, h2, w2, h3, w3;
+    out_hw(h, w, p->resize1, &h1, &w1);
+    out_hw(h1, w1, p->resize2, &h2, &w2);
+    out_hw(h2, w2, p->resize3, &h3, &w3);
+    size_t m = static_cast<size_t>(h) * w;
+    if (static_cast<size_t>(h1) * w1 > m) m = static_cast<size_t>(h1) * w1;
+    if (static_cast<size_t>(h2) * w2 > m) m = static_cast<size_t>(h2) * w2;
+    if (static_cast<size_t>(h3) * w3 > m) m = static_cast<size_t>(h3) * w3;
+    return m * 3 * static_cast<size_t>(p->batch);
+}
+static size_t up256(size_t v) { return (v + 255) / 256 * 256; }
+
+size_t resr_degrade_workspace_bytes(const resr_degrade_plan* p) {
+    if (!p || p->batch <= 0 || p->hr_h <= 0 || p->hr_w <= 0) return 0;
+    const size_t img = up256(degrade_max_elems(p) * 4);
+    return 2 * img + up256(resr_usm_workspace_bytes(p->batch, 3, p->hr_h, p->hr_w)) + up256(resr_poisson_workspace_bytes(p->batch)) +
+           up256(static_cast<size_t>(p->batch) * 4);
+}
+
+int resr_degrade_batch(const resr_degrade_plan* p, const float* hr, const float* kernel1, const float* kernel2,
+                       const float* sinc_kernel, float* lr_out, float* hr_out, void* workspace, size_t workspace_bytes,
+                       void* stream) {
+    if (!p || !hr || !lr_out || !hr_out || !workspace || !sinc_kernel) return set_error(RESR_E_INVALID, "null argument");
+    if ((p->blur1 && !kernel1) || (p->blur2 && !kernel2) || !p->jpeg1_quality || !p->jpeg2_quality)
+        return set_error(RESR_E_INVALID, "plan needs kernels / jpeg qualities");
+    if (workspace_bytes < resr_degrade_workspace_bytes(p)) return set_error(RESR_E_NOMEM, "degradation workspace too small");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int B = p->batch, k = p->kernel_size > 0 ? p->kernel_size : 21;
+    uint8_t* base = static_cast<uint8_t*>(workspace);
+    const size_t img = up256(degrade_max_elems(p) * 4);
+    float* bufs[2] = {reinterpret_cast<float*>(base), reinterpret_cast<float*>(base + img)};
+    float* usm_ws = reinterpret_cast<float*>(base + 2 * img);
+    void* pws = base + 2 * img + up256(resr_usm_workspace_bytes(B, 3, p->hr_h, p->hr_w));
+    float* qtmp = reinterpret_cast<float*>(static_cast<uint8_t*>(pws) + up256(resr_poisson_workspace_bytes(B)));
+    int cur = 0, h = p->hr_h, w = p->hr_w;
+#define RESR_STEP(expr) do { const int rc__ = (expr); if (rc__ != RESR_OK) return rc__; } while (0)
+    auto resize = [&](const resr_resize_spec& r) -> int {
+        int oh, ow;
+        if (r.scale > 0) { oh = static_cast<int>(floor(static_cast<double>(h) * r.scale)); ow = static_cast<int>(floor(static_cast<double>(w) * r.scale)); }
+        else { oh = r.out_h; ow = r.out_w; }
+        if (oh == h && ow == w && (r.scale <= 0 || r.scale == 1.0)) return RESR_OK;  // bit-exact identity
+        const int rc = resize_impl(bufs[cur], bufs[cur ^ 1], B * 3, h, w, oh, ow, r.mode, r.scale > 0 ? r.scale : 0.0,
+                                   r.scale > 0 ? r.scale : 0.0, s);
+        cur ^= 1; h = oh; w = ow;
+        return rc;
+    };
+    auto blur = [&](const float* kern, int kb) -> int {
+        const int rc = filter2d_impl(bufs[cur], kern, bufs[cur ^ 1], B, 3, h, w, k, kb, s);
+        cur ^= 1;
+        return rc;
+    };
+    auto jpeg = [&](const float* quality) -> int {
+        const int rc = jpeg_impl(bufs[cur], bufs[cur ^ 1], quality, qtmp, B, h, w, 1, nullptr, nullptr, nullptr, s);
+        cur ^= 1;
+        return rc;
+    };
+    auto noise = [&](const resr_noise_spec& n, int which) -> int {
+        if (!n.param) return set_error(RESR_E_INVALID, "noise spec without parameters");
+        const float* gray = n.gray_any ? n.gray : nullptr;
+        int rc;
+        if (n.type == 0) {
+            if (n.draws_color) rc = resr_gaussian_noise_apply(bufs[cur], bufs[cur ^ 1], n.param, n.gray, n.draws_color,
+                                                              n.gray_any ? n.draws_gray : nullptr, B, 3, h, w, 1, 0, stream);
+            else if (!p->rng_state) return set_error(RESR_E_INVALID, "in-kernel noise needs plan->rng_state");
+            else rc = resr_gaussian_noise_sampled(bufs[cur], bufs[cur ^ 1], n.param, gray, B, 3, h, w, 1, 0, n.seed,
+                                                  p->rng_state + 4 * which, stream);
+        } else {
+            if (n.draws_color) rc = resr_poisson_noise_apply(bufs[cur], bufs[cur ^ 1], n.param, n.gray, n.draws_color,
+                                                             n.gray_any ? n.draws_gray : nullptr, B, 3, h, w, 1, 0, pws,
+                                                             resr_poisson_workspace_bytes(B), 0, stream);
+            else if (!p->rng_state) return set_error(RESR_E_INVALID, "in-kernel noise needs plan->rng_state");
+            else rc = resr_poisson_noise_sampled(bufs[cur], bufs[cur ^ 1], n.param, gray, B, 3, h, w, 1, 0, n.seed,
+                                                 p->rng_state + 4 * which + 2, pws, resr_poisson_workspace_bytes(B), stream);
+        }
+        cur ^= 1;
+        return rc;
+    };
+    RESR_STEP(usm_impl(hr, bufs[cur], usm_ws, B, 3, h, w, p->usm_radius > 0 ? p->usm_radius : 50, p->usm_sigma,
+                       p->usm_weight, p->usm_threshold, s));                                        // train:268
+    if (p->blur1) RESR_STEP(blur(kernel1, 1));                                                       // train:275-276
+    RESR_STEP(resize(p->resize1));                                                                   // train:279-288
+    RESR_STEP(noise(p->noise1, 0));                                                                  // train:291-304
+    RESR_STEP(jpeg(p->jpeg1_quality));                                                               // train:307-309
+    if (p->blur2) RESR_STEP(blur(kernel2, 1));                                                       // train:313-314
+    RESR_STEP(resize(p->resize2));                                                                   // train:317-329
+    RESR_STEP(noise(p->noise2, 1));                                                                  // train:332-345
+    if (p->final_order == 0) {                                                                       // train:347-358
+        RESR_STEP(resize(p->resize3));
+        RESR_STEP(blur(sinc_kernel, p->sinc_batched));
+        RESR_STEP(jpeg(p->jpeg2_quality));
+    } else {                                                                                         // train:360-371
+        RESR_STEP(jpeg(p->jpeg2_quality));
+        RESR_STEP(resize(p->resize3));
+        RESR_STEP(blur(sinc_kernel, p->sinc_batched));
+    }
+#undef RESR_STEP
+    const int up = p->upscale > 0 ? p->upscale : 4, ls = p->image_size / up;                         // train:374-377
+    int rc = resr_crop(bufs[cur], lr_out, B * 3, h, w, p->crop_top / up, p->crop_left / up, ls, ls, 1, stream);
+    if (rc != RESR_OK) return rc;
+    return resr_crop(hr, hr_out, B * 3, p->hr_h, p->hr_w, p->crop_top, p->crop_left, p->image_size, p->image_size, 0, stream);
+}
+
 }  // extern "C"

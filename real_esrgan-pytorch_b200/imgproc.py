@@ -21,7 +21,7 @@ from torch import nn
 from . import _lib
 
 __all__ = ["filter2d_torch", "USMSharp", "DiffJPEG", "random_add_gaussian_noise_torch",
-           "random_add_poisson_noise_torch", "random_crop", "interpolate", "degrade_batch", "DegradePipeline",
+           "random_add_poisson_noise_torch", "random_crop", "interpolate", "degrade_batch", "degrade_batch_native", "DegradePipeline",
            "plan_to_device"]
 
 _MODES = {"area": 0, "bilinear": 1, "bicubic": 2}
@@ -442,6 +442,75 @@ def degrade_batch(hr: torch.Tensor, kernel1: torch.Tensor, kernel2: torch.Tensor
     ls = c["image_size"] // c["upscale"]
     lr = _crop(out, c["hr_top"] // c["upscale"], c["hr_left"] // c["upscale"], ls, ls, round_to_u8=True)
     hr_c = _crop(hr, c["hr_top"], c["hr_left"], c["image_size"], c["image_size"])
+    return lr, hr_c
+
+
+_rng_state_cache = {}
+
+
+def degrade_batch_native(hr: torch.Tensor, kernel1: torch.Tensor, kernel2: torch.Tensor, sinc_kernel: torch.Tensor, plan: dict):
+    """Same block as `degrade_batch`, sequenced inside the library by ONE C-ABI call (`resr_degrade_batch`): the plan dict
+    is flattened into the POD `resr_degrade_plan` (host decisions + device pointers). Returns (lr, hr_crop)."""
+    dev = hr.device
+    b, c, h, w = hr.size()
+    keep = []  # device tensors referenced by raw pointers must outlive the call
+
+    def d(t):
+        t = _dev(t, dev)
+        keep.append(t)
+        return _lib.ptr(t)
+
+    P = _lib.DegradePlan()
+    P.batch, P.hr_h, P.hr_w = b, h, w
+    P.usm_radius, P.usm_sigma, P.usm_weight, P.usm_threshold = 50, 0, 0.5, 10.0
+    P.blur1, P.blur2, P.final_order = int(plan["blur1"]), int(plan["blur2"]), int(plan["final_order"])
+    P.kernel_size, P.sinc_batched = int(kernel1.size(-1)), int(sinc_kernel.size(0) != 1)
+    for name in ("resize1", "resize2", "resize3"):
+        r, spec = plan[name], getattr(P, name)
+        spec.mode, spec.out_h, spec.out_w = int(r["mode"]), int(r["out_h"]), int(r["out_w"])
+        spec.scale = float(r["scale"]) if r.get("scale") is not None else 0.0
+    need_rng = False
+    for name in ("noise1", "noise2"):
+        n, spec = plan[name], getattr(P, name)
+        gray = _dev(n["gray"], dev)
+        g_any = n.get("gray_any")
+        spec.gray_any = int(bool(gray.sum() > 0) if g_any is None else bool(g_any))
+        keep.append(gray)
+        spec.gray = _lib.ptr(gray)
+        spec.seed = int(n.get("seed", 0))
+        if n["type"] == "gaussian":
+            spec.type, spec.param = 0, d(n["sigma"])
+            if n.get("noise_color") is not None:
+                spec.draws_color = d(n["noise_color"])
+                spec.draws_gray = d(n["noise_gray"]) if n.get("noise_gray") is not None else None
+            else:
+                need_rng = True
+        else:
+            spec.type, spec.param = 1, d(n["scale"])
+            if n.get("samples_color") is not None:
+                spec.draws_color = d(n["samples_color"])
+                spec.draws_gray = d(n["samples_gray"]) if n.get("samples_gray") is not None else None
+            else:
+                need_rng = True
+    P.jpeg1_quality, P.jpeg2_quality = d(plan["jpeg1_quality"]), d(plan["jpeg2_quality"])
+    cr = plan["crop"]
+    P.crop_top, P.crop_left, P.image_size, P.upscale = int(cr["hr_top"]), int(cr["hr_left"]), int(cr["image_size"]), int(cr["upscale"])
+    if need_rng:
+        key = (dev.type, dev.index)
+        st = _rng_state_cache.get(key)
+        if st is None:
+            st = torch.zeros(8, dtype=torch.int64, device=dev)
+            _rng_state_cache[key] = st
+        P.rng_state = _lib.ptr(st)
+    x, k1, k2, sk = _prep(hr), _prep(kernel1), _prep(kernel2), _prep(sinc_kernel)
+    ls = P.image_size // P.upscale
+    lr = torch.empty(b, 3, ls, ls, dtype=torch.float32, device=dev)
+    hr_c = torch.empty(b, 3, P.image_size, P.image_size, dtype=torch.float32, device=dev)
+    need = _lib.lib().resr_degrade_workspace_bytes(ctypes.byref(P))
+    ws = torch.empty(need + 256, dtype=torch.uint8, device=dev)
+    wp = ws.data_ptr() + (-ws.data_ptr()) % 256
+    _lib.check(_lib.lib().resr_degrade_batch(ctypes.byref(P), _lib.ptr(x), _lib.ptr(k1), _lib.ptr(k2), _lib.ptr(sk), _lib.ptr(lr),
+                                             _lib.ptr(hr_c), wp, need, _lib.stream_ptr()))
     return lr, hr_c
 
 

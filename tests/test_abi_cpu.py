@@ -106,3 +106,31 @@ def test_tile_plan_is_an_exact_integer_cover():
             assert wy0 == max(y0 - halo, 0) and wy1 == min(y1 + halo, h) and wx0 == max(x0 - halo, 0) and wx1 == min(x1 + halo, w)
         assert (cover == 1).all()
     assert len(resr_b200.model.plan_tiles(2048, 2048, 512, 1024, 16)) == 8
+
+
+def test_pod_plan_layout_matches_the_header(tmp_path):
+    """ctypes mirrors of the POD structs in include/resr.h have the C compiler's size and field offsets."""
+    import shutil
+    import subprocess
+    import resr_b200
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler")
+    L = resr_b200._lib
+    src = tmp_path / "sz.c"
+    src.write_text('''#include <stdio.h>
+#include <stddef.h>
+#include "resr.h"
+int main(void) {
+    printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(resr_degrade_plan), sizeof(resr_resize_spec), sizeof(resr_noise_spec),
+           offsetof(resr_degrade_plan, noise1), offsetof(resr_degrade_plan, rng_state), sizeof(resr_conv_desc),
+           sizeof(resr_kernel_params));
+    return 0;
+}
+''')
+    exe = tmp_path / "sz"
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    subprocess.run(["gcc", "-I", inc, str(src), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    want = [ctypes.sizeof(L.DegradePlan), ctypes.sizeof(L.ResizeSpec), ctypes.sizeof(L.NoiseSpec), L.DegradePlan.noise1.offset,
+            L.DegradePlan.rng_state.offset, ctypes.sizeof(L.ConvDesc), ctypes.sizeof(L.KernelParams)]
+    assert got == want

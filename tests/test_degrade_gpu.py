@@ -228,6 +228,39 @@ def test_block_end_to_end(block):
     assert bad <= 0.02 * tot
 
 
+def test_block_one_call_abi_equals_op_sequence(block):
+    """resr_degrade_batch (the whole block behind ONE C-ABI call, POD plan) is bit-identical to the same block sequenced
+    from Python through the op-level entry points, on the recorded reference plans (host-fed draws) and on a synthetic
+    plan whose first resize goes through the scale_factor path."""
+    import resr_b200
+    ip = resr_b200.imgproc
+    for seed in block["seeds"]:
+        tag = f"s{seed}."
+        args = (_t(block[tag + "hr"]), _t(block[tag + "k1"]), _t(block[tag + "k2"]), _t(block[tag + "sk"]), _plan(block, seed))
+        lr_a, hr_a = ip.degrade_batch(*args)
+        lr_b, hr_b = ip.degrade_batch_native(*args)
+        assert torch.equal(lr_a, lr_b) and torch.equal(hr_a, hr_b)
+    plan = resr_b200.plan.synth_plan(3, 96, 80, seed=11, image_size=64)
+    for name in ("noise1", "noise2"):  # make every draw host-fed so that both paths see the same numbers
+        n = plan[name]
+        if n["type"] == "poisson":
+            r = plan["resize1"] if name == "noise1" else plan["resize2"]
+            rng = np.random.default_rng(5)
+            n["samples_color"] = rng.poisson(20.0, (3, 3, r["out_h"], r["out_w"])).astype(np.float32)
+            n["samples_gray"] = rng.poisson(20.0, (3, 1, r["out_h"], r["out_w"])).astype(np.float32)
+    g = torch.Generator().manual_seed(0)
+    hr = torch.rand(3, 3, 96, 80, generator=g).cuda()
+    k = torch.zeros(3, 21, 21)
+    k[:, 7:14, 7:14] = 1 / 49
+    k = k.cuda()
+    sk = torch.zeros(1, 21, 21)
+    sk[0, 10, 10] = 1
+    sk = sk.cuda()
+    lr_a, hr_a = ip.degrade_batch(hr, k, k, sk, plan)
+    lr_b, hr_b = ip.degrade_batch_native(hr, k, k, sk, plan)
+    assert torch.equal(lr_a, lr_b) and torch.equal(hr_a, hr_b)
+
+
 def test_kernel_synthesis_device(golden_dir):
     """Device float64 synthesis (resr_synthesize_kernels) vs the reference kernels: same seeds, same RNG order."""
     import math
