@@ -107,6 +107,8 @@ struct resr_generator {
     // second stream of the backward pass: the weight-gradient chain of a layer runs beside the data-gradient chain
     cudaStream_t side_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_dy = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_dyc[2] = {nullptr, nullptr};  // dYcat buffer of a dense block has been transposed (side stream)
+    bool ev_dyc_valid[2] = {false, false};
     uint8_t* wpack_t = nullptr;   // transposed packs for the backward data-gradient convolutions (lazily allocated)
     float* zero_bias = nullptr;
     bool packed_t = false;

@@ -108,6 +108,16 @@ __global__ void __launch_bounds__(256) scale_f32_to_bf16_kernel(const float* __r
     }
 }
 
+// out[p][choff + c] = bf16(sa * a[p][c]) for c < 64: a dense [P][64] fp32 tensor into a channel slice of a wider NHWC buffer
+__global__ void __launch_bounds__(256) scale_f32_to_bf16_slice_kernel(const float* __restrict__ a, float sa, uint16_t* __restrict__ out,
+                                                                     size_t P, int cstride, int choff) {
+    const size_t n = P * 64;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(sa * a[i]);
+        out[(i >> 6) * cstride + choff + (i & 63)] = *reinterpret_cast<const uint16_t*>(&h);
+    }
+}
+
 __global__ void __launch_bounds__(256) axpby_f32_kernel(const float* __restrict__ a, float sa, const float* __restrict__ b, float sb,
                                                        float* __restrict__ out, size_t n) {
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
@@ -269,6 +279,7 @@ static size_t up1k(size_t v) { return (v + 1023) / 1024 * 1024; }
 
 struct TrainWs {
     size_t xin, c[70], f[4], t1, t2, t3, t4, yraw;       // forward
+    size_t dycat[2], dbcat;
     size_t g, dya, dyb, dx[3], dskip, biga, bigb, mida, midb, xt, dyt, partial, loss;  // backward
     size_t total;
 };
@@ -287,6 +298,9 @@ static TrainWs train_layout(size_t N, size_t H, size_t W, int num_sms) {
     L.t4 = take(16 * P * 64 * 2);
     L.yraw = take(16 * P * 3 * 4);
     L.g = take(P * 192 * 4);
+    L.dycat[0] = take(P * 192 * 2);
+    L.dycat[1] = take(P * 192 * 2);
+    L.dbcat = take(192 * 4);
     L.dya = take(P * 64 * 2);
     L.dyb = take(P * 64 * 2);
     for (int i = 0; i < 3; ++i) L.dx[i] = take(P * 64 * 4);
@@ -296,7 +310,7 @@ static TrainWs train_layout(size_t N, size_t H, size_t W, int num_sms) {
     L.mida = take(4 * P * 64 * 2);
     L.midb = take(4 * P * 64 * 2);
     L.xt = take(16 * P * 64 * 2 > P * 192 * 2 ? 16 * P * 64 * 2 : P * 192 * 2);
-    L.dyt = take(3 * 16 * P * 64 * 2);
+    L.dyt = take(3 * 16 * P * 64 * 2);  // also holds the three 192-channel copies of a dense block's dYcat (3 * 192 * P)
     L.partial = take(wgrad_partial_bytes(num_sms));
     L.loss = take(64);
     L.total = o;
@@ -323,6 +337,8 @@ using namespace resr;
 namespace {
 
 struct Bufs {
+    uint16_t *dycat[2];
+    float* dbcat;
     uint16_t *xin, *c[70], *t1, *t2, *t3, *t4, *dya, *dyb, *biga, *bigb, *mida, *midb, *xt, *dyt;
     float *f[4], *yraw, *g, *dx[3], *dskip, *partial;
     double* loss;
@@ -338,6 +354,8 @@ Bufs carve(void* ws, const TrainWs& L) {
     B.t3 = reinterpret_cast<uint16_t*>(b + L.t3); B.t4 = reinterpret_cast<uint16_t*>(b + L.t4);
     B.yraw = reinterpret_cast<float*>(b + L.yraw);
     B.g = reinterpret_cast<float*>(b + L.g);
+    B.dycat[0] = reinterpret_cast<uint16_t*>(b + L.dycat[0]); B.dycat[1] = reinterpret_cast<uint16_t*>(b + L.dycat[1]);
+    B.dbcat = reinterpret_cast<float*>(b + L.dbcat);
     B.dya = reinterpret_cast<uint16_t*>(b + L.dya); B.dyb = reinterpret_cast<uint16_t*>(b + L.dyb);
     for (int i = 0; i < 3; ++i) B.dx[i] = reinterpret_cast<float*>(b + L.dx[i]);
     B.dskip = reinterpret_cast<float*>(b + L.dskip);
@@ -436,6 +454,8 @@ cudaStream_t wgrad_stream(resr_generator* g, cudaStream_t s) {
         cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&g->ev_dy, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&g->ev_join, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&g->ev_dyc[0], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&g->ev_dyc[1], cudaEventDisableTiming);
     }
     return g->side_stream;
 }
@@ -484,6 +504,7 @@ int backward_common(resr_generator* g, float* grads, int N, int H, int W, const 
     const Geo g0 = make_geo(g, H, W), g1 = make_geo(g, 2 * H, 2 * W), g2 = make_geo(g, 4 * H, 4 * W);
     const size_t P = static_cast<size_t>(N) * H * W;
     ensure_transposed_packs(g, s, true);
+    g->ev_dyc_valid[0] = g->ev_dyc_valid[1] = false;
     cudaMemsetAsync(grads, 0, table().n_params * sizeof(float), s);  // bias gradients are accumulated with atomics
     cudaMemsetAsync(B.dya, 0, P * 64 * 2, s);
     cudaMemsetAsync(B.dyb, 0, P * 64 * 2, s);
@@ -534,47 +555,66 @@ int backward_common(resr_generator* g, float* grads, int N, int H, int W, const 
             const int r = 3 * i + j;       // concat buffer / RDB index
             const int k5 = 1 + 5 * r + 4;  // layer index of this RDB's conv5
             const float* D = dbuf[jj];
-            // channels-first copy of the whole concat buffer: the X operand of all five weight gradients
-            {
-                cudaStream_t wst = wgrad_stream(g, s);
-                fork_to(g, s, wst);
-                nhwc16_to_cf_kernel<false><<<dim3(static_cast<unsigned>((P + 255) / 256), 6), 256, 0, wst>>>(B.c[r], 192, 0, 192, 192, P, W, 0, B.xt, nullptr);
-            }
+            // The five output gradients of the block live side by side in ONE 192-channel buffer
+            //     dYcat = [dY1 | dY2 | dY3 | dY4 | dY5]   (channels 0, 32, 64, 96, 128)
+            // (double-buffered across blocks): the data-gradient chain below is five back-to-back launches with no
+            // dependency on the weight-gradient side, which then needs ONE transpose, ONE split-K GEMM X^T x dYcat
+            // (all five layers share X = the block's concat buffer) and ONE reduction per block.
+            uint16_t* dyc = B.dycat[r & 1];
+            cudaStream_t wst = wgrad_stream(g, s);
+            if (wst != s && g->ev_dyc_valid[r & 1]) cudaStreamWaitEvent(s, g->ev_dyc[r & 1], 0);  // its previous user was transposed
             // conv5: dY5 = 0.2 * d(xout)
-            scale_f32_to_bf16_kernel<<<egrid(P * 64), 256, 0, s>>>(D, 0.2f * dscale[jj], nullptr, 0.f, B.dya, P * 64);
-            RESR_TRY(layer_wgrad(g, k5, nullptr, 0, 1, true, 192, B.dya, N, g0, B, grads, s));
+            scale_f32_to_bf16_slice_kernel<<<egrid(P * 64), 256, 0, s>>>(D, 0.2f * dscale[jj], dyc, P, 192, 128);
             {
                 ConvIO io = bwd_io(g, k5);  // 6 output slices: 0..4 -> G (first writer), 5 -> masked dY of conv4
-                io.in16 = B.dya;
+                io.in16 = dyc + 128; io.in_c = 192;
                 io.outf = B.g; io.outf_c = 192; io.noutf_mask = 1u << 5;
-                io.out16 = B.dyb; io.out16_fixed = 1; io.no16_mask = 0x1Fu;
+                io.out16 = dyc; io.out16_c = 192; io.out16_choff = 96; io.out16_fixed = 1; io.no16_mask = 0x1Fu;
                 io.mask16 = B.c[r]; io.mask16_c = 192;
                 RESR_TRY(launch_conv_io(g, g0, N, io, s));
             }
-            uint16_t* cur = B.dyb;
-            uint16_t* nxt = B.dya;
             for (int q = 3; q >= 1; --q) {  // conv4, conv3, conv2: accumulate into G, top slice -> masked dY of conv(q)
                 const int kq = 1 + 5 * r + q;
-                RESR_TRY(layer_wgrad(g, kq, nullptr, 0, 1, true, 192, cur, N, g0, B, grads, s));
                 const int nsl = table().c[kq].t_nslices;  // 5, 4, 3
                 ConvIO io = bwd_io(g, kq);
-                io.in16 = cur; io.ep_mode = EP_ADD2;
+                io.in16 = dyc + 32 * q; io.in_c = 192; io.ep_mode = EP_ADD2;
                 io.res1 = B.g; io.res1_c = 192;
                 io.outf = B.g; io.outf_c = 192; io.noutf_mask = 1u << (nsl - 1);
-                io.out16 = nxt; io.out16_fixed = 1; io.no16_mask = (1u << (nsl - 1)) - 1u;
+                io.out16 = dyc; io.out16_c = 192; io.out16_choff = 32 * (q - 1); io.out16_fixed = 1; io.no16_mask = (1u << (nsl - 1)) - 1u;
                 io.mask16 = B.c[r]; io.mask16_c = 192;
                 RESR_TRY(launch_conv_io(g, g0, N, io, s));
-                uint16_t* t = cur; cur = nxt; nxt = t;
             }
             {   // conv1: d(xin) = conv1's data gradient + G[0:64] + d(xout)
                 const int k1 = 1 + 5 * r;
-                RESR_TRY(layer_wgrad(g, k1, nullptr, 0, 1, true, 192, cur, N, g0, B, grads, s));
                 ConvIO io = bwd_io(g, k1);
-                io.in16 = cur; io.ep_mode = EP_ADD2;
+                io.in16 = dyc; io.in_c = 192; io.ep_mode = EP_ADD2;
                 io.res1 = B.g; io.res1_c = 192;
                 io.res2 = D; io.res2_c = 64; io.res2_scale = dscale[jj];
                 io.outf = dxin[jj]; io.outf_c = 64;
                 RESR_TRY(launch_conv_io(g, g0, N, io, s));
+            }
+            {   // weight + bias gradients of the five layers (side stream): dYcat is complete once conv2's launch is done
+                fork_to(g, s, wst);
+                const dim3 tg(static_cast<unsigned>((P + 255) / 256), 6);
+                nhwc16_to_cf_kernel<false><<<tg, 256, 0, wst>>>(B.c[r], 192, 0, 192, 192, P, W, 0, B.xt, nullptr);
+                cudaMemsetAsync(B.dbcat, 0, 192 * sizeof(float), wst);
+                nhwc16_to_cf_kernel<true><<<tg, 256, 0, wst>>>(dyc, 192, 0, 192, 192, P, W, 1, B.dyt, B.dbcat);
+                if (wst != s) {
+                    cudaEventRecord(g->ev_dyc[r & 1], wst);
+                    g->ev_dyc_valid[r & 1] = true;
+                }
+                WgradRdbTable tb;
+                for (int cs = 0; cs < 6; ++cs) {
+                    const int kl = 1 + 5 * r + (cs < 4 ? cs : 4);
+                    const ConvSpec& c = table().c[kl];
+                    tb.dw[cs] = grads + c.p_off;
+                    tb.cin[cs] = c.cin;
+                    tb.co_base[cs] = cs < 4 ? 0 : (cs - 4) * 32;
+                    tb.db[cs] = grads + c.p_off + static_cast<size_t>(c.cout) * c.cin * 9 + tb.co_base[cs];
+                }
+                tb.dbcat = B.dbcat;
+                const int rc = wgrad_launch_rdb(B.xt, B.dyt, N, H, W, B.partial, tb, g->num_sms, wst);
+                if (rc != 0) return set_error(RESR_E_CUDA, "dense-block wgrad failed (%d)", rc);
             }
         }
         // d(x0) = d(rdb1 input) + d(out)   (model.py:129-130)

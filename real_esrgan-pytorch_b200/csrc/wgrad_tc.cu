@@ -41,7 +41,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constant
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
     const int unit = blockIdx.x;               // (mb, cs)
-    const int mb = unit / a.n_cs, cs = unit % a.n_cs;
+    const int mb = a.nunits ? a.unit_mb[unit] : unit / a.n_cs, cs = a.nunits ? a.unit_cs[unit] : unit % a.n_cs;
     const int split = blockIdx.y;
     const long long k0 = a.kstages_total * split / gridDim.y;
     const long long k1 = a.kstages_total * (split + 1) / gridDim.y;
@@ -109,7 +109,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constant
         const int m = q * 32 + lane;  // ci row within the block
         wg_wait(done, 0, a, 3);
         tc_fence_after();
-        float* dst = a.partial + ((((static_cast<size_t>(split) * a.n_mb + mb) * a.n_cs + cs) * 3) * 128 + m) * 96;
+        float* dst = a.partial + (((static_cast<size_t>(split) * gridDim.x + unit) * 3) * 128 + m) * 96;
         const bool any = k1 > k0;
 #pragma unroll 1
         for (int dy = 0; dy < 3; ++dy) {
@@ -149,6 +149,29 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
         for (int sp = 0; sp < nsplit; ++sp) s += partial[sp * stride + e];
         dw[((static_cast<size_t>(co) * cin + ci) * 3 + dy) * 3 + dx] = s;
     }
+}
+
+// The same reduction for the five layers of a dense block at once (wgrad_launch_rdb): unit u = (mb, cs) from the explicit list,
+// slice cs -> (layer gradient, cin, first output channel) from the table; the last 192 threads copy the bias gradients.
+struct WgradUnits { int n; unsigned char mb[16], cs[16]; };
+__global__ void __launch_bounds__(256) wgrad_reduce_rdb_kernel(const float* __restrict__ partial, const WgradRdbTable tb,
+                                                              const WgradUnits un, int nsplit) {
+    const size_t stride = static_cast<size_t>(un.n) * 3 * 128 * 96;
+    for (size_t e = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; e < stride; e += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int col = e % 96;
+        size_t t = e / 96;
+        const int cil = t % 128; t /= 128;
+        const int dy = t % 3;
+        const int u = static_cast<int>(t / 3);
+        const int mb = un.mb[u], cs = un.cs[u];
+        const int ci = mb * 128 + cil, cin = tb.cin[cs], co = tb.co_base[cs] + (col & 31), dx = col >> 5;
+        if (ci >= cin) continue;
+        float s = 0.f;
+        for (int sp = 0; sp < nsplit; ++sp) s += partial[sp * stride + e];
+        tb.dw[cs][((static_cast<size_t>(co) * cin + ci) * 3 + dy) * 3 + dx] = s;
+    }
+    const size_t gt = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (gt < 192 && tb.dbcat) tb.db[gt >> 5][gt & 31] = tb.dbcat[gt];
 }
 
 // db[co] += sum_p dY^T[co][p]  (channels-first bf16); grid (cout, chunks), db must be zero-initialised.
@@ -200,6 +223,46 @@ static int make_cf_map(CUtensorMap* out, const void* base, int C, int N, int H, 
 size_t wgrad_partial_bytes(int num_sms) {
     // worst case: 4 units (cin 192, cout 64) x (num_sms / 4) splits, or 1 unit x num_sms splits
     return static_cast<size_t>(num_sms + 8) * 3 * 128 * 96 * sizeof(float);
+}
+
+int wgrad_launch_rdb(const uint16_t* xt, const uint16_t* dyt, int N, int H, int W, float* partial, const WgradRdbTable& tb,
+                     int num_sms, cudaStream_t s) {
+    if (W % 8 != 0) return -2;
+    WgradArgs a;
+    memset(&a, 0, sizeof(a));
+    a.N = N; a.H = H; a.W = W; a.cin = 192; a.cout = 192;
+    a.n_mb = 2; a.n_cs = 6;
+    a.segs_per_row = (W + 63) / 64;
+    a.kstages_total = static_cast<long long>(N) * H * a.segs_per_row;
+    a.partial = partial;
+    a.nstages = kWgMaxStages;
+    a.dy_rows = 192;
+    WgradUnits un;
+    memset(&un, 0, sizeof(un));
+    // ci block 0 (channels 0..127) for every slice; ci block 1 (128..191) only where the layer has more than 128 inputs
+    for (int cs = 0; cs < 6; ++cs) { un.mb[un.n] = 0; un.cs[un.n++] = static_cast<unsigned char>(cs); }
+    for (int cs = 0; cs < 6; ++cs)
+        if (tb.cin[cs] > 128) { un.mb[un.n] = 1; un.cs[un.n++] = static_cast<unsigned char>(cs); }
+    a.nunits = un.n;
+    memcpy(a.unit_mb, un.mb, 16);
+    memcpy(a.unit_cs, un.cs, 16);
+    long long nsplit = num_sms / un.n;
+    if (nsplit > a.kstages_total / 16) nsplit = a.kstages_total / 16;
+    if (nsplit < 1) nsplit = 1;
+    CUtensorMap mx, my;
+    int rc = make_cf_map(&mx, xt, 192, N, H, W, 128);
+    rc |= make_cf_map(&my, dyt, 3 * 192, N, H, W, 32);
+    if (rc != 0) return rc;
+    const int smem = 1024 + kWgMaxStages * kWgStageBytes + 256;
+    static bool attr_rdb = false;
+    if (!attr_rdb) {
+        if (cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -3;
+        attr_rdb = true;
+    }
+    wgrad_tc_kernel<<<dim3(un.n, static_cast<unsigned>(nsplit)), 256, smem, s>>>(mx, my, a);
+    const size_t stride = static_cast<size_t>(un.n) * 3 * 128 * 96;
+    wgrad_reduce_rdb_kernel<<<static_cast<unsigned>((stride + 255) / 256), 256, 0, s>>>(partial, tb, un, static_cast<int>(nsplit));
+    return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 
 int wgrad_launch(const uint16_t* xt, int x_channels, const uint16_t* dyt, int dy_channels, int N, int H, int W, int cin, int cout,
