@@ -365,3 +365,35 @@ def test_gaussian_noise_sampled_in_kernel_statistics():
     assert (n0[0] - n0[1]).abs().max().item() < 1e-6              # gray: same field on the three channels ...
     assert (n0 - n1).abs().max().item() < 1e-6                    # ... and on every gray sample of the batch
     assert (og[2, 0] - og[2, 1]).abs().max().item() > 1e-3        # colour sample keeps independent channels
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5])
+def test_pipeline_graph_with_device_drawn_noise(seed):
+    """Random plans (every branch mix the seeds reach) with ALL noise drawn inside the kernels, through the CUDA-graph
+    pipeline, the Python-sequenced block and the one-call C ABI: shapes, u8 grid, finite values, fresh draws per replay."""
+    import resr_b200
+    ip = resr_b200.imgproc
+    b, h, w = 4, 128, 160
+    plan = resr_b200.plan.synth_plan(b, h, w, seed=seed, image_size=96, device_noise=True)
+    g = torch.Generator().manual_seed(seed)
+    hr = torch.rand(b, 3, h, w, generator=g).cuda()
+    k = torch.zeros(b, 21, 21)
+    k[:, 8:13, 8:13] = 1 / 25
+    k = k.cuda()
+    sk = torch.zeros(b, 21, 21)
+    sk[:, 10, 10] = 1
+    sk = sk.cuda()
+    pipe = ip.DegradePipeline(hr, k, k, sk, plan)
+    outs = []
+    for _ in range(2):
+        lr, hrc = pipe()
+        outs.append(lr.clone())
+        assert lr.shape == (b, 3, 24, 24) and hrc.shape == (b, 3, 96, 96)
+        assert torch.isfinite(lr).all() and lr.min().item() >= 0 and lr.max().item() <= 1
+        assert (lr * 255 - torch.round(lr * 255)).abs().max().item() < 1e-4
+    assert not torch.equal(outs[0], outs[1])               # replays draw fresh noise
+    for fn in (ip.degrade_batch, ip.degrade_batch_native):
+        lr, hrc = fn(hr, k, k, sk, plan)
+        assert lr.shape == (b, 3, 24, 24) and torch.isfinite(lr).all()
+        assert torch.equal(hrc, outs and pipe()[1])
