@@ -27,6 +27,41 @@ def test_every_declared_symbol_is_exported_and_bound():
     assert sorted(L.SIGNATURES) == declared, "ctypes SIGNATURES and include/resr.h disagree"
 
 
+def test_ctypes_argument_counts_and_kinds_match_the_header():
+    """Every prototype of include/resr.h against the ctypes signature table: same number of parameters, pointers bound as
+    pointers, integers / floats / size_t as such (ctypes would pass a wrong list silently)."""
+    import resr_b200
+    L = resr_b200._lib
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "resr.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    protos = dict(re.findall(r"\b(resr_[a-z0-9_]+)\s*\(([^;{}]*?)\)\s*;", hdr, flags=re.S))
+    checked = 0
+    for name, (res, args) in L.SIGNATURES.items():
+        params = [a.strip() for a in protos[name].replace("\n", " ").split(",")]
+        if params == ["void"] or params == [""]:
+            params = []
+        assert len(params) == len(args), f"{name}: header has {len(params)} parameters, ctypes binds {len(args)}"
+        for decl, ct in zip(params, args):
+            is_ptr_h = "*" in decl
+            is_ptr_c = ct in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(ct, "contents") or getattr(ct, "_type_", None) not in (
+                "i", "f", "d", "l", "q", "L", "Q", "I")
+            if is_ptr_h:
+                assert is_ptr_c, f"{name}: '{decl}' is a pointer in the header, bound as {ct}"
+            else:
+                assert not (ct in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(ct, "contents")), f"{name}: '{decl}' bound as a pointer"
+                if decl.startswith(("float", "double")):
+                    assert ct in (ctypes.c_float, ctypes.c_double), f"{name}: '{decl}' bound as {ct}"
+                    assert (ct is ctypes.c_double) == decl.startswith("double"), f"{name}: '{decl}' bound as {ct}"
+                elif decl.startswith("size_t"):
+                    assert ct is ctypes.c_size_t, f"{name}: '{decl}' bound as {ct}"
+                elif decl.startswith(("unsigned long long", "long long")):
+                    assert ctypes.sizeof(ct) == 8, f"{name}: '{decl}' bound as {ct}"
+                else:
+                    assert ct is ctypes.c_int, f"{name}: '{decl}' bound as {ct}"
+            checked += 1
+    assert checked > 250
+
+
 def test_abi_constants():
     import resr_b200
     lib = resr_b200._lib.lib()
