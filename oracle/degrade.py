@@ -25,9 +25,12 @@ def reflect_index(i, n):
     return np.where(i >= n, 2 * (n - 1) - i, i)
 
 
-def filter2d(img, kernel):
+def filter2d(img, kernel, method="auto"):
     """imgproc.py:1089-1121 filter2d_torch: reflect-pad k//2, cross-correlation (no flip); kernel [B,k,k] is applied
-    per sample to all channels, kernel [1,k,k] to every sample."""
+    per sample to all channels, kernel [1,k,k] to every sample. float64 accumulation, one rounding to float32.
+    method "direct": tap-by-tap sum (the definition); "fft": the same float64 cross-correlation evaluated with
+    scipy.signal.fftconvolve (agrees with "direct" to ~1e-15; tests/test_oracle_cpu.py checks it) so that BASELINE-size
+    inputs (16x3x256x256, 51x51 taps) finish in seconds; "auto" picks "fft" for large problems."""
     b, c, h, w = img.shape
     k = kernel.shape[-1]
     if k % 2 != 1:
@@ -37,9 +40,19 @@ def filter2d(img, kernel):
     xs = reflect_index(np.arange(-r, w + r), w)
     pad = img[:, :, ys][:, :, :, xs].astype(np.float64)
     kern = np.broadcast_to(kernel.astype(np.float64), (b, k, k)) if kernel.shape[0] == 1 else kernel.astype(np.float64)
+    if method == "auto":
+        method = "fft" if float(b) * c * h * w * k * k > 2e8 else "direct"
+    if method == "fft":
+        from scipy.signal import fftconvolve
+        out = np.empty((b, c, h, w), np.float64)
+        for i in range(b):  # correlation == convolution with the flipped kernel
+            out[i] = fftconvolve(pad[i], kern[i, ::-1, ::-1][None], mode="valid", axes=(1, 2))
+        return out.astype(f32)
     out = np.zeros((b, c, h, w), np.float64)
     for i in range(k):
         for j in range(k):
+            if not np.any(kern[:, i, j]):
+                continue  # zero-padded border of the 7..21 supports (dataset.py:102-103)
             out += kern[:, i, j][:, None, None, None] * pad[:, :, i:i + h, j:j + w]
     return out.astype(f32)
 

@@ -9,9 +9,12 @@ fallback: importing works anywhere, computing needs the built library and a B200
 """
 from . import _lib  # noqa: F401
 from . import autograd  # noqa: F401
+from . import compat  # noqa: F401
 from . import imgproc  # noqa: F401
 from . import model  # noqa: F401
 from . import optim  # noqa: F401
 from . import plan  # noqa: F401
 
-__all__ = ["_lib", "autograd", "imgproc", "model", "optim", "plan"]
+from .compat import patch_reference  # noqa: F401,E402
+
+__all__ = ["_lib", "autograd", "compat", "imgproc", "model", "optim", "plan", "patch_reference"]

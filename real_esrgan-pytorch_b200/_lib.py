@@ -145,9 +145,10 @@ def check(rc):
         raise ResrError(f"libresr error {rc}: {msg.decode() if msg else '?'}")
 
 
-def stream_ptr():
+def stream_ptr(device=None):
+    """Current CUDA stream of `device` (default: the current device) as the `void* stream` of the C ABI."""
     import torch
-    return c_void_p(torch.cuda.current_stream().cuda_stream)
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 def ptr(t):

@@ -46,21 +46,37 @@ class _GeneratorFn(torch.autograd.Function):
         gen._ensure_packed()
         y = torch.empty((n, 3, 4 * h, 4 * w), dtype=torch.float32, device=x.device)
         wp, wbytes = _train_workspace(gen, n, h, w, x.device)
-        _lib.check(_lib.lib().resr_generator_forward_train(gen._native(), _lib.ptr(xc), _lib.ptr(y), n, h, w, wp, wbytes,
-                                                           _lib.stream_ptr()))
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().resr_generator_forward_train(gen._native(), _lib.ptr(xc), _lib.ptr(y), n, h, w, wp, wbytes,
+                                                               _lib.stream_ptr(x.device)))
+        # The saved activations live in the generator's single training workspace: stamp this forward so that the
+        # matching backward can tell whether a later forward (or a weight repack) has overwritten them.
+        gen._fwd_generation += 1
         ctx.gen = gen
         ctx.shape = (n, h, w)
+        ctx.generation = gen._fwd_generation
+        ctx.packed_version = gen._packed_version
         return y
 
     @staticmethod
     def backward(ctx, dy):
         gen = ctx.gen
         n, h, w = ctx.shape
+        if ctx.needs_input_grad[0]:
+            raise _lib.ResrError("resr_b200.Generator does not produce a gradient w.r.t. its input: detach() the LR batch")
+        if gen._fwd_generation != ctx.generation:
+            raise _lib.ResrError(
+                "backward of a stale forward: another training-mode forward of this Generator ran in between and "
+                "overwrote the saved activations (one shared workspace per Generator). Call backward() before the next "
+                "forward, or run the second forward under torch.no_grad().")
+        if gen._packed_version is not ctx.packed_version and gen._packed_version != ctx.packed_version:
+            raise _lib.ResrError("the weights were repacked between forward and backward (parameters changed)")
         dyc = dy.detach().contiguous().float()
         flat = torch.empty(_lib.lib().resr_generator_num_params(), dtype=torch.float32, device=dy.device)
         wp, wbytes = _train_workspace(gen, n, h, w, dy.device)
-        _lib.check(_lib.lib().resr_generator_backward(gen._native(), _lib.ptr(dyc), _lib.ptr(flat), n, h, w, wp, wbytes,
-                                                      _lib.stream_ptr()))
+        with torch.cuda.device(dy.device):
+            _lib.check(_lib.lib().resr_generator_backward(gen._native(), _lib.ptr(dyc), _lib.ptr(flat), n, h, w, wp, wbytes,
+                                                          _lib.stream_ptr(dy.device)))
         grads, pos = [], 0
         for p in gen.parameters():
             grads.append(flat[pos:pos + p.numel()].view_as(p) if p.requires_grad else None)
@@ -87,9 +103,11 @@ def l1_loss_backward(gen, lr: torch.Tensor, hr: torch.Tensor, accumulate: bool =
     loss = torch.empty((), dtype=torch.float32, device=dev)
     wp, wbytes = _train_workspace(gen, n, h, w, dev)
     lib = _lib.lib()
-    _lib.check(lib.resr_generator_forward_train(gen._native(), _lib.ptr(xc), _lib.ptr(sr), n, h, w, wp, wbytes, _lib.stream_ptr()))
-    _lib.check(lib.resr_generator_backward_l1(gen._native(), _lib.ptr(hrc), _lib.ptr(flat), _lib.ptr(loss), n, h, w, wp, wbytes,
-                                              _lib.stream_ptr()))
+    gen._fwd_generation += 1  # invalidates any autograd graph still holding activations in this workspace
+    with torch.cuda.device(dev):
+        _lib.check(lib.resr_generator_forward_train(gen._native(), _lib.ptr(xc), _lib.ptr(sr), n, h, w, wp, wbytes, _lib.stream_ptr(dev)))
+        _lib.check(lib.resr_generator_backward_l1(gen._native(), _lib.ptr(hrc), _lib.ptr(flat), _lib.ptr(loss), n, h, w, wp, wbytes,
+                                                  _lib.stream_ptr(dev)))
     _scatter_grads(gen, flat, accumulate)
     return loss, sr, flat
 
@@ -126,10 +144,12 @@ class TrainStep:
             if hr is not None:
                 self.hr.copy_(hr, non_blocking=True)
             gen._ensure_packed()
+            gen._fwd_generation += 1
             wp, wbytes = _train_workspace(gen, n, h, w, self.lr.device)
-            _lib.check(_lib.lib().resr_generator_train_step_l1(
-                gen._native(), _lib.ptr(self.lr), _lib.ptr(self.hr), _lib.ptr(self.sr), _lib.ptr(self.flat), _lib.ptr(self.loss), n, h,
-                w, wp, wbytes, _lib.stream_ptr()))
+            with torch.cuda.device(self.lr.device):
+                _lib.check(_lib.lib().resr_generator_train_step_l1(
+                    gen._native(), _lib.ptr(self.lr), _lib.ptr(self.hr), _lib.ptr(self.sr), _lib.ptr(self.flat), _lib.ptr(self.loss), n, h,
+                    w, wp, wbytes, _lib.stream_ptr(self.lr.device)))
             if self.world > 1:
                 allreduce_mean_(self.flat, self.group, self.world)
         cur.wait_stream(self.stream)

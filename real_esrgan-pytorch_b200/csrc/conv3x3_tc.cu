@@ -28,6 +28,7 @@
 #include <cstring>
 
 #include "conv3x3.cuh"
+#include "device_state.h"
 #include "ptx.cuh"
 
 // Kernel perturbation flags for bottleneck experiments (tools/power_probe.py); compiled out of the product build.
@@ -705,11 +706,11 @@ int conv3x3_make_tmap_f32(CUtensorMap* out, const void* base, int N, int H, int 
 
 template <int NOUT>
 static cudaError_t launch_t(const ConvMaps& maps, const ConvArgs& args, dim3 grid, int threads, cudaStream_t stream) {
-    static bool attr = false;
-    if (!attr) {
+    static PerDevice<bool> attr;  // function attributes are per device
+    if (!attr.cur()) {
         const cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
         if (e != cudaSuccess) return e;
-        attr = true;
+        attr.cur() = true;
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));

@@ -6,6 +6,7 @@
 #include <cstring>
 
 #include "../../include/resr.h"
+#include "device_state.h"
 #include "errors.h"
 
 namespace resr {
@@ -153,10 +154,10 @@ static int filter2d_impl(const float* in, const float* kern, float* out, int B, 
     if (k / 2 >= H || k / 2 >= W) return set_error(RESR_E_INVALID, "reflect padding %d needs a larger image (%dx%d)", k / 2, H, W);
     const int tw = kF2dTile + k - 1;
     const size_t smem = (static_cast<size_t>(tw) * (tw + 1) + static_cast<size_t>(k) * k) * sizeof(float);
-    static size_t attr_set = 0;
-    if (smem > 48 * 1024 && smem > attr_set) {
+    static PerDevice<size_t> attr_set;  // function attributes are per device
+    if (smem > 48 * 1024 && smem > attr_set.cur()) {
         cudaFuncSetAttribute(filter2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        attr_set = smem;
+        attr_set.cur() = smem;
     }
     dim3 grid((W + kF2dTile - 1) / kF2dTile, (H + kF2dTile - 1) / kF2dTile, B * C);
     filter2d_kernel<<<grid, 256, smem, s>>>(in, kern, out, B, C, H, W, k, kb);
@@ -348,12 +349,13 @@ static int usm_set_taps(int radius, int sigma, int* k_out) {
     }
     float tf[kUsmMaxTaps];
     for (int i = 0; i < radius; ++i) tf[i] = static_cast<float>(taps[i] / sum);
-    static int cached_radius = -1, cached_sigma = -1;
-    if (cached_radius != radius || cached_sigma != sigma) {
+    // the constant bank is per device: remember (radius, sigma) + 1 per device (0 = nothing uploaded yet)
+    static PerDevice<long long> cached;
+    const long long key = (static_cast<long long>(radius) << 32) + sigma + 1;
+    if (cached.cur() != key) {
         if (cudaMemcpyToSymbol(c_usm_taps, tf, radius * sizeof(float)) != cudaSuccess)
             return set_error(RESR_E_CUDA, "cudaMemcpyToSymbol failed");
-        cached_radius = radius;
-        cached_sigma = sigma;
+        cached.cur() = key;
     }
     *k_out = radius;
     return RESR_OK;
@@ -373,10 +375,10 @@ static int usm_impl(const float* x, float* out, float* ws, int B, int C, int H, 
     const size_t sh = (256 + k - 1) * sizeof(float), sv = static_cast<size_t>(64 + k - 1) * 32 * sizeof(float);
     if (k == kUsmK) {
         const size_t smem = (static_cast<size_t>(kUsmIn) * kUsmPitchA + static_cast<size_t>(kUsmIn) * kUsmPitchB) * sizeof(float);
-        static bool attr = false;
-        if (!attr) {
+        static PerDevice<bool> attr;
+        if (!attr.cur()) {
             cudaFuncSetAttribute(usm_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-            attr = true;
+            attr.cur() = true;
         }
         const dim3 gf((W + kUsmT - 1) / kUsmT, (H + kUsmT - 1) / kUsmT, B * C);
         usm_fused_kernel<<<gf, 512, smem, s>>>(x, x, res, mask, H, W, 0, weight, threshold);
@@ -831,8 +833,8 @@ __global__ void __launch_bounds__(256) jpeg_kernel(const float* __restrict__ x, 
 }
 
 static int jpeg_init_tables() {
-    static bool done = false;
-    if (done) return RESR_OK;
+    static PerDevice<bool> done;  // __device__ / __constant__ tables live per device
+    if (done.cur()) return RESR_OK;
     static float T[4096], Ti[4096];
     const double pi = 3.14159265358979323846;
     for (int x = 0; x < 8; ++x)
@@ -856,7 +858,7 @@ static int jpeg_init_tables() {
     if (cudaMemcpyToSymbol(g_dct_table, T, sizeof(T)) != cudaSuccess || cudaMemcpyToSymbol(g_idct_table, Ti, sizeof(Ti)) != cudaSuccess || cudaMemcpyToSymbol(c_ytab, yt, sizeof(yt)) != cudaSuccess ||
         cudaMemcpyToSymbol(c_ctab, ct, sizeof(ct)) != cudaSuccess)
         return set_error(RESR_E_CUDA, "JPEG table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
-    done = true;
+    done.cur() = true;
     return RESR_OK;
 }
 

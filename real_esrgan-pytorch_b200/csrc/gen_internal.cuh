@@ -104,6 +104,8 @@ struct resr_generator {
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_fwd[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
     unsigned long long host_calls = 0;
+    int host_shape[3] = {0, 0, 0};   // shape / workspace of the previous pipelined host call (staging-slot layout)
+    const void* host_ws = nullptr;
     // second stream of the backward pass: the weight-gradient chain of a layer runs beside the data-gradient chain
     cudaStream_t side_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_dy = nullptr, ev_join = nullptr;

@@ -182,7 +182,7 @@ static WsLayout ws_layout(size_t N, size_t H, size_t W) {
     return L;
 }
 
-static int build_plan(resr_generator* g, int N, int H, int W, void* ws) {
+static int build_plan(resr_generator* g, int N, int H, int W, void* ws, cudaStream_t s) {
     Plan& p = g->plan;
     p.valid = false;
     p.steps.clear();
@@ -210,8 +210,10 @@ static int build_plan(resr_generator* g, int N, int H, int W, void* ws) {
         geo[s].mode = geo[s].BN == 1 ? 0 : 1;
         if (g->force_mode >= 0) geo[s].mode = (geo[s].BN == 1) ? g->force_mode : 1;
     }
-    // (one-time hygiene: no layer reads a channel that has not been written, the activation tensor maps end at Cin)
-    for (int i = 0; i < 3; ++i) cudaMemsetAsync(cbuf[i], 0, static_cast<size_t>(N) * H * W * 192 * 2, 0);
+    // (one-time hygiene: no layer reads a channel that has not been written, the activation tensor maps end at Cin).
+    // Issued on the CALLER's stream: ordered after whatever forward is still in flight on this workspace and capturable
+    // into a CUDA graph (the legacy default stream is neither).
+    for (int i = 0; i < 3; ++i) cudaMemsetAsync(cbuf[i], 0, static_cast<size_t>(N) * H * W * 192 * 2, s);
 
     const Table& T = table();
     int map_rc = 0;
@@ -327,7 +329,7 @@ static int build_plan(resr_generator* g, int N, int H, int W, void* ws) {
         ++conv;
     }
     if (map_rc != 0) return set_error(RESR_E_CUDA, "tensor map / shared memory planning failed (%d)", map_rc);
-    if (cudaStreamSynchronize(0) != cudaSuccess) return set_error(RESR_E_CUDA, "workspace init failed");
+    if (cudaGetLastError() != cudaSuccess) return set_error(RESR_E_CUDA, "workspace init failed");
     p.valid = true;
     return RESR_OK;
 }
@@ -429,7 +431,7 @@ int resr_generator_forward(resr_generator_t* g, const float* x, float* y, int n,
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     Plan& p = g->plan;
     if (!p.valid || p.N != n || p.H != h || p.W != w || p.ws != workspace) {
-        const int rc = build_plan(g, n, h, w, workspace);
+        const int rc = build_plan(g, n, h, w, workspace, s);
         if (rc != RESR_OK) return rc;
     }
     const size_t total = static_cast<size_t>(n) * h * w * 8;
@@ -485,6 +487,14 @@ int resr_generator_forward_host_async(resr_generator_t* g, const float* x_host, 
             cudaEventCreateWithFlags(&g->ev_d2h[i], cudaEventDisableTiming);
         }
     }
+    if (g->host_calls > 0 && (g->host_shape[0] != n || g->host_shape[1] != h || g->host_shape[2] != w || g->host_ws != workspace)) {
+        // a different shape (or workspace) moves the staging slots: drain every queued copy / forward before they are reused
+        cudaStreamSynchronize(g->h2d_stream);
+        cudaStreamSynchronize(s);
+        cudaStreamSynchronize(g->d2h_stream);
+        g->host_calls = 0;
+    }
+    g->host_shape[0] = n; g->host_shape[1] = h; g->host_shape[2] = w; g->host_ws = workspace;
     const int slot = static_cast<int>(g->host_calls & 1);
     const bool reused = g->host_calls >= 2;  // this slot has been through a full cycle before
     uint8_t* base = static_cast<uint8_t*>(workspace) + off0 + static_cast<size_t>(slot) * (in_al + out_al);

@@ -16,6 +16,7 @@
 #include <cstring>
 
 #include "conv3x3.cuh"
+#include "device_state.h"
 #include "ptx.cuh"
 #include "wgrad.cuh"
 
@@ -207,6 +208,9 @@ static PFN_encodeTiled wg_encode_fn() {
 }
 
 // channels-first bf16 tensor [C][N][H][W]; box = 64 px x rows channels
+// (function attributes are per device)
+static int wgrad_set_smem_attr(int smem);
+
 static int make_cf_map(CUtensorMap* out, const void* base, int C, int N, int H, int W, int rows) {
     PFN_encodeTiled enc = wg_encode_fn();
     if (!enc) return -1;
@@ -223,6 +227,15 @@ static int make_cf_map(CUtensorMap* out, const void* base, int C, int N, int H, 
 size_t wgrad_partial_bytes(int num_sms) {
     // worst case: 4 units (cin 192, cout 64) x (num_sms / 4) splits, or 1 unit x num_sms splits
     return static_cast<size_t>(num_sms + 8) * 3 * 128 * 96 * sizeof(float);
+}
+
+static int wgrad_set_smem_attr(int smem) {
+    static PerDevice<bool> attr;
+    if (!attr.cur()) {
+        if (cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -3;
+        attr.cur() = true;
+    }
+    return 0;
 }
 
 int wgrad_launch_rdb(const uint16_t* xt, const uint16_t* dyt, int N, int H, int W, float* partial, const WgradRdbTable& tb,
@@ -254,11 +267,7 @@ int wgrad_launch_rdb(const uint16_t* xt, const uint16_t* dyt, int N, int H, int 
     rc |= make_cf_map(&my, dyt, 3 * 192, N, H, W, 32);
     if (rc != 0) return rc;
     const int smem = 1024 + kWgMaxStages * kWgStageBytes + 256;
-    static bool attr_rdb = false;
-    if (!attr_rdb) {
-        if (cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -3;
-        attr_rdb = true;
-    }
+    if (wgrad_set_smem_attr(smem) != 0) return -3;
     wgrad_tc_kernel<<<dim3(un.n, static_cast<unsigned>(nsplit)), 256, smem, s>>>(mx, my, a);
     const size_t stride = static_cast<size_t>(un.n) * 3 * 128 * 96;
     wgrad_reduce_rdb_kernel<<<static_cast<unsigned>((stride + 255) / 256), 256, 0, s>>>(partial, tb, un, static_cast<int>(nsplit));
@@ -288,11 +297,7 @@ int wgrad_launch(const uint16_t* xt, int x_channels, const uint16_t* dyt, int dy
     a.dy_rows = dy_channels;
     if (rc != 0) return rc;
     const int smem = 1024 + kWgMaxStages * kWgStageBytes + 256;
-    static bool attr = false;
-    if (!attr) {
-        if (cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -3;
-        attr = true;
-    }
+    if (wgrad_set_smem_attr(smem) != 0) return -3;
     wgrad_tc_kernel<<<dim3(units, static_cast<unsigned>(nsplit)), 256, smem, s>>>(mx, my, a);
     const size_t pstride = static_cast<size_t>(a.n_mb) * a.n_cs * 3 * 128 * 96;
     wgrad_reduce_kernel<<<static_cast<unsigned>((pstride + 255) / 256), 256, 0, s>>>(partial, dw, cin, cout, a.n_mb, a.n_cs,

@@ -27,6 +27,23 @@ __all__ = ["filter2d_torch", "USMSharp", "DiffJPEG", "random_add_gaussian_noise_
 _MODES = {"area": 0, "bilinear": 1, "bicubic": 2}
 
 
+def _on_device(fn):
+    """Runs `fn` with the CUDA device of its first tensor argument current, so that the library call, its stream
+    (`_lib.stream_ptr()`) and its per-device tables all refer to the device that owns the data."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        for a in args:
+            if torch.is_tensor(a):
+                if a.is_cuda and a.device.index != torch.cuda.current_device():
+                    with torch.cuda.device(a.device):
+                        return fn(*args, **kwargs)
+                break
+        return fn(*args, **kwargs)
+    return wrapper
+
+
 def _prep(image: torch.Tensor) -> torch.Tensor:
     if not image.is_cuda:
         raise _lib.ResrError("resr_b200.imgproc runs on CUDA tensors only; there is no CPU path")
@@ -45,6 +62,7 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
     return ws
 
 
+@_on_device
 def filter2d_torch(image: torch.Tensor, kernel: torch.Tensor) -> torch.Tensor:
     """PyTorch-API twin of cv2.filter2D: reflect pad + cross-correlation (reference imgproc.py:1089-1121)."""
     k = kernel.size(-1)
@@ -78,6 +96,7 @@ class USMSharp(nn.Module):
         k1 = k1 / k1.sum()
         self.register_buffer("kernel", torch.outer(k1, k1).float().unsqueeze_(0))
 
+    @_on_device
     def forward(self, x: torch.Tensor, weight: float, threshold: int) -> torch.Tensor:
         b, c, h, w = x.size()
         xi = _prep(x)
@@ -99,6 +118,7 @@ class DiffJPEG(nn.Module):
         if differentiable:
             raise NotImplementedError("resr_b200.DiffJPEG implements differentiable=False (the path the training loops use)")
 
+    @_on_device
     def forward(self, x: torch.Tensor, quality, *, return_coefficients: bool = False, clamp_input: bool = False):
         """clamp_input=True fuses the torch.clamp(out, 0, 1) the training loop applies first (train_realesrnet.py:308)."""
         b, c, h, w = x.size()
@@ -129,6 +149,7 @@ class DiffJPEG(nn.Module):
         return out
 
 
+@_on_device
 def gaussian_noise_apply(image, sigma, gray, noise_color, noise_gray, clip=True, rounds=False):
     """Deterministic core of random_add_gaussian_noise_torch: all draws are arguments."""
     b, c, h, w = image.size()
@@ -169,6 +190,7 @@ def _poisson_workspace(b: int, device) -> torch.Tensor:
     return ws
 
 
+@_on_device
 def unique_count_u8(image: torch.Tensor, with_gray: bool = True):
     """Per-sample number of distinct u8 levels of the colour image and of its luma (reference imgproc.py:892, 903),
     computed on the device without host syncs. Returns int32 tensors (colour, gray)."""
@@ -182,6 +204,7 @@ def unique_count_u8(image: torch.Tensor, with_gray: bool = True):
     return cc, cg
 
 
+@_on_device
 def poisson_rates(image: torch.Tensor, with_gray: bool):
     b, c, h, w = image.size()
     x = _prep(image)
@@ -193,6 +216,7 @@ def poisson_rates(image: torch.Tensor, with_gray: bool):
     return rc, rg
 
 
+@_on_device
 def poisson_noise_apply(image, scale, gray, samples_color, samples_gray, clip=True, rounds=False, reuse_counts=False):
     """Deterministic core of random_add_poisson_noise_torch: all draws are arguments. reuse_counts=True: the unique
     counts of `image` were just computed by poisson_rates(image, ...) (same gray setting) and are reused."""
@@ -211,6 +235,7 @@ _pctr_cache = {}
 _gctr_cache = {}
 
 
+@_on_device
 def gaussian_noise_sampled(image, sigma, gray, seed: int, clip=True, rounds=False):
     """Production form of the Gaussian-noise stage for the plan-driven pipeline: the normal deviates are drawn inside the
     kernel (Philox), the gray field is one H x W field shared by the batch (imgproc.py:853-856). `gray=None`: no sample uses
@@ -229,6 +254,7 @@ def gaussian_noise_sampled(image, sigma, gray, seed: int, clip=True, rounds=Fals
     return out
 
 
+@_on_device
 def poisson_noise_sampled(image, scale, gray, seed: int, clip=True, rounds=False):
     """Production form of the Poisson stage for the plan-driven pipeline: draws are made inside the kernel (Philox
     counter RNG + exact PTRS / multiplication samplers), so the stage is a memset, the
@@ -264,6 +290,7 @@ def random_add_poisson_noise_torch(image: torch.Tensor, scale_range: tuple = (0,
     return poisson_noise_apply(image, scale, gray, samples_color, samples_gray, clip, rounds, reuse_counts=True)
 
 
+@_on_device
 def _crop(image, top, left, h_out, w_out, round_to_u8=False):
     b, c, h, w = image.size()
     x = _prep(image)
@@ -284,6 +311,7 @@ def random_crop(lr_images: torch.Tensor, hr_images: torch.Tensor, hr_image_size:
     return lr, hr
 
 
+@_on_device
 def interpolate(image: torch.Tensor, size=None, scale_factor=None, mode: str = "bilinear") -> torch.Tensor:
     """torch.nn.functional.interpolate for modes area / bilinear / bicubic (align_corners=False, no antialias) with
     ATen's index rules; scale_factor= uses 1/scale_factor as the coordinate scale, size= uses in/out."""
@@ -399,12 +427,24 @@ class DegradePipeline:
         return self.lr, self.hr_crop
 
 
+_block_mods = None
+
+
+def _block_modules():
+    """USMSharp(50, 0) / DiffJPEG(False) of the degradation block (train_realesrnet.py:231-235), built once: the 51 x 51
+    buffer of USMSharp is a host-side outer product that has no business in a per-batch call."""
+    global _block_mods
+    if _block_mods is None:
+        _block_mods = (USMSharp(50, 0), DiffJPEG(False))
+    return _block_mods
+
+
+@_on_device
 def degrade_batch(hr: torch.Tensor, kernel1: torch.Tensor, kernel2: torch.Tensor, sinc_kernel: torch.Tensor, plan: dict,
                   stages: list = None):
     """The reference's second-order degradation block (train_realesrnet.py:267-377) with every host decision and
     random tensor taken from `plan` (layout: oracle/plan.py). Returns (lr, hr_crop); lr is detached and on the u8 grid."""
-    usm = USMSharp(50, 0)
-    jpeger = DiffJPEG(False)
+    usm, jpeger = _block_modules()
     dev = hr.device
 
     def rec(name, t):
@@ -448,6 +488,7 @@ def degrade_batch(hr: torch.Tensor, kernel1: torch.Tensor, kernel2: torch.Tensor
 _rng_state_cache = {}
 
 
+@_on_device
 def degrade_batch_native(hr: torch.Tensor, kernel1: torch.Tensor, kernel2: torch.Tensor, sinc_kernel: torch.Tensor, plan: dict):
     """Same block as `degrade_batch`, sequenced inside the library by ONE C-ABI call (`resr_degrade_batch`): the plan dict
     is flattened into the POD `resr_degrade_plan` (host decisions + device pointers). Returns (lr, hr_crop)."""

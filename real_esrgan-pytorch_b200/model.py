@@ -3,8 +3,9 @@
 `Generator(in_channels, out_channels, upscale_factor)` is an nn.Module whose parameters carry exactly the reference
 names, shapes, initialisation and RNG consumption order (so `torch.manual_seed(s); Generator(3, 3, 4)` reproduces
 the reference weights and reference checkpoints load unchanged), but whose forward is ONE call into the C ABI
-(`resr_generator_forward`, include/resr.h) running hand-written sm_100a kernels. The sub-modules exist only to own
-parameters; they have no forward of their own — there is no PyTorch fallback path.
+(`resr_generator_forward`, include/resr.h) running hand-written sm_100a kernels. `ResidualDenseBlock.forward` and
+`ResidualResidualDenseBlock.forward` (model.py:87-98, 123-132) run block by block through the same tensor-core
+convolution (`resr_conv3x3`). There is no PyTorch fallback path.
 """
 import ctypes
 
@@ -20,18 +21,63 @@ def _conv(cin: int, cout: int) -> nn.Conv2d:
     return nn.Conv2d(cin, cout, (3, 3), (1, 1), (1, 1))
 
 
-class _ParamsOnly(nn.Module):
-    def forward(self, *args, **kwargs):  # pragma: no cover - guard
-        raise _lib.ResrError(
-            f"{type(self).__name__} only owns parameters; run the whole Generator (C ABI resr_generator_forward). "
-            "There is no per-block PyTorch path.")
+def _conv_native(x16, conv: nn.Conv2d, *, lrelu=0, ep_mode=0, out16=None, out16_choff=0, outf=None, res1=None, res2=None):
+    """One nn.Conv2d(3x3, pad 1) of a block through the tensor-core kernel (C ABI resr_conv3x3): NHWC fp16 operands,
+    fp32 accumulation and epilogue, fp32 NHWC residuals."""
+    n, h, w, c_total = x16.shape
+    d = _lib.ConvDesc()
+    d.in16 = x16.data_ptr()
+    d.n, d.h, d.w, d.c_total, d.cin, d.cout = n, h, w, c_total, conv.in_channels, conv.out_channels
+    d.fmt_in, d.mode = 0, -1
+    wt = conv.weight.detach().float().contiguous()
+    bs = conv.bias.detach().float().contiguous() if conv.bias is not None else None
+    d.weight, d.bias = wt.data_ptr(), (bs.data_ptr() if bs is not None else None)
+    d.ep_mode, d.lrelu, d.clamp01 = ep_mode, lrelu, 0
+    if out16 is not None:
+        d.out16, d.out16_fmt, d.out16_cstride, d.out16_choff, d.out16_up2 = out16.data_ptr(), 0, out16.shape[-1], out16_choff, 0
+    if outf is not None:
+        d.outf, d.outf_cstride, d.outf_choff = outf.data_ptr(), outf.shape[-1], 0
+    if res1 is not None:
+        d.res1, d.res_cstride, d.res_choff = res1.data_ptr(), res1.shape[-1], 0
+    if res2 is not None:
+        d.res2 = res2.data_ptr()
+    with torch.cuda.device(x16.device):
+        _lib.check(_lib.lib().resr_conv3x3(ctypes.byref(d), _lib.stream_ptr(x16.device)))
 
 
-class ResidualDenseBlock(_ParamsOnly):
-    """Parameter container of one RDB (reference model.py:64-106): conv1..4 (C+32k -> 32), conv5 (C+128 -> C)."""
+def _check_block_input(x: torch.Tensor, channels: int):
+    if x.dim() != 4 or x.size(1) != channels:
+        raise ValueError(f"expected [N, {channels}, H, W] input, got {tuple(x.shape)}")
+    if not x.is_cuda:
+        raise _lib.ResrError("resr_b200 blocks run on a CUDA (sm_100a) device only; there is no CPU path")
+    if torch.is_grad_enabled() and x.requires_grad:
+        raise _lib.ResrError("block-level forward is inference only; train through Generator (autograd.generator_apply)")
+
+
+def _rdb_native(block, cat16: torch.Tensor, res_f32: torch.Tensor, *, ep_mode=1, res2=None, out16=None):
+    """The five convolutions of one dense block on its in-place concat buffer `cat16` ([N,H,W,192] fp16, channels
+    [0, 64) = block input). Returns the fp32 NHWC block output (and also writes it as fp16 into out16[..., :64])."""
+    for k in range(4):  # model.py:90-93: out_k = lrelu(conv_k(cat[x, out_1..k-1])) written in place (no torch.cat copy)
+        _conv_native(cat16, getattr(block, f"conv{k + 1}"), lrelu=1, out16=cat16, out16_choff=64 + 32 * k)
+    outf = torch.empty(cat16.shape[:3] + (64,), dtype=torch.float32, device=cat16.device)
+    _conv_native(cat16, block.conv5, ep_mode=ep_mode, res1=res_f32, res2=res2, outf=outf, out16=out16)  # model.py:94-96
+    return outf
+
+
+def _to_cat16(x_nhwc_f32: torch.Tensor) -> torch.Tensor:
+    n, h, w, c = x_nhwc_f32.shape
+    cat16 = torch.zeros((n, h, w, 192), dtype=torch.float16, device=x_nhwc_f32.device)
+    cat16[..., :c] = x_nhwc_f32
+    return cat16
+
+
+class ResidualDenseBlock(nn.Module):
+    """One RDB (reference model.py:64-106): conv1..4 (C+32k -> 32) + LeakyReLU, conv5 (C+128 -> C), out = conv5 * 0.2 + x.
+    forward() runs the five convolutions through the tensor-core kernel on an in-place concat buffer."""
 
     def __init__(self, channels: int, growth_channels: int) -> None:
         super().__init__()
+        self.channels, self.growth_channels = channels, growth_channels
         for k in range(5):
             setattr(self, f"conv{k + 1}",
                     _conv(channels + growth_channels * k, growth_channels if k < 4 else channels))
@@ -42,15 +88,35 @@ class ResidualDenseBlock(_ParamsOnly):
                 m.weight.data *= 0.1
                 nn.init.constant_(m.bias, 0)
 
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if (self.channels, self.growth_channels) != (64, 32):
+            raise _lib.ResrError("the native dense block implements channels=64, growth_channels=32 (the RRDBNet configuration)")
+        _check_block_input(x, 64)
+        with torch.no_grad():
+            xf = x.detach().float().permute(0, 2, 3, 1).contiguous()   # fp32 NHWC residual (model.py:88 identity)
+            out = _rdb_native(self, _to_cat16(xf), xf)
+            return out.permute(0, 3, 1, 2).contiguous()
 
-class ResidualResidualDenseBlock(_ParamsOnly):
-    """Parameter container of one RRDB (reference model.py:109-132)."""
+
+class ResidualResidualDenseBlock(nn.Module):
+    """One RRDB (reference model.py:109-132): out = rdb3(rdb2(rdb1(x))) * 0.2 + x, 15 tensor-core convolutions."""
 
     def __init__(self, channels: int, growth_channels: int) -> None:
         super().__init__()
         self.rdb1 = ResidualDenseBlock(channels, growth_channels)
         self.rdb2 = ResidualDenseBlock(channels, growth_channels)
         self.rdb3 = ResidualDenseBlock(channels, growth_channels)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        _check_block_input(x, 64)
+        with torch.no_grad():
+            xf = x.detach().float().permute(0, 2, 3, 1).contiguous()
+            cats = [_to_cat16(xf), torch.zeros_like(_to_cat16(xf)), None]
+            cats[2] = torch.zeros_like(cats[1])
+            o1 = _rdb_native(self.rdb1, cats[0], xf, out16=cats[1])                       # model.py:124-126
+            o2 = _rdb_native(self.rdb2, cats[1], o1, out16=cats[2])
+            out = _rdb_native(self.rdb3, cats[2], o2, ep_mode=2, res2=xf)                 # model.py:127-130
+            return out.permute(0, 3, 1, 2).contiguous()
 
 
 class Generator(nn.Module):
@@ -69,28 +135,60 @@ class Generator(nn.Module):
         self.conv3 = nn.Sequential(_conv(64, 64), nn.LeakyReLU(0.2, True))
         self.conv4 = _conv(64, out_channels)
         self._handle = None
+        self._handle_device = None
         self._packed_version = None
         self._flat = None
         self._workspace = None
+        self._static_weights = False
+        self._fwd_generation = 0   # bumped by every training-mode forward (autograd.py ties a backward to its forward)
 
     # ------------------------------------------------------------------ native plumbing
+    def _device(self):
+        return next(self.parameters()).device
+
     def _native(self):
+        """The library handle of the device the parameters live on (one handle per device); recreated after
+        `.to(other_device)`."""
+        dev = self._device()
+        if not dev.type == "cuda":
+            raise _lib.ResrError("resr_b200.Generator runs on a CUDA (sm_100a) device only; move it with .cuda() / .to(device)")
+        if self._handle is not None and self._handle_device != dev:
+            with torch.cuda.device(self._handle_device):
+                torch.cuda.synchronize()
+                _lib.lib().resr_generator_destroy(self._handle)
+            self._handle, self._packed_version, self._workspace = None, None, None
+            if hasattr(self, "_train_ws"):
+                del self._train_ws
         if self._handle is None:
             h = ctypes.c_void_p()
-            _lib.check(_lib.lib().resr_generator_create(ctypes.byref(h), 3, 3, 4))
-            self._handle = h
+            with torch.cuda.device(dev):
+                _lib.check(_lib.lib().resr_generator_create(ctypes.byref(h), 3, 3, 4))
+            self._handle, self._handle_device = h, dev
         return self._handle
 
     def __del__(self):
         h = getattr(self, "_handle", None)
         if h is not None:
             try:
-                _lib.lib().resr_generator_destroy(h)
+                with torch.cuda.device(self._handle_device):
+                    _lib.lib().resr_generator_destroy(h)
             except Exception:
                 pass
 
     def _param_version(self):
-        return tuple(p._version for p in self.parameters()) + (next(self.parameters()).device,)
+        """Identity of the weights the packed tensor-core tiles were built from. `_version` alone misses `param.data = t`
+        (EMA.apply_shadow / restore, reference model.py:51-61), `load_state_dict(assign=True)` and dtype round trips, so
+        the storage pointer, dtype and device of every parameter are part of the key."""
+        return tuple((p._version, p.data_ptr(), p.dtype) for p in self.parameters()) + (self._device(),)
+
+    def assume_static_weights(self, flag: bool = True):
+        """Serving loops with frozen weights: skip the per-call walk over the 702 parameters (pack once, then trust
+        the caller). `invalidate()` forces a repack."""
+        self._static_weights = bool(flag)
+        return self
+
+    def invalidate(self):
+        self._packed_version = None
 
     def flat_parameters(self) -> torch.Tensor:
         """All parameters in state_dict order as one contiguous fp32 device vector (layout of resr_generator_tensor_span)."""
@@ -100,6 +198,8 @@ class Generator(nn.Module):
         return flat
 
     def _ensure_packed(self):
+        if self._static_weights and self._packed_version is not None:
+            return
         ver = self._param_version()
         if self._packed_version != ver:
             master = getattr(self, "_flat_master", None)
@@ -108,7 +208,10 @@ class Generator(nn.Module):
                 self._flat = master  # parameters are views of one flat vector (optim.FlatAdamEMA): nothing to gather
             else:
                 self._flat = self.flat_parameters()
-            _lib.check(_lib.lib().resr_generator_load_params(self._native(), _lib.ptr(self._flat), _lib.stream_ptr()))
+            dev = self._device()
+            h = self._native()
+            with torch.cuda.device(dev):
+                _lib.check(_lib.lib().resr_generator_load_params(h, _lib.ptr(self._flat), _lib.stream_ptr(dev)))
             self._packed_version = ver
 
     def _get_workspace(self, n: int, h: int, w: int, device, extra: int = 0) -> torch.Tensor:
@@ -134,9 +237,15 @@ class Generator(nn.Module):
             raise ValueError(f"expected [N, 3, H, W] input, got {tuple(x.shape)}")
         if not x.is_cuda:
             raise _lib.ResrError("resr_b200.Generator runs on a CUDA (sm_100a) device only; there is no CPU path")
-        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
-            from . import autograd  # training path
-            return autograd.generator_apply(self, x)
+        if x.device != self._device():
+            raise _lib.ResrError(f"input on {x.device} but the generator lives on {self._device()}")
+        if torch.is_grad_enabled():
+            if x.requires_grad:
+                # the reference feeds a detached LR batch (train_realesrnet.py:377-384); the conv1 data gradient is not built
+                raise _lib.ResrError("resr_b200.Generator does not produce a gradient w.r.t. its input: detach() the LR batch")
+            if any(p.requires_grad for p in self.parameters()):
+                from . import autograd  # training path
+                return autograd.generator_apply(self, x)
         return self.infer(x)
 
     @torch.no_grad()
@@ -147,8 +256,9 @@ class Generator(nn.Module):
         y = torch.empty((n, 3, 4 * h, 4 * w), dtype=torch.float32, device=x.device)
         ws = self._get_workspace(n, h, w, x.device)
         wp, wbytes = self._aligned(ws)
-        _lib.check(_lib.lib().resr_generator_forward(self._native(), _lib.ptr(xc), _lib.ptr(y), n, h, w, wp, wbytes,
-                                                     _lib.stream_ptr()))
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().resr_generator_forward(self._native(), _lib.ptr(xc), _lib.ptr(y), n, h, w, wp, wbytes,
+                                                         _lib.stream_ptr(x.device)))
         return y
 
     @torch.no_grad()
@@ -165,7 +275,7 @@ class Generator(nn.Module):
         wp, wbytes = self._aligned(ws)
         with torch.cuda.device(device):
             _lib.check(_lib.lib().resr_generator_forward_host(self._native(), _lib.ptr(xc), _lib.ptr(y_host), n, h, w,
-                                                              wp, wbytes, _lib.stream_ptr()))
+                                                              wp, wbytes, _lib.stream_ptr(device)))
         return y_host
 
 
@@ -188,7 +298,7 @@ class Generator(nn.Module):
         wp, wbytes = self._aligned(ws)
         with torch.cuda.device(device):
             _lib.check(_lib.lib().resr_generator_forward_host_async(self._native(), _lib.ptr(x_host), _lib.ptr(y_host), n, h,
-                                                                    w, wp, wbytes, _lib.stream_ptr()))
+                                                                    w, wp, wbytes, _lib.stream_ptr(device)))
         return y_host
 
     def host_sync(self):

@@ -169,3 +169,37 @@ int main(void) {
     want = [ctypes.sizeof(L.DegradePlan), ctypes.sizeof(L.ResizeSpec), ctypes.sizeof(L.NoiseSpec), L.DegradePlan.noise1.offset,
             L.DegradePlan.rng_state.offset, ctypes.sizeof(L.ConvDesc), ctypes.sizeof(L.KernelParams)]
     assert got == want
+
+
+def test_patch_reference_rebinds_the_three_names_without_touching_call_sites():
+    """compat.patch_reference: `model`, `imgproc`, `F` of a reference-script namespace point at the mirrors; F keeps
+    every torch.nn.functional attribute and only reroutes the interpolate calls the degradation block makes."""
+    import types
+    import torch.nn.functional as F
+    import resr_b200
+    ns = types.SimpleNamespace(model=object(), imgproc=object(), F=F, np=None)
+    assert resr_b200.patch_reference(ns) == ["model", "imgproc", "F"]
+    assert ns.model is resr_b200.model and ns.imgproc is resr_b200.imgproc
+    assert ns.F.leaky_relu is F.leaky_relu and ns.F.l1_loss is F.l1_loss
+    x = torch.rand(1, 3, 8, 10)
+    for kw in (dict(scale_factor=2, mode="nearest"), dict(size=(5, 7), mode="bicubic"), dict(scale_factor=0.5, mode="area")):
+        assert torch.equal(ns.F.interpolate(x, **kw), F.interpolate(x, **kw))  # CPU tensors fall through to torch
+    d = {"F": F, "imgproc": 1}
+    assert resr_b200.patch_reference(d) == ["imgproc", "F"] and "model" not in d
+
+
+def test_param_version_key_sees_data_swaps():
+    """the repack key must change when `param.data` is re-pointed (which does not bump `_version`)."""
+    import resr_b200
+    g = resr_b200.model.Generator(3, 3, 4)
+    v0 = g._param_version()
+    p = list(g.parameters())[10]
+    old = p.data
+    p.data = old.clone()
+    v1 = g._param_version()
+    assert v1 != v0
+    p.data = old
+    assert g._param_version() == v0
+    with torch.no_grad():
+        p.mul_(1.0)
+    assert g._param_version() != v0

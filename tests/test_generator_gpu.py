@@ -131,3 +131,96 @@ def test_generator_awkward_shapes(shape):
     err = (y - ref).abs().max().item()
     psnr = 10 * np.log10(1.0 / max(torch.mean((y - ref) ** 2).item(), 1e-20))
     assert err <= 2e-2 and psnr >= 45.0, (err, psnr)
+
+
+def test_weight_swap_through_param_data_is_seen():
+    """`param.data = t` (EMA.apply_shadow / restore, reference model.py:51-61) does not bump `_version`; the
+    packed tensor-core weights must follow anyway."""
+    from oracle import generator as og
+    g, sd = _make(0)
+    sd2 = og.random_state_dict(1)
+    torch.manual_seed(5)
+    x = torch.rand(1, 3, 16, 24)
+    with torch.no_grad():
+        y0 = g(x.cuda()).cpu()
+        backup = {n: p.data for n, p in g.named_parameters()}
+        for n, p in g.named_parameters():      # apply_shadow
+            p.data = sd2[n].cuda()
+        y1 = g(x.cuda()).cpu()
+        for n, p in g.named_parameters():      # restore
+            p.data = backup[n]
+        y2 = g(x.cuda()).cpu()
+    assert (y1 - og.generator_forward(x, sd2)).abs().max().item() <= MAX_ABS
+    assert not torch.equal(y0, y1) and torch.equal(y0, y2)
+    # frozen-weights serving mode skips the walk; invalidate() forces the repack
+    g.assume_static_weights(True)
+    with torch.no_grad():
+        for n, p in g.named_parameters():
+            p.data = sd2[n].cuda()
+        assert torch.equal(g(x.cuda()).cpu(), y0)
+        g.invalidate()
+        assert torch.equal(g(x.cuda()).cpu(), y1)
+
+
+def test_dense_block_forwards_vs_oracle():
+    """ResidualDenseBlock.forward / ResidualResidualDenseBlock.forward (reference model.py:87-98, 123-132) through
+    resr_conv3x3, against the fp32 oracle of the same blocks."""
+    from oracle import generator as og
+    g, sd = _make(2)
+    torch.manual_seed(8)
+    x = torch.randn(2, 64, 20, 136) * 0.5
+    rrdb = g.trunk[3]
+    with torch.no_grad():
+        y_rdb = rrdb.rdb2(x.cuda()).cpu()
+        y_rrdb = rrdb(x.cuda()).cpu()
+    ref_rdb = og.rdb_forward(x, sd, "trunk.3.rdb2")
+    ref_rrdb = og.rrdb_forward(x, sd, "trunk.3")
+    e1, e2 = (y_rdb - ref_rdb).abs().max().item(), (y_rrdb - ref_rrdb).abs().max().item()
+    print(f"rdb max-abs {e1:.2e}, rrdb max-abs {e2:.2e} (|x| up to {x.abs().max():.1f})")
+    assert e1 <= 4e-3 and e2 <= 4e-3
+    with pytest.raises(ValueError):
+        rrdb(torch.rand(1, 3, 8, 8, device="cuda"))
+
+
+def test_input_gradient_request_raises():
+    import resr_b200
+    g, _ = _make(0)
+    x = torch.rand(1, 3, 8, 8, device="cuda", requires_grad=True)
+    with pytest.raises(resr_b200._lib.ResrError):
+        g(x)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_second_device_first_in_one_process():
+    """Per-device tables / function attributes: run everything on cuda:1 BEFORE cuda:0 has been
+    touched by the library, with cuda:0 the current device, then on cuda:0, and compare."""
+    import resr_b200
+    from oracle import generator as og
+    ip = resr_b200.imgproc
+    sd = og.random_state_dict(3)
+    rng = np.random.default_rng(0)
+    img = torch.from_numpy(rng.random((2, 3, 64, 80), dtype=np.float32))
+    q = torch.tensor([35.0, 80.0])
+    x = torch.rand(1, 3, 16, 24)
+    outs = []
+    for dev in ("cuda:1", "cuda:0"):
+        g = resr_b200.model.Generator(3, 3, 4)
+        g.load_state_dict(sd)
+        g = g.to(dev).eval()
+        with torch.no_grad():
+            y = g(x.to(dev))
+        u = ip.USMSharp(50, 0)(img.to(dev), 0.5, 10)
+        j = ip.DiffJPEG(False)(img.to(dev), q.to(dev).clone())
+        k = torch.zeros(1, 21, 21, device=dev)
+        k[0, 8:13, 8:13] = 1 / 25
+        f = ip.filter2d_torch(img.to(dev), k)
+        assert y.device == torch.device(dev) and u.device == torch.device(dev)
+        outs.append([t.cpu() for t in (y, u, j, f)])
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    assert (outs[0][0] - og.generator_forward(x, sd)).abs().max().item() <= MAX_ABS
+    assert outs[0][1].abs().sum().item() > 0 and outs[0][2].abs().sum().item() > 0
+    # a generator moved between devices re-creates its handle and repacks
+    g = g.to("cuda:1")
+    with torch.no_grad():
+        assert torch.equal(g(x.to("cuda:1")).cpu(), outs[0][0])

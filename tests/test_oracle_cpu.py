@@ -163,3 +163,16 @@ def test_kernel_synthesis_oracle_and_rng_order(golden_dir):
     for i in range(4):
         om, ks, pad = z[f"sinc_{i}_args"]
         assert np.abs(ok.sinc(float(om), int(ks), int(pad)) - z[f"sinc_{i}"]).max() <= 1e-15
+
+
+def test_filter2d_fft_path_equals_direct_definition():
+    """The FFT evaluation used for BASELINE-size inputs is the same float64 cross-correlation as the tap-by-tap sum."""
+    from oracle import degrade as od
+    rng = np.random.default_rng(4)
+    x = rng.random((2, 3, 61, 83), dtype=np.float32)
+    k = rng.random((2, 21, 21)).astype(np.float32)
+    k[:, :3] = 0
+    k /= k.sum((1, 2), keepdims=True)
+    assert np.abs(od.filter2d(x, k, "direct").astype(np.float64) - od.filter2d(x, k, "fft")).max() <= 1e-7
+    ku = od.usm_kernel_2d()
+    assert np.abs(od.filter2d(x, ku, "direct").astype(np.float64) - od.filter2d(x, ku, "fft")).max() <= 1e-7

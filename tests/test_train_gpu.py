@@ -194,3 +194,28 @@ def test_training_loop_step_graph_plus_fused_optimizer_reduces_the_loss():
     print("losses", [round(v, 5) for v in losses])
     assert losses[-1] < losses[0] * 0.9 and min(losses[4:]) < min(losses[:2])
     assert torch.isfinite(opt.flat).all() and torch.isfinite(opt.shadow).all()
+
+
+def test_stale_backward_is_refused():
+    """the saved activations live in ONE workspace per Generator; a second training-mode forward before the
+    first backward must not silently produce gradients for the wrong activations."""
+    import resr_b200
+    from oracle import generator as og
+    g = resr_b200.model.Generator(3, 3, 4)
+    g.load_state_dict(og.random_state_dict(0))
+    g = g.cuda().train()
+    x1 = torch.rand(1, 3, 8, 16, device="cuda")
+    x2 = torch.rand(1, 3, 8, 16, device="cuda")
+    sr1 = g(x1)
+    sr2 = g(x2)                      # overwrites the activations sr1's graph refers to
+    with pytest.raises(resr_b200._lib.ResrError):
+        sr1.mean().backward()
+    sr2.mean().backward()            # the latest forward is still consistent
+    assert next(g.parameters()).grad is not None
+    # an inference forward (no_grad) in between is harmless: it uses the inference workspace
+    g.zero_grad(set_to_none=True)
+    sr3 = g(x1)
+    with torch.no_grad():
+        g(x2)
+    sr3.mean().backward()
+    assert torch.isfinite(next(g.parameters()).grad).all()
