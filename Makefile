@@ -18,7 +18,13 @@ $(LIB): $(OBJS)
 	@mkdir -p $(PKG)/lib
 	$(NVCC) -shared -o $@ $(OBJS) -cudart static
 
+# development variants (A/B runs on one box through RESR_LIB_PATH): make variant NAME=prof DEFS=-DRESR_PROFILE_WAITS
+variant:
+	@mkdir -p build/variants/$(NAME)
+	for f in $(SRCS); do $(NVCC) $(NVFLAGS) $(DEFS) -c $$f -o build/variants/$(NAME)/$$(basename $$f .cu).o || exit 1; done
+	$(NVCC) -shared -o build/variants/libresr_$(NAME).so build/variants/$(NAME)/*.o -cudart static
+
 clean:
 	rm -rf build $(LIB)
 
-.PHONY: all clean
+.PHONY: all clean variant

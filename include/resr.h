@@ -79,6 +79,9 @@ int resr_generator_host_sync(resr_generator_t* g);
 
 /* Number of kernels of this library that one resr_generator_forward launches (for bench accounting). */
 int resr_generator_launches_per_forward(void);
+/* Development aid: wait-time counters of the CTA-pair convolution kernel (16 x u64 clock cycles summed over CTAs; all
+ * zero unless the library was built with -DRESR_PROFILE_WAITS). out16_host may be NULL; reset != 0 clears them. */
+int resr_debug_wait_profile(unsigned long long* out16_host, int reset);
 
 /* One 3x3 convolution through the same tensor-core kernel (test / building block).
  * in16: NHWC 16-bit activations [n,h,w,c_total]; the first `cin` channels are convolved.

@@ -29,6 +29,7 @@ struct ConvArgs {
     int nepi;       // epilogue warp groups (1 or 2), rows alternate between them
     int fmt_in;     // MMA operand format: 0 fp16, 1 bf16
     long long rows_total;  // ncg * H
+    long long rows_total_pair;  // ceil(ncg / 2) * H: work units of the CTA-pair kernel (filled by its launcher)
     const uint8_t* wpack;  // [slice][chunk][dx][(dy,co) x 64ch] 16-bit, 128B-swizzled, ready for a bulk copy
     const float* bias;     // [nslices * NOUT]
     // epilogue
@@ -87,6 +88,26 @@ cudaError_t conv3x3_launch(const ConvMaps& maps, const ConvArgs& args, int cout_
 
 // Fills nstages / nepi from the shared-memory budget. Returns false if the configuration does not fit.
 bool conv3x3_plan_smem(ConvArgs* args, int cout_slice);
+
+// ---- CTA-pair kernel (conv3x3_pair.cu): tcgen05 cta_group::2, M = 256; reads the same weight packs.
+// nout: accumulator columns per output row of a pair (64 = two 32-channel pack slices per pair, 32, or 16).
+bool conv3x3_pair_plan_smem(ConvArgs* args, int nout);
+cudaError_t conv3x3_pair_launch(const ConvMaps& maps, const ConvArgs& args, int nout, int nslices, int num_sms,
+                                cudaStream_t stream);
+
+// Development builds (-DRESR_PROFILE_WAITS): copies / resets the pair kernel's wait-time counters (16 x u64 cycles).
+int conv3x3_wait_profile(unsigned long long* out16, int reset);
+
+// Kernel choice for one convolution whose weights are packed in `pack_nout`-channel slices (`pack_nslices` of them).
+struct ConvLaunchCfg {
+    int pair;     // 1: CTA-pair kernel, 0: single-CTA kernel
+    int nout;     // channels per launch slice
+    int nslices;  // blockIdx.y extent
+};
+// Picks the kernel (pairs whenever there are at least two column groups to pair up; RESR_CONV_PAIR=0 forces the
+// single-CTA kernel), fills args->nstages / nepi. Returns false if the configuration does not fit in shared memory.
+bool conv3x3_choose(ConvArgs* args, int pack_nout, int pack_nslices, ConvLaunchCfg* cfg);
+cudaError_t conv3x3_run(const ConvMaps& maps, const ConvArgs& args, const ConvLaunchCfg& cfg, int num_sms, cudaStream_t stream);
 
 // Tensor maps. base: NHWC tensor [N,H,W,C].
 int conv3x3_make_tmap_act(CUtensorMap* out, const void* base, int N, int H, int W, int C, int mode, int BW, int BN,

@@ -82,6 +82,7 @@ struct Step {
     int conv;   // index into the layer table
     ConvMaps maps;
     ConvArgs a;
+    ConvLaunchCfg cfg;  // which kernel runs it (CTA pair or single CTA) and its slicing
 };
 
 struct Plan {

@@ -251,7 +251,7 @@ static int build_plan(resr_generator* g, int N, int H, int W, void* ws, cudaStre
         st.a.has_res1 = 1; st.a.res_choff = 0; st.a.res1 = src; st.a.res1_cstride = 64;
     };
     auto push = [&](Step& st) {
-        if (!conv3x3_plan_smem(&st.a, T.c[st.conv].nout)) map_rc |= 1 << 20;
+        if (!conv3x3_choose(&st.a, T.c[st.conv].nout, T.c[st.conv].nslices, &st.cfg)) map_rc |= 1 << 20;
         p.steps.push_back(st);
     };
 
@@ -345,6 +345,11 @@ int resr_version(void) { return 1; }
 size_t resr_generator_num_params(void) { return table().n_params; }
 int resr_generator_num_tensors(void) { return 2 * kNumConvs; }
 int resr_generator_launches_per_forward(void) { return 1 + kNumConvs; }
+
+int resr_debug_wait_profile(unsigned long long* out16_host, int reset) {
+    if (conv3x3_wait_profile(out16_host, reset) != 0) return set_error(RESR_E_CUDA, "wait profile copy failed");
+    return RESR_OK;
+}
 
 int resr_generator_tensor_span(int index, size_t* offset, size_t* count) {
     if (index < 0 || index >= 2 * kNumConvs || !offset || !count) return set_error(RESR_E_INVALID, "bad tensor index");
@@ -440,8 +445,7 @@ int resr_generator_forward(resr_generator_t* g, const float* x, float* y, int n,
     for (size_t i = 0; i < p.steps.size(); ++i) {
         Step& st = p.steps[i];
         if (i + 1 == p.steps.size()) st.a.out_nchw = y;
-        const ConvSpec& cs = T.c[st.conv];
-        const cudaError_t e = conv3x3_launch(st.maps, st.a, cs.nout, cs.nslices, g->num_sms, s);
+        const cudaError_t e = conv3x3_run(st.maps, st.a, st.cfg, g->num_sms, s);
         if (e != cudaSuccess) return set_error(RESR_E_CUDA, "conv %d launch: %s", st.conv, cudaGetErrorString(e));
     }
     return RESR_OK;
@@ -588,10 +592,11 @@ int resr_conv3x3(const resr_conv_desc* d, void* stream) {
     a.out_nchw = d->out_nchw; a.out_nchw_c = d->out_nchw_c;
     a.dbg = d->dbg;
     a.dbg_flags = d->dbg_flags;
-    if (!conv3x3_plan_smem(&a, nout)) rc |= 1 << 20;
+    ConvLaunchCfg cfg;
+    if (!conv3x3_choose(&a, nout, nslices, &cfg)) rc |= 1 << 20;
     if (nout == 16 && (d->out16 || d->outf || d->res1)) rc |= 1 << 21;  // the 16-wide slice only feeds the NCHW output
     cudaError_t e = cudaSuccess;
-    if (rc == 0) e = conv3x3_launch(maps, a, nout, nslices, sms, s);
+    if (rc == 0) e = conv3x3_run(maps, a, cfg, sms, s);
     const cudaError_t e2 = cudaStreamSynchronize(s);
     cudaFree(wp);
     cudaFree(bp);
