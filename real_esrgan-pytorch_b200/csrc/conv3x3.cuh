@@ -26,7 +26,8 @@ struct ConvArgs {
     int mode;       // 0: one TMA load of BW+2 px per (row, chunk), dx taken by shifting the smem descriptor
                     // 1: three TMA loads per (row, chunk), one per dx (any BW x BN split)
     int nstages;    // activation ring depth
-    int nepi;       // epilogue warp groups (1 or 2), rows alternate between them
+    int nepi;       // epilogue warp groups (1 .. 3), rows alternate between them
+    int epi_bufs;   // pair kernel: staging tiles per epilogue group (2 = a pass never waits for the previous pass's TMA store)
     int fmt_in;     // MMA operand format: 0 fp16, 1 bf16
     long long rows_total;  // ncg * H
     long long rows_total_pair;  // ceil(ncg / 2) * H: work units of the CTA-pair kernel (filled by its launcher)

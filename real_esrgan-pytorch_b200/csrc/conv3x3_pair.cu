@@ -65,10 +65,14 @@ struct RowRange {
 constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
 __device__ __forceinline__ uint64_t desc_of(uint32_t lo) { return (static_cast<uint64_t>(kDescHi) << 32) | lo; }
 
-__host__ __device__ inline int epi_group_bytes_pair(const ConvArgs& a, int subw) {
+// one staging buffer of an epilogue group: [fp32 tile][16-bit tile]
+__host__ __device__ inline int epi_buf_bytes_pair(const ConvArgs& a, int subw) {
     const int f = a.has_outf ? kTileFBytes : 0;
     const int h = a.has_out16 ? 128 * subw * 2 : 0;
     return f + (h + 1023) / 1024 * 1024;
+}
+__host__ __device__ inline int epi_group_bytes_pair(const ConvArgs& a, int subw) {
+    return (a.epi_bufs == 2 ? 2 : 1) * epi_buf_bytes_pair(a, subw);
 }
 
 template <int S>
@@ -361,8 +365,10 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
         const int q = warp & 3;        // TMEM lane quadrant this warp may access
         const int m = q * 32 + lane;   // M row == TMEM lane == pixel of this CTA's tile
         const bool lead_warp = ((warp - 4) & 3) == 0;
-        uint8_t* tileR = epi + gi * epi_bytes;
-        uint8_t* tile16 = tileR + (a.has_outf ? kTileFBytes : 0);
+        uint8_t* const tile_base = epi + gi * epi_bytes;
+        const int buf_bytes = epi_buf_bytes_pair(a, SUBW);
+        const bool two_bufs = a.epi_bufs == 2;
+        uint32_t pass = 0;   // staged passes of this group so far (selects the staging buffer)
         const uint32_t lane_base = tbase + (static_cast<uint32_t>(q * 32) << 16);
         const uint32_t free0 = map_to_cta(smem_u32(slot_free), 0);  // the leader's slot barriers
         const int img_in_tile = m / a.BW;
@@ -493,11 +499,16 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
                             }
                         }
                     }
-                    if (staged) {  // the output tiles are free once the previous pass's TMA stores have read them
+                    uint8_t* const tileR = tile_base + ((two_bufs && (pass & 1u)) ? buf_bytes : 0);  // fp32 output tile
+                    uint8_t* const tile16 = tileR + (a.has_outf ? kTileFBytes : 0);                  // 16-bit output tile
+                    if (staged) {
+                        // the staging buffer is free once the TMA stores that last used it have read it: the previous pass's
+                        // (one buffer) or the pass before that (two buffers: the wait is normally already satisfied)
                         PROF_T0(p_t);
-                        if (lead_warp) tma_store_wait_read();
+                        if (lead_warp) { if (two_bufs) tma_store_wait_read1(); else tma_store_wait_read(); }
                         named_bar_sync(1 + gi, 128);
                         PROF_ADD(p_tile, p_t);
+                        ++pass;
                     }
                     if (a.ep_mode == EP_RRDB) {
                         if (a.res16) {
@@ -647,14 +658,19 @@ bool conv3x3_pair_plan_smem(ConvArgs* a, int nout) {
     if (env) nepi = atoi(env);
     if (nepi < 1) nepi = 1;
     if (nepi > 3) nepi = 3;
+    static const int env_bufs = getenv("RESR_CONV_EPI_BUFS") ? atoi(getenv("RESR_CONV_EPI_BUFS")) : 2;
     for (;; --nepi) {
         a->nepi = nepi;
-        const int fixed = 1024 + wbytes + nepi * epi_group_bytes_pair(*a, subw) + kMiscBytes;
-        int ns = (kSmemMax - fixed) / kStageBytes;
-        if (ns > kMaxStages) ns = kMaxStages;
-        if (ns >= 4 || nepi == 1) {
-            a->nstages = ns;
-            return ns >= 2;
+        for (int bufs = env_bufs == 2 ? 2 : 1; bufs >= 1; --bufs) {
+            a->epi_bufs = bufs;
+            const int fixed = 1024 + wbytes + nepi * epi_group_bytes_pair(*a, subw) + kMiscBytes;
+            int ns = (kSmemMax - fixed) / kStageBytes;
+            if (ns > kMaxStages) ns = kMaxStages;
+            // two staging tiles per group only where they do not eat into the activation ring (>= 6 stages left)
+            if ((bufs == 2 && ns >= 6) || (bufs == 1 && (ns >= 4 || nepi == 1))) {
+                a->nstages = ns;
+                return ns >= 2;
+            }
         }
     }
 }
@@ -725,7 +741,12 @@ bool conv3x3_choose(ConvArgs* a, int pack_nout, int pack_nslices, ConvLaunchCfg*
     cfg->pair = 0;
     cfg->nout = pack_nout;
     cfg->nslices = pack_nslices;
-    if (env_pair && a->ncg >= 2) {
+    // Pairs pay off once every pair has a real strip of rows: below ~6 rows per pair (cfg4's 16x3x64x64 training batch:
+    // 256 pair-rows over 74 pairs) the launch is dominated by its prologue and the two halo rows per strip, and the
+    // single-CTA kernel is as fast or faster (measured 25.6 vs 26.4 ms per training step). RESR_CONV_PAIR=2 forces pairs.
+    const long long pair_rows = static_cast<long long>((a->ncg + 1) / 2) * a->H;
+    const bool big_enough = pair_rows >= 6 * 74 || env_pair == 2;
+    if (env_pair && a->ncg >= 2 && big_enough) {
         ConvArgs t = *a;
         int nout = pack_nout, nslices = pack_nslices;
         if (env_n64 && pack_nout == 32 && pack_nslices % 2 == 0) { nout = 64; nslices = pack_nslices / 2; }

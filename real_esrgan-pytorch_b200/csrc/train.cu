@@ -266,9 +266,10 @@ static int launch_conv_io(const resr_generator* g, const Geo& q, int N, const Co
     a.res2 = io.res2; a.res2_cstride = io.res2_c; a.res2_scale = io.res2_scale;
     a.mask16 = io.mask16; a.mask16_cstride = io.mask16_c; a.mask16_choff = io.mask16_choff;
     a.out_nchw = io.out_nchw; a.out_nchw_raw = io.out_nchw_raw; a.out_nchw_c = io.out_nchw_c;
-    if (!conv3x3_plan_smem(&a, io.nout)) rc |= 1 << 20;
+    ConvLaunchCfg cfg;  // CTA-pair kernel whenever two column groups can be paired (conv3x3_pair.cu)
+    if (!conv3x3_choose(&a, io.nout, io.nslices, &cfg)) rc |= 1 << 20;
     if (rc != 0) return set_error(RESR_E_CUDA, "conv planning failed (%d)", rc);
-    const cudaError_t e = conv3x3_launch(m, a, io.nout, io.nslices, g->num_sms, s);
+    const cudaError_t e = conv3x3_run(m, a, cfg, g->num_sms, s);
     if (e != cudaSuccess) return set_error(RESR_E_CUDA, "conv launch: %s", cudaGetErrorString(e));
     return RESR_OK;
 }
