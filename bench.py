@@ -1,22 +1,29 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of BASELINE.json ("x4 RRDBNet LR Mpix/s + degraded pairs/s ... % of roofline").
+"""bench.py — headline benchmark of BASELINE.json ("x4 RRDBNet LR Mpix/s + degraded pairs/s at 1/2/4/8 B200, % of roofline").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision fp16|bf16]
 
-Our arm (default): one step = one RRDBNet x4 forward of a 64x3x128x128 LR batch (BASELINE.json configs[2]) per GPU,
-batch-sharded (every rank owns its own 64 images, no collective on the data path). Rank 0 prints ONE JSON line:
-  value      device-timed LR Mpix/s, inputs resident in HBM (CUDA events on the launch stream, max over ranks)
-  e2e        the same through the host-buffer C ABI call (pinned H2D + forward + D2H inside the timed region)
-  roofline   tensor-core roofline of the conv kernel against MEASURED_PEAKS.json
-  cpu_baseline  the fp32 oracle port of the reference forward on this box's host cores (bounded sample)
-  degradation   secondary object: degraded pairs/s of the second-order pipeline (configs[1], canonical plan S0)
-                with its HBM roofline (stage-sum bytes)
-`--impl reference`: the reference's own CPU implementation of the path (oracle port; /root/reference does not exist
-on the GPU box) timed on the host cores, one 1x3x128x128 image per step.
+Our arm (default). One step = one RRDBNet x4 forward of the 64x3x128x128 LR batch of BASELINE.json configs[2], batch-
+sharded over the N ranks (64 / N images per rank: STRONG scaling, the configuration BASELINE names; no collective on the
+data path). Rank 0 prints ONE JSON line:
+  value         device-timed LR Mpix/s of the whole job, inputs resident in HBM (CUDA events, max over ranks)
+  e2e           the same through the host-buffer C ABI call (pinned H2D + forward + D2H inside the timed region)
+  roofline      tensor-core roofline of the conv kernels against MEASURED_PEAKS.json
+  cpu_baseline  (N = 1) the fp32 oracle port of the reference forward on this box's host cores (bounded sample)
+  weak          (N > 1) secondary: every rank runs its own 64 images
+  tiled         secondary, configs[4]: 1x3x2048x2048 -> 8192x8192 by full-width halo bands dealt to the N ranks, gathered
+                into rank 0's buffer by NCCL send / recv, end to end from / to pinned host memory
+  degradation   secondary, configs[1]: degraded pairs/s of the second-order pipeline (canonical plan S0, real sinc and
+                mixed blur kernels), device-timed + e2e (HR from pinned host every step) + HBM and FMA rooflines + CPU port
+  training      secondary, configs[3]: degradation + generator forward / L1 / backward (+ NCCL all-reduce) per GPU
+`--impl reference`: the reference's own CPU implementation of the path (oracle port; /root/reference does not exist on
+the GPU box) timed on the host cores, one 1x3x128x128 image per step.
 """
 import argparse
 import json
+import math
 import os
+import random
 import subprocess
 import sys
 import threading
@@ -30,15 +37,20 @@ import torch  # noqa: E402
 
 FLOP_PER_LR_PIXEL = 35853696.0  # SURVEY.md §8a layer table
 METRIC = "x4 RRDBNet LR Mpix/s"
+TOTAL_BATCH = 64                # BASELINE.json configs[2]
 
 
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    out = {"hbm": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
     if os.path.exists(p):
         d = json.load(open(p))
-        return {"hbm": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d["bf16_tflops_sustained"],
-                "source": "MEASURED_PEAKS.json"}
-    return {"hbm": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+        out = {"hbm": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d["bf16_tflops_sustained"],
+               "source": "MEASURED_PEAKS.json"}
+    # fp32 FMA peak measured on this pool's B200 with tools/fma_peak.cu (register-resident FFMA chains)
+    f = os.path.join(ROOT, "profiles", "r02_fma_peak.json")
+    out["tfma"] = json.load(open(f))["fp32_tfma_sustained"] if os.path.exists(f) else 36.2
+    return out
 
 
 class ClockSampler:
@@ -92,10 +104,68 @@ class ClockSampler:
         bits = 0
         for r in self.rows:
             bits |= r[1]
-        # NVML clocks-event-reason bits
         names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
         reasons = [n for b, n in names.items() if bits & b]
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm)}
+
+
+class Dist:
+    """Rank plumbing: barrier + max-over-ranks of device-timed milliseconds."""
+
+    def __init__(self):
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.device = None
+
+    def init(self):
+        import torch.distributed as dist
+        torch.cuda.set_device(self.local)
+        self.device = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.device)
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_ms(self, *ms):
+        t = torch.tensor(list(ms), device=self.device, dtype=torch.float64)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t.tolist()]
+
+    def finish(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            dist.destroy_process_group()
+
+
+def timed(fn, steps, D, fin=None, warm=0):
+    """`steps` calls of fn(k) bracketed by barrier + synchronize on both sides, CUDA events on the current stream."""
+    for k in range(warm):
+        fn(k)
+    if fin:
+        fin()
+    D.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for k in range(steps):
+        fn(k)
+    if fin:
+        fin()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    D.barrier()
+    return ms
+
+
+# ------------------------------------------------------------------------------------------------- CPU baselines
 
 
 def cpu_generator_baseline(seconds_budget=20.0, max_iters=5):
@@ -117,108 +187,138 @@ def cpu_generator_baseline(seconds_budget=20.0, max_iters=5):
             "sample": f"{len(times)} fp32 forwards of 1x3x128x128 (BASELINE configs[0]), median {med:.3f} s"}
 
 
+def cpu_degradation_baseline(kernels_np, seconds_budget=15.0, batch=4):
+    """numpy oracle port of train_realesrnet.py:267-377 (oracle/degrade.py) on `batch` HR crops of the same workload
+    (canonical plan S0, the same kind of kernels), noise drawn on the fly as the reference does."""
+    import resr_b200
+    from oracle import degrade as od
+    rng = np.random.default_rng(0)
+    hr = rng.random((batch, 3, 256, 256), dtype=np.float32)
+    plan = resr_b200.plan.canonical_plan_s0(batch, 256, 256, seed=0)
+    plan["noise1"]["noise_color"] = None   # drawn inside the timed region, like torch.randn in the reference
+    k1, k2, sk = (k[:batch] for k in kernels_np)
+    od.degrade_batch(hr[:1], k1[:1], k2[:1], sk[:1], resr_b200.plan.canonical_plan_s0(1, 256, 256, seed=0), draw_rng=rng)  # warm-up (imports, FFT plans)
+    times = []
+    t_all = time.perf_counter()
+    while len(times) < 5 and (time.perf_counter() - t_all) < seconds_budget:
+        t0 = time.perf_counter()
+        od.degrade_batch(hr, k1, k2, sk, plan, draw_rng=rng)
+        times.append(time.perf_counter() - t0)
+    med = sorted(times)[len(times) // 2]
+    return {"value": batch / med, "unit": "pairs/s", "cores": 1, "kind": "port",
+            "sample": f"{len(times)} runs of the numpy port on {batch}x3x256x256 HR crops (plan S0), median {med:.3f} s; "
+                      "numpy / scipy.fft are single-threaded apart from BLAS inside the JPEG DCT"}
+
+
 # ------------------------------------------------------------------------------------------------- degradation
 
 
-def degradation_bench(device, steps, warmup, peaks, B=16):
-    """configs[1]: B x 3 x 256 x 256 HR crops (B = 16) through the canonical plan S0; device-timed with resident inputs.
-    B = 256 is the large-batch variant SURVEY.md §8d asks for (launch latencies amortised)."""
+def s0_kernels(B, device, seed=0):
+    """kernel1 / kernel2 / sinc kernel for the canonical plan S0: mixed Gaussian-family / sinc blur kernels with the
+    reference's distributions (dataset.py:81-141) synthesised on the device (resr_synthesize_kernels); the final kernel is
+    a REAL sinc for every sample (S0 says "sinc"; the dataset draws one with p = 0.8)."""
     import resr_b200
     ip = resr_b200.imgproc
+    P = dict(resr_b200.plan.DEGRADATION_MODEL_PARAMETERS)
+    P["sinc_kernel_probability3"] = 1.0
+    random.seed(seed)
+    np.random.seed(seed)
+    return ip.synthesize_degradation_kernels(B, P, device)
+
+
+def s0_stage_bytes(B, H=256, W=256):
+    """Stage-sum algorithmic bytes of S0: 4 B x (elements read + written) per EXECUTED stage. The third
+    resize of S0 is a same-size resize (bit-exact identity, skipped: not counted); the Poisson stage reads its input twice
+    (level census, then the noise pass) and draws its samples in the kernel (no sample tensor is read)."""
+    E0 = B * 3 * H * W
+    e1, e2 = E0 // 4, E0 // 16
+    stages = {"usm": 2 * E0, "blur1": 2 * E0, "resize1": E0 + e1, "noise1": 2 * e1 + e1, "jpeg1": 2 * e1, "blur2": 2 * e1,
+              "resize2": e1 + e2, "noise2": 2 * e2, "sinc": 2 * e2, "jpeg2": 2 * e2, "round_crop": 2 * e2}
+    fma = {"usm": 4 * 51 * E0, "blur1": None, "blur2": None, "sinc": None}
+    return 4 * sum(stages.values()), stages, fma
+
+
+def stencil_fmas(k1, k2, sk, H=256, W=256):
+    """Necessary FMAs of the S0 stencils: separable 51-tap USM (2 blurs x 2 passes) + per-sample trimmed supports."""
+    def support(k):
+        nz = (k != 0).nonzero()
+        ext = (nz[:, 1:] - 10).abs().amax(1)
+        out = torch.zeros(k.shape[0], dtype=torch.long)
+        out.scatter_reduce_(0, nz[:, 0].cpu(), (2 * ext + 1).cpu(), reduce="amax")
+        return out
+    s1, s2, s3 = support(k1), support(k2), support(sk)
+    px0, px1, px2 = 3 * H * W, 3 * H * W // 4, 3 * H * W // 16
+    return float(4 * 51 * px0 * k1.shape[0] + (s1 * s1).sum() * px0 + (s2 * s2).sum() * px1 + (s3 * s3).sum() * px2)
+
+
+def degradation_bench(D, steps, warmup, peaks, B=16, want_e2e=True):
+    """configs[1]: B x 3 x 256 x 256 HR crops through the canonical plan S0."""
+    import resr_b200
+    ip = resr_b200.imgproc
+    device = D.device
     H, W = 256, 256
     plan = resr_b200.plan.canonical_plan_s0(B, H, W, seed=0)
-    g = torch.Generator(device="cpu").manual_seed(0)
-    hr = torch.rand(B, 3, H, W, generator=g).to(device)
-    k = torch.zeros(B, 21, 21)
-    ax = torch.arange(21) - 10.0
-    for i in range(B):  # isotropic Gaussians of assorted support, zero-padded to 21 (dataset.py:102-103)
-        ks = 7 + 2 * (i % 8)
-        s = 0.5 + 0.3 * i
-        kk = torch.exp(-(ax[:, None] ** 2 + ax[None] ** 2) / (2 * s * s))
-        kk[(ax.abs() > ks // 2)[:, None] | (ax.abs() > ks // 2)[None]] = 0
-        k[i] = kk / kk.sum()
-    k1 = k.to(device)
-    k2 = k.flip(0).contiguous().to(device)
-    sk = torch.zeros(B, 21, 21)
-    sk[:, 10, 10] = 1
-    sk = sk.to(device)
-    # One CUDA graph for the whole plan-driven launch sequence; every plan tensor is resident on the device.
-    pipe = ip.DegradePipeline(hr, k1, k2, sk, plan)
+    g = torch.Generator(device="cpu").manual_seed(100 + D.rank)
+    hr_host = torch.rand(B, 3, H, W, generator=g).pin_memory()
+    k1, k2, sk = s0_kernels(B, device)
+    pipe = ip.DegradePipeline(hr_host.to(device), k1, k2, sk, plan)
+    ms = timed(lambda k: pipe(), steps, D, warm=max(3, warmup))
+    out = {"ms_dev": ms}
+    if want_e2e:
+        # end to end: every step copies its HR batch from pinned host memory into the pipeline's input buffer and reads the
+        # LR batch back; two pipelines alternate so that the copies of one step overlap the kernels of the other
+        pipes = [pipe, ip.DegradePipeline(hr_host.to(device), k1, k2, sk, plan)]
+        streams = [torch.cuda.Stream(device=device) for _ in range(2)]
+        lr_host = [torch.empty(B, 3, H // 4, W // 4).pin_memory() for _ in range(2)]
 
-    def step():
-        return pipe()
+        def step(k):
+            i = k & 1
+            with torch.cuda.stream(streams[i]):
+                pipes[i].hr.copy_(hr_host, non_blocking=True)
+                lr, _ = pipes[i]()
+                lr_host[i].copy_(lr, non_blocking=True)
 
-    for _ in range(max(3, warmup)):
-        step()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        lr, hrc = step()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
-    # stage-sum algorithmic bytes of S0 (SURVEY.md §8d): 4 B x (elements read + written) per executed stage
-    E0 = B * 3 * H * W
-    e1_, e2_ = E0 // 4, E0 // 16
-    stage_bytes = 4 * (2 * E0 + 2 * E0 + (E0 + e1_) + (2 * e1_ + e1_) + 2 * e1_ + 2 * e1_ + (e1_ + e2_) + (2 * e2_ + e2_)
-                       + 2 * e2_ + 2 * e2_ + 2 * e2_ + 2 * e2_)
-    gbs = stage_bytes / (ms * 1e-3) / 1e9
-    return {"metric": "degraded pairs/s", "value": B / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms,
-            "config": {"workload": f"second-order degradation, {B}x3x256x256 HR -> {B}x3x64x64 LR, canonical plan S0 "
-                                   "(SURVEY.md §8d): Gaussian noise tensors host-fed and resident, Poisson draws made "
-                                   "inside the fused noise kernel (Philox) in the timed region; one CUDA-graph replay per batch"},
-            "gpu_launches_per_step": 14,
-            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
-                         "traffic": None, "algorithmic_bytes_per_step": stage_bytes,
-                         "note": "stage-sum bytes / whole-pipeline time; blur stencils are FMA-bound (SURVEY.md §8d caveat)"}}
+        def fin():
+            for s in streams:
+                torch.cuda.current_stream(device).wait_stream(s)
+
+        for s in streams:
+            s.wait_stream(torch.cuda.current_stream(device))
+        out["ms_e2e"] = timed(step, steps, D, fin=fin, warm=4)
+        out["h2d"], out["d2h"] = hr_host.numel() * 4, lr_host[0].numel() * 4
+    out["fma"] = stencil_fmas(k1, k2, sk)
+    out["kernels_np"] = tuple(k.cpu().numpy() for k in (k1, k2, sk))
+    return out
 
 
 # ------------------------------------------------------------------------------------------------- training step
 
 
-def training_bench(device, steps, warmup, peaks, world):
+def training_bench(D, steps, warmup, peaks):
     """configs[3]: RealESRNet training-step core per GPU — plan-driven degradation of 16 HR crops (256^2 -> LR 64^2),
     generator forward + L1 + backward, and (world > 1) the NCCL all-reduce of the flat gradient vector. Optimizer / EMA
     are outside the north-star path."""
-    import torch.distributed as dist
-
     import resr_b200
     ip = resr_b200.imgproc
+    device, world = D.device, D.world
     B, H, W = 16, 256, 256
     plan = resr_b200.plan.canonical_plan_s0(B, H, W, seed=1)
     g = torch.Generator(device="cpu").manual_seed(2)
     hr = torch.rand(B, 3, H, W, generator=g).to(device)
-    k = torch.zeros(B, 21, 21)
-    k[:, 8:13, 8:13] = 1 / 25
-    k = k.to(device)
-    pipe = ip.DegradePipeline(hr, k, k, k, plan)
+    k1, k2, sk = s0_kernels(B, device, seed=3)   # reference-range supports (7 .. 21), real sinc
+    pipe = ip.DegradePipeline(hr, k1, k2, sk, plan)
     torch.manual_seed(0)
     gen = resr_b200.model.Generator(3, 3, 4).to(device).train()
     ts = resr_b200.autograd.TrainStep(gen, B, H // 4, W // 4, device, None, world)
+    state = {}
 
-    def step():
+    def step(k):
         lr, hr_c = pipe()
-        return ts.step(lr, hr_c, scatter=False)
+        state["loss"], _, _ = ts.step(lr, hr_c, scatter=False)
 
-    for _ in range(max(3, warmup)):
-        loss, _, _ = step()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        loss, _, _ = step()
-    e1.record()
-    torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1) / steps], device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    ms = timed(step, steps, D, warm=max(3, warmup))
+    ms = D.max_ms(ms)[0]
     tflops = 3 * FLOP_PER_LR_PIXEL * B * (H // 4) * (W // 4) / (ms * 1e-3) / 1e12
-    # optimizer side (SURVEY.md §8 row f1, outside the north-star metric): fused Adam + EMA over the flat vectors and the
-    # repack of the tensor-core weight tiles that the next forward needs
     opt_info = None
     try:
         opt = resr_b200.optim.FlatAdamEMA(gen)
@@ -234,17 +334,82 @@ def training_bench(device, steps, warmup, peaks, world):
             gen._ensure_packed()
         o1.record()
         torch.cuda.synchronize()
-        oms = o0.elapsed_time(o1) / 5
-        opt_info = {"ms_per_step": oms, "what": "resr_adam_ema_step (36 B per parameter) + repack of all tensor-core weight tiles (2 launches)"}
+        opt_info = {"ms_per_step": o0.elapsed_time(o1) / 5,
+                    "what": "resr_adam_ema_step (36 B per parameter) + repack of all tensor-core weight tiles (2 launches)"}
     except Exception as e:
         opt_info = {"error": repr(e)}
     return {"metric": "training pairs/s", "value": world * B / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms, "n_gpus": world,
-            "loss": float(loss.item()), "cuda_graph": bool(ts.is_graph), "optimizer": opt_info,
-            "config": {"workload": "per GPU: degradation (plan S0, CUDA graph) of 16x3x256x256 HR + RRDBNet x4 forward/L1/backward "
-                                   "on 16x3x64x64 LR (one CUDA graph), flat-gradient NCCL all-reduce when n_gpus > 1; no optimizer"},
+            "scaling": "weak", "loss": float(state["loss"].item()), "cuda_graph": bool(ts.is_graph), "optimizer": opt_info,
+            "config": {"workload": "per GPU: degradation (plan S0, mixed / sinc kernels, CUDA graph) of 16x3x256x256 HR + RRDBNet x4 "
+                                   "forward/L1/backward on 16x3x64x64 LR (one CUDA graph), flat-gradient NCCL all-reduce when n_gpus > 1; "
+                                   "no optimizer"},
             "roofline": {"bound": "tensor", "achieved": tflops, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                          "frac": tflops / peaks["tf_sustained"], "traffic": None,
                          "note": "algorithmic FLOPs = 3 x forward (SURVEY.md §8d): 7.05 TFLOP per GPU-step"}}
+
+
+# ------------------------------------------------------------------------------------------------- tiled inference (cfg5)
+
+
+def tiled_bench(D, gen, steps, peaks):
+    """configs[4]: 1x3x2048x2048 LR -> 1x3x8192x8192 SR. The image is cut into 8 full-width bands of 256 LR rows, each read
+    with a 16-row halo (model.plan_tiles), dealt round-robin to the ranks; every rank uploads the LR image from pinned host
+    memory, runs its bands, and the SR bands are gathered into rank 0's 8192^2 buffer with NCCL send / recv (contiguous
+    per-channel row blocks, no staging copy); rank 0 copies the result to pinned host memory. All of it is inside the timer."""
+    import torch.distributed as dist
+
+    import resr_b200
+    device, world, rank = D.device, D.world, D.rank
+    Hh = Ww = 2048
+    tile_h, halo, s = 256, 16, 4
+    g = torch.Generator(device="cpu").manual_seed(7)
+    x_host = torch.rand(1, 3, Hh, Ww, generator=g).pin_memory()
+    tiles = resr_b200.model.plan_tiles(Hh, Ww, tile_h, Ww, halo)
+    out = torch.empty((1, 3, s * Hh, s * Ww), dtype=torch.float32, device=device) if rank == 0 else None
+    y_host = torch.empty((1, 3, s * Hh, s * Ww), dtype=torch.float32).pin_memory() if rank == 0 else None
+    x_dev = torch.empty((1, 3, Hh, Ww), dtype=torch.float32, device=device)
+
+    def step(k):
+        x_dev.copy_(x_host, non_blocking=True)
+        ops, keep = [], []
+        for i, (y0, y1, x0, x1, wy0, wy1, wx0, wx1) in enumerate(tiles):
+            owner = i % world
+            if owner == rank:
+                sr = gen.infer(x_dev[:, :, wy0:wy1, :])
+                piece = sr[:, :, s * (y0 - wy0):s * (y0 - wy0) + s * (y1 - y0), :]
+                if rank == 0:
+                    out[:, :, s * y0:s * y1, :] = piece
+                else:
+                    for c in range(3):
+                        t = piece[0, c].contiguous()
+                        keep.append(t)
+                        ops.append(dist.P2POp(dist.isend, t, 0))
+            elif rank == 0:
+                for c in range(3):
+                    ops.append(dist.P2POp(dist.irecv, out[0, c, s * y0:s * y1, :], owner))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        if rank == 0:
+            y_host.copy_(out, non_blocking=True)
+
+    ms = timed(step, steps, D, warm=1)
+    ms = D.max_ms(ms)[0]
+    px = Hh * Ww
+    halo_factor = sum((t[5] - t[4]) for t in tiles) / Hh
+    tflops = FLOP_PER_LR_PIXEL * px * halo_factor / (ms * 1e-3) / 1e12
+    checksum = float(y_host[0, :, ::512, ::512].double().sum()) if rank == 0 else None
+    return {"metric": "tiled x4 inference LR Mpix/s", "value": px / (ms * 1e-3) / 1e6, "unit": "LR Mpix/s", "ms_per_step": ms,
+            "n_gpus": world, "scaling": "strong", "steps": steps,
+            "config": {"workload": "1x3x2048x2048 LR -> 1x3x8192x8192 SR (BASELINE.json configs[4]), 8 full-width bands of 256 LR rows "
+                                   f"+ 16-row halo ({halo_factor:.3f}x pixels computed), round-robin over {world} rank(s), NCCL send/recv "
+                                   "gather into rank 0's buffer; timed end to end from / to pinned host memory"},
+            "e2e": {"value": px / (ms * 1e-3) / 1e6, "unit": "LR Mpix/s", "h2d_bytes_per_step": x_host.numel() * 4 * world,
+                    "d2h_bytes_per_step": 3 * 16 * px * 4, "gather_bytes_per_step": 3 * 16 * px * 4 * (world - 1) // world,
+                    "checksum": checksum},
+            "roofline": {"bound": "tensor", "achieved": tflops, "peak": peaks["tf_sustained"] * world, "unit": "TFLOP/s",
+                         "frac": tflops / (peaks["tf_sustained"] * world),
+                         "note": "halo pixels counted as work; copies and gather are inside the time"}}
 
 
 # ------------------------------------------------------------------------------------------------- arms
@@ -268,143 +433,173 @@ def run_reference(args):
     val = 128 * 128 / dt / 1e6
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "LR Mpix/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "RRDBNet x4 (23 RRDB, nf=64, gc=32) forward, random init; each step a bounded sample "
                                    "of the 64x3x128x128 workload: one 1x3x128x128 image on the host CPU"},
             "cpu_baseline": {"value": val, "unit": "LR Mpix/s", "cores": torch.get_num_threads(), "kind": "port",
                              "sample": "1x3x128x128 fp32 forward per step, oracle port of model.py (reference tree is not on the GPU box)"},
             "e2e": {"value": val, "unit": "LR Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    try:  # secondary: the degradation half of the metric on the same host cores (numpy port, bounded sample)
+        import resr_b200
+        from oracle import kernels as ok
+        P = resr_b200.plan.DEGRADATION_MODEL_PARAMETERS
+        random.seed(0)
+        np.random.seed(0)
+        ks = []
+        for _ in range(4):
+            p, _ = resr_b200.imgproc.draw_mixed_kernel_params(P["gaussian_kernel_type"], P["gaussian_kernel_probability1"], 21,
+                                                              P["gaussian_sigma_range1"], P["gaussian_sigma_range1"], [-math.pi, math.pi],
+                                                              P["generalized_kernel_beta_range1"], P["plateau_kernel_beta_range1"])
+            ks.append(ok.from_params(p, 21))
+        k = np.stack(ks).astype(np.float32)
+        sk = np.stack([ok.from_params({"type": "sinc", "kernel_size": 21, "cutoff": 2.0}, 21)] * 4).astype(np.float32)
+        line["degradation"] = cpu_degradation_baseline((k, k, sk))
+    except Exception as e:
+        line["degradation"] = {"error": repr(e)}
     print(json.dumps(line), flush=True)
 
 
 def run_ours(args):
-    import torch.distributed as dist
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    D = Dist()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA (B200) device: there is no CPU fallback for the product path")
-    torch.cuda.set_device(local)
-    device = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+    D.init()
+    world, rank, device = D.world, D.rank, D.device
     import resr_b200
     L = resr_b200._lib
     peaks = measured_peaks()
     torch.set_grad_enabled(False)
 
-    N, H, W = args.batch, 128, 128
+    H = W = 128
+    if args.batch:
+        n_strong = args.batch
+    else:
+        n_strong = max(1, TOTAL_BATCH // world)   # strong scaling: the 64 images of configs[2] sharded over the ranks
     torch.manual_seed(0)
     gen = resr_b200.model.Generator(3, 3, 4).to(device).eval()
-    gcpu = torch.Generator().manual_seed(1234 + rank)
-    x_host = torch.rand(N, 3, H, W, generator=gcpu).pin_memory()
-    y_host = torch.empty(N, 3, 4 * H, 4 * W).pin_memory()
-    x = x_host.to(device)
+    if args.precision != "fp16":
+        gen.set_precision(args.precision)
+    gen.assume_static_weights(True)
+    launches = L.lib().resr_generator_launches_per_forward()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def forward_leg(n):
+        gcpu = torch.Generator().manual_seed(1234 + rank)
+        x_host = torch.rand(n, 3, H, W, generator=gcpu).pin_memory()
+        y_hosts = [torch.empty(n, 3, 4 * H, 4 * W).pin_memory() for _ in range(2)]
+        x = x_host.to(device)
+        state = {}
 
-    # ---- device-resident timing
-    for _ in range(max(3, args.warmup)):
-        y = gen(x)
-    barrier()
-    with ClockSampler(local) as clocks:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(args.steps):
-            y = gen(x)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / args.steps
-    t = torch.tensor([ms], device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    barrier()
-    # ---- end-to-end through the host-buffer ABI calls: every step copies its input from pinned host memory and its
-    # result back to pinned host memory inside the timed region. (a) blocking call, (b) pipelined serving call: the
-    # copies of neighbouring steps overlap the current step's compute (two staging slots, two result buffers).
-    def timed_e2e(fn, fin):
-        for _ in range(2):
-            fn(0)
-        fin()
-        barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for k in range(e2e_steps):
-            fn(k)
-        fin()
-        b.record()
-        torch.cuda.synchronize()
-        tt = torch.tensor([a.elapsed_time(b) / e2e_steps], device=device)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        return float(tt.item())
+        def dev_step(k):
+            state["y"] = gen(x)
 
-    e2e_steps = max(4, min(args.steps, 10))
-    y_hosts = [y_host, torch.empty_like(y_host).pin_memory()]
-    ms_e2e_blocking = timed_e2e(lambda k: gen.infer_host(x_host, y_host, device), lambda: None)
-    ms_e2e = timed_e2e(lambda k: gen.infer_host_async(x_host, y_hosts[k & 1], device), gen.host_sync)
-    checksum = float(y_host[0, :, ::64, ::64].double().sum())
+        with ClockSampler(D.local) as clocks:
+            ms = timed(dev_step, args.steps, D, warm=max(3, args.warmup))
+        e2e_steps = max(4, min(args.steps, 10))
+        ms_block = timed(lambda k: gen.infer_host(x_host, y_hosts[0], device), e2e_steps, D, warm=2)
+        ms_pipe = timed(lambda k: gen.infer_host_async(x_host, y_hosts[k & 1], device), e2e_steps, D, fin=gen.host_sync, warm=2)
+        ms, ms_block, ms_pipe = D.max_ms(ms, ms_block, ms_pipe)
+        return {"n": n, "ms": ms, "ms_block": ms_block, "ms_pipe": ms_pipe, "clocks": clocks.summary(),
+                "h2d": x_host.numel() * 4, "d2h": y_hosts[0].numel() * 4,
+                "checksum": float(y_hosts[0][0, :, ::64, ::64].double().sum())}
 
-    # ---- degradation leg: every rank degrades its own batches (no collective on the path); aggregate = world x B / max time
+    head = forward_leg(n_strong)
+    weak = forward_leg(TOTAL_BATCH) if (world > 1 and not args.batch and not args.no_weak) else None
+
+    line = None
+    if rank == 0:
+        px = world * head["n"] * H * W
+        tflops = FLOP_PER_LR_PIXEL * px / (head["ms"] * 1e-3) / 1e12
+        prec = {"fp16": "fp16 MMA operands (16-bit tensor-core rate, same as bf16), fp32 accumulate and fp32 epilogue arithmetic; the "
+                        "trunk residual stream is the fp16 conv input (saturating at 65504)",
+                "bf16": "bf16 MMA operands and stored activations, fp32 accumulate, fp32 residual masters for the trunk (north_star recipe)"}
+        line = {
+            "metric": METRIC, "value": px / (head["ms"] * 1e-3) / 1e6, "unit": "LR Mpix/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": head["ms"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": f"RRDBNet x4 (23 RRDB, nf=64, gc=32) inference, {world * head['n']}x3x{H}x{W} LR in total "
+                                   f"(BASELINE.json configs[2]), {head['n']} images per GPU, random init; batch-sharded, no collective",
+                       "precision": prec[args.precision],
+                       "l2": "working set (GBs of activations per forward) is far larger than the 126 MB L2; no flush needed"},
+            "e2e": {"value": px / (head["ms_pipe"] * 1e-3) / 1e6, "unit": "LR Mpix/s", "ms_per_step": head["ms_pipe"],
+                    "h2d_bytes_per_step": head["h2d"], "d2h_bytes_per_step": head["d2h"],
+                    "api": "resr_generator_forward_host_async + resr_generator_host_sync (pinned host buffers, pipelined)",
+                    "blocking_call": {"value": px / (head["ms_block"] * 1e-3) / 1e6, "ms_per_step": head["ms_block"],
+                                      "api": "resr_generator_forward_host"},
+                    "checksum": head["checksum"]},
+            "gpu_launches": launches * args.steps,
+            "clocks": head["clocks"],
+            "roofline": {"bound": "tensor", "achieved": tflops, "peak": peaks["tf_sustained"] * world, "unit": "TFLOP/s",
+                         "frac": tflops / (peaks["tf_sustained"] * world),
+                         # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the launches of one forward at cfg3
+                         # (ncu capture under profiles/, see profiles/README.md)
+                         "traffic": TRAFFIC_PER_LAUNCH if (head["n"], world) == (64, 1) else None,
+                         "kernel": "conv3x3_pair_kernel (tcgen05 cta_group::2; 351 conv launches per forward; algorithmic FLOPs "
+                                   "35,853,696 per LR pixel)",
+                         "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step), x n_gpus"},
+        }
+        if weak is not None:
+            wpx = world * weak["n"] * H * W
+            line["weak"] = {"value": wpx / (weak["ms"] * 1e-3) / 1e6, "unit": "LR Mpix/s", "ms_per_step": weak["ms"],
+                            "images_per_gpu": weak["n"], "e2e": wpx / (weak["ms_pipe"] * 1e-3) / 1e6,
+                            "roofline_frac": FLOP_PER_LR_PIXEL * wpx / (weak["ms"] * 1e-3) / 1e12 / (peaks["tf_sustained"] * world)}
+
+    # ---- configs[4]: tiled large-image inference over the ranks, with the gather
+    tiled = None
+    if not args.no_tiled:
+        try:
+            tiled = tiled_bench(D, gen, 2 if world == 1 else 3, peaks)
+        except Exception as e:
+            tiled = {"error": repr(e)}
+            D.barrier()
+    gen._workspace = None   # the 2048-wide bands held ~20 GB of activations
+    torch.cuda.empty_cache()
+
+    # ---- configs[1]: degradation; every rank degrades its own batches (no collective on the path)
     deg = None
     if not args.no_degrade:
-        big, err = None, None
+        err, r16, r256 = None, None, None
         try:
-            deg = degradation_bench(device, max(10, args.steps), args.warmup, peaks)
-            big = degradation_bench(device, 10, 3, peaks, B=256)  # large-batch regime
+            r16 = degradation_bench(D, max(20, args.steps), args.warmup, peaks, B=16)
+            r256 = degradation_bench(D, 10, 3, peaks, B=256, want_e2e=False)  # large-batch regime
         except Exception as e:  # keep the headline even if the secondary leg breaks
             err = repr(e)
-        # the collective runs on every rank whatever happened above (a failed rank contributes +inf)
-        tt = torch.tensor([deg["ms_per_step"] if err is None else float("inf"),
-                           big["ms_per_step"] if err is None else float("inf")], device=device)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        m16, m256 = float(tt[0].item()), float(tt[1].item())
-        if err is not None or m16 == float("inf"):
-            deg = {"error": err or "another rank failed"}
-        else:
-            deg["ms_per_step"] = m16
-            deg["value"] = world * 16 / (m16 * 1e-3)
-            deg["n_gpus"] = world
-            deg["roofline"]["achieved"] = deg["roofline"]["algorithmic_bytes_per_step"] / (m16 * 1e-3) / 1e9
-            deg["roofline"]["frac"] = deg["roofline"]["achieved"] / peaks["hbm"]
-            deg["roofline"]["note"] += "; per GPU"
-            deg["large_batch"] = {"batch_per_gpu": 256, "value": world * 256 / (m256 * 1e-3), "unit": big["unit"], "ms_per_step": m256,
-                                  "roofline_frac": big["roofline"]["algorithmic_bytes_per_step"] / (m256 * 1e-3) / 1e9 / peaks["hbm"]}
+        vals = D.max_ms(*( [r16["ms_dev"], r16["ms_e2e"], r256["ms_dev"]] if err is None else [float("inf")] * 3))
+        if rank == 0:
+            if err is not None or vals[0] == float("inf"):
+                deg = {"error": err or "another rank failed"}
+            else:
+                m16, me2e, m256 = vals
+                sbytes, stages, _ = s0_stage_bytes(16)
+                gbs = sbytes / (m16 * 1e-3) / 1e9
+                tfma = r16["fma"] / (m16 * 1e-3) / 1e12
+                deg = {"metric": "degraded pairs/s", "value": world * 16 / (m16 * 1e-3), "unit": "pairs/s", "ms_per_step": m16,
+                       "n_gpus": world, "scaling": "weak",
+                       "config": {"workload": "second-order degradation, 16x3x256x256 HR -> 16x3x64x64 LR per GPU, canonical plan S0 "
+                                              "(SURVEY.md §8d) with mixed Gaussian-family / sinc blur kernels of support 7..21 and a real "
+                                              "sinc final kernel; Gaussian noise tensors host-fed and resident, Poisson draws made inside "
+                                              "the fused noise kernel (Philox); one CUDA-graph replay per batch"},
+                       "e2e": {"value": world * 16 / (me2e * 1e-3), "unit": "pairs/s", "ms_per_step": me2e,
+                               "h2d_bytes_per_step": r16["h2d"], "d2h_bytes_per_step": r16["d2h"],
+                               "api": "imgproc.DegradePipeline x 2 (alternating CUDA graphs): HR batch from pinned host memory every "
+                                      "step, LR batch read back to pinned host memory; HR crop stays on the device for the training step"},
+                       "gpu_launches_per_step": DEGRADE_LAUNCHES,
+                       "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
+                                    "traffic": DEGRADE_TRAFFIC, "algorithmic_bytes_per_step": sbytes,
+                                    "note": "stage-sum bytes / whole-pipeline time, per GPU; the blur stencils are fp32-FMA work: see fma"},
+                       "fma": {"achieved_tfma": tfma, "peak_tfma": peaks["tfma"], "frac": tfma / peaks["tfma"],
+                               "necessary_fma_per_step": r16["fma"],
+                               "note": "necessary FMAs (separable 51-tap USM, per-sample trimmed blur supports) / whole-pipeline time vs the "
+                                       "fp32 FMA peak measured with tools/fma_peak.cu (profiles/r02_fma_peak.json)"},
+                       "large_batch": {"batch_per_gpu": 256, "value": world * 256 / (m256 * 1e-3), "unit": "pairs/s", "ms_per_step": m256,
+                                       "roofline_frac": s0_stage_bytes(256)[0] / (m256 * 1e-3) / 1e9 / peaks["hbm"]}}
+                if world == 1 and not args.no_cpu:
+                    try:
+                        deg["cpu_baseline"] = cpu_degradation_baseline(r16["kernels_np"])
+                    except Exception as e:
+                        deg["cpu_baseline"] = {"error": repr(e)}
     if rank == 0:
-        px = N * H * W
-        launches = L.lib().resr_generator_launches_per_forward()
-        tflops = FLOP_PER_LR_PIXEL * px / (ms * 1e-3) / 1e12
-        line = {
-            "metric": METRIC, "value": world * px / (ms * 1e-3) / 1e6, "unit": "LR Mpix/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
-            "config": {"workload": f"RRDBNet x4 (23 RRDB, nf=64, gc=32) inference, {N}x3x{H}x{W} LR per GPU, random init "
-                                   "(BASELINE.json configs[2]); batch-sharded, no collective",
-                       "precision": "fp16 MMA operands (16-bit tensor-core rate, same as bf16), fp32 accumulate and fp32 epilogue arithmetic; the trunk residual stream is the fp16 conv input (saturating at 65504)",
-                       "l2": "working set (9 GB of activations per forward) is far larger than the 126 MB L2; no flush needed"},
-            "e2e": {"value": world * px / (ms_e2e * 1e-3) / 1e6, "unit": "LR Mpix/s", "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": y_host.numel() * 4,
-                    "api": "resr_generator_forward_host_async + resr_generator_host_sync (pinned host buffers, pipelined)",
-                    "blocking_call": {"value": world * px / (ms_e2e_blocking * 1e-3) / 1e6, "ms_per_step": ms_e2e_blocking,
-                                      "api": "resr_generator_forward_host"},
-                    "checksum": checksum},
-            "gpu_launches": launches * args.steps,
-            "clocks": clocks.summary(),
-            "roofline": {"bound": "tensor", "achieved": tflops, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                         "frac": tflops / peaks["tf_sustained"],
-                         # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the five launches of one
-                         # dense block (345 of the 351 launches are such blocks) at cfg3: ncu --set full capture in
-                         # profiles/r01_v5_rdb_ncu_full.csv (182 / 323 / 328 / 470 / 525 MB; algorithmic 201 / 268 / 335 /
-                         # 402 / 671 MB -- conv5's residual and second slice hit L2)
-                         "traffic": 365.7e6 if (N, H, W) == (64, 128, 128) else None,
-                         "kernel": "conv3x3_tc_kernel (351 launches per forward; algorithmic FLOPs 35,853,696 per LR pixel)",
-                         "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)"},
-        }
+        if tiled is not None:
+            line["tiled"] = tiled
         if deg is not None:
             line["degradation"] = deg
         if world == 1 and not args.no_cpu:
@@ -412,15 +607,19 @@ def run_ours(args):
     train = None
     if not args.no_train:  # every rank takes part (all-reduce)
         try:
-            train = training_bench(device, max(5, min(args.steps, 20)), args.warmup, peaks, world)
+            train = training_bench(D, max(5, min(args.steps, 20)), args.warmup, peaks)
         except Exception as e:
             train = {"error": repr(e)}
     if rank == 0:
         line["training"] = train
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    D.finish()
+
+
+# ncu-measured DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum), see profiles/README.md for the captures
+TRAFFIC_PER_LAUNCH = None      # bytes per conv launch, mean over one cfg3 forward
+DEGRADE_TRAFFIC = None         # bytes per S0 batch (sum over the pipeline's launches)
+DEGRADE_LAUNCHES = 14
 
 
 def main():
@@ -429,8 +628,12 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="LR images per GPU (64 = BASELINE configs[2])")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16"],
+                    help="MMA operand / activation format of the generator (bf16 = north_star's recipe with fp32 residual masters)")
+    ap.add_argument("--batch", type=int, default=0, help="LR images per GPU (default 64 / n_gpus: strong scaling of configs[2])")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--no-weak", action="store_true", help="skip the secondary weak-scaling forward leg (N > 1)")
+    ap.add_argument("--no-tiled", action="store_true", help="skip the secondary tiled-inference leg (configs[4])")
     ap.add_argument("--no-degrade", action="store_true", help="skip the secondary degradation leg")
     ap.add_argument("--no-train", action="store_true", help="skip the secondary training-step leg")
     args = ap.parse_args()

@@ -57,6 +57,13 @@ int resr_generator_tensor_span(int index, size_t* offset, size_t* count);
 int resr_generator_load_params(resr_generator_t* g, const float* flat_params, void* stream);
 
 size_t resr_generator_workspace_bytes(int n, int h, int w);
+/* Inference precision recipe of a handle (north_star names bf16; fp16 is the default because it is more accurate at the
+ * same tensor rate): 0 = fp16 MMA operands, the trunk's residual stream is the fp16 conv input itself; 1 = bf16 MMA
+ * operands and stored activations with fp32 masters of the residual stream (model.py:94-96, 129-130 evaluated in fp32).
+ * After a change the caller must call resr_generator_load_params again (the weight packs carry the operand format).
+ * resr_generator_workspace_bytes_for: workspace of THIS handle's recipe (the bf16 recipe adds four fp32 master buffers). */
+int resr_generator_set_precision(resr_generator_t* g, int precision);
+size_t resr_generator_workspace_bytes_for(const resr_generator_t* g, int n, int h, int w);
 
 /* y[n,3,4h,4w] = clamp(G(x[n,3,h,w]), 0, 1). x, y fp32 NCHW contiguous. model.py:255-275. */
 int resr_generator_forward(resr_generator_t* g, const float* x, float* y, int n, int h, int w, void* workspace,
@@ -79,6 +86,11 @@ int resr_generator_host_sync(resr_generator_t* g);
 
 /* Number of kernels of this library that one resr_generator_forward launches (for bench accounting). */
 int resr_generator_launches_per_forward(void);
+/* Kernel policy of the 3x3 convolutions: 0 = single-CTA kernel only, 1 = CTA-pair kernel (tcgen05 cta_group::2) when
+ * every pair gets a real strip of rows (default; env RESR_CONV_PAIR sets the initial value), 2 = CTA pairs whenever two
+ * column groups exist (tests use it to push small / awkward shapes through the pair kernel). Returns the previous policy;
+ * a value outside 0..2 only queries. Takes effect for plans built afterwards (new shapes / workspaces). */
+int resr_set_conv_pair_policy(int policy);
 /* Development aid: wait-time counters of the CTA-pair convolution kernel (16 x u64 clock cycles summed over CTAs; all
  * zero unless the library was built with -DRESR_PROFILE_WAITS). out16_host may be NULL; reset != 0 clears them. */
 int resr_debug_wait_profile(unsigned long long* out16_host, int reset);

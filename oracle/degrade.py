@@ -370,9 +370,11 @@ def round_and_crop(out, hr, hr_top, hr_left, image_size, upscale):
 # --------------------------------------------------------------------------------------------- whole block
 
 
-def degrade_batch(hr, kernel1, kernel2, sinc_kernel, plan, stages=None):
+def degrade_batch(hr, kernel1, kernel2, sinc_kernel, plan, stages=None, draw_rng=None):
     """train_realesrnet.py:267-377 driven by a recorded plan (dict, see oracle/plan.py). Returns (lr, hr_crop).
-    If `stages` is a list, every intermediate image is appended to it."""
+    If `stages` is a list, every intermediate image is appended to it. Plans without recorded random tensors (the
+    CPU-baseline timing of bench.py) draw them here from `draw_rng` (numpy Generator) at the point the reference calls
+    torch.randn / torch.poisson (imgproc.py:854-858, 895, 906)."""
     def rec(name, t):
         if stages is not None:
             stages.append((name, t))
@@ -380,8 +382,19 @@ def degrade_batch(hr, kernel1, kernel2, sinc_kernel, plan, stages=None):
 
     def noise(x, p):
         if p["type"] == "gaussian":
-            return gaussian_noise_apply(x, p["sigma"], p["gray"], p["noise_color"], p.get("noise_gray"))
-        return poisson_noise_apply(x, p["scale"], p["gray"], p["samples_color"], p.get("samples_gray"))
+            nc, ng = p.get("noise_color"), p.get("noise_gray")
+            if nc is None:
+                if p["gray"].sum() > 0:
+                    ng = draw_rng.standard_normal(x.shape[2:], dtype=f32)
+                nc = draw_rng.standard_normal(x.shape, dtype=f32)
+            return gaussian_noise_apply(x, p["sigma"], p["gray"], nc, ng)
+        sc, sg = p.get("samples_color"), p.get("samples_gray")
+        if sc is None:
+            with_gray = bool(p["gray"].sum() > 0)
+            r = poisson_rates(x, with_gray)
+            sg = draw_rng.poisson(r["rate_g"]).astype(f32) if with_gray else None
+            sc = draw_rng.poisson(r["rate"]).astype(f32)
+        return poisson_noise_apply(x, p["scale"], p["gray"], sc, sg)
 
     out = rec("usm", usm_sharp(hr, 0.5, 10))
     if plan["blur1"]:

@@ -74,12 +74,15 @@ SIGNATURES = {
     "resr_generator_tensor_span": (c_int, [c_int, POINTER(c_size_t), POINTER(c_size_t)]),
     "resr_generator_load_params": (c_int, [c_void_p, c_void_p, c_void_p]),
     "resr_generator_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "resr_generator_workspace_bytes_for": (c_size_t, [c_void_p, c_int, c_int, c_int]),
+    "resr_generator_set_precision": (c_int, [c_void_p, c_int]),
     "resr_generator_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "resr_generator_forward_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "resr_generator_forward_host_async": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "resr_generator_host_sync": (c_int, [c_void_p]),
     "resr_generator_launches_per_forward": (c_int, []),
     "resr_debug_wait_profile": (c_int, [c_void_p, c_int]),
+    "resr_set_conv_pair_policy": (c_int, [c_int]),
     "resr_conv3x3": (c_int, [POINTER(ConvDesc), c_void_p]),
     "resr_nchw_to_nhwc16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "resr_filter2d": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),

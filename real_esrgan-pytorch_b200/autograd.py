@@ -13,6 +13,8 @@ from . import _lib
 
 
 def _train_workspace(gen, n, h, w, device):
+    if gen.precision != "fp16":
+        raise _lib.ResrError("the training path uses the fp16 forward recipe: call gen.set_precision('fp16') first")
     need = _lib.lib().resr_generator_train_workspace_bytes(n, h, w)
     ws = getattr(gen, "_train_ws", None)
     if ws is None or ws.numel() < need + 1024 or ws.device != device:

@@ -107,6 +107,7 @@ struct ConvLaunchCfg {
 };
 // Picks the kernel (pairs whenever there are at least two column groups to pair up; RESR_CONV_PAIR=0 forces the
 // single-CTA kernel), fills args->nstages / nepi. Returns false if the configuration does not fit in shared memory.
+int conv3x3_set_pair_policy(int policy);  // returns the previous policy; -1 only queries
 bool conv3x3_choose(ConvArgs* args, int pack_nout, int pack_nslices, ConvLaunchCfg* cfg);
 cudaError_t conv3x3_run(const ConvMaps& maps, const ConvArgs& args, const ConvLaunchCfg& cfg, int num_sms, cudaStream_t stream);
 

@@ -735,8 +735,17 @@ int conv3x3_wait_profile(unsigned long long* out16, int reset) {
     return 0;
 }
 
+// 0: never pair, 1: pair when the problem is large enough (default), 2: pair whenever two column groups exist
+static int g_pair_policy = -1;
+int conv3x3_set_pair_policy(int policy) {
+    if (g_pair_policy < 0) g_pair_policy = getenv("RESR_CONV_PAIR") ? atoi(getenv("RESR_CONV_PAIR")) : 1;
+    const int prev = g_pair_policy;
+    if (policy >= 0 && policy <= 2) g_pair_policy = policy;
+    return prev;
+}
+
 bool conv3x3_choose(ConvArgs* a, int pack_nout, int pack_nslices, ConvLaunchCfg* cfg) {
-    static const int env_pair = getenv("RESR_CONV_PAIR") ? atoi(getenv("RESR_CONV_PAIR")) : 1;
+    const int env_pair = conv3x3_set_pair_policy(-1);
     static const int env_n64 = getenv("RESR_CONV_PAIR_N64") ? atoi(getenv("RESR_CONV_PAIR_N64")) : 1;
     cfg->pair = 0;
     cfg->nout = pack_nout;

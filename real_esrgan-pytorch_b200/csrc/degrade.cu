@@ -3,6 +3,7 @@
 // :1124-1494, random_crop :1894) and the sequencing in train_realesrnet.py:267-377. See DESIGN.md §5.
 #include <curand_kernel.h>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/resr.h"
@@ -23,17 +24,18 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {  // ATen reflection_p
 }
 
 // ===================================================================================== filter2d (a8)
-// One block = 64 x 64 output tile of one (sample, channel) plane; 256 threads = 32 columns x 8 row groups, each thread
-// owns 8 consecutive rows of 2 columns (x and x+32). The reflect-padded halo tile and the taps live in shared memory.
-// The kernels of the degradation model are 7..21 supports zero-padded to 21 (dataset.py:102-103): the block finds
-// the centred square support KS of its sample and runs the KS-specialised body, whose (row, output) loops are fully
-// unrolled with the current tap column in registers: 16*KS FMAs per (2*(KS+7) + KS) shared loads.
-static constexpr int kF2dTile = 64;
-static constexpr int kF2dRows = 8;
+// One block = 64 x (8 * R) output tile of one (sample, channel) plane; 256 threads = 32 columns x 8 row groups, each
+// thread owns R consecutive rows of 2 columns (x and x+32). The reflect-padded halo tile and the taps live in shared
+// memory. The kernels of the degradation model are 7..21 supports zero-padded to 21 (dataset.py:102-103): the block
+// finds the centred square support KS of its sample and runs the KS-specialised body, whose (row, output) loops are fully
+// unrolled with the current tap column in registers: 2*R*KS FMAs per (2*(KS+R-1) + KS) shared loads.
+// R is chosen per launch so that small images still fill the GPU: 8 rows per thread at 256^2 (768 blocks at cfg2),
+// 4 at 128^2, 2 at 64^2 (the 64 x 64 tile of round 1 left 100 of the 148 SMs idle there).
+static constexpr int kF2dTileW = 64;
 
-template <int KS>
-__device__ __forceinline__ void filter2d_body(const float* __restrict__ tile, int tpitch, const float* __restrict__ taps, int k,
-                                              int off, int tx, int ty0, float (&acc)[2][kF2dRows]) {
+template <int KS, int R, int tpitch>
+__device__ __forceinline__ void filter2d_body(const float* __restrict__ tile, const float* __restrict__ taps, int k,
+                                              int off, int tx, int ty0, float (&acc)[2][R]) {
     // taps: full k x k array; the KS x KS centred window starts at (off, off). tile row 0 / col 0 correspond to output
     // (0,0) shifted by -(k/2); the window adds `off` again.
     for (int kx = 0; kx < KS; ++kx) {
@@ -42,10 +44,10 @@ __device__ __forceinline__ void filter2d_body(const float* __restrict__ tile, in
         for (int ky = 0; ky < KS; ++ky) w[ky] = taps[(off + ky) * k + off + kx];
         const float* col = tile + (ty0 + off) * tpitch + tx + off + kx;
 #pragma unroll
-        for (int rr = 0; rr < KS + kF2dRows - 1; ++rr) {
+        for (int rr = 0; rr < KS + R - 1; ++rr) {
             const float v0 = col[rr * tpitch], v1 = col[rr * tpitch + 32];
 #pragma unroll
-            for (int j = 0; j < kF2dRows; ++j) {
+            for (int j = 0; j < R; ++j) {
                 const int ky = rr - j;
                 if (ky >= 0 && ky < KS) {
                     acc[0][j] = fmaf(v0, w[ky], acc[0][j]);
@@ -56,19 +58,24 @@ __device__ __forceinline__ void filter2d_body(const float* __restrict__ tile, in
     }
 }
 
-__global__ void __launch_bounds__(256) filter2d_kernel(const float* __restrict__ in, const float* __restrict__ kern,
+// PITCH: row pitch of the shared-memory tile, a compile-time constant so that the (fully unrolled) window loads carry
+// immediate offsets instead of one address computation each: 85 for k <= 21 (the degradation model), 127 up to k = 63.
+template <int R, int PITCH>
+__global__ void __launch_bounds__(R == 16 ? 128 : 256) filter2d_kernel(const float* __restrict__ in, const float* __restrict__ kern,
                                                        float* __restrict__ out, int B, int C, int H, int W, int k,
                                                        int kern_batched) {
+    constexpr int NW = R == 16 ? 4 : 8;   // warps per block
+    constexpr int TH = NW * R;            // tile height
     extern __shared__ float sm[];
     const int r = k / 2;
-    const int tw = kF2dTile + k - 1;
-    const int tpitch = tw + 1;
-    float* tile = sm;                  // [tw][tw + 1]
-    float* taps = sm + tw * tpitch;    // [k][k]
+    const int tw = kF2dTileW + k - 1, th = TH + k - 1;
+    constexpr int tpitch = PITCH;
+    float* tile = sm;                  // [th][PITCH]
+    float* taps = sm + th * tpitch;    // [k][k]
     __shared__ int s_ext;              // max |offset from centre| of a non-zero tap
     const int plane = blockIdx.z;      // b * C + c
     const int b = plane / C;
-    const int x0 = blockIdx.x * kF2dTile, y0 = blockIdx.y * kF2dTile;
+    const int x0 = blockIdx.x * kF2dTileW, y0 = blockIdx.y * TH;
     const float* src = in + static_cast<size_t>(plane) * H * W;
     const float* kp = kern + (kern_batched ? static_cast<size_t>(b) * k * k : 0);
     if (threadIdx.x == 0) s_ext = 0;
@@ -81,49 +88,60 @@ __global__ void __launch_bounds__(256) filter2d_kernel(const float* __restrict__
     __syncthreads();
     const int ext = s_ext;
     const int off = r - ext;           // first row/col of the centred support inside the k x k array
-    {   // only the halo the trimmed support needs is fetched: tile rows / columns [off, tw - off). One tile row per warp
-        // pass, coalesced along x; the reflected columns of this lane are computed once. Positions the tile overhang
-        // would touch beyond the image are clamped: their outputs are never stored.
+    {   // only the halo the trimmed support needs is fetched: tile rows [off, th - off) / columns [off, tw - off). One tile
+        // row per warp pass, coalesced along x; the reflected columns of this lane are computed once. Positions the tile
+        // overhang would touch beyond the image are clamped: their outputs are never stored.
         const int lane = threadIdx.x & 31;
         int cxk[4];          // tw <= 64 + 62
 #pragma unroll
         for (int q = 0; q < 4; ++q) cxk[q] = min(max(reflect_idx(x0 + off + lane + 32 * q - r, W), 0), W - 1);
         const int span = tw - 2 * off;
-        for (int ty = off + (threadIdx.x >> 5); ty < tw - off; ty += 8) {
-            const int cy = min(max(reflect_idx(y0 + ty - r, H), 0), H - 1);
-            const float* srow = src + static_cast<size_t>(cy) * W;
-            float* trow = tile + ty * tpitch + off;
+        for (int ty = off + (threadIdx.x >> 5); ty < th - off; ty += 2 * NW) {  // two rows (8 loads per lane) in flight
+            float v[2][4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (lane + 32 * q < span) trow[lane + 32 * q] = srow[cxk[q]];
+            for (int u = 0; u < 2; ++u) {
+                const int cy = min(max(reflect_idx(y0 + min(ty + u * NW, th - off - 1) - r, H), 0), H - 1);
+                const float* srow = src + static_cast<size_t>(cy) * W;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) v[u][q] = srow[cxk[q]];
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (ty + u * NW < th - off) {
+                    float* trow = tile + (ty + u * NW) * tpitch + off;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (lane + 32 * q < span) trow[lane + 32 * q] = v[u][q];
+                }
+            }
         }
     }
     __syncthreads();
     const int tx = threadIdx.x & 31;
-    const int ty0 = (threadIdx.x >> 5) * kF2dRows;
-    float acc[2][kF2dRows];
+    const int ty0 = (threadIdx.x >> 5) * R;   // NW warps x R rows
+    float acc[2][R];
 #pragma unroll
-    for (int j = 0; j < kF2dRows; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
+    for (int j = 0; j < R; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
     switch (2 * ext + 1) {
-        case 1: filter2d_body<1>(tile, tpitch, taps, k, off, tx, ty0, acc); break;
-        case 3: filter2d_body<3>(tile, tpitch, taps, k, off, tx, ty0, acc); break;
-        case 5: filter2d_body<5>(tile, tpitch, taps, k, off, tx, ty0, acc); break;
-        case 7: filter2d_body<7>(tile, tpitch, taps, k, off, tx, ty0, acc); break;
-        case 9: filter2d_body<9>(tile, tpitch, taps, k, off, tx, ty0, acc); break;
-        case 11: filter2d_body<11>(tile, tpitch, taps, k, off, tx, ty0, acc); break;
-        case 13: filter2d_body<13>(tile, tpitch, taps, k, off, tx, ty0, acc); break;
-        case 15: filter2d_body<15>(tile, tpitch, taps, k, off, tx, ty0, acc); break;
-        case 17: filter2d_body<17>(tile, tpitch, taps, k, off, tx, ty0, acc); break;
-        case 19: filter2d_body<19>(tile, tpitch, taps, k, off, tx, ty0, acc); break;
-        case 21: filter2d_body<21>(tile, tpitch, taps, k, off, tx, ty0, acc); break;
+        case 1: filter2d_body<1, R, PITCH>(tile, taps, k, off, tx, ty0, acc); break;
+        case 3: filter2d_body<3, R, PITCH>(tile, taps, k, off, tx, ty0, acc); break;
+        case 5: filter2d_body<5, R, PITCH>(tile, taps, k, off, tx, ty0, acc); break;
+        case 7: filter2d_body<7, R, PITCH>(tile, taps, k, off, tx, ty0, acc); break;
+        case 9: filter2d_body<9, R, PITCH>(tile, taps, k, off, tx, ty0, acc); break;
+        case 11: filter2d_body<11, R, PITCH>(tile, taps, k, off, tx, ty0, acc); break;
+        case 13: filter2d_body<13, R, PITCH>(tile, taps, k, off, tx, ty0, acc); break;
+        case 15: filter2d_body<15, R, PITCH>(tile, taps, k, off, tx, ty0, acc); break;
+        case 17: filter2d_body<17, R, PITCH>(tile, taps, k, off, tx, ty0, acc); break;
+        case 19: filter2d_body<19, R, PITCH>(tile, taps, k, off, tx, ty0, acc); break;
+        case 21: filter2d_body<21, R, PITCH>(tile, taps, k, off, tx, ty0, acc); break;
         default: {  // generic odd support (k <= 63): rolled loops
             const int ks = 2 * ext + 1;
             for (int kx = 0; kx < ks; ++kx)
-                for (int rr = 0; rr < ks + kF2dRows - 1; ++rr) {
+                for (int rr = 0; rr < ks + R - 1; ++rr) {
                     const float v0 = tile[(ty0 + off + rr) * tpitch + tx + off + kx];
                     const float v1 = tile[(ty0 + off + rr) * tpitch + tx + 32 + off + kx];
 #pragma unroll
-                    for (int j = 0; j < kF2dRows; ++j) {
+                    for (int j = 0; j < R; ++j) {
                         const int ky = rr - j;
                         if (ky >= 0 && ky < ks) {
                             const float wv = taps[(off + ky) * k + off + kx];
@@ -139,11 +157,37 @@ __global__ void __launch_bounds__(256) filter2d_kernel(const float* __restrict__
         const int gx = x0 + tx + 32 * c;
         if (gx < W) {
 #pragma unroll
-            for (int j = 0; j < kF2dRows; ++j) {
+            for (int j = 0; j < R; ++j) {
                 const int gy = y0 + ty0 + j;
                 if (gy < H) out[static_cast<size_t>(plane) * H * W + static_cast<size_t>(gy) * W + gx] = acc[c][j];
             }
         }
+    }
+}
+
+template <int R>
+static void filter2d_launch(const float* in, const float* kern, float* out, int B, int C, int H, int W, int k, int kb,
+                            cudaStream_t s) {
+    constexpr int NW = R == 16 ? 4 : 8;
+    constexpr int TH = NW * R;
+    const int th = TH + k - 1;
+    dim3 grid((W + kF2dTileW - 1) / kF2dTileW, (H + TH - 1) / TH, B * C);
+    if (k <= 21) {
+        const size_t smem = (static_cast<size_t>(th) * 85 + static_cast<size_t>(k) * k) * sizeof(float);
+        static PerDevice<size_t> attr_set;  // function attributes are per device
+        if (smem > 48 * 1024 && smem > attr_set.cur()) {
+            cudaFuncSetAttribute(filter2d_kernel<R, 85>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+            attr_set.cur() = smem;
+        }
+        filter2d_kernel<R, 85><<<grid, 32 * NW, smem, s>>>(in, kern, out, B, C, H, W, k, kb);
+    } else {
+        const size_t smem = (static_cast<size_t>(th) * 127 + static_cast<size_t>(k) * k) * sizeof(float);
+        static PerDevice<size_t> attr_set;
+        if (smem > 48 * 1024 && smem > attr_set.cur()) {
+            cudaFuncSetAttribute(filter2d_kernel<R, 127>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+            attr_set.cur() = smem;
+        }
+        filter2d_kernel<R, 127><<<grid, 32 * NW, smem, s>>>(in, kern, out, B, C, H, W, k, kb);
     }
 }
 
@@ -152,15 +196,16 @@ static int filter2d_impl(const float* in, const float* kern, float* out, int B, 
     if (k % 2 != 1) return set_error(RESR_E_INVALID, "Wrong kernel size.");  // imgproc.py:1106 ValueError
     if (k > 63) return set_error(RESR_E_INVALID, "kernel size %d > 63 unsupported", k);
     if (k / 2 >= H || k / 2 >= W) return set_error(RESR_E_INVALID, "reflect padding %d needs a larger image (%dx%d)", k / 2, H, W);
-    const int tw = kF2dTile + k - 1;
-    const size_t smem = (static_cast<size_t>(tw) * (tw + 1) + static_cast<size_t>(k) * k) * sizeof(float);
-    static PerDevice<size_t> attr_set;  // function attributes are per device
-    if (smem > 48 * 1024 && smem > attr_set.cur()) {
-        cudaFuncSetAttribute(filter2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        attr_set.cur() = smem;
-    }
-    dim3 grid((W + kF2dTile - 1) / kF2dTile, (H + kF2dTile - 1) / kF2dTile, B * C);
-    filter2d_kernel<<<grid, 256, smem, s>>>(in, kern, out, B, C, H, W, k, kb);
+    // rows per thread: 16 (64 x 64 tile, 128 threads: 32*KS FMAs per 3*KS+30 shared loads, the stencil is shared-memory
+    // bandwidth bound below ~4 FMAs per load) when that still gives ~4 blocks per SM, else the largest of 8 / 4 / 2 that
+    // gives ~2 blocks per SM
+    const long long cols = (W + kF2dTileW - 1) / kF2dTileW, planes = static_cast<long long>(B) * C;
+    auto blocks = [&](int R) { return cols * ((H + 8 * R - 1) / (8 * R)) * planes; };
+    static const int env_r16 = getenv("RESR_F2D_R16") ? atoi(getenv("RESR_F2D_R16")) : 0;  // measured: no faster than 8
+    if (env_r16 && cols * ((H + 63) / 64) * planes >= 592) filter2d_launch<16>(in, kern, out, B, C, H, W, k, kb, s);
+    else if (blocks(8) >= 296) filter2d_launch<8>(in, kern, out, B, C, H, W, k, kb, s);
+    else if (blocks(4) >= 296) filter2d_launch<4>(in, kern, out, B, C, H, W, k, kb, s);
+    else filter2d_launch<2>(in, kern, out, B, C, H, W, k, kb, s);
     RESR_LAUNCH_CHECK("filter2d");
     return RESR_OK;
 }
@@ -233,105 +278,137 @@ __global__ void __launch_bounds__(256) usm_vpass_kernel(const float* __restrict_
     }
 }
 
-// Fused separable blur for the 51-tap case the training loops use (USMSharp(50, 0)): one block = 64 x 64 outputs.
-// The reflect-padded (64+50)^2 input tile is loaded once; the horizontal pass writes a (64+50) x 64 intermediate into
-// shared memory, the vertical pass and the pointwise tail finish in registers. Each thread slides a register window
-// over 8 consecutive outputs (58 loads, 408 FMAs with the taps as constant-bank operands).
-static constexpr int kUsmK = 51, kUsmT = 64, kUsmIn = kUsmT + kUsmK - 1;  // 114
-static constexpr int kUsmPitchA = kUsmIn + 1, kUsmPitchB = kUsmT + 1;      // odd pitches: conflict-free columns
+// The 51-tap case the training loops use (USMSharp(50, 0)): each blur is a horizontal pass into a scratch image (it
+// stays in the 126 MB L2) and a vertical pass with the pointwise tail fused. Both passes are plain 1-D stencils with NO
+// recomputation: a thread slides a register window over 16 consecutive outputs ALONG the filter direction (66 shared
+// loads + 816 FMAs with the taps as uniform-register operands), and the lane index runs ACROSS it, so that the window
+// loads of a warp are conflict-free (horizontal pass: lane = row, odd row pitch; vertical pass: lane = column).
+// Global loads are issued in batches ahead of their use (tile rows four at a time, the tail's operands before the
+// window): ncu showed the first version of these kernels waiting on the long scoreboard for most of its cycles.
+static constexpr int kUsmK = 51, kUsmR = kUsmK / 2, kUsmO = 16;   // outputs per thread
+static constexpr int kUsmHCols = 64, kUsmHRows = 32, kUsmHPitch = kUsmHCols + kUsmK - 1 + 1;  // 115: odd
+static constexpr int kUsmVCols = 64, kUsmVRows = 64, kUsmVIn = kUsmVRows + kUsmK - 1;         // 114 input rows
 
-__device__ __forceinline__ void usm_window8(const float* __restrict__ p, int stride, float (&acc)[8]) {
+__device__ __forceinline__ void usm_window16(const float* __restrict__ p, int stride, float (&acc)[kUsmO]) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int j = 0; j < kUsmO; ++j) acc[j] = 0.f;
 #pragma unroll
-    for (int t = 0; t < kUsmK + 7; ++t) {
+    for (int t = 0; t < kUsmK + kUsmO - 1; ++t) {
         const float v = p[t * stride];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < kUsmO; ++j) {
             const int tap = t - j;
             if (tap >= 0 && tap < kUsmK) acc[j] = fmaf(v, c_usm_taps[tap], acc[j]);
         }
     }
 }
 
-__global__ void __launch_bounds__(512) usm_fused_kernel(const float* __restrict__ src, const float* __restrict__ x,
-                                                        float* __restrict__ res, float* __restrict__ mask_or_out, int H,
-                                                        int W, int stage, float weight, float threshold) {
-    extern __shared__ float usm_sm[];
-    float* A = usm_sm;                              // [114][115] input tile (x for stage 0, mask for stage 1)
-    float* Bm = usm_sm + kUsmIn * kUsmPitchA;       // [114][65] horizontally blurred rows
+// tmp = conv_x(src), reflect padding. Block = 32 rows x 64 columns of outputs, 128 threads: lane = row, warp = 16 columns.
+__global__ void __launch_bounds__(128) usm_h51_kernel(const float* __restrict__ src, float* __restrict__ tmp, int H, int W) {
+    __shared__ float A[kUsmHRows * kUsmHPitch];
     const int plane = blockIdx.z;
-    const int x0 = blockIdx.x * kUsmT, y0 = blockIdx.y * kUsmT;
+    const int x0 = blockIdx.x * kUsmHCols, y0 = blockIdx.y * kUsmHRows;
     const size_t pbase = static_cast<size_t>(plane) * H * W;
-    const int r = kUsmK / 2;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    {   // one tile row per warp pass, coalesced along x; the reflected column of each of this lane's 4 tile columns is
-        // computed once, the rows are issued four at a time so that 16 loads are in flight per thread
+    {   // tile rows: warp w takes rows w, w+4, ...; 4 rows (16 loads per lane) in flight, coalesced along x
         int gxk[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) gxk[k] = min(max(reflect_idx(x0 + lane + 32 * k - r, W), 0), W - 1);
-        const bool last_ok = lane + 96 < kUsmIn;
-        for (int ty = warp; ty < kUsmIn; ty += 64) {
+        for (int k = 0; k < 4; ++k) gxk[k] = min(max(reflect_idx(x0 + lane + 32 * k - kUsmR, W), 0), W - 1);
+        const bool last_ok = lane + 96 < kUsmHCols + kUsmK - 1;
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
             float v[4][4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int t = ty + 16 * u;
-                const int gy = min(max(reflect_idx(y0 + min(t, kUsmIn - 1) - r, H), 0), H - 1);
-                const float* srow = src + pbase + static_cast<size_t>(gy) * W;
+                const int ty = warp + 4 * (pass * 4 + u);
+                const float* srow = src + pbase + static_cast<size_t>(min(y0 + ty, H - 1)) * W;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) v[u][k] = srow[gxk[k]];
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int t = ty + 16 * u;
-                if (t < kUsmIn) {
+                const int ty = warp + 4 * (pass * 4 + u);
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) A[t * kUsmPitchA + lane + 32 * k] = v[u][k];
-                    if (last_ok) A[t * kUsmPitchA + lane + 96] = v[u][3];
-                }
+                for (int k = 0; k < 3; ++k) A[ty * kUsmHPitch + lane + 32 * k] = v[u][k];
+                if (last_ok) A[ty * kUsmHPitch + lane + 96] = v[u][3];
             }
         }
     }
     __syncthreads();
-    {   // horizontal pass: lane = row (within a group of 32 rows), 2 column groups of 8 per warp (16 warps)
-        const int row = (warp & 3) * 32 + lane;
-        if (row < kUsmIn) {
-#pragma unroll 1
-            for (int cgi = 0; cgi < 2; ++cgi) {
-                const int c0 = ((warp >> 2) * 2 + cgi) * 8;
-                float acc[8];
-                usm_window8(A + row * kUsmPitchA + c0, 1, acc);
+    const int gy = y0 + lane;
+    const int c0 = warp * kUsmO;
+    float acc[kUsmO];
+    usm_window16(A + lane * kUsmHPitch + c0, 1, acc);
+    if (gy < H) {
+        float* o = tmp + pbase + static_cast<size_t>(gy) * W + x0 + c0;
+        if (x0 + c0 + kUsmO <= W && (W & 3) == 0) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) Bm[row * kUsmPitchB + c0 + j] = acc[j];
-            }
+            for (int j = 0; j < kUsmO; j += 4) reinterpret_cast<float4*>(o)[j >> 2] = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < kUsmO; ++j)
+                if (x0 + c0 + j < W) o[j] = acc[j];
         }
     }
-    __syncthreads();
-    // vertical pass: thread = column x (0..63), one group of 8 rows each (8 groups)
+}
+
+// conv_y(tmp) + the pointwise tail. Block = 64 x 64 outputs, 256 threads: thread = column, 16 consecutive rows each.
+//   stage 0: blur = conv_y(tmp); res = x - blur; mask = |res| * 255 > threshold     -> res, mask_or_out
+//   stage 1: soft = conv_y(tmp); out = soft * clip(x + weight * res, 0, 1) + (1 - soft) * x
+__global__ void __launch_bounds__(256) usm_v51_kernel(const float* __restrict__ tmp, const float* __restrict__ x,
+                                                      float* __restrict__ res, float* __restrict__ mask_or_out, int H, int W,
+                                                      int stage, float weight, float threshold) {
+    __shared__ float Bm[kUsmVIn * kUsmVCols];
+    const int plane = blockIdx.z;
+    const int x0 = blockIdx.x * kUsmVCols, y0 = blockIdx.y * kUsmVRows;
+    const size_t pbase = static_cast<size_t>(plane) * H * W;
     const int cx = threadIdx.x & 63;
-#pragma unroll 1
-    for (int rgi = 0; rgi < 1; ++rgi) {
-        const int r0 = (threadIdx.x >> 6) * 8;
-        float acc[8];
-        usm_window8(Bm + r0 * kUsmPitchB + cx, kUsmPitchB, acc);
-        const int gx = x0 + cx;
-        if (gx >= W) continue;
+    const int gxc = min(x0 + cx, W - 1);
+    {   // 114 rows x 64 columns, coalesced; this thread's rows are g, g+4, ...: 8 loads in flight per batch
+        const int g = threadIdx.x >> 6;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int gy = y0 + r0 + j;
-            if (gy >= H) break;
-            const size_t o = pbase + static_cast<size_t>(gy) * W + gx;
-            if (stage == 0) {
-                const float xv = A[(r0 + j + r) * kUsmPitchA + cx + r];
-                const float rv = xv - acc[j];                                         // imgproc.py:1528
-                res[o] = rv;
-                mask_or_out[o] = (fabsf(rv) * 255.f > threshold) ? 1.f : 0.f;         // imgproc.py:1530-1531
-            } else {
-                const float xv = x[o], rv = res[o];
-                float sh = __fadd_rn(xv, __fmul_rn(weight, rv));                      // imgproc.py:1533
-                sh = fminf(fmaxf(sh, 0.f), 1.f);                                      // imgproc.py:1534
-                mask_or_out[o] = __fadd_rn(__fmul_rn(acc[j], sh), __fmul_rn(1.f - acc[j], xv));  // imgproc.py:1535
+        for (int base = 0; base < kUsmVIn; base += 32) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int ty = min(base + g + 4 * u, kUsmVIn - 1);
+                const int gy = min(max(reflect_idx(y0 + ty - kUsmR, H), 0), H - 1);
+                v[u] = tmp[pbase + static_cast<size_t>(gy) * W + gxc];
             }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int ty = base + g + 4 * u;
+                if (ty < kUsmVIn) Bm[ty * kUsmVCols + cx] = v[u];
+            }
+        }
+    }
+    const int r0 = (threadIdx.x >> 6) * kUsmO;
+    const int gx = x0 + cx;
+    // the tail's operands, requested before the window so that their latency hides behind 816 FMAs
+    float xv[kUsmO], rv[kUsmO];
+#pragma unroll
+    for (int j = 0; j < kUsmO; ++j) {
+        const size_t o = pbase + static_cast<size_t>(min(y0 + r0 + j, H - 1)) * W + gxc;
+        xv[j] = x[o];
+        rv[j] = stage == 0 ? 0.f : res[o];
+    }
+    __syncthreads();
+    float acc[kUsmO];
+    usm_window16(Bm + r0 * kUsmVCols + cx, kUsmVCols, acc);
+    if (gx >= W) return;
+#pragma unroll
+    for (int j = 0; j < kUsmO; ++j) {
+        const int gy = y0 + r0 + j;
+        if (gy >= H) break;
+        const size_t o = pbase + static_cast<size_t>(gy) * W + gx;
+        if (stage == 0) {
+            const float r = xv[j] - acc[j];                                       // imgproc.py:1528
+            res[o] = r;
+            mask_or_out[o] = (fabsf(r) * 255.f > threshold) ? 1.f : 0.f;          // imgproc.py:1530-1531
+        } else {
+            float sh = __fadd_rn(xv[j], __fmul_rn(weight, rv[j]));                // imgproc.py:1533
+            sh = fminf(fmaxf(sh, 0.f), 1.f);                                      // imgproc.py:1534
+            mask_or_out[o] = __fadd_rn(__fmul_rn(acc[j], sh), __fmul_rn(1.f - acc[j], xv[j]));  // imgproc.py:1535
         }
     }
 }
@@ -374,15 +451,12 @@ static int usm_impl(const float* x, float* out, float* ws, int B, int C, int H, 
     const dim3 gh((W + 255) / 256, H, B * C), gv((W + 31) / 32, (H + 63) / 64, B * C);
     const size_t sh = (256 + k - 1) * sizeof(float), sv = static_cast<size_t>(64 + k - 1) * 32 * sizeof(float);
     if (k == kUsmK) {
-        const size_t smem = (static_cast<size_t>(kUsmIn) * kUsmPitchA + static_cast<size_t>(kUsmIn) * kUsmPitchB) * sizeof(float);
-        static PerDevice<bool> attr;
-        if (!attr.cur()) {
-            cudaFuncSetAttribute(usm_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-            attr.cur() = true;
-        }
-        const dim3 gf((W + kUsmT - 1) / kUsmT, (H + kUsmT - 1) / kUsmT, B * C);
-        usm_fused_kernel<<<gf, 512, smem, s>>>(x, x, res, mask, H, W, 0, weight, threshold);
-        usm_fused_kernel<<<gf, 512, smem, s>>>(mask, x, res, out, H, W, 1, weight, threshold);
+        const dim3 g51h((W + kUsmHCols - 1) / kUsmHCols, (H + kUsmHRows - 1) / kUsmHRows, B * C);
+        const dim3 g51v((W + kUsmVCols - 1) / kUsmVCols, (H + kUsmVRows - 1) / kUsmVRows, B * C);
+        usm_h51_kernel<<<g51h, 128, 0, s>>>(x, tmp, H, W);
+        usm_v51_kernel<<<g51v, 256, 0, s>>>(tmp, x, res, mask, H, W, 0, weight, threshold);
+        usm_h51_kernel<<<g51h, 128, 0, s>>>(mask, tmp, H, W);
+        usm_v51_kernel<<<g51v, 256, 0, s>>>(tmp, x, res, out, H, W, 1, weight, threshold);
     } else {
         usm_hpass_kernel<<<gh, 256, sh, s>>>(x, tmp, H, W, k);
         usm_vpass_kernel<<<gv, 256, sv, s>>>(tmp, x, res, mask, H, W, k, 0, weight, threshold);
@@ -720,143 +794,238 @@ __global__ void __launch_bounds__(256) poisson_rates_kernel(const float* __restr
 }
 
 // ===================================================================================== JPEG (a12)
-// One 256-thread block loops over 16 x 16 MCUs (4 Y blocks + Cb + Cr). DCT / IDCT are the reference's direct 64-term
-// contractions with its own cos-product table (imgproc.py:1238-1243), held in shared memory.
-__device__ float g_dct_table[4096];   // [x][y][u][v] = cos((2x+1)u pi/16) cos((2y+1)v pi/16), float64 -> float32
-__device__ float g_idct_table[4096];  // transpose: [x][y][u][v] = cos((2u+1)x pi/16) cos((2v+1)y pi/16)
-__constant__ float c_ytab[64];       // transposed Annex-K luma table (imgproc.py:40-45), [u][v]
-__constant__ float c_ctab[64];       // chroma table (imgproc.py:46-49)
+// One WARP per 16 x 16 MCU (4 Y blocks + Cb + Cr), eight MCUs in flight per block, no block-level synchronisation. The
+// reference's 64-term contraction with its cos-product table (imgproc.py:1238-1249, 1358-1368) is evaluated in its
+// separable form, D[u,v] = sum_x C[x][u] * (sum_y p[x][y] * C[y][v]) with C[x][u] = cos((2x+1) u pi / 16): the same sum
+// in a different fp32 order (the reference's own order is whatever its BLAS picks), 16 instead of 64 FMAs per
+// coefficient, and the 8 x 8 cos matrix lives in 48 registers per lane instead of two 16 KB shared-memory tables that
+// every block had to reload. Quantisation (table * factor, round-half-even) is the reference arithmetic, op for op.
+__device__ float g_cos8[64];          // [x][u] = (float) cos((2x+1) u pi / 16)
+__device__ float g_qtab[2][64];       // [0] transposed Annex-K luma table (imgproc.py:40-45), [1] chroma table (:46-49), [u][v]
 
-__global__ void __launch_bounds__(256) jpeg_kernel(const float* __restrict__ x, float* __restrict__ out,
-                                                   const float* __restrict__ quality, float* __restrict__ factor_out,
-                                                   int B, int H, int W, int clamp_in, float* __restrict__ qy,
-                                                   float* __restrict__ qcb, float* __restrict__ qcr) {
-    __shared__ float T[4096];
-    __shared__ float Ti[4096];
-    __shared__ float pix[6][64];   // level-shifted samples of the 6 blocks, [x*8+y] = row-major inside the block
-    __shared__ float coef[6][64];  // dequantised, alpha-scaled coefficients
-    __shared__ float cbf[16][17], crf[16][17];
-    for (int i = threadIdx.x; i < 4096; i += 256) { T[i] = g_dct_table[i]; Ti[i] = g_idct_table[i]; }
+static constexpr int kJpegWarps = 8;
+
+__global__ void __launch_bounds__(32 * kJpegWarps) jpeg_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                                               const float* __restrict__ quality, float* __restrict__ factor_out,
+                                                               int B, int H, int W, int clamp_in, float* __restrict__ qy,
+                                                               float* __restrict__ qcb, float* __restrict__ qcr) {
+    __shared__ __align__(16) float s_pix[kJpegWarps][6][64];   // samples -> dequantised coefficients -> reconstruction
+    __shared__ __align__(16) float s_tmp[kJpegWarps][6][64];   // row-transformed intermediate
+    __shared__ __align__(16) float s_chr[kJpegWarps][2][256];  // full-resolution Cb, Cr of the MCU
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float (*pix)[64] = s_pix[warp];
+    float (*tmp)[64] = s_tmp[warp];
+    float (*chr)[256] = s_chr[warp];
+    // this lane's two transform outputs per 8 x 8 block: row a = lane / 4, columns b0 = 2 * (lane % 4), b0 + 1
+    const int a = lane >> 2, b0 = (lane & 3) * 2;
+    float c_col[8][2];   // C[i][b0 + j]   (forward row pass: sum over y = i)
+    float c_row[2][8];   // C[b0 + j][i]   (inverse row pass: sum over v = i)
+    float c_a_col[8];    // C[i][a]        (forward column pass: sum over x = i)
+    float c_a_row[8];    // C[a][i]        (inverse column pass: sum over u = i)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        c_col[i][0] = g_cos8[i * 8 + b0];
+        c_col[i][1] = g_cos8[i * 8 + b0 + 1];
+        c_row[0][i] = g_cos8[b0 * 8 + i];
+        c_row[1][i] = g_cos8[(b0 + 1) * 8 + i];
+        c_a_col[i] = g_cos8[i * 8 + a];
+        c_a_row[i] = g_cos8[a * 8 + i];
+    }
+    // quantisation constants of this lane's two coefficients (u = a, v = b0 + j)
+    float tab_y[2], tab_c[2], alpha[2], scale[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int u = a, v = b0 + j;
+        tab_y[j] = g_qtab[0][u * 8 + v];
+        tab_c[j] = g_qtab[1][u * 8 + v];
+        alpha[j] = (u == 0 ? 0.70710678118654752f : 1.f) * (v == 0 ? 0.70710678118654752f : 1.f);
+        scale[j] = (u == 0 && v == 0) ? 0.125f : ((u == 0 || v == 0) ? static_cast<float>(0.25 * 0.70710678118654752) : 0.25f);
+    }
     const int Hp = (H + 15) / 16 * 16, Wp = (W + 15) / 16 * 16;
     const int mw = Wp / 16, mh = Hp / 16;
     const int nmcu = B * mh * mw;
-    const int t = threadIdx.x;
-    const int py = t >> 4, px = t & 15;
     const size_t HW = static_cast<size_t>(H) * W;
-    __syncthreads();
-    for (int m = blockIdx.x; m < nmcu; m += gridDim.x) {
+    const int py = lane >> 1, px0 = (lane & 1) * 8;   // this lane's 8 consecutive pixels of the MCU
+    const bool vec_ok = (W & 3) == 0;
+    for (int m = blockIdx.x * kJpegWarps + warp; m < nmcu; m += gridDim.x * kJpegWarps) {
         const int b = m / (mh * mw);
         const int my = (m / mw) % mh, mx = m % mw;
         // quality -> factor in fp32 tensor arithmetic (imgproc.py:1124-1141 applied per element at :1478-1479)
         const float q = quality[b];
         const float factor = __fdiv_rn(q < 50.f ? __fdiv_rn(5000.f, q) : __fsub_rn(200.f, __fmul_rn(q, 2.f)), 100.f);
-        if (factor_out && my == 0 && mx == 0 && t == 0) factor_out[b] = factor;
-        const int gy = my * 16 + py, gx = mx * 16 + px;
-        float r = 0.f, g = 0.f, bl = 0.f;  // zero padding to a multiple of 16 (imgproc.py:1489)
-        if (gy < H && gx < W) {
-            const size_t o = static_cast<size_t>(b) * 3 * HW + static_cast<size_t>(gy) * W + gx;
-            r = x[o]; g = x[o + HW]; bl = x[o + 2 * HW];
-            if (clamp_in) { r = fminf(fmaxf(r, 0.f), 1.f); g = fminf(fmaxf(g, 0.f), 1.f); bl = fminf(fmaxf(bl, 0.f), 1.f); }
-        }
-        r = __fmul_rn(r, 255.f); g = __fmul_rn(g, 255.f); bl = __fmul_rn(bl, 255.f);  // imgproc.py:1318
-        // imgproc.py:1195-1208 (matrix rows as float32 constants)
-        const float yv = 0.299f * r + 0.587f * g + 0.114f * bl;
-        const float cb = -0.168736f * r + -0.331264f * g + 0.5f * bl + 128.f;
-        const float cr = 0.5f * r + -0.418688f * g + -0.081312f * bl + 128.f;
-        pix[(py >> 3) * 2 + (px >> 3)][(py & 7) * 8 + (px & 7)] = yv - 128.f;
-        cbf[py][px] = cb;
-        crf[py][px] = cr;
-        __syncthreads();
-        if (t < 128) {  // 2x2 mean (imgproc.py:1216-1219)
-            const int c = t >> 6, i = t & 63, cy = i >> 3, cx = i & 7;
-            float (*src)[17] = c ? crf : cbf;
-            const float s = (src[2 * cy][2 * cx] + src[2 * cy][2 * cx + 1]) + (src[2 * cy + 1][2 * cx] + src[2 * cy + 1][2 * cx + 1]);
-            pix[4 + c][i] = s * 0.25f - 128.f;
-        }
-        __syncthreads();
-        // forward DCT + quantise + dequantise: 384 coefficients over 256 threads (two rounds)
-        for (int ci = t; ci < 384; ci += 256) {
-            const int blk = ci >> 6, uv = ci & 63;
-            float acc = 0.f;
-#pragma unroll 8
-            for (int xy = 0; xy < 64; ++xy) acc = fmaf(pix[blk][xy], T[xy * 64 + uv], acc);
-            const int u = uv >> 3, v = uv & 7;
-            const float alpha = (u == 0 ? 0.70710678118654752f : 1.f) * (v == 0 ? 0.70710678118654752f : 1.f);
-            const float scale = (u == 0 && v == 0) ? 0.125f : ((u == 0 || v == 0) ? static_cast<float>(0.25 * 0.70710678118654752) : 0.25f);
-            const float d = __fmul_rn(scale, acc);                                // imgproc.py:1249
-            const float tq = __fmul_rn(blk < 4 ? c_ytab[uv] : c_ctab[uv], factor);  // imgproc.py:1270, 1289
-            const float qc = rintf(__fdiv_rn(d, tq));                             // imgproc.py:1272-1274
-            if (qy) {  // optional dump of the quantised coefficients (tests)
-                if (blk < 4) {
-                    const int byi = my * 2 + (blk >> 1), bxi = mx * 2 + (blk & 1);
-                    qy[(static_cast<size_t>(b) * (Hp / 8) * (Wp / 8) + static_cast<size_t>(byi) * (Wp / 8) + bxi) * 64 + uv] = qc;
-                } else {
-                    float* dst = blk == 4 ? qcb : qcr;
-                    dst[(static_cast<size_t>(b) * mh * mw + static_cast<size_t>(my) * mw + mx) * 64 + uv] = qc;
-                }
+        if (factor_out && my == 0 && mx == 0 && lane == 0) factor_out[b] = factor;
+        const int gy = my * 16 + py, gx0 = mx * 16 + px0;
+        const size_t o0 = static_cast<size_t>(b) * 3 * HW + static_cast<size_t>(gy) * W + gx0;
+        float rgb[3][8];
+        if (gy < H && gx0 + 8 <= W && vec_ok) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float4 v0 = *reinterpret_cast<const float4*>(x + o0 + c * HW);
+                const float4 v1 = *reinterpret_cast<const float4*>(x + o0 + c * HW + 4);
+                rgb[c][0] = v0.x; rgb[c][1] = v0.y; rgb[c][2] = v0.z; rgb[c][3] = v0.w;
+                rgb[c][4] = v1.x; rgb[c][5] = v1.y; rgb[c][6] = v1.z; rgb[c][7] = v1.w;
             }
-            coef[blk][uv] = __fmul_rn(__fmul_rn(qc, tq), alpha);                  // imgproc.py:1331, 1366
+        } else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) rgb[c][i] = (gy < H && gx0 + i < W) ? x[o0 + c * HW + i] : 0.f;  // zero padding (imgproc.py:1489)
         }
-        __syncthreads();
-        // inverse DCT per pixel: out[u,v] = 0.25 * sum_{x,y} coef[x,y] * cos((2u+1)x..)cos((2v+1)y..) + 128
-        float rec[3];
         {
-            const int blk = (py >> 3) * 2 + (px >> 3), uv = (py & 7) * 8 + (px & 7);
-            float acc = 0.f;
-#pragma unroll 8
-            for (int xy = 0; xy < 64; ++xy) acc = fmaf(coef[blk][xy], Ti[xy * 64 + uv], acc);
-            rec[0] = __fadd_rn(__fmul_rn(0.25f, acc), 128.f);
+            const int blk = (py >> 3) * 2 + (lane & 1);
+            float yv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float r = rgb[0][i], g = rgb[1][i], bl = rgb[2][i];
+                if (clamp_in) { r = fminf(fmaxf(r, 0.f), 1.f); g = fminf(fmaxf(g, 0.f), 1.f); bl = fminf(fmaxf(bl, 0.f), 1.f); }
+                r = __fmul_rn(r, 255.f); g = __fmul_rn(g, 255.f); bl = __fmul_rn(bl, 255.f);  // imgproc.py:1318
+                // imgproc.py:1195-1208 (matrix rows as float32 constants)
+                yv[i] = (0.299f * r + 0.587f * g + 0.114f * bl) - 128.f;
+                chr[0][py * 16 + px0 + i] = -0.168736f * r + -0.331264f * g + 0.5f * bl + 128.f;
+                chr[1][py * 16 + px0 + i] = 0.5f * r + -0.418688f * g + -0.081312f * bl + 128.f;
+            }
+            float4* dst = reinterpret_cast<float4*>(&pix[blk][(py & 7) * 8]);
+            dst[0] = make_float4(yv[0], yv[1], yv[2], yv[3]);
+            dst[1] = make_float4(yv[4], yv[5], yv[6], yv[7]);
         }
-        __syncthreads();  // everyone is done reading pix[] as forward-DCT input; reuse cbf/crf for decoded chroma
-        if (t < 128) {
-            const int c = t >> 6, uv = t & 63;
-            float acc = 0.f;
-#pragma unroll 8
-            for (int xy = 0; xy < 64; ++xy) acc = fmaf(coef[4 + c][xy], Ti[xy * 64 + uv], acc);
-            (c ? crf : cbf)[uv >> 3][uv & 7] = __fadd_rn(__fmul_rn(0.25f, acc), 128.f);
+        __syncwarp();
+        {   // 2x2 mean (imgproc.py:1216-1219): 2 planes x 64 samples, 4 per lane
+            const int c = lane >> 4;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int i = (lane & 15) * 4 + t, cy = i >> 3, cx = i & 7;
+                const float* src = chr[c];
+                const float sum = (src[(2 * cy) * 16 + 2 * cx] + src[(2 * cy) * 16 + 2 * cx + 1]) +
+                                  (src[(2 * cy + 1) * 16 + 2 * cx] + src[(2 * cy + 1) * 16 + 2 * cx + 1]);
+                pix[4 + c][i] = sum * 0.25f - 128.f;
+            }
         }
-        __syncthreads();
-        rec[1] = cbf[py >> 1][px >> 1] - 128.f;  // nearest 2x repeat (imgproc.py:1392-1400) + shift (:1412)
-        rec[2] = crf[py >> 1][px >> 1] - 128.f;
-        if (gy < H && gx < W) {
-            // imgproc.py:1405-1419
-            const float ro = rec[0] + 1.402f * rec[2];
-            const float go = rec[0] + -0.344136f * rec[1] + -0.714136f * rec[2];
-            const float bo = rec[0] + 1.772f * rec[1];
-            const size_t o = static_cast<size_t>(b) * 3 * HW + static_cast<size_t>(gy) * W + gx;
-            out[o] = __fdiv_rn(fminf(255.f, fmaxf(0.f, ro)), 255.f);  // imgproc.py:1453-1455
-            out[o + HW] = __fdiv_rn(fminf(255.f, fmaxf(0.f, go)), 255.f);
-            out[o + 2 * HW] = __fdiv_rn(fminf(255.f, fmaxf(0.f, bo)), 255.f);
+        __syncwarp();
+        // ---- forward DCT, row pass: tmp[x][v] = sum_y p[x][y] * C[y][v]   (x = a, v = b0 + j)
+#pragma unroll
+        for (int blk = 0; blk < 6; ++blk) {
+            const float4 p0 = *reinterpret_cast<const float4*>(&pix[blk][a * 8]);
+            const float4 p1 = *reinterpret_cast<const float4*>(&pix[blk][a * 8 + 4]);
+            const float p[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+            float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+            for (int y = 0; y < 8; ++y) { t0 = fmaf(p[y], c_col[y][0], t0); t1 = fmaf(p[y], c_col[y][1], t1); }
+            *reinterpret_cast<float2*>(&tmp[blk][a * 8 + b0]) = make_float2(t0, t1);
         }
-        __syncthreads();
+        __syncwarp();
+        // ---- column pass + quantise + dequantise: D[u][v] = sum_x C[x][u] * tmp[x][v]   (u = a, v = b0 + j)
+#pragma unroll
+        for (int blk = 0; blk < 6; ++blk) {
+            float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+            for (int xx = 0; xx < 8; ++xx) {
+                const float2 t = *reinterpret_cast<const float2*>(&tmp[blk][xx * 8 + b0]);
+                acc0 = fmaf(c_a_col[xx], t.x, acc0);
+                acc1 = fmaf(c_a_col[xx], t.y, acc1);
+            }
+            const float accs[2] = {acc0, acc1};
+            float cf[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int uv = a * 8 + b0 + j;
+                const float d = __fmul_rn(scale[j], accs[j]);                            // imgproc.py:1249
+                const float tq = __fmul_rn(blk < 4 ? tab_y[j] : tab_c[j], factor);        // imgproc.py:1270, 1289
+                const float qc = rintf(__fdiv_rn(d, tq));                                // imgproc.py:1272-1274
+                if (qy) {  // optional dump of the quantised coefficients (tests)
+                    if (blk < 4) {
+                        const int byi = my * 2 + (blk >> 1), bxi = mx * 2 + (blk & 1);
+                        qy[(static_cast<size_t>(b) * (Hp / 8) * (Wp / 8) + static_cast<size_t>(byi) * (Wp / 8) + bxi) * 64 + uv] = qc;
+                    } else {
+                        float* dst = blk == 4 ? qcb : qcr;
+                        dst[(static_cast<size_t>(b) * mh * mw + static_cast<size_t>(my) * mw + mx) * 64 + uv] = qc;
+                    }
+                }
+                cf[j] = __fmul_rn(__fmul_rn(qc, tq), alpha[j]);                           // imgproc.py:1331, 1366
+            }
+            *reinterpret_cast<float2*>(&pix[blk][a * 8 + b0]) = make_float2(cf[0], cf[1]);  // everyone is past the row pass
+        }
+        __syncwarp();
+        // ---- inverse DCT, row pass: t2[u][y'] = sum_v coef[u][v] * C[y'][v]   (u = a, y' = b0 + j)
+#pragma unroll
+        for (int blk = 0; blk < 6; ++blk) {
+            const float4 p0 = *reinterpret_cast<const float4*>(&pix[blk][a * 8]);
+            const float4 p1 = *reinterpret_cast<const float4*>(&pix[blk][a * 8 + 4]);
+            const float p[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+            float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+            for (int v = 0; v < 8; ++v) { t0 = fmaf(p[v], c_row[0][v], t0); t1 = fmaf(p[v], c_row[1][v], t1); }
+            *reinterpret_cast<float2*>(&tmp[blk][a * 8 + b0]) = make_float2(t0, t1);
+        }
+        __syncwarp();
+        // ---- column pass: rec[x'][y'] = 0.25 * sum_u C[x'][u] * t2[u][y'] + 128   (x' = a, y' = b0 + j)
+#pragma unroll
+        for (int blk = 0; blk < 6; ++blk) {
+            float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const float2 t = *reinterpret_cast<const float2*>(&tmp[blk][u * 8 + b0]);
+                acc0 = fmaf(c_a_row[u], t.x, acc0);
+                acc1 = fmaf(c_a_row[u], t.y, acc1);
+            }
+            *reinterpret_cast<float2*>(&pix[blk][a * 8 + b0]) =
+                make_float2(__fadd_rn(__fmul_rn(0.25f, acc0), 128.f), __fadd_rn(__fmul_rn(0.25f, acc1), 128.f));  // imgproc.py:1367-1368
+        }
+        __syncwarp();
+        {   // chroma nearest 2x repeat (imgproc.py:1392-1400), shift (:1412), YCbCr -> RGB (:1405-1419), clamp, / 255
+            const int blk = (py >> 3) * 2 + (lane & 1);
+            const float4 y0v = *reinterpret_cast<const float4*>(&pix[blk][(py & 7) * 8]);
+            const float4 y1v = *reinterpret_cast<const float4*>(&pix[blk][(py & 7) * 8 + 4]);
+            const float yy[8] = {y0v.x, y0v.y, y0v.z, y0v.w, y1v.x, y1v.y, y1v.z, y1v.w};
+            const float4 cbv = *reinterpret_cast<const float4*>(&pix[4][(py >> 1) * 8 + (px0 >> 1)]);
+            const float4 crv = *reinterpret_cast<const float4*>(&pix[5][(py >> 1) * 8 + (px0 >> 1)]);
+            const float cb4[4] = {cbv.x, cbv.y, cbv.z, cbv.w}, cr4[4] = {crv.x, crv.y, crv.z, crv.w};
+            float o3[3][8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float r0 = yy[i], r1 = cb4[i >> 1] - 128.f, r2 = cr4[i >> 1] - 128.f;
+                const float ro = r0 + 1.402f * r2;
+                const float go = r0 + -0.344136f * r1 + -0.714136f * r2;
+                const float bo = r0 + 1.772f * r1;
+                o3[0][i] = __fdiv_rn(fminf(255.f, fmaxf(0.f, ro)), 255.f);  // imgproc.py:1453-1455
+                o3[1][i] = __fdiv_rn(fminf(255.f, fmaxf(0.f, go)), 255.f);
+                o3[2][i] = __fdiv_rn(fminf(255.f, fmaxf(0.f, bo)), 255.f);
+            }
+            if (gy < H && gx0 + 8 <= W && vec_ok) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    *reinterpret_cast<float4*>(out + o0 + c * HW) = make_float4(o3[c][0], o3[c][1], o3[c][2], o3[c][3]);
+                    *reinterpret_cast<float4*>(out + o0 + c * HW + 4) = make_float4(o3[c][4], o3[c][5], o3[c][6], o3[c][7]);
+                }
+            } else if (gy < H) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (gx0 + i < W) out[o0 + c * HW + i] = o3[c][i];
+            }
+        }
+        __syncwarp();
     }
 }
 
 static int jpeg_init_tables() {
-    static PerDevice<bool> done;  // __device__ / __constant__ tables live per device
+    static PerDevice<bool> done;  // __device__ tables live per device
     if (done.cur()) return RESR_OK;
-    static float T[4096], Ti[4096];
     const double pi = 3.14159265358979323846;
-    for (int x = 0; x < 8; ++x)
-        for (int y = 0; y < 8; ++y)
-            for (int u = 0; u < 8; ++u)
-                for (int v = 0; v < 8; ++v)
-                    T[((x * 8 + y) * 8 + u) * 8 + v] =
-                        static_cast<float>(std::cos((2 * x + 1) * u * pi / 16) * std::cos((2 * y + 1) * v * pi / 16));
-    for (int a = 0; a < 64; ++a)
-        for (int b = 0; b < 64; ++b) Ti[a * 64 + b] = T[b * 64 + a];
+    float c8[64];
+    for (int xx = 0; xx < 8; ++xx)
+        for (int u = 0; u < 8; ++u) c8[xx * 8 + u] = static_cast<float>(std::cos((2 * xx + 1) * u * pi / 16));
     static const float ybase[64] = {16, 11, 10, 16, 24, 40, 51, 61, 12, 12, 14, 19, 26, 58, 60, 55, 14, 13, 16, 24, 40, 57,
                                     69, 56, 14, 17, 22, 29, 51, 87, 80, 62, 18, 22, 37, 56, 68, 109, 103, 77, 24, 35, 55,
                                     64, 81, 104, 113, 92, 49, 64, 78, 87, 103, 121, 120, 101, 72, 92, 95, 98, 112, 100, 103, 99};
     static const float cbase[16] = {17, 18, 24, 47, 18, 21, 26, 66, 24, 26, 56, 99, 47, 66, 99, 99};
-    float yt[64], ct[64];
+    float qt[2][64];
     for (int u = 0; u < 8; ++u)
         for (int v = 0; v < 8; ++v) {
-            yt[u * 8 + v] = ybase[v * 8 + u];  // .T (imgproc.py:45)
-            ct[u * 8 + v] = (u < 4 && v < 4) ? cbase[v * 4 + u] : 99.f;
+            qt[0][u * 8 + v] = ybase[v * 8 + u];  // .T (imgproc.py:45)
+            qt[1][u * 8 + v] = (u < 4 && v < 4) ? cbase[v * 4 + u] : 99.f;
         }
-    if (cudaMemcpyToSymbol(g_dct_table, T, sizeof(T)) != cudaSuccess || cudaMemcpyToSymbol(g_idct_table, Ti, sizeof(Ti)) != cudaSuccess || cudaMemcpyToSymbol(c_ytab, yt, sizeof(yt)) != cudaSuccess ||
-        cudaMemcpyToSymbol(c_ctab, ct, sizeof(ct)) != cudaSuccess)
+    if (cudaMemcpyToSymbol(g_cos8, c8, sizeof(c8)) != cudaSuccess || cudaMemcpyToSymbol(g_qtab, qt, sizeof(qt)) != cudaSuccess)
         return set_error(RESR_E_CUDA, "JPEG table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
     done.cur() = true;
     return RESR_OK;
@@ -867,8 +1036,9 @@ static int jpeg_impl(const float* x, float* out, const float* quality, float* fa
     const int rc = jpeg_init_tables();
     if (rc != RESR_OK) return rc;
     const int nmcu = B * ((H + 15) / 16) * ((W + 15) / 16);
-    const int grid = nmcu < 148 * 4 ? nmcu : 148 * 4;
-    jpeg_kernel<<<grid, 256, 0, s>>>(x, out, quality, factor_out, B, H, W, clamp_in, qy, qcb, qcr);
+    int grid = (nmcu + kJpegWarps - 1) / kJpegWarps;
+    if (grid > 148 * 8) grid = 148 * 8;   // beyond that, warps loop over MCUs
+    jpeg_kernel<<<grid, 32 * kJpegWarps, 0, s>>>(x, out, quality, factor_out, B, H, W, clamp_in, qy, qcb, qcr);
     RESR_LAUNCH_CHECK("jpeg");
     return RESR_OK;
 }

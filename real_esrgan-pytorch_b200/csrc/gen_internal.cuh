@@ -90,6 +90,7 @@ struct Plan {
     void* ws = nullptr;
     std::vector<Step> steps;
     uint16_t* xin = nullptr;
+    int pair_policy = -1;  // conv3x3_set_pair_policy value the steps were planned under
     bool valid = false;
 };
 
@@ -123,6 +124,7 @@ struct resr_generator {
     bool loaded = false;
     int num_sms = 148;
     int force_mode = -1;
+    int precision = 0;            // inference recipe: 0 = fp16 operands / fp16 residual stream, 1 = bf16 operands + fp32 residual masters
     resr::Plan plan;
 };
 

@@ -135,7 +135,8 @@ int launch_pack_all(resr_generator* g, const float* flat, int transposed, cudaSt
             j.p_off = c.p_off;
             j.cin = c.cin; j.cout = c.cout;
             if (!transposed) {
-                j.w_off = c.w_off; j.b_off = c.b_off; j.nout = c.nout; j.nslices = c.nslices; j.nchunks = c.nchunks; j.fmt = c.fmt;
+                j.w_off = c.w_off; j.b_off = c.b_off; j.nout = c.nout; j.nslices = c.nslices; j.nchunks = c.nchunks;
+                j.fmt = g->precision == 1 ? 1 : c.fmt;
             } else {
                 j.w_off = c.wt_off; j.b_off = 0; j.nout = 32; j.nslices = c.t_nslices; j.nchunks = c.t_nchunks; j.fmt = 1;
             }
@@ -160,9 +161,9 @@ void launch_pack_conv(const float* w, const float* bias, uint16_t* wp, float* bp
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct WsLayout {
-    size_t xin, c[3], f0, t1, t2, t3, t4, total;
+    size_t xin, c[3], f0, m[4], t1, t2, t3, t4, total;
 };
-static WsLayout ws_layout(size_t N, size_t H, size_t W) {
+static WsLayout ws_layout(size_t N, size_t H, size_t W, int precision = 0) {
     const size_t P = N * H * W;
     WsLayout L;
     size_t o = 0;
@@ -174,6 +175,7 @@ static WsLayout ws_layout(size_t N, size_t H, size_t W) {
     L.xin = take(P * 64 * 2);
     for (int i = 0; i < 3; ++i) L.c[i] = take(P * 192 * 2);
     L.f0 = take(P * 64 * 4);
+    for (int i = 0; i < 4; ++i) L.m[i] = precision == 1 ? take(P * 64 * 4) : 0;  // bf16 recipe: fp32 masters of the residual stream
     L.t1 = take(4 * P * 64 * 2);
     L.t2 = take(16 * P * 64 * 2);
     L.t3 = take(16 * P * 64 * 2);
@@ -187,7 +189,9 @@ static int build_plan(resr_generator* g, int N, int H, int W, void* ws, cudaStre
     p.valid = false;
     p.steps.clear();
     p.N = N; p.H = H; p.W = W; p.ws = ws;
-    const WsLayout L = ws_layout(N, H, W);
+    p.pair_policy = conv3x3_set_pair_policy(-1);
+    const int prec = g->precision;
+    const WsLayout L = ws_layout(N, H, W, prec);
     uint8_t* base = static_cast<uint8_t*>(ws);
     uint16_t* xin = reinterpret_cast<uint16_t*>(base + L.xin);
     // three 192-channel concat buffers: [0] holds the RRDB input (and receives the RRDB output in place), [1] / [2] the
@@ -195,6 +199,8 @@ static int build_plan(resr_generator* g, int N, int H, int W, void* ws, cudaStre
     uint16_t* cbuf[3];
     for (int i = 0; i < 3; ++i) cbuf[i] = reinterpret_cast<uint16_t*>(base + L.c[i]);
     float* F0 = reinterpret_cast<float*>(base + L.f0);
+    float* M[4];
+    for (int i = 0; i < 4; ++i) M[i] = reinterpret_cast<float*>(base + L.m[i]);
     uint16_t* t1 = reinterpret_cast<uint16_t*>(base + L.t1);
     uint16_t* t2 = reinterpret_cast<uint16_t*>(base + L.t2);
     uint16_t* t3 = reinterpret_cast<uint16_t*>(base + L.t3);
@@ -231,7 +237,7 @@ static int build_plan(resr_generator* g, int N, int H, int W, void* ws, cudaStre
         a.nchunks = cs.nchunks;
         a.tail_ksteps = conv3x3_tail_ksteps(cs.cin);
         a.mode = q.mode;
-        a.fmt_in = cs.fmt;
+        a.fmt_in = prec == 1 ? 1 : cs.fmt;
         a.rows_total = static_cast<long long>(a.ncg) * q.H;
         a.wpack = g->wpack + cs.w_off;
         a.bias = g->bias + cs.b_off;
@@ -240,7 +246,7 @@ static int build_plan(resr_generator* g, int N, int H, int W, void* ws, cudaStre
     };
     auto set_out16 = [&](Step& st, int s, void* dst, int c_total, int choff, int fmt, int up2) {
         const Geo& q = geo[s];
-        st.a.has_out16 = 1; st.a.out16_fmt = fmt; st.a.out16_choff = choff; st.a.out16_up2 = up2;
+        st.a.has_out16 = 1; st.a.out16_fmt = prec == 1 ? 1 : fmt; st.a.out16_choff = choff; st.a.out16_up2 = up2;
         map_rc |= conv3x3_make_tmap_out16(&st.maps.o16, dst, N, q.H, q.W, c_total, T.c[st.conv].nout, q.BW, q.BN, up2);
     };
     auto set_outf = [&](Step& st, float* dst) {
@@ -280,12 +286,18 @@ static int build_plan(resr_generator* g, int N, int H, int W, void* ws, cudaStre
                 ++conv;
             }
             Step st = make_step(conv, 0, cin_buf, 192);  // model.py:94-96 (+ :129-130 for the third RDB)
-            set_res16(st, cin_buf);
-            if (j < 2) {
-                st.a.ep_mode = EP_RDB;
+            st.a.ep_mode = j < 2 ? EP_RDB : EP_RRDB;
+            if (prec == 1) {
+                // bf16 recipe (north_star): the residual stream is kept in fp32 masters next to the bf16 operands. Dense
+                // block t reads master t % 4 (conv1's fp32 output for t = 0) and writes master (t + 1) % 4; the RRDB skip
+                // reads the master of the RRDB input, which no block of the same RRDB overwrites.
+                const int t = i * 3 + j;
+                set_res1(st, t == 0 ? F0 : M[t % 4]);
+                if (j == 2) { st.a.res2 = i == 0 ? F0 : M[(3 * i) % 4]; st.a.res2_cstride = 64; }
+                set_outf(st, M[(t + 1) % 4]);
             } else {
-                st.a.ep_mode = EP_RRDB;
-                st.a.res2 = cbuf[0]; st.a.res2_cstride = 192;
+                set_res16(st, cin_buf);
+                if (j == 2) { st.a.res2 = cbuf[0]; st.a.res2_cstride = 192; }
             }
             set_out16(st, 0, cbuf[(j + 1) % 3], 192, 0, 0, 0);
             push(st);
@@ -345,6 +357,8 @@ int resr_version(void) { return 1; }
 size_t resr_generator_num_params(void) { return table().n_params; }
 int resr_generator_num_tensors(void) { return 2 * kNumConvs; }
 int resr_generator_launches_per_forward(void) { return 1 + kNumConvs; }
+
+int resr_set_conv_pair_policy(int policy) { return conv3x3_set_pair_policy(policy); }
 
 int resr_debug_wait_profile(unsigned long long* out16_host, int reset) {
     if (conv3x3_wait_profile(out16_host, reset) != 0) return set_error(RESR_E_CUDA, "wait profile copy failed");
@@ -426,21 +440,39 @@ size_t resr_generator_workspace_bytes(int n, int h, int w) {
     return ws_layout(n, h, w).total;
 }
 
+size_t resr_generator_workspace_bytes_for(const resr_generator_t* g, int n, int h, int w) {
+    if (!g || n <= 0 || h <= 0 || w <= 0) return 0;
+    return ws_layout(n, h, w, g->precision).total;
+}
+
+int resr_generator_set_precision(resr_generator_t* g, int precision) {
+    if (!g) return set_error(RESR_E_INVALID, "null argument");
+    if (precision != 0 && precision != 1) return set_error(RESR_E_INVALID, "precision must be 0 (fp16) or 1 (bf16 + fp32 residual masters)");
+    if (g->precision != precision) {
+        g->precision = precision;
+        g->loaded = false;        // the packed weights are in the old operand format: the caller reloads its parameters
+        g->plan.valid = false;
+        cudaFree(g->pack_jobs);   // the batched pack table carries the operand format
+        g->pack_jobs = nullptr;
+    }
+    return RESR_OK;
+}
+
 int resr_generator_forward(resr_generator_t* g, const float* x, float* y, int n, int h, int w, void* workspace,
                            size_t workspace_bytes, void* stream) {
     if (!g || !x || !y || !workspace) return set_error(RESR_E_INVALID, "null argument");
     if (n <= 0 || h <= 0 || w <= 0) return set_error(RESR_E_INVALID, "bad shape %dx3x%dx%d", n, h, w);
     if (!g->loaded) return set_error(RESR_E_INVALID, "resr_generator_load_params has not been called");
-    if (workspace_bytes < resr_generator_workspace_bytes(n, h, w)) return set_error(RESR_E_NOMEM, "workspace too small");
+    if (workspace_bytes < resr_generator_workspace_bytes_for(g, n, h, w)) return set_error(RESR_E_NOMEM, "workspace too small");
     if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0) return set_error(RESR_E_INVALID, "workspace must be 1024-byte aligned");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     Plan& p = g->plan;
-    if (!p.valid || p.N != n || p.H != h || p.W != w || p.ws != workspace) {
+    if (!p.valid || p.N != n || p.H != h || p.W != w || p.ws != workspace || p.pair_policy != conv3x3_set_pair_policy(-1)) {
         const int rc = build_plan(g, n, h, w, workspace, s);
         if (rc != RESR_OK) return rc;
     }
     const size_t total = static_cast<size_t>(n) * h * w * 8;
-    nchw_to_nhwc16_kernel<<<grid_for(total, 256), 256, 0, s>>>(x, p.xin, n, 3, h, w, 64, 0);
+    nchw_to_nhwc16_kernel<<<grid_for(total, 256), 256, 0, s>>>(x, p.xin, n, 3, h, w, 64, g->precision == 1 ? 1 : 0);
     const Table& T = table();
     for (size_t i = 0; i < p.steps.size(); ++i) {
         Step& st = p.steps[i];
@@ -456,7 +488,7 @@ int resr_generator_forward_host(resr_generator_t* g, const float* x_host, float*
     if (!x_host || !y_host) return set_error(RESR_E_INVALID, "null argument");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t in_bytes = static_cast<size_t>(n) * 3 * h * w * 4, out_bytes = in_bytes * 16;
-    const size_t need = resr_generator_workspace_bytes(n, h, w);
+    const size_t need = resr_generator_workspace_bytes_for(g, n, h, w);
     // device staging for x and y lives at the end of the caller's workspace
     const size_t off_x = (need + 1023) / 1024 * 1024, off_y = off_x + (in_bytes + 1023) / 1024 * 1024;
     if (workspace_bytes < off_y + out_bytes) return set_error(RESR_E_NOMEM, "workspace too small for host staging (need %zu)", off_y + out_bytes);
@@ -476,7 +508,7 @@ int resr_generator_forward_host_async(resr_generator_t* g, const float* x_host, 
     if (!g || !x_host || !y_host) return set_error(RESR_E_INVALID, "null argument");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t in_bytes = static_cast<size_t>(n) * 3 * h * w * 4, out_bytes = in_bytes * 16;
-    const size_t need = resr_generator_workspace_bytes(n, h, w);
+    const size_t need = resr_generator_workspace_bytes_for(g, n, h, w);
     const size_t in_al = (in_bytes + 1023) / 1024 * 1024, out_al = (out_bytes + 1023) / 1024 * 1024;
     const size_t off0 = (need + 1023) / 1024 * 1024;
     if (workspace_bytes < off0 + 2 * (in_al + out_al))

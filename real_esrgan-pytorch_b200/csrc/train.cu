@@ -637,6 +637,7 @@ int check_train_args(resr_generator_t* g, int n, int h, int w, void* ws, size_t 
     if (!g || !ws) return set_error(RESR_E_INVALID, "null argument");
     if (n <= 0 || h <= 0 || w <= 0) return set_error(RESR_E_INVALID, "bad shape");
     if (w % 8 != 0) return set_error(RESR_E_INVALID, "training path needs W %% 8 == 0 (channels-first TMA strides), got %d", w);
+    if (g->precision != 0) return set_error(RESR_E_INVALID, "the training path uses the fp16 forward recipe: resr_generator_set_precision(g, 0) first");
     if (!g->loaded || !g->flat_params) return set_error(RESR_E_INVALID, "resr_generator_load_params has not been called");
     if (ws_bytes < resr_generator_train_workspace_bytes(n, h, w)) return set_error(RESR_E_NOMEM, "training workspace too small");
     if ((reinterpret_cast<uintptr_t>(ws) & 1023) != 0) return set_error(RESR_E_INVALID, "workspace must be 1024-byte aligned");

@@ -327,6 +327,10 @@ def interpolate(image: torch.Tensor, size=None, scale_factor=None, mode: str = "
         sh, sw = (scale_factor, scale_factor) if not isinstance(scale_factor, (tuple, list)) else scale_factor
         oh, ow = int(math.floor(float(h) * sh)), int(math.floor(float(w) * sw))
     x = _prep(image)
+    if (oh, ow) == (h, w) and (size is not None or (float(sh) == 1.0 and float(sw) == 1.0)):
+        # same-size resize: all three modes return the input bit for bit (`scale_factor=1` of the first
+        # resize, the third resize after a "keep" second one) -- no launch
+        return x.clone() if x.data_ptr() == image.data_ptr() else x
     out = torch.empty(b, c, oh, ow, dtype=torch.float32, device=x.device)
     _lib.check(_lib.lib().resr_resize(_lib.ptr(x), _lib.ptr(out), b * c, h, w, oh, ow, _MODES[mode], float(sh), float(sw),
                                       _lib.stream_ptr()))

@@ -17,6 +17,9 @@ from . import _lib
 __all__ = ["ResidualDenseBlock", "ResidualResidualDenseBlock", "Generator", "plan_tiles", "infer_tiled"]
 
 
+_PRECISIONS = {"fp16": 0, "bf16": 1}
+
+
 def _conv(cin: int, cout: int) -> nn.Conv2d:
     return nn.Conv2d(cin, cout, (3, 3), (1, 1), (1, 1))
 
@@ -140,6 +143,7 @@ class Generator(nn.Module):
         self._flat = None
         self._workspace = None
         self._static_weights = False
+        self._precision = "fp16"
         self._fwd_generation = 0   # bumped by every training-mode forward (autograd.py ties a backward to its forward)
 
     # ------------------------------------------------------------------ native plumbing
@@ -163,8 +167,28 @@ class Generator(nn.Module):
             h = ctypes.c_void_p()
             with torch.cuda.device(dev):
                 _lib.check(_lib.lib().resr_generator_create(ctypes.byref(h), 3, 3, 4))
+                _lib.check(_lib.lib().resr_generator_set_precision(h, _PRECISIONS[self._precision]))
             self._handle, self._handle_device = h, dev
         return self._handle
+
+    def set_precision(self, precision: str):
+        """Inference recipe: "fp16" (default: fp16 tensor-core operands, the trunk's residual stream is the fp16 conv
+        input) or "bf16" (BASELINE.json north_star: bf16 operands and activations + fp32 masters of the residual stream).
+        Both run at the same tensor-core rate; fp16 is ~2x closer to the fp32 reference. Training always uses fp16."""
+        if precision not in _PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}")
+        if precision != self._precision:
+            self._precision = precision
+            if self._handle is not None:
+                with torch.cuda.device(self._handle_device):
+                    torch.cuda.synchronize()
+                    _lib.check(_lib.lib().resr_generator_set_precision(self._handle, _PRECISIONS[precision]))
+            self._packed_version = None
+        return self
+
+    @property
+    def precision(self) -> str:
+        return self._precision
 
     def __del__(self):
         h = getattr(self, "_handle", None)
@@ -215,7 +239,7 @@ class Generator(nn.Module):
             self._packed_version = ver
 
     def _get_workspace(self, n: int, h: int, w: int, device, extra: int = 0) -> torch.Tensor:
-        need = _lib.lib().resr_generator_workspace_bytes(n, h, w) + extra
+        need = _lib.lib().resr_generator_workspace_bytes_for(self._native(), n, h, w) + extra
         ws = self._workspace
         if ws is None or ws.numel() < need + 1024 or ws.device != device:
             ws = torch.empty(need + 1024, dtype=torch.uint8, device=device)
@@ -291,7 +315,8 @@ class Generator(nn.Module):
         self._ensure_packed()
         extra = 2 * (x_host.numel() * 4 * 17 + 4096)
         cur = self._workspace
-        if cur is not None and (cur.device != device or cur.numel() < _lib.lib().resr_generator_workspace_bytes(n, h, w) + extra + 1024):
+        if cur is not None and (cur.device != device or
+                                cur.numel() < _lib.lib().resr_generator_workspace_bytes_for(self._native(), n, h, w) + extra + 1024):
             self.host_sync()  # queued copies still use the workspace that is about to be replaced
             torch.cuda.synchronize(device)
         ws = self._get_workspace(n, h, w, device, extra)

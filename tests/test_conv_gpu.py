@@ -45,6 +45,17 @@ def _run_conv(x16, cin, weight, bias, *, fmt, mode=-1, ep_mode=0, lrelu=0, clamp
     torch.cuda.synchronize()
 
 
+@pytest.fixture(params=["auto", "pairs"], autouse=True)
+def conv_kernel_policy(request):
+    """Every case runs twice: default kernel choice (small shapes take the single-CTA kernel) and with the CTA-pair
+    kernel forced wherever two column groups exist (conv3x3_pair.cu, tcgen05 cta_group::2)."""
+    import resr_b200
+    lib = resr_b200._lib.lib()
+    prev = lib.resr_set_conv_pair_policy(2 if request.param == "pairs" else 1)
+    yield request.param
+    lib.resr_set_conv_pair_policy(prev)
+
+
 CASES = [
     # n, h, w, cin, c_total, cout, mode
     (2, 12, 128, 64, 64, 32, 0),

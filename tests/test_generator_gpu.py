@@ -18,6 +18,16 @@ def _psnr(a, b):
     return 99.0 if mse == 0 else 10 * math.log10(1.0 / mse)
 
 
+@pytest.fixture(params=["auto", "pairs"])
+def kernel_policy(request):
+    """"pairs": the CTA-pair conv kernel wherever two column groups exist, also at small / awkward shapes."""
+    import resr_b200
+    lib = resr_b200._lib.lib()
+    prev = lib.resr_set_conv_pair_policy(2 if request.param == "pairs" else 1)
+    yield request.param
+    lib.resr_set_conv_pair_policy(prev)
+
+
 def _make(seed):
     import resr_b200
     from oracle import generator as og
@@ -28,7 +38,7 @@ def _make(seed):
 
 
 @pytest.mark.parametrize("seed,shape", [(0, (1, 3, 32, 32)), (1, (2, 3, 24, 40)), (2, (3, 3, 16, 64)), (3, (1, 3, 20, 128))])
-def test_generator_vs_oracle(seed, shape):
+def test_generator_vs_oracle(seed, shape, kernel_policy):
     from oracle import generator as og
     g, sd = _make(seed)
     torch.manual_seed(100 + seed)
@@ -76,7 +86,7 @@ def test_generator_cfg1_shape_channels_last_and_modes(golden_dir):
     assert err <= MAX_ABS and ps >= MIN_PSNR
 
 
-def test_tiled_inference_matches_whole_image():
+def test_tiled_inference_matches_whole_image(kernel_policy):
     """configs[4] mechanism at a small size: halo tiles (with ragged edge tiles) reproduce the whole-image forward."""
     import resr_b200
     g, _ = _make(4)
@@ -118,7 +128,7 @@ def test_pipelined_host_calls_match_blocking_call():
 @pytest.mark.gpu
 @pytest.mark.parametrize("shape", [(1, 3, 1, 1), (1, 3, 2, 3), (1, 3, 5, 7), (2, 3, 9, 130), (1, 3, 3, 257), (5, 3, 8, 8),
                                    (3, 3, 7, 16), (17, 3, 6, 64), (1, 3, 1, 128), (2, 3, 130, 9)])
-def test_generator_awkward_shapes(shape):
+def test_generator_awkward_shapes(shape, kernel_policy):
     """Single-pixel images, one-row images, ragged widths (W = 130, 257: a 2 / 1 pixel last segment), every lane split
     (W = 8, 16, 64 -> 16, 8, 2 images per M tile) with image counts that do not fill the last tile."""
     from oracle import generator as og
@@ -224,3 +234,33 @@ def test_second_device_first_in_one_process():
     g = g.to("cuda:1")
     with torch.no_grad():
         assert torch.equal(g(x.to("cuda:1")).cpu(), outs[0][0])
+
+
+@pytest.mark.parametrize("policy", [1, 2])
+def test_bf16_recipe_within_contract(policy):
+    """north_star's recipe as a switch: bf16 operands + fp32 residual masters (set_precision("bf16")); both recipes meet
+    the contract, fp16 is the closer one."""
+    import resr_b200
+    from oracle import generator as og
+    prev = resr_b200._lib.lib().resr_set_conv_pair_policy(policy)
+    try:
+        g, sd = _make(1)
+        torch.manual_seed(21)
+        x = torch.rand(2, 3, 40, 136)
+        ref = og.generator_forward(x, sd)
+        with torch.no_grad():
+            y16 = g(x.cuda()).cpu()
+            g.set_precision("bf16")
+            ybf = g(x.cuda()).cpu()
+            g.set_precision("fp16")
+            y16b = g(x.cuda()).cpu()
+    finally:
+        resr_b200._lib.lib().resr_set_conv_pair_policy(prev)
+    e16, ebf = (y16 - ref).abs().max().item(), (ybf - ref).abs().max().item()
+    print(f"fp16 max-abs {e16:.3e} / {_psnr(y16, ref):.1f} dB; bf16 max-abs {ebf:.3e} / {_psnr(ybf, ref):.1f} dB")
+    assert ebf <= MAX_ABS and _psnr(ybf, ref) >= MIN_PSNR
+    assert e16 <= MAX_ABS and torch.equal(y16, y16b)
+    assert not torch.equal(y16, ybf)
+    g.set_precision("bf16")
+    with pytest.raises(resr_b200._lib.ResrError):
+        resr_b200.autograd.l1_loss_backward(g, x[:, :, :8, :8].cuda(), torch.rand(2, 3, 32, 32).cuda())

@@ -45,9 +45,11 @@ def _cos(a, b):
 
 
 @pytest.mark.parametrize("seed,shape", [(0, (1, 3, 16, 24)), (1, (2, 3, 16, 64)), (2, (3, 3, 5, 8)), (3, (1, 3, 9, 136))])
-def test_generator_loss_and_gradients_vs_oracle_autograd(seed, shape):
+@pytest.mark.parametrize("policy", [1, 2])
+def test_generator_loss_and_gradients_vs_oracle_autograd(seed, shape, policy):
     import resr_b200
     from oracle import generator as og
+    prev = resr_b200._lib.lib().resr_set_conv_pair_policy(policy)  # 2: forward / data-gradient convs on CTA pairs
     sd = og.random_state_dict(seed)
     g = resr_b200.model.Generator(3, 3, 4)
     g.load_state_dict(sd)
@@ -58,6 +60,7 @@ def test_generator_loss_and_gradients_vs_oracle_autograd(seed, shape):
     ref_loss, ref_grads, ref_sr = og.l1_loss_and_grads(x, hr, sd)
     loss, sr, flat = resr_b200.autograd.l1_loss_backward(g, x.cuda(), hr.cuda())
     torch.cuda.synchronize()
+    resr_b200._lib.lib().resr_set_conv_pair_policy(prev)
     assert (sr.cpu() - ref_sr).abs().max().item() <= 2e-2
     rel = abs(loss.item() - ref_loss.item()) / ref_loss.item()
     ref_flat = torch.cat([ref_grads[k].reshape(-1) for k in sd])

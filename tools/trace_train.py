@@ -37,3 +37,19 @@ mid = len(ev) // 2
 t0 = ev[mid]["ts"]
 for e in ev[mid:mid + 24]:
     print(f"{e['ts']-t0:9.1f} +{e['dur']:6.1f} us  stream {e['args'].get('stream')}  {e['name'][:40]}  grid {e['args'].get('grid')}")
+# per-kernel-name totals and the time span of forward / backward phases
+import collections
+tot = collections.Counter()
+cnt = collections.Counter()
+for e in ev:
+    nm = e["name"].split("(")[0].split("<")[0][-36:]
+    tot[nm] += e["dur"]
+    cnt[nm] += 1
+for nm, d in tot.most_common(14):
+    print(f"  {nm:38s} n={cnt[nm]:5d} total {d/1e3:7.2f} ms  mean {d/cnt[nm]:6.1f} us")
+by_stream = collections.Counter()
+for e in ev:
+    by_stream[e["args"].get("stream")] += e["dur"]
+print("busy per stream (ms):", {k: round(v / 1e3, 2) for k, v in by_stream.items()})
+first_bwd = next(i for i, e in enumerate(ev) if "out_grad" in e["name"])
+print(f"forward span {(ev[first_bwd]['ts'] - ev[0]['ts'])/1e3:.2f} ms, backward span {(ev[-1]['ts'] + ev[-1]['dur'] - ev[first_bwd]['ts'])/1e3:.2f} ms")
