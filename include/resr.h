@@ -71,6 +71,18 @@ int resr_generator_forward(resr_generator_t* g, const float* x, float* y, int n,
 
 /* Same, but x_host / y_host are (pinned) HOST buffers: H2D, forward, D2H on `stream`, then a stream synchronise.
  * This is the call inference.py:46-56 turns into. */
+/* I/O edges fused into the first / last kernels: x_u8 is an NHWC u8 RGB batch [n,h,w,3] as decoded by
+ * cv2.imread + cvtColor (inference.py:40-46: image / 255 -> image_to_tensor, imgproc.py:1540-1567), y_u8 the NHWC u8 result
+ * [n,4h,4w,3] that tensor_to_image (imgproc.py:1570-1596: mul(255).clamp(0,255), uint8 truncation) would produce from the
+ * fp32 output. 16x fewer bytes than the fp32 tensors on the way in, 4x fewer on the way out. _host: pinned host buffers,
+ * H2D + forward + D2H + synchronise inside the call (staging at the end of the workspace: + n*3*h*w*17 bytes + 2 KB). */
+int resr_generator_forward_u8(resr_generator_t* g, const unsigned char* x_u8, unsigned char* y_u8, int n, int h, int w,
+                              void* workspace, size_t workspace_bytes, void* stream);
+int resr_generator_forward_u8_host(resr_generator_t* g, const unsigned char* x_u8_host, unsigned char* y_u8_host, int n, int h, int w,
+                                   void* workspace, size_t workspace_bytes, void* stream);
+/* imgproc.tensor_to_image(tensor, range_norm, half) (imgproc.py:1570-1596) on the device: NCHW fp32 [1,c,h,w] -> HWC u8. */
+int resr_tensor_to_image_u8(const float* x, unsigned char* out_hwc, int c, int h, int w, int range_norm, int half, void* stream);
+
 int resr_generator_forward_host(resr_generator_t* g, const float* x_host, float* y_host, int n, int h, int w,
                                 void* workspace, size_t workspace_bytes, void* stream);
 

@@ -9,6 +9,7 @@ fallback: importing works anywhere, computing needs the built library and a B200
 """
 from . import _lib  # noqa: F401
 from . import autograd  # noqa: F401
+from . import checkpoint  # noqa: F401
 from . import compat  # noqa: F401
 from . import imgproc  # noqa: F401
 from . import model  # noqa: F401
@@ -17,4 +18,4 @@ from . import plan  # noqa: F401
 
 from .compat import patch_reference  # noqa: F401,E402
 
-__all__ = ["_lib", "autograd", "compat", "imgproc", "model", "optim", "plan", "patch_reference"]
+__all__ = ["_lib", "autograd", "checkpoint", "compat", "imgproc", "model", "optim", "plan", "patch_reference"]

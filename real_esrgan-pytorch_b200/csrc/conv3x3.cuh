@@ -53,6 +53,8 @@ struct ConvArgs {
     int res2_cstride;
     float* out_nchw;       // NCHW fp32 output with out_nchw_c channels (or null)
     int out_nchw_c;
+    unsigned char* out_u8; // NHWC u8 image output with out_nchw_c channels (or null): tensor_to_image fused into the last conv
+                           // (imgproc.py:1594: mul(255).clamp(0, 255) then astype(uint8) = truncation)
     // ---- backward (data-gradient) extensions; all zero in the forward pass
     unsigned slice_nores_mask;  // bit s: Cout slice s does not read res1
     unsigned slice_noutf_mask;  // bit s: slice s does not write the fp32 output

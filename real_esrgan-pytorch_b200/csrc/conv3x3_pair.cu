@@ -631,6 +631,14 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
                             if (cc < a.out_nchw_c) o[static_cast<size_t>(cc) * plane] = val[c];
                         }
                     }
+                    if (a.out_u8 && valid) {   // clamp01 has been applied: v * 255 lies in [0, 255], the cast truncates
+                        unsigned char* o = a.out_u8 + ((static_cast<size_t>(n) * a.H + y) * a.W + x) * a.out_nchw_c;
+#pragma unroll
+                        for (int c = 0; c < SUBW; ++c) {
+                            const int cc = ls * SUBW + c;
+                            if (cc < a.out_nchw_c) o[cc] = static_cast<unsigned char>(fminf(fmaxf(__fmul_rn(val[c], 255.f), 0.f), 255.f));
+                        }
+                    }
                 }
             }
             v0 += n_acc;

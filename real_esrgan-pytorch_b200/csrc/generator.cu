@@ -116,6 +116,57 @@ __global__ void nchw_to_nhwc16_kernel(const float* __restrict__ x, uint16_t* __r
     }
 }
 
+// NHWC u8 image -> NHWC 16-bit with channels zero-padded to c_pad: image_to_tensor (imgproc.py:1557: to_tensor = / 255 in
+// fp32) fused with the layout change of the first convolution's input.
+__global__ void u8nhwc_to_nhwc16_kernel(const unsigned char* __restrict__ x, uint16_t* __restrict__ out, size_t npix, int C, int c_pad,
+                                        int fmt) {
+    const int groups = c_pad / 8;
+    const size_t total = npix * groups;
+    for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int gch = idx % groups;
+        const size_t pix = idx / groups;
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float v[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int c = gch * 8 + 2 * j + e;
+                v[e] = c < C ? __fdiv_rn(static_cast<float>(x[pix * C + c]), 255.f) : 0.f;
+            }
+            if (fmt == 1) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(v[0], v[1]);
+                pk[j] = *reinterpret_cast<uint32_t*>(&h);
+            } else {
+                __half2 h = __floats2half2_rn(v[0], v[1]);
+                pk[j] = *reinterpret_cast<uint32_t*>(&h);
+            }
+        }
+        reinterpret_cast<uint4*>(out + pix * c_pad)[gch] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+}
+
+// imgproc.tensor_to_image (imgproc.py:1570-1596) on the device: NCHW float -> HWC u8 of image 0.
+__global__ void tensor_to_image_kernel(const float* __restrict__ x, unsigned char* __restrict__ out, int C, size_t HW, int range_norm,
+                                       int half) {
+    const size_t total = HW * C;
+    for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int c = idx % C;
+        const size_t p = idx / C;
+        float v = x[static_cast<size_t>(c) * HW + p];
+        if (range_norm) v = __fdiv_rn(__fadd_rn(v, 1.f), 2.f);            // imgproc.py:1587-1588
+        if (half) {                                                        // :1591-1592: the arithmetic then runs in fp16
+            const __half h = __hmul(__float2half_rn(v), __float2half_rn(255.f));
+            v = fminf(fmaxf(__half2float(h), 0.f), 255.f);
+        } else {
+            v = fminf(fmaxf(__fmul_rn(v, 255.f), 0.f), 255.f);              // :1594
+        }
+        out[idx] = static_cast<unsigned char>(v);                           // astype("uint8"): truncation
+    }
+}
+
 int grid_for(size_t total, int block) {
     size_t g = (total + block - 1) / block;
     if (g > 148 * 16) g = 148 * 16;
@@ -458,9 +509,52 @@ int resr_generator_set_precision(resr_generator_t* g, int precision) {
     return RESR_OK;
 }
 
+static int forward_any(resr_generator_t* g, const float* x, const unsigned char* x_u8, float* y, unsigned char* y_u8, int n, int h, int w,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
 int resr_generator_forward(resr_generator_t* g, const float* x, float* y, int n, int h, int w, void* workspace,
                            size_t workspace_bytes, void* stream) {
-    if (!g || !x || !y || !workspace) return set_error(RESR_E_INVALID, "null argument");
+    if (!x || !y) return set_error(RESR_E_INVALID, "null argument");
+    return forward_any(g, x, nullptr, y, nullptr, n, h, w, workspace, workspace_bytes, stream);
+}
+
+int resr_generator_forward_u8(resr_generator_t* g, const unsigned char* x_u8, unsigned char* y_u8, int n, int h, int w, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+    if (!x_u8 || !y_u8) return set_error(RESR_E_INVALID, "null argument");
+    return forward_any(g, nullptr, x_u8, nullptr, y_u8, n, h, w, workspace, workspace_bytes, stream);
+}
+
+int resr_generator_forward_u8_host(resr_generator_t* g, const unsigned char* x_host, unsigned char* y_host, int n, int h, int w,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
+    if (!g || !x_host || !y_host) return set_error(RESR_E_INVALID, "null argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t in_bytes = static_cast<size_t>(n) * 3 * h * w, out_bytes = in_bytes * 16;
+    const size_t need = resr_generator_workspace_bytes_for(g, n, h, w);
+    const size_t off_x = (need + 1023) / 1024 * 1024, off_y = off_x + (in_bytes + 1023) / 1024 * 1024;
+    if (workspace_bytes < off_y + out_bytes) return set_error(RESR_E_NOMEM, "workspace too small for u8 host staging (need %zu)", off_y + out_bytes);
+    unsigned char* xd = static_cast<unsigned char*>(workspace) + off_x;
+    unsigned char* yd = static_cast<unsigned char*>(workspace) + off_y;
+    if (cudaMemcpyAsync(xd, x_host, in_bytes, cudaMemcpyHostToDevice, s) != cudaSuccess) return set_error(RESR_E_CUDA, "H2D failed");
+    const int rc = resr_generator_forward_u8(g, xd, yd, n, h, w, workspace, need, stream);
+    if (rc != RESR_OK) return rc;
+    if (cudaMemcpyAsync(y_host, yd, out_bytes, cudaMemcpyDeviceToHost, s) != cudaSuccess) return set_error(RESR_E_CUDA, "D2H failed");
+    const cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return set_error(RESR_E_CUDA, "forward_u8_host: %s", cudaGetErrorString(e));
+    return RESR_OK;
+}
+
+int resr_tensor_to_image_u8(const float* x, unsigned char* out_hwc, int c, int h, int w, int range_norm, int half, void* stream) {
+    if (!x || !out_hwc || c <= 0 || h <= 0 || w <= 0) return set_error(RESR_E_INVALID, "bad argument");
+    const size_t HW = static_cast<size_t>(h) * w;
+    tensor_to_image_kernel<<<grid_for(HW * c, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, out_hwc, c, HW, range_norm, half);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(RESR_E_CUDA, "tensor_to_image: %s", cudaGetErrorString(e));
+    return RESR_OK;
+}
+
+static int forward_any(resr_generator_t* g, const float* x, const unsigned char* x_u8, float* y, unsigned char* y_u8, int n, int h, int w,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+    if (!g || !workspace) return set_error(RESR_E_INVALID, "null argument");
     if (n <= 0 || h <= 0 || w <= 0) return set_error(RESR_E_INVALID, "bad shape %dx3x%dx%d", n, h, w);
     if (!g->loaded) return set_error(RESR_E_INVALID, "resr_generator_load_params has not been called");
     if (workspace_bytes < resr_generator_workspace_bytes_for(g, n, h, w)) return set_error(RESR_E_NOMEM, "workspace too small");
@@ -472,11 +566,12 @@ int resr_generator_forward(resr_generator_t* g, const float* x, float* y, int n,
         if (rc != RESR_OK) return rc;
     }
     const size_t total = static_cast<size_t>(n) * h * w * 8;
-    nchw_to_nhwc16_kernel<<<grid_for(total, 256), 256, 0, s>>>(x, p.xin, n, 3, h, w, 64, g->precision == 1 ? 1 : 0);
+    if (x_u8) u8nhwc_to_nhwc16_kernel<<<grid_for(total, 256), 256, 0, s>>>(x_u8, p.xin, static_cast<size_t>(n) * h * w, 3, 64, g->precision == 1 ? 1 : 0);
+    else nchw_to_nhwc16_kernel<<<grid_for(total, 256), 256, 0, s>>>(x, p.xin, n, 3, h, w, 64, g->precision == 1 ? 1 : 0);
     const Table& T = table();
     for (size_t i = 0; i < p.steps.size(); ++i) {
         Step& st = p.steps[i];
-        if (i + 1 == p.steps.size()) st.a.out_nchw = y;
+        if (i + 1 == p.steps.size()) { st.a.out_nchw = y; st.a.out_u8 = y_u8; }
         const cudaError_t e = conv3x3_run(st.maps, st.a, st.cfg, g->num_sms, s);
         if (e != cudaSuccess) return set_error(RESR_E_CUDA, "conv %d launch: %s", st.conv, cudaGetErrorString(e));
     }

@@ -20,7 +20,7 @@ from torch import nn
 
 from . import _lib
 
-__all__ = ["filter2d_torch", "USMSharp", "DiffJPEG", "random_add_gaussian_noise_torch",
+__all__ = ["image_to_tensor", "tensor_to_image", "filter2d_torch", "USMSharp", "DiffJPEG", "random_add_gaussian_noise_torch",
            "random_add_poisson_noise_torch", "random_crop", "interpolate", "degrade_batch", "degrade_batch_native", "DegradePipeline",
            "plan_to_device"]
 
@@ -60,6 +60,48 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
         ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
         _ws_cache[key] = ws
     return ws
+
+
+def image_to_tensor(image, range_norm: bool, half: bool) -> torch.Tensor:
+    """Reference imgproc.py:1540-1567 (torchvision `to_tensor`, restated so that torchvision is not needed): HWC ndarray
+    -> CHW tensor; uint8 data is divided by 255, float data keeps its values; optional [-1, 1] scaling and fp16 cast. A
+    host-side layout operation exactly as in the reference; the fused device form is `Generator.infer_u8`."""
+    import numpy as np
+    if not isinstance(image, np.ndarray):
+        raise TypeError(f"pic should be ndarray. Got {type(image)}")
+    if image.ndim == 2:
+        image = image[:, :, None]
+    if image.ndim != 3:
+        raise ValueError(f"pic should be 2/3 dimensional. Got {image.ndim} dimensions.")
+    tensor = torch.from_numpy(np.ascontiguousarray(image.transpose((2, 0, 1))))
+    if tensor.dtype == torch.uint8:
+        tensor = tensor.to(dtype=torch.get_default_dtype()).div(255)
+    if range_norm:
+        tensor = tensor.mul(2.0).sub(1.0)
+    if half:
+        tensor = tensor.half()
+    return tensor
+
+
+def tensor_to_image(tensor: torch.Tensor, range_norm: bool, half: bool):
+    """Reference imgproc.py:1570-1596: [1, C, H, W] (or [C, H, W]) tensor in [0, 1] -> HWC uint8 ndarray,
+    `mul(255).clamp(0, 255)` then `astype("uint8")` (truncation). CUDA tensors are converted on the device
+    (resr_tensor_to_image_u8) so that only H * W * C bytes cross PCIe; host tensors take the reference's own path."""
+    if tensor.dim() == 4 and tensor.size(0) != 1:
+        raise ValueError("tensor_to_image converts one image: expected [1, C, H, W]")
+    if not tensor.is_cuda:
+        if range_norm:
+            tensor = tensor.add(1.0).div(2.0)
+        if half:
+            tensor = tensor.half()
+        return tensor.squeeze(0).permute(1, 2, 0).mul(255).clamp(0, 255).cpu().numpy().astype("uint8")
+    x = tensor.detach().reshape(tensor.shape[-3:]).contiguous().float()
+    c, h, w = x.shape
+    out = torch.empty((h, w, c), dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().resr_tensor_to_image_u8(_lib.ptr(x), _lib.ptr(out), c, h, w, int(bool(range_norm)), int(bool(half)),
+                                                      _lib.stream_ptr(x.device)))
+    return out.cpu().numpy()
 
 
 @_on_device

@@ -286,6 +286,47 @@ class Generator(nn.Module):
         return y
 
     @torch.no_grad()
+    def infer_u8(self, x_u8: torch.Tensor) -> torch.Tensor:
+        """Image in, image out: x_u8 is an NHWC uint8 RGB batch [N, H, W, 3] on the device (what cv2.imread + cvtColor
+        hold); returns the NHWC uint8 SR batch [N, 4H, 4W, 3]. `image / 255` + image_to_tensor (inference.py:40-46) is fused
+        into the first layout kernel and tensor_to_image (inference.py:56, imgproc.py:1594) into the last convolution: the
+        result equals tensor_to_image(self(image_to_tensor(x / 255))) bit for bit."""
+        if x_u8.dim() != 4 or x_u8.size(3) != 3 or x_u8.dtype != torch.uint8:
+            raise ValueError(f"expected a uint8 [N, H, W, 3] batch, got {tuple(x_u8.shape)} {x_u8.dtype}")
+        if not x_u8.is_cuda:
+            raise _lib.ResrError("resr_b200.Generator runs on a CUDA (sm_100a) device only; there is no CPU path")
+        n, h, w, _ = x_u8.shape
+        xc = x_u8.contiguous()
+        self._ensure_packed()
+        y = torch.empty((n, 4 * h, 4 * w, 3), dtype=torch.uint8, device=x_u8.device)
+        ws = self._get_workspace(n, h, w, x_u8.device)
+        wp, wbytes = self._aligned(ws)
+        with torch.cuda.device(x_u8.device):
+            _lib.check(_lib.lib().resr_generator_forward_u8(self._native(), _lib.ptr(xc), _lib.ptr(y), n, h, w, wp, wbytes,
+                                                            _lib.stream_ptr(x_u8.device)))
+        return y
+
+    @torch.no_grad()
+    def infer_u8_host(self, x_host: torch.Tensor, y_host: torch.Tensor = None, device=None) -> torch.Tensor:
+        """infer_u8 with HOST uint8 tensors (pinned recommended): H2D + forward + D2H inside the C ABI; 3 bytes per LR pixel
+        in, 48 bytes per LR pixel out (the fp32 host call moves 12 and 192)."""
+        device = device or self._device()
+        n, h, w, _ = x_host.shape
+        if x_host.dtype != torch.uint8 or x_host.size(3) != 3:
+            raise ValueError("expected a uint8 [N, H, W, 3] host batch")
+        xc = x_host.contiguous()
+        if y_host is None:
+            y_host = torch.empty((n, 4 * h, 4 * w, 3), dtype=torch.uint8, pin_memory=True)
+        self._ensure_packed()
+        extra = xc.numel() * 17 + 4096
+        ws = self._get_workspace(n, h, w, device, extra)
+        wp, wbytes = self._aligned(ws)
+        with torch.cuda.device(device):
+            _lib.check(_lib.lib().resr_generator_forward_u8_host(self._native(), _lib.ptr(xc), _lib.ptr(y_host), n, h, w, wp, wbytes,
+                                                                 _lib.stream_ptr(device)))
+        return y_host
+
+    @torch.no_grad()
     def infer_host(self, x_host: torch.Tensor, y_host: torch.Tensor = None, device=None) -> torch.Tensor:
         """End-to-end call with HOST tensors (pinned recommended): H2D + forward + D2H inside the C ABI."""
         device = device or next(self.parameters()).device

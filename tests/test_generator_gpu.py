@@ -264,3 +264,35 @@ def test_bf16_recipe_within_contract(policy):
     g.set_precision("bf16")
     with pytest.raises(resr_b200._lib.ResrError):
         resr_b200.autograd.l1_loss_backward(g, x[:, :, :8, :8].cuda(), torch.rand(2, 3, 32, 32).cuda())
+
+
+def test_u8_image_io_is_the_reference_conversion_fused():
+    """f4: image / 255 -> image_to_tensor fused into the first kernel, tensor_to_image (mul(255).clamp(0, 255), uint8
+    truncation; reference imgproc.py:1540-1596, inference.py:40-56) into the last convolution: bit-exact against applying
+    the reference's own conversions around the fp32 forward."""
+    import resr_b200
+    ip = resr_b200.imgproc
+    g, _ = _make(6)
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, (2, 40, 136, 3), dtype=np.uint8)
+    with torch.no_grad():
+        y_u8 = g.infer_u8(torch.from_numpy(img).cuda())
+        # the reference's path around the same generator: numpy / 255 -> image_to_tensor -> model -> tensor_to_image
+        ref = []
+        for i in range(2):
+            lr = ip.image_to_tensor(img[i].astype(np.float32) / 255.0, False, False).unsqueeze_(0)
+            sr = g(lr.cuda())
+            ref.append(sr.squeeze(0).permute(1, 2, 0).mul(255).clamp(0, 255).cpu().numpy().astype("uint8"))
+            assert np.array_equal(ip.tensor_to_image(sr, False, False), ref[-1])          # device conversion
+            assert np.array_equal(ip.tensor_to_image(sr.cpu(), False, False), ref[-1])    # host path
+    assert y_u8.shape == (2, 160, 544, 3) and y_u8.dtype == torch.uint8
+    assert np.array_equal(y_u8.cpu().numpy(), np.stack(ref))
+    y_host = g.infer_u8_host(torch.from_numpy(img).pin_memory())
+    assert np.array_equal(y_host.numpy(), np.stack(ref))
+    # range_norm / half variants of tensor_to_image against the reference expression
+    t = torch.rand(1, 3, 17, 23, device="cuda") * 2 - 1
+    for rn, hf in ((True, False), (False, True), (True, True)):
+        tt = t.add(1.0).div(2.0) if rn else t
+        tt = tt.half() if hf else tt
+        want = tt.squeeze(0).permute(1, 2, 0).mul(255).clamp(0, 255).cpu().numpy().astype("uint8")
+        assert np.array_equal(ip.tensor_to_image(t, rn, hf), want), (rn, hf)

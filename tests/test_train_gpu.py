@@ -222,3 +222,46 @@ def test_stale_backward_is_refused():
         g(x2)
     sr3.mean().backward()
     assert torch.isfinite(next(g.parameters()).grad).all()
+
+
+def test_checkpoint_round_trip_in_reference_format(tmp_path):
+    """f4: the reference's .pth.tar layout (train_realesrnet.py:117-129): our file feeds torch.optim.Adam / a fresh
+    Generator exactly like a reference file, and a resumed FlatAdamEMA continues bit-identically."""
+    import resr_b200
+    from oracle import generator as og
+    ck = resr_b200.checkpoint
+    g = resr_b200.model.Generator(3, 3, 4)
+    g.load_state_dict(og.random_state_dict(0))
+    g = g.cuda().train()
+    opt = resr_b200.optim.FlatAdamEMA(g, lr=2e-4, betas=(0.9, 0.99))
+    torch.manual_seed(0)
+    grads = [torch.randn(opt.flat.numel(), device="cuda") * 1e-3 for _ in range(3)]
+    for gr in grads[:2]:
+        opt.step(gr)
+    path = str(tmp_path / "g_epoch_1.pth.tar")
+    ck.save_checkpoint(path, g, opt, epoch=1, best_niqe=7.5, scheduler_state={"last_epoch": 1})
+    file = torch.load(path, map_location="cpu")
+    assert set(file) >= {"epoch", "best_niqe", "state_dict", "ema_state_dict", "optimizer", "scheduler"}
+    assert set(file["state_dict"]) == set(og.random_state_dict(0)) and all(k.startswith("model.") for k in file["ema_state_dict"])
+    # (a) reference side: a plain torch Adam over a fresh generator accepts the optimizer state and takes the same step
+    g_ref = resr_b200.model.Generator(3, 3, 4)
+    g_ref.load_state_dict({k.replace("model.", ""): v for k, v in file["state_dict"].items()})   # inference.py:33
+    g_ref = g_ref.cuda()
+    adam = torch.optim.Adam(g_ref.parameters(), 2e-4, (0.9, 0.99))
+    adam.load_state_dict(file["optimizer"])
+    pos = 0
+    for p in g_ref.parameters():
+        p.grad = grads[2][pos:pos + p.numel()].view_as(p).clone()
+        pos += p.numel()
+    adam.step()
+    # (b) our side: resume into a fresh generator + optimizer, take the same third step
+    g2 = resr_b200.model.Generator(3, 3, 4).cuda().train()
+    opt2 = resr_b200.optim.FlatAdamEMA(g2, lr=1.0, betas=(0.5, 0.5))
+    ck.load_checkpoint(path, g2, opt2)
+    assert opt2.step_count == 2 and opt2.lr == 2e-4 and tuple(opt2.betas) == (0.9, 0.99)
+    assert torch.equal(opt2.shadow, opt.shadow) and torch.equal(opt2.flat, opt.flat)
+    opt.step(grads[2])
+    opt2.step(grads[2])
+    assert torch.equal(opt2.flat, opt.flat) and torch.equal(opt2.shadow, opt.shadow)
+    ref_flat = torch.cat([p.detach().reshape(-1) for p in g_ref.parameters()])
+    assert (ref_flat - opt.flat).abs().max().item() <= 2e-7
