@@ -222,6 +222,24 @@ typedef struct resr_kernel_params {
 } resr_kernel_params;
 int resr_synthesize_kernels(const resr_kernel_params* params_host, int count, int pad, double* out_f64, float* out_f32,
                             void* stream);
+/* The same synthesis from parameters that already live on the device (kmax = largest kernel_size among them, <= pad). */
+int resr_synthesize_kernels_device(const resr_kernel_params* params_dev, int count, int kmax, int pad, double* out_f64,
+                                   float* out_f32, void* stream);
+/* Device-side replacement of the per-sample host loop of dataset.py:81-141: draws, for every sample of a batch, the
+ * parameters of kernel1, kernel2 and the final sinc / delta kernel (params_dev: [batch][3]) with the reference's
+ * distributions (config.py:20-39) from a Philox counter RNG; *call_state (device u64, may be NULL) advances per call so
+ * that a fixed seed yields fresh draws on every call / graph replay. Feed the result to resr_synthesize_kernels_device. */
+typedef struct resr_kernel_draw_config {
+    int n_sizes, sizes[16];           /* gaussian_kernel_range */
+    int sinc_size_split;              /* sizes below it draw cutoff in [pi/3, pi], the others in [pi/5, pi] (dataset.py:85-88: 13) */
+    int final_size;                   /* sinc_kernel_size: size of the delta kernel */
+    double sinc_prob1, sinc_prob2, sinc_prob3;
+    double prob1[6], prob2[6];        /* gaussian_kernel_probability1/2 over (iso, aniso, generalized iso/aniso, plateau iso/aniso) */
+    double sigma_range1[2], sigma_range2[2];
+    double gen_beta_range1[2], gen_beta_range2[2], plateau_beta_range1[2], plateau_beta_range2[2];
+} resr_kernel_draw_config;
+int resr_draw_degradation_kernel_params(const resr_kernel_draw_config* cfg, int batch, unsigned long long seed,
+                                        unsigned long long* call_state, resr_kernel_params* params_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Hot path 1, training: forward that keeps activations, fused L1 loss, full backward.

@@ -63,6 +63,16 @@ class KernelParams(Structure):
                 ("cutoff", c_double)]
 
 
+class KernelDrawConfig(Structure):
+    """struct resr_kernel_draw_config (include/resr.h)."""
+    _fields_ = [("n_sizes", c_int), ("sizes", c_int * 16), ("sinc_size_split", c_int), ("final_size", c_int),
+                ("sinc_prob1", c_double), ("sinc_prob2", c_double), ("sinc_prob3", c_double),
+                ("prob1", c_double * 6), ("prob2", c_double * 6),
+                ("sigma_range1", c_double * 2), ("sigma_range2", c_double * 2),
+                ("gen_beta_range1", c_double * 2), ("gen_beta_range2", c_double * 2),
+                ("plateau_beta_range1", c_double * 2), ("plateau_beta_range2", c_double * 2)]
+
+
 # name -> (restype, argtypes); every symbol include/resr.h declares must be listed here (tests check both ways).
 SIGNATURES = {
     "resr_version": (c_int, []),
@@ -112,6 +122,8 @@ SIGNATURES = {
     "resr_adam_ema_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_float, c_float,
                                    c_float, ctypes.c_longlong, c_float, c_float, c_void_p]),
     "resr_synthesize_kernels": (c_int, [POINTER(KernelParams), c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "resr_synthesize_kernels_device": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "resr_draw_degradation_kernel_params": (c_int, [POINTER(KernelDrawConfig), c_int, ctypes.c_ulonglong, c_void_p, c_void_p, c_void_p]),
     "resr_generator_train_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "resr_generator_forward_train": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "resr_generator_backward_l1": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t,

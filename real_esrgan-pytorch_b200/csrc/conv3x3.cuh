@@ -27,6 +27,9 @@ struct ConvArgs {
                     // 1: three TMA loads per (row, chunk), one per dx (any BW x BN split)
     int nstages;    // activation ring depth
     int nepi;       // epilogue warp groups (1 .. 3), rows alternate between them
+    int reverse;    // pair kernel: traverse the work back to front (rows bottom-up, column groups last to first, dy taps
+                    // flipped when the weights are gathered). Consecutive layers alternate direction, so a launch starts
+                    // on the data its predecessor touched last -- what is still in the 126 MB L2.
     int epi_bufs;   // pair kernel: staging tiles per epilogue group (2 = a pass never waits for the previous pass's TMA store)
     int fmt_in;     // MMA operand format: 0 fp16, 1 bf16
     long long rows_total;  // ncg * H

@@ -289,23 +289,27 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
         // ------------------------------------------------------------------ TMA producer (one elected lane issues)
         if (elect_one()) {
             mbar_expect_tx(wbar, wbytes);
-            // this CTA's half of every (chunk, dx) tile, gathered from the [slice32][chunk][dx][(dy, co32) x 64] pack
+            // this CTA's half of every (chunk, dx) tile, gathered from the [slice32][chunk][dx][(dy, co32) x 64] pack in blocks of
+            // G rows (a block never straddles a dy boundary); in reverse mode the dy blocks are taken in flipped order
+            constexpr int G = NOUT == 64 ? 32 : NOUT / 2;          // rows per gathered block
+            constexpr int BPD = NOUT / G;                           // blocks per dy: 2
+            constexpr int NB = 3 * BPD / 2;                         // blocks per CTA: 3
             for (int c = 0; c < a.nchunks; ++c) {
                 for (int dx = 0; dx < 3; ++dx) {
                     uint8_t* dst = wsm + (c * 3 + dx) * WHALF;
-                    if (NOUT == 64) {
-                        // N rows in (dy, co 0..63) order = six 32-row blocks (dy, half); rank r holds blocks 3r .. 3r+2
 #pragma unroll
-                        for (int j = 0; j < 3; ++j) {
-                            const int blk = static_cast<int>(rank) * 3 + j, dy = blk >> 1, sl = blk & 1;
-                            const uint8_t* src = a.wpack + ((static_cast<size_t>(slice * 2 + sl) * a.nchunks + c) * 3 + dx) * (96 * 128) +
-                                                 static_cast<size_t>(dy) * 32 * 128;
-                            bulk_load_1d(dst + j * 32 * 128, src, 32 * 128, wbar);
-                        }
-                    } else {
-                        const uint8_t* src = a.wpack + ((static_cast<size_t>(slice) * a.nchunks + c) * 3 + dx) * (NT * 128) +
-                                             static_cast<size_t>(rank) * WHALF;
-                        bulk_load_1d(dst, src, WHALF, wbar);
+                    for (int j = 0; j < NB; ++j) {
+                        const int blk = static_cast<int>(rank) * NB + j;   // position in the (dy', part) order of the MMA's N rows
+                        const int dyv = blk / BPD, part = blk % BPD;
+                        const int dy = a.reverse ? 2 - dyv : dyv;
+                        const uint8_t* src;
+                        if (NOUT == 64)   // part = 32-channel pack slice
+                            src = a.wpack + ((static_cast<size_t>(slice * 2 + part) * a.nchunks + c) * 3 + dx) * (96 * 128) +
+                                  static_cast<size_t>(dy) * 32 * 128;
+                        else              // part = half of the slice's channels
+                            src = a.wpack + ((static_cast<size_t>(slice) * a.nchunks + c) * 3 + dx) * (NT * 128) +
+                                  static_cast<size_t>(dy * NOUT + part * G) * 128;
+                        bulk_load_1d(dst + j * G * 128, src, G * 128, wbar);
                     }
                 }
             }
@@ -319,8 +323,10 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
         const uint32_t full0 = map_to_cta(smem_u32(full), 0);  // the leader's stage barriers
         PROF_DECL(p_empty);
         PROF_T0(p_t0);
+        const int ncg2 = (a.ncg + 1) >> 1;
         for (long long g = rr.g0; g < rr.g1;) {
-            const int cg = 2 * static_cast<int>(g / H) + static_cast<int>(rank);  // may be == ncg (odd count): all out of bounds
+            const int cg2 = static_cast<int>(g / H);
+            const int cg = 2 * (a.reverse ? ncg2 - 1 - cg2 : cg2) + static_cast<int>(rank);  // may be == ncg (odd count): all out of bounds
             const int ya = static_cast<int>(g % H);
             const int yb = static_cast<int>(min(static_cast<long long>(H), ya + (rr.g1 - g)));
             const int n0 = (cg / a.nxs) * a.BN;
@@ -336,7 +342,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
                             // rank 1 re-uses a stage only after the commit that follows the leader's wait on this phase)
                             if (rank == 0) mbar_expect_tx(full + stage, 2 * tx_bytes);
                             tma_load_4d_pair(stg + stage * kStageBytes, &tmapA, full0 + (stage << 3), c * 64,
-                                             a.mode == 0 ? x0 - 1 : x0 + dx - 1, r, n0);
+                                             a.mode == 0 ? x0 - 1 : x0 + dx - 1, a.reverse ? H - 1 - r : r, n0);
                         }
                         __syncwarp();
                         if (++stage == a.nstages) { stage = 0; phase ^= 1; }
@@ -392,8 +398,10 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
         PROF_DECL(p_acc); PROF_DECL(p_tile);
         PROF_T0(p_t0);
         uint32_t v0 = 0;
+        const int ncg2 = (a.ncg + 1) >> 1;
         for (long long g = rr.g0; g < rr.g1;) {
-            const int cg = 2 * static_cast<int>(g / H) + static_cast<int>(rank);
+            const int cg2 = static_cast<int>(g / H);
+            const int cg = 2 * (a.reverse ? ncg2 - 1 - cg2 : cg2) + static_cast<int>(rank);
             const int ya = static_cast<int>(g % H);
             const int yb = static_cast<int>(min(static_cast<long long>(H), ya + (rr.g1 - g)));
             const int n0 = (cg / a.nxs) * a.BN;
@@ -406,8 +414,9 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
             for (int j = 0; j < n_acc; ++j) {
                 const uint32_t v = v0 + j;
                 if (static_cast<int>(v % a.nepi) != gi) continue;
-                const int y = ra - 1 + j;
-                const bool emit = (y >= ya) && (y < yb);
+                const int yv = ra - 1 + j;                       // row in traversal order
+                const bool emit = (yv >= ya) && (yv < yb);
+                const int y = a.reverse ? H - 1 - yv : yv;       // image row
                 const uint32_t slot = ring_slot<S>(v);
                 const uint32_t col = slot * NOUT;
                 const uint32_t col2 = (S + slot) * NOUT;  // overflow twin (ring positions 0 and 1 only)

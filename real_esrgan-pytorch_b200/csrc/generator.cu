@@ -309,6 +309,10 @@ static int build_plan(resr_generator* g, int N, int H, int W, void* ws, cudaStre
     };
     auto push = [&](Step& st) {
         if (!conv3x3_choose(&st.a, T.c[st.conv].nout, T.c[st.conv].nslices, &st.cfg)) map_rc |= 1 << 20;
+        // serpentine order: every other pair-kernel launch walks its rows / column groups back to front, so that it starts
+        // on what the previous layer touched last (L2-resident) instead of on what it touched first (long evicted)
+        static const int serp = getenv("RESR_CONV_SERPENTINE") ? atoi(getenv("RESR_CONV_SERPENTINE")) : 1;
+        st.a.reverse = (serp && st.cfg.pair) ? static_cast<int>(p.steps.size() & 1) : 0;
         p.steps.push_back(st);
     };
 

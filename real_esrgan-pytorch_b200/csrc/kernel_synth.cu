@@ -1,6 +1,7 @@
 // Blur-kernel synthesis on the device in float64.
 // Reference: /root/reference/imgproc.py:72-90 (_mesh_grid), :170-204 (sigma matrix, density), :225-327 (Gaussian,
 // generalized Gaussian, plateau), :576-603 (sinc via Bessel J1); sequencing and zero padding to 21: dataset.py:81-141.
+#include <curand_kernel.h>
 #include <cmath>
 
 #include "../../include/resr.h"
@@ -75,7 +76,104 @@ __global__ void __launch_bounds__(1024) kernel_synth_kernel(const resr_kernel_pa
     }
 }
 
+// The random decisions of dataset.py:81-141 (kernel1, kernel2, final sinc / delta of every sample) drawn on the device:
+// one thread per sample, Philox4x32-10 (subsequence = sample, offset advances per call), the reference's distributions
+// (uniform size choice, sinc with probability p, categorical kernel family, uniform sigma / theta, the two-sided beta
+// draw of imgproc.py:405-409 / 466-470). Not the reference's RNG STREAM -- host-fed parameters remain the parity path.
+__device__ __forceinline__ double draw_u(curandStatePhilox4_32_10_t* st, double lo, double hi) {
+    return lo + (hi - lo) * curand_uniform_double(st);   // (0, 1]
+}
+
+__device__ void draw_mixed(curandStatePhilox4_32_10_t* st, const resr_kernel_draw_config& c, int which, int ks, resr_kernel_params* o) {
+    const double* prob = which == 0 ? c.prob1 : c.prob2;
+    const double* srange = which == 0 ? c.sigma_range1 : c.sigma_range2;
+    const double* grange = which == 0 ? c.gen_beta_range1 : c.gen_beta_range2;
+    const double* prange = which == 0 ? c.plateau_beta_range1 : c.plateau_beta_range2;
+    double tot = 0.0;
+    for (int i = 0; i < 6; ++i) tot += prob[i];
+    double u = curand_uniform_double(st) * tot, acc = 0.0;
+    int kt = 5;
+    for (int i = 0; i < 6; ++i) {
+        acc += prob[i];
+        if (u <= acc) { kt = i; break; }
+    }
+    // order of config.py:24-25: isotropic, anisotropic, generalized_isotropic, generalized_anisotropic, plateau_iso, plateau_aniso
+    const bool iso = (kt % 2) == 0;
+    o->type = kt / 2;  // 0 Gaussian, 1 generalized, 2 plateau
+    o->kernel_size = ks;
+    o->isotropic = iso ? 1 : 0;
+    o->reserved = 0;
+    o->sigma_x = draw_u(st, srange[0], srange[1]);
+    if (iso) { o->sigma_y = o->sigma_x; o->theta = 0.0; }
+    else { o->sigma_y = draw_u(st, srange[0], srange[1]); o->theta = draw_u(st, -M_PI, M_PI); }
+    o->beta = 1.0;
+    if (o->type != 0) {
+        const double* br = o->type == 1 ? grange : prange;
+        o->beta = curand_uniform_double(st) < 0.5 ? draw_u(st, br[0], 1.0) : draw_u(st, 1.0, br[1]);
+    }
+    o->cutoff = 1.0;
+}
+
+__global__ void draw_kernel_params_kernel(const resr_kernel_draw_config cfg, int batch, unsigned long long seed,
+                                          unsigned long long* __restrict__ call_state, resr_kernel_params* __restrict__ out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long call = call_state ? *call_state : 0ull;
+    if (b < batch) {
+        curandStatePhilox4_32_10_t st;
+        curand_init(seed, static_cast<unsigned long long>(b), call * 64ull, &st);
+        for (int which = 0; which < 2; ++which) {
+            resr_kernel_params* o = out + 3 * b + which;
+            const int ks = cfg.sizes[min(static_cast<int>(curand_uniform_double(&st) * cfg.n_sizes), cfg.n_sizes - 1)];
+            if (curand_uniform_double(&st) < (which == 0 ? cfg.sinc_prob1 : cfg.sinc_prob2)) {   // dataset.py:84-91, 108-115
+                o->type = 3; o->kernel_size = ks; o->isotropic = 1; o->reserved = 0;
+                o->sigma_x = o->sigma_y = 1.0; o->theta = 0.0; o->beta = 1.0;
+                o->cutoff = ks < cfg.sinc_size_split ? draw_u(&st, M_PI / 3, M_PI) : draw_u(&st, M_PI / 5, M_PI);
+            } else {
+                draw_mixed(&st, cfg, which, ks, o);
+            }
+        }
+        resr_kernel_params* o = out + 3 * b + 2;   // dataset.py:131-139
+        o->isotropic = 1; o->reserved = 0; o->sigma_x = o->sigma_y = 1.0; o->theta = 0.0; o->beta = 1.0; o->cutoff = 1.0;
+        if (curand_uniform_double(&st) < cfg.sinc_prob3) {
+            o->type = 3;
+            o->kernel_size = cfg.sizes[min(static_cast<int>(curand_uniform_double(&st) * cfg.n_sizes), cfg.n_sizes - 1)];
+            o->cutoff = draw_u(&st, M_PI / 3, M_PI);
+        } else {
+            o->type = 4;
+            o->kernel_size = cfg.final_size;
+        }
+    }
+}
+
+__global__ void bump_counter_kernel(unsigned long long* c) { *c += 1ull; }  // stream-ordered after every reader of the old value
+
 }  // namespace resr
+
+extern "C" int resr_draw_degradation_kernel_params(const resr_kernel_draw_config* cfg, int batch, unsigned long long seed,
+                                                   unsigned long long* call_state, resr_kernel_params* params_dev, void* stream) {
+    using namespace resr;
+    if (!cfg || !params_dev || batch <= 0) return set_error(RESR_E_INVALID, "bad argument");
+    if (cfg->n_sizes < 1 || cfg->n_sizes > 16) return set_error(RESR_E_INVALID, "n_sizes must be 1..16");
+    for (int i = 0; i < cfg->n_sizes; ++i)
+        if (cfg->sizes[i] % 2 != 1 || cfg->sizes[i] < 1 || cfg->sizes[i] > 31) return set_error(RESR_E_INVALID, "Kernel size must be an odd number.");
+    draw_kernel_params_kernel<<<(batch + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(*cfg, batch, seed, call_state, params_dev);
+    if (call_state) bump_counter_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(call_state);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(RESR_E_CUDA, "draw_kernel_params: %s", cudaGetErrorString(e));
+    return RESR_OK;
+}
+
+extern "C" int resr_synthesize_kernels_device(const resr_kernel_params* params_dev, int count, int kmax, int pad, double* out_f64,
+                                              float* out_f32, void* stream) {
+    using namespace resr;
+    if (!params_dev || count <= 0 || (!out_f64 && !out_f32)) return set_error(RESR_E_INVALID, "bad argument");
+    if (kmax % 2 != 1 || kmax < 1 || kmax > 31 || pad < kmax) return set_error(RESR_E_INVALID, "kmax must be odd, <= 31 and <= pad");
+    const int threads = (kmax * kmax + 31) / 32 * 32;
+    kernel_synth_kernel<<<count, threads, 0, static_cast<cudaStream_t>(stream)>>>(params_dev, out_f64, out_f32, pad);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(RESR_E_CUDA, "kernel_synth: %s", cudaGetErrorString(e));
+    return RESR_OK;
+}
 
 extern "C" int resr_synthesize_kernels(const resr_kernel_params* params_host, int count, int pad, double* out_f64, float* out_f32,
                                        void* stream) {

@@ -690,10 +690,62 @@ def random_mixed_kernels(kernel_type, kernel_prob, kernel_size, sigma_x_range, s
     return k
 
 
+_draw_state = {}
+
+
+def draw_config(parameters: dict) -> "_lib.KernelDrawConfig":
+    """config.degradation_model_parameters_dict (config.py:20-39) -> the POD struct of resr_draw_degradation_kernel_params."""
+    import numpy as np
+    P = parameters
+    c = _lib.KernelDrawConfig()
+    sizes = list(P["gaussian_kernel_range"])
+    c.n_sizes = len(sizes)
+    for i, v in enumerate(sizes):
+        c.sizes[i] = int(v)
+    c.sinc_size_split = int(np.median(sizes))
+    c.final_size = int(P["sinc_kernel_size"])
+    c.sinc_prob1, c.sinc_prob2, c.sinc_prob3 = (float(P[f"sinc_kernel_probability{i}"]) for i in (1, 2, 3))
+    for i in range(6):
+        c.prob1[i] = float(P["gaussian_kernel_probability1"][i])
+        c.prob2[i] = float(P["gaussian_kernel_probability2"][i])
+    for i in range(2):
+        c.sigma_range1[i], c.sigma_range2[i] = float(P["gaussian_sigma_range1"][i]), float(P["gaussian_sigma_range2"][i])
+        c.gen_beta_range1[i], c.gen_beta_range2[i] = float(P["generalized_kernel_beta_range1"][i]), float(P["generalized_kernel_beta_range2"][i])
+        c.plateau_beta_range1[i], c.plateau_beta_range2[i] = float(P["plateau_kernel_beta_range1"][i]), float(P["plateau_kernel_beta_range2"][i])
+    return c
+
+
+def draw_degradation_kernels_device(batch: int, parameters: dict, device=None, seed: int = 0, return_params: bool = False):
+    """kernel1, kernel2, sinc_kernel for `batch` samples with NO host loop: the per-sample random
+    decisions of dataset.py:81-141 are drawn by a device kernel (Philox, the reference's distributions) and evaluated in
+    float64 by the synthesis kernel — two launches per batch whatever its size. Every call draws fresh parameters for a
+    fixed `seed`. Returns three [batch, P, P] fp32 CUDA tensors (P = largest kernel size)."""
+    device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    cfg = draw_config(parameters)
+    pad = int(parameters["gaussian_kernel_range"][-1])
+    kmax = max(max(parameters["gaussian_kernel_range"]), int(parameters["sinc_kernel_size"]))
+    pad = max(pad, kmax)
+    key = (device.type, device.index)
+    st = _draw_state.get(key)
+    if st is None:
+        st = torch.zeros(1, dtype=torch.int64, device=device)
+        _draw_state[key] = st
+    params = torch.empty(batch * 3 * ctypes.sizeof(_lib.KernelParams), dtype=torch.uint8, device=device)
+    out = torch.empty(batch * 3, pad, pad, dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        _lib.check(_lib.lib().resr_draw_degradation_kernel_params(ctypes.byref(cfg), batch, int(seed) & (2 ** 64 - 1), _lib.ptr(st),
+                                                                  _lib.ptr(params), _lib.stream_ptr(device)))
+        _lib.check(_lib.lib().resr_synthesize_kernels_device(_lib.ptr(params), batch * 3, kmax, pad, None, _lib.ptr(out),
+                                                             _lib.stream_ptr(device)))
+    out = out.view(batch, 3, pad, pad)
+    ks = (out[:, 0].contiguous(), out[:, 1].contiguous(), out[:, 2].contiguous())
+    return ks + (params,) if return_params else ks
+
+
 def synthesize_degradation_kernels(batch: int, parameters: dict, device=None):
     """kernel1, kernel2, sinc_kernel for `batch` samples, sequenced per sample exactly as dataset.py:81-141 does
     (same `random` / `np.random` draw order), synthesised in ONE device launch. Returns three [batch, 21, 21] fp32
-    CUDA tensors."""
+    CUDA tensors. (`draw_degradation_kernels_device` also makes the random decisions on the device.)"""
     import numpy as np
     P = parameters
     ps = []

@@ -397,3 +397,67 @@ def test_pipeline_graph_with_device_drawn_noise(seed):
         lr, hrc = fn(hr, k, k, sk, plan)
         assert lr.shape == (b, 3, 24, 24) and torch.isfinite(lr).all()
         assert torch.equal(hrc, outs and pipe()[1])
+
+
+@pytest.mark.gpu
+def test_device_side_kernel_parameter_draws_follow_the_reference_distributions():
+    """f3: resr_draw_degradation_kernel_params replaces the per-sample host loop of dataset.py:81-141. The draws come from
+    another RNG stream than the reference's, so they are checked as DISTRIBUTIONS (config.py:20-39), and the kernels made
+    from them against the float64 oracle evaluated on the same parameters."""
+    import ctypes
+    import resr_b200
+    from oracle import kernels as ok
+    ip, L = resr_b200.imgproc, resr_b200._lib
+    P = resr_b200.plan.DEGRADATION_MODEL_PARAMETERS
+    n = 30000
+    k1, k2, sk, params = ip.draw_degradation_kernels_device(n, P, seed=123, return_params=True)
+    assert k1.shape == (n, 21, 21) and k1.dtype == torch.float32
+    for t in (k1, k2, sk):
+        assert np.abs(t.sum((1, 2)).cpu().numpy() - 1).max() < 1e-5
+    raw = params.cpu().numpy().tobytes()
+    arr = (L.KernelParams * (3 * n)).from_buffer_copy(raw)
+    names = {0: "gaussian", 1: "generalized", 2: "plateau", 3: "sinc", 4: "delta"}
+    tol = 4.5 / np.sqrt(n)   # ~4.5 sigma of a binomial proportion (p(1-p) <= 1/4 -> sigma <= 0.5/sqrt(n))
+    for which, probs, srange in ((0, P["gaussian_kernel_probability1"], P["gaussian_sigma_range1"]),
+                                 (1, P["gaussian_kernel_probability2"], P["gaussian_sigma_range2"])):
+        ps = [arr[3 * i + which] for i in range(n)]
+        types = np.array([p.type for p in ps])
+        sizes = np.array([p.kernel_size for p in ps])
+        iso = np.array([p.isotropic for p in ps])
+        assert set(np.unique(sizes)) == set(P["gaussian_kernel_range"])
+        for s in P["gaussian_kernel_range"]:
+            assert abs((sizes == s).mean() - 1 / 8) < tol
+        assert abs((types == 3).mean() - 0.1) < tol                     # sinc_kernel_probability
+        mixed = types != 3
+        want = {(0, 1): probs[0], (0, 0): probs[1], (1, 1): probs[2], (1, 0): probs[3], (2, 1): probs[4], (2, 0): probs[5]}
+        for (ty, is_iso), pr in want.items():
+            got = ((types == ty) & (iso == is_iso)).sum() / mixed.sum()
+            assert abs(got - pr) < 1.5 * tol, (ty, is_iso, got, pr)
+        sx = np.array([p.sigma_x for p in ps])[mixed]
+        assert sx.min() >= srange[0] and sx.max() <= srange[1] and abs(sx.mean() - sum(srange) / 2) < 0.03
+        aniso = mixed & (iso == 0)
+        th = np.array([p.theta for p in ps])[aniso]
+        assert th.min() >= -np.pi and th.max() <= np.pi and abs(th.mean()) < 0.08
+        beta_g = np.array([p.beta for p in ps])[types == 1]
+        assert beta_g.min() >= 0.5 and beta_g.max() <= 4 and abs((beta_g < 1).mean() - 0.5) < 3 * tol
+        beta_p = np.array([p.beta for p in ps])[types == 2]
+        assert beta_p.min() >= 1 and beta_p.max() <= 2
+        cut = np.array([p.cutoff for p in ps])[types == 3]
+        small = sizes[types == 3] < 13
+        assert cut[small].min() >= np.pi / 3 - 1e-12 and cut[~small].min() >= np.pi / 5 - 1e-12 and cut.max() <= np.pi + 1e-12
+    third = [arr[3 * i + 2] for i in range(n)]
+    t3 = np.array([p.type for p in third])
+    assert set(np.unique(t3)) == {3, 4} and abs((t3 == 3).mean() - 0.8) < tol
+    assert all(p.kernel_size == 21 for p in third if p.type == 4)
+    # kernels evaluated from the drawn parameters == float64 oracle on the same parameters
+    for idx in range(0, 60):
+        p = arr[idx]
+        d = {"type": names[p.type], "kernel_size": p.kernel_size, "isotropic": bool(p.isotropic), "sigma_x": p.sigma_x,
+             "sigma_y": p.sigma_y, "theta": p.theta, "beta": p.beta, "cutoff": p.cutoff}
+        ref = ok.from_params(d, 21)
+        got = (k1, k2, sk)[idx % 3][idx // 3].cpu().numpy()
+        assert np.abs(got - ref).max() <= 1e-7
+    # fresh draws per call for a fixed seed
+    k1b, _, _ = ip.draw_degradation_kernels_device(16, P, seed=123)
+    k1c, _, _ = ip.draw_degradation_kernels_device(16, P, seed=123)
+    assert not torch.equal(k1b, k1c)
