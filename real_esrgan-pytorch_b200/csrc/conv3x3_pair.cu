@@ -271,7 +271,8 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
     }
     if (threadIdx.x >= 128 && threadIdx.x < 128 + NOUT) bias_s[threadIdx.x - 128] = a.bias[slice * NOUT + threadIdx.x - 128];
     tc_fence_before();
-    cluster_sync_all();   // barriers of BOTH CTAs are initialised before anyone signals across the pair
+    __syncthreads();      // CTA-level ordering of the prologue's shared-memory writes (TMEM base, bias, barrier words) ...
+    cluster_sync_all();   // ... and both CTAs' barriers are initialised before anyone signals across the pair
     tc_fence_after();
     const uint32_t tbase = *tmem_ptr;
     grid_dep_launch();

@@ -114,6 +114,7 @@ struct resr_generator {
     cudaEvent_t ev_dyc[2] = {nullptr, nullptr};  // dYcat buffer of a dense block has been transposed (side stream)
     bool ev_dyc_valid[2] = {false, false};
     uint8_t* wpack_t = nullptr;   // transposed packs for the backward data-gradient convolutions (lazily allocated)
+    uint8_t* wpack_t2 = nullptr;  // mirrored dense-block data-gradient packs (train.cu), laid out like the forward packs
     float* zero_bias = nullptr;
     bool packed_t = false;
     const float* flat_params = nullptr;  // last parameter vector handed to load_params (device memory, caller-owned)
@@ -136,6 +137,7 @@ int grid_for(size_t total, int block);
 // (re)builds the transposed packs if the handle has them allocated or `force` is set (train.cu)
 void ensure_transposed_packs(resr_generator* g, cudaStream_t s, bool force);
 int launch_pack_all(resr_generator* g, const float* flat, int transposed, cudaStream_t s);
+int launch_pack_rdb_bwd(resr_generator* g, const float* flat, uint8_t* wpack_t2, cudaStream_t s);
 void launch_pack_conv(const float* w, const float* bias, uint16_t* wp, float* bp, int cin, int cout, int nout, int nslices,
                       int nchunks, int fmt, int transposed, cudaStream_t s);
 }  // namespace resr

@@ -83,6 +83,49 @@ __global__ void __launch_bounds__(256) pack_all_kernel(const float* __restrict__
                    blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x, static_cast<size_t>(gridDim.x) * blockDim.x);
 }
 
+// Data-gradient packs of a dense block in "mirrored dense block" form (train.cu backward): step b (4, 3, 2, 1, 0) maps
+//     dYcat' = [dY5 (64) | dY4 (32) | dY3 | dY2 | dY1]   (its first 64 + 32 * (4 - b) channels = the layers AFTER block b)
+// to the gradient of concat-buffer block b (b = 0: the block input x, 64 channels; b >= 1: out_b, 32 channels):
+//     W'_b[co'][ci'][dy][dx] = W_l[co_l][cin_index(b, co')][2 - dy][2 - dx],   (l, co_l) = the layer / channel ci' belongs to.
+// Step b has exactly the shape of forward layer conv(5 - b) (Cin 64 / 96 / 128 / 160 / 192, Cout 32 / 32 / 32 / 32 / 64), so
+// its tiles are stored at that layer's pack offset in a second pack buffer. blockIdx.y = step, blockIdx.z = dense block.
+__global__ void __launch_bounds__(256) pack_rdb_bwd_kernel(const float* __restrict__ flat, const PackJob* __restrict__ jobs,
+                                                          uint8_t* __restrict__ wpack) {
+    const int r = blockIdx.z, b = 4 - static_cast<int>(blockIdx.y);     // blockIdx.y = 0..4 <-> b = 4..0 <-> forward shape conv1..conv5
+    const PackJob shape = jobs[1 + 5 * r + blockIdx.y];                 // pack geometry (offset, nout, nslices, nchunks) of that shape
+    const int cin_p = 64 + 32 * (4 - b);                                // channels of dYcat' this step reads
+    const int cout_p = b == 0 ? 64 : 32;
+    const int NT = 3 * shape.nout;
+    uint16_t* wp = reinterpret_cast<uint16_t*>(wpack + shape.w_off);
+    const size_t total = static_cast<size_t>(shape.nslices) * shape.nchunks * 3 * NT * 64;
+    for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int k = idx % 64;
+        size_t t = idx / 64;
+        const int n = t % NT;
+        t /= NT;
+        const int dx = t % 3;
+        t /= 3;
+        const int chunk = t % shape.nchunks;
+        const int slice = static_cast<int>(t / shape.nchunks);
+        const int co = slice * shape.nout + n % shape.nout;   // channel inside concat block b
+        const int dy = n / shape.nout;
+        const int ci = chunk * 64 + k;                          // channel of dYcat'
+        float v = 0.f;
+        if (co < cout_p && ci < cin_p) {
+            const int l = ci < 64 ? 5 : 4 - (ci - 64) / 32;     // forward layer (1..5) whose output gradient this channel is
+            const int co_l = ci < 64 ? ci : (ci - 64) % 32;
+            const int cin_l = 64 + 32 * (l - 1);
+            const int cin_idx = b == 0 ? co : 64 + 32 * (b - 1) + co;   // input channel of layer l that is block b's channel co
+            const PackJob lay = jobs[1 + 5 * r + (l - 1)];
+            v = flat[lay.p_off + ((static_cast<size_t>(co_l) * cin_l + cin_idx) * 3 + (2 - dy)) * 3 + (2 - dx)];
+        }
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        const size_t tile = ((static_cast<size_t>(slice) * shape.nchunks + chunk) * 3 + dx) * NT * 64;  // elements
+        wp[tile + static_cast<size_t>(n) * 64 + ((((k >> 3) ^ (n & 7)) << 3) | (k & 7))] = *reinterpret_cast<const uint16_t*>(&h);
+    }
+}
+
 // NCHW fp32 -> NHWC 16-bit with channels zero-padded to c_pad (multiple of 8).
 __global__ void nchw_to_nhwc16_kernel(const float* __restrict__ x, uint16_t* __restrict__ out, int N, int C, int H, int W,
                                       int c_pad, int fmt) {
@@ -200,6 +243,13 @@ int launch_pack_all(resr_generator* g, const float* flat, int transposed, cudaSt
     const int first = transposed ? 1 : 0;
     pack_all_kernel<<<dim3(24, kNumConvs - first), 256, 0, s>>>(flat, *slot + first, transposed ? g->wpack_t : g->wpack, g->bias,
                                                                 transposed);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+// The mirrored dense-block data-gradient packs of all 69 blocks (needs the forward pack-job table on the device).
+int launch_pack_rdb_bwd(resr_generator* g, const float* flat, uint8_t* wpack_t2, cudaStream_t s) {
+    if (!g->pack_jobs) return -1;  // built by the forward pack (load_params always runs first)
+    pack_rdb_bwd_kernel<<<dim3(8, 5, kNumRRDB * 3), 256, 0, s>>>(flat, static_cast<const PackJob*>(g->pack_jobs), wpack_t2);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
@@ -456,6 +506,7 @@ void resr_generator_destroy(resr_generator_t* g) {
     cudaFree(g->wpack);
     cudaFree(g->bias);
     cudaFree(g->wpack_t);
+    cudaFree(g->wpack_t2);
     cudaFree(g->pack_jobs);
     cudaFree(g->pack_jobs_t);
     cudaFree(g->zero_bias);

@@ -323,11 +323,13 @@ void ensure_transposed_packs(resr_generator* g, cudaStream_t s, bool force) {
     if (!g->wpack_t) {
         if (!force) return;  // inference-only handle
         cudaMalloc(&g->wpack_t, T.packt_bytes);
+        cudaMalloc(&g->wpack_t2, T.pack_bytes);
         cudaMalloc(&g->zero_bias, 256 * sizeof(float));
         cudaMemsetAsync(g->zero_bias, 0, 256 * sizeof(float), s);
     }
     if (g->packed_t || !g->flat_params) return;
     launch_pack_all(g, g->flat_params, 1, s);
+    launch_pack_rdb_bwd(g, g->flat_params, g->wpack_t2, s);
     g->packed_t = true;
 }
 
@@ -554,44 +556,36 @@ int backward_common(resr_generator* g, float* grads, int N, int H, int W, const 
         for (int jj = 0; jj < 3; ++jj) {
             const int j = 2 - jj;          // rdb3, rdb2, rdb1
             const int r = 3 * i + j;       // concat buffer / RDB index
-            const int k5 = 1 + 5 * r + 4;  // layer index of this RDB's conv5
             const float* D = dbuf[jj];
-            // The five output gradients of the block live side by side in ONE 192-channel buffer
-            //     dYcat = [dY1 | dY2 | dY3 | dY4 | dY5]   (channels 0, 32, 64, 96, 128)
-            // (double-buffered across blocks): the data-gradient chain below is five back-to-back launches with no
-            // dependency on the weight-gradient side, which then needs ONE transpose, ONE split-K GEMM X^T x dYcat
-            // (all five layers share X = the block's concat buffer) and ONE reduction per block.
+            // Data gradient of the block as a MIRRORED DENSE BLOCK. The five output gradients live side by side in ONE
+            // 192-channel buffer, latest layer first,
+            //     dYcat' = [dY5 (64) | dY4 (32) | dY3 | dY2 | dY1]
+            // (double-buffered across blocks). The gradient of out_b needs every later layer's dY, which is exactly a
+            // channel PREFIX of dYcat': step b = 4, 3, 2, 1 is a convolution 64 / 96 / 128 / 160 -> 32 with the
+            // mirrored packs (generator.cu pack_rdb_bwd_kernel), masked by LeakyReLU'(out_b) and written in place as
+            // the next 32 channels; step 0 is 192 -> 64 and yields d(block input). Same launch shapes as the forward
+            // block, all accumulation over layers happens in the MMA's K dimension: the fp32 gradient buffer that
+            // round 1 read and re-wrote once per layer (210 MB per block) and its 20 K = 32 / 64 output slices are gone.
             uint16_t* dyc = B.dycat[r & 1];
             cudaStream_t wst = wgrad_stream(g, s);
             if (wst != s && g->ev_dyc_valid[r & 1]) cudaStreamWaitEvent(s, g->ev_dyc[r & 1], 0);  // its previous user was transposed
-            // conv5: dY5 = 0.2 * d(xout)
-            scale_f32_to_bf16_slice_kernel<<<egrid(P * 64), 256, 0, s>>>(D, 0.2f * dscale[jj], dyc, P, 192, 128);
-            {
-                ConvIO io = bwd_io(g, k5);  // 6 output slices: 0..4 -> G (first writer), 5 -> masked dY of conv4
-                io.in16 = dyc + 128; io.in_c = 192;
-                io.outf = B.g; io.outf_c = 192; io.noutf_mask = 1u << 5;
-                io.out16 = dyc; io.out16_c = 192; io.out16_choff = 96; io.out16_fixed = 1; io.no16_mask = 0x1Fu;
-                io.mask16 = B.c[r]; io.mask16_c = 192;
-                RESR_TRY(launch_conv_io(g, g0, N, io, s));
-            }
-            for (int q = 3; q >= 1; --q) {  // conv4, conv3, conv2: accumulate into G, top slice -> masked dY of conv(q)
-                const int kq = 1 + 5 * r + q;
-                const int nsl = table().c[kq].t_nslices;  // 5, 4, 3
-                ConvIO io = bwd_io(g, kq);
-                io.in16 = dyc + 32 * q; io.in_c = 192; io.ep_mode = EP_ADD2;
-                io.res1 = B.g; io.res1_c = 192;
-                io.outf = B.g; io.outf_c = 192; io.noutf_mask = 1u << (nsl - 1);
-                io.out16 = dyc; io.out16_c = 192; io.out16_choff = 32 * (q - 1); io.out16_fixed = 1; io.no16_mask = (1u << (nsl - 1)) - 1u;
-                io.mask16 = B.c[r]; io.mask16_c = 192;
-                RESR_TRY(launch_conv_io(g, g0, N, io, s));
-            }
-            {   // conv1: d(xin) = conv1's data gradient + G[0:64] + d(xout)
-                const int k1 = 1 + 5 * r;
-                ConvIO io = bwd_io(g, k1);
-                io.in16 = dyc; io.in_c = 192; io.ep_mode = EP_ADD2;
-                io.res1 = B.g; io.res1_c = 192;
-                io.res2 = D; io.res2_c = 64; io.res2_scale = dscale[jj];
-                io.outf = dxin[jj]; io.outf_c = 64;
+            // dY5 = 0.2 * d(xout)
+            scale_f32_to_bf16_slice_kernel<<<egrid(P * 64), 256, 0, s>>>(D, 0.2f * dscale[jj], dyc, P, 192, 0);
+            for (int b = 4; b >= 0; --b) {
+                const ConvSpec& shape = table().c[1 + 5 * r + (4 - b)];   // step b has the shape of forward conv(5 - b)
+                ConvIO io;
+                io.wpack = g->wpack_t2 + shape.w_off; io.bias = g->zero_bias;
+                io.nout = shape.nout; io.nslices = shape.nslices; io.nchunks = shape.nchunks; io.fmt = 1;
+                io.kvalid = 64 + 32 * (4 - b);
+                io.in16 = dyc; io.in_c = 192;
+                if (b > 0) {   // dY_b = LeakyReLU'(out_b) * (sum over later layers), bf16, next 32 channels of dYcat'
+                    io.out16 = dyc; io.out16_c = 192; io.out16_choff = 64 + 32 * (4 - b); io.out16_fmt = 1;
+                    io.mask16 = B.c[r]; io.mask16_c = 192; io.mask16_choff = 64 + 32 * (b - 1);
+                } else {       // d(xin) = sum over the five layers + d(xout) * (1 or 0.2)   (model.py:94-96, 129-130)
+                    io.ep_mode = EP_ADD2;
+                    io.res2 = D; io.res2_c = 64; io.res2_scale = dscale[jj];
+                    io.outf = dxin[jj]; io.outf_c = 64;
+                }
                 RESR_TRY(launch_conv_io(g, g0, N, io, s));
             }
             {   // weight + bias gradients of the five layers (side stream): dYcat is complete once conv2's launch is done
@@ -605,12 +599,12 @@ int backward_common(resr_generator* g, float* grads, int N, int H, int W, const 
                     g->ev_dyc_valid[r & 1] = true;
                 }
                 WgradRdbTable tb;
-                for (int cs = 0; cs < 6; ++cs) {
-                    const int kl = 1 + 5 * r + (cs < 4 ? cs : 4);
+                for (int cs = 0; cs < 6; ++cs) {   // slices of dYcat': conv5 (two halves), conv4, conv3, conv2, conv1
+                    const int kl = 1 + 5 * r + (cs < 2 ? 4 : 5 - cs);
                     const ConvSpec& c = table().c[kl];
                     tb.dw[cs] = grads + c.p_off;
                     tb.cin[cs] = c.cin;
-                    tb.co_base[cs] = cs < 4 ? 0 : (cs - 4) * 32;
+                    tb.co_base[cs] = cs < 2 ? cs * 32 : 0;
                     tb.db[cs] = grads + c.p_off + static_cast<size_t>(c.cout) * c.cin * 9 + tb.co_base[cs];
                 }
                 tb.dbcat = B.dbcat;
