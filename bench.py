@@ -354,8 +354,10 @@ def training_bench(D, steps, warmup, peaks):
 def tiled_bench(D, gen, steps, peaks):
     """configs[4]: 1x3x2048x2048 LR -> 1x3x8192x8192 SR. The image is cut into 8 full-width bands of 256 LR rows, each read
     with a 16-row halo (model.plan_tiles), dealt round-robin to the ranks; every rank uploads the LR image from pinned host
-    memory, runs its bands, and the SR bands are gathered into rank 0's 8192^2 buffer with NCCL send / recv (contiguous
-    per-channel row blocks, no staging copy); rank 0 copies the result to pinned host memory. All of it is inside the timer."""
+    memory, runs its bands, and the SR bands are gathered into rank 0's 8192^2 buffer with NCCL send / recv (contiguous row
+    blocks, no staging copy); rank 0 copies the result to pinned host memory. All of it is inside the timer. Two variants:
+    fp32 tensors in and out (what `model(lr_tensor)` returns, inference.py:53), and the u8 image path of inference.py:40-59
+    (u8 image in, u8 image out: image_to_tensor / tensor_to_image fused into the first / last kernel, 4x fewer result bytes)."""
     import torch.distributed as dist
 
     import resr_b200
@@ -363,50 +365,80 @@ def tiled_bench(D, gen, steps, peaks):
     Hh = Ww = 2048
     tile_h, halo, s = 256, 16, 4
     g = torch.Generator(device="cpu").manual_seed(7)
-    x_host = torch.rand(1, 3, Hh, Ww, generator=g).pin_memory()
+    img_host = torch.randint(0, 256, (1, Hh, Ww, 3), generator=g, dtype=torch.uint8).pin_memory()      # decoded LR image (HWC u8)
+    x_host = (img_host.permute(0, 3, 1, 2).float() / 255.0).contiguous().pin_memory()                  # the same image as a tensor
     tiles = resr_b200.model.plan_tiles(Hh, Ww, tile_h, Ww, halo)
-    out = torch.empty((1, 3, s * Hh, s * Ww), dtype=torch.float32, device=device) if rank == 0 else None
-    y_host = torch.empty((1, 3, s * Hh, s * Ww), dtype=torch.float32).pin_memory() if rank == 0 else None
-    x_dev = torch.empty((1, 3, Hh, Ww), dtype=torch.float32, device=device)
-
-    def step(k):
-        x_dev.copy_(x_host, non_blocking=True)
-        ops, keep = [], []
-        for i, (y0, y1, x0, x1, wy0, wy1, wx0, wx1) in enumerate(tiles):
-            owner = i % world
-            if owner == rank:
-                sr = gen.infer(x_dev[:, :, wy0:wy1, :])
-                piece = sr[:, :, s * (y0 - wy0):s * (y0 - wy0) + s * (y1 - y0), :]
-                if rank == 0:
-                    out[:, :, s * y0:s * y1, :] = piece
-                else:
-                    for c in range(3):
-                        t = piece[0, c].contiguous()
-                        keep.append(t)
-                        ops.append(dist.P2POp(dist.isend, t, 0))
-            elif rank == 0:
-                for c in range(3):
-                    ops.append(dist.P2POp(dist.irecv, out[0, c, s * y0:s * y1, :], owner))
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-        if rank == 0:
-            y_host.copy_(out, non_blocking=True)
-
-    ms = timed(step, steps, D, warm=1)
-    ms = D.max_ms(ms)[0]
     px = Hh * Ww
     halo_factor = sum((t[5] - t[4]) for t in tiles) / Hh
+
+    def run(u8):
+        if u8:
+            out = torch.empty((1, s * Hh, s * Ww, 3), dtype=torch.uint8, device=device) if rank == 0 else None
+            y_host = torch.empty((1, s * Hh, s * Ww, 3), dtype=torch.uint8).pin_memory() if rank == 0 else None
+            x_dev = torch.empty((1, Hh, Ww, 3), dtype=torch.uint8, device=device)
+            src = img_host
+        else:
+            out = torch.empty((1, 3, s * Hh, s * Ww), dtype=torch.float32, device=device) if rank == 0 else None
+            y_host = torch.empty((1, 3, s * Hh, s * Ww), dtype=torch.float32).pin_memory() if rank == 0 else None
+            x_dev = torch.empty((1, 3, Hh, Ww), dtype=torch.float32, device=device)
+            src = x_host
+
+        def step(k):
+            x_dev.copy_(src, non_blocking=True)
+            ops, keep = [], []
+            for i, (y0, y1, x0, x1, wy0, wy1, wx0, wx1) in enumerate(tiles):
+                owner = i % world
+                r0, r1 = s * (y0 - wy0), s * (y0 - wy0) + s * (y1 - y0)
+                if owner == rank:
+                    if u8:
+                        piece = gen.infer_u8(x_dev[:, wy0:wy1])[:, r0:r1]               # [1, rows, 4W, 3]: one contiguous block
+                        parts = [(piece[0], out[0, s * y0:s * y1] if rank == 0 else None)]
+                    else:
+                        sr = gen.infer(x_dev[:, :, wy0:wy1, :])
+                        parts = [(sr[0, c, r0:r1], out[0, c, s * y0:s * y1] if rank == 0 else None) for c in range(3)]
+                    for piece_c, dst in parts:
+                        if rank == 0:
+                            dst.copy_(piece_c)
+                        else:
+                            t = piece_c.contiguous()
+                            keep.append(t)
+                            ops.append(dist.P2POp(dist.isend, t, 0))
+                elif rank == 0:
+                    dsts = [out[0, s * y0:s * y1]] if u8 else [out[0, c, s * y0:s * y1] for c in range(3)]
+                    for dst in dsts:
+                        ops.append(dist.P2POp(dist.irecv, dst, owner))
+            if ops:
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+            if rank == 0:
+                y_host.copy_(out, non_blocking=True)
+
+        ms = timed(step, steps, D, warm=1)
+        ms = D.max_ms(ms)[0]
+        chk = None
+        if rank == 0:
+            chk = float(y_host[0, ::512, ::512].double().sum()) if u8 else float(y_host[0, :, ::512, ::512].double().sum())
+        nbytes_in = src.numel() * src.element_size()
+        nbytes_out = 3 * 16 * px * (1 if u8 else 4)
+        return {"value": px / (ms * 1e-3) / 1e6, "unit": "LR Mpix/s", "ms_per_step": ms, "h2d_bytes_per_step": nbytes_in * world,
+                "d2h_bytes_per_step": nbytes_out, "gather_bytes_per_step": nbytes_out * (world - 1) // world, "checksum": chk}
+
+    f32 = run(False)
+    gen._workspace = None
+    torch.cuda.empty_cache()
+    u8 = run(True)
+    ms = f32["ms_per_step"]
     tflops = FLOP_PER_LR_PIXEL * px * halo_factor / (ms * 1e-3) / 1e12
-    checksum = float(y_host[0, :, ::512, ::512].double().sum()) if rank == 0 else None
-    return {"metric": "tiled x4 inference LR Mpix/s", "value": px / (ms * 1e-3) / 1e6, "unit": "LR Mpix/s", "ms_per_step": ms,
+    tflops8 = FLOP_PER_LR_PIXEL * px * halo_factor / (u8["ms_per_step"] * 1e-3) / 1e12
+    return {"metric": "tiled x4 inference LR Mpix/s", "value": f32["value"], "unit": "LR Mpix/s", "ms_per_step": ms,
             "n_gpus": world, "scaling": "strong", "steps": steps,
             "config": {"workload": "1x3x2048x2048 LR -> 1x3x8192x8192 SR (BASELINE.json configs[4]), 8 full-width bands of 256 LR rows "
                                    f"+ 16-row halo ({halo_factor:.3f}x pixels computed), round-robin over {world} rank(s), NCCL send/recv "
-                                   "gather into rank 0's buffer; timed end to end from / to pinned host memory"},
-            "e2e": {"value": px / (ms * 1e-3) / 1e6, "unit": "LR Mpix/s", "h2d_bytes_per_step": x_host.numel() * 4 * world,
-                    "d2h_bytes_per_step": 3 * 16 * px * 4, "gather_bytes_per_step": 3 * 16 * px * 4 * (world - 1) // world,
-                    "checksum": checksum},
+                                   "gather into rank 0's buffer; timed end to end from / to pinned host memory (fp32 tensors)"},
+            "e2e": f32,
+            "u8_image": dict(u8, api="Generator.infer_u8 per band (resr_generator_forward_u8): u8 HWC image in, u8 HWC image out, the "
+                                     "conversions of inference.py:40-46, 56 fused into the first / last kernel",
+                             roofline_frac=tflops8 / (peaks["tf_sustained"] * world)),
             "roofline": {"bound": "tensor", "achieved": tflops, "peak": peaks["tf_sustained"] * world, "unit": "TFLOP/s",
                          "frac": tflops / (peaks["tf_sustained"] * world),
                          "note": "halo pixels counted as work; copies and gather are inside the time"}}
