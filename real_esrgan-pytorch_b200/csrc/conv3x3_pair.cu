@@ -212,6 +212,19 @@ template <int W>
 __device__ __forceinline__ void tmem_zero_w(uint32_t taddr) {
     if (W == 32) tmem_st_zero32(taddr); else tmem_st_zero16(taddr);
 }
+// Re-arm an accumulator with the layer's BIAS instead of zero: the MMAs then accumulate on top of it and the epilogue
+// needs no bias add (32 FADDs + their shared loads per pass for 8 vector loads; the epilogue warps are issue-bound:
+// 41.0 -> 39.8 ms per cfg3 forward, same-box A/B in profiles/r02_epilogue_ab.txt).
+template <int W>
+__device__ __forceinline__ void tmem_init_bias(uint32_t taddr, const float* __restrict__ bias_w) {
+    float b[W];
+#pragma unroll
+    for (int i = 0; i < W / 4; ++i) {
+        const float4 q = reinterpret_cast<const float4*>(bias_w)[i];
+        b[4 * i] = q.x; b[4 * i + 1] = q.y; b[4 * i + 2] = q.z; b[4 * i + 3] = q.w;
+    }
+    if (W == 32) tmem_st32(taddr, b); else tmem_st16(taddr, b);
+}
 
 }  // namespace
 
@@ -385,8 +398,8 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
             for (int s = s_lo; s < s_hi; ++s) {
 #pragma unroll
                 for (int c = 0; c < NOUT; c += SUBW) {
-                    tmem_zero_w<SUBW>(lane_base + s * NOUT + c);
-                    if (s < 2) tmem_zero_w<SUBW>(lane_base + (S + s) * NOUT + c);
+                    tmem_init_bias<SUBW>(lane_base + s * NOUT + c, bias_s + c);
+                    if (s < 2) tmem_zero_w<SUBW>(lane_base + (S + s) * NOUT + c);   // overflow twin: plain zero
                 }
             }
             tmem_st_wait();
@@ -396,7 +409,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
                 for (int s = s_lo; s < s_hi; ++s) mbar_arrive_cluster(free0 + (s << 3));
         }
         grid_dep_wait();  // residual reads / output writes below touch buffers of the previous kernel
-        PROF_DECL(p_acc); PROF_DECL(p_tile);
+        PROF_DECL(p_acc); PROF_DECL(p_tile); PROF_DECL(p_drain); PROF_DECL(p_math); PROF_DECL(p_store); PROF_DECL(p_rows);
         PROF_T0(p_t0);
         uint32_t v0 = 0;
         const int ncg2 = (a.ncg + 1) >> 1;
@@ -457,6 +470,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
                         waited = true;
                     }
                     float val[SUBW];
+                    PROF_T0(p_td);
                     tmem_ld_w<SUBW>(lane_base + col + h * SUBW, val);
                     if (dual) {
                         float val2[SUBW];
@@ -468,17 +482,21 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
                     } else {
                         tmem_ld_wait();
                     }
-                    tmem_zero_w<SUBW>(lane_base + col + h * SUBW);
+                    tmem_init_bias<SUBW>(lane_base + col + h * SUBW, bias_s + h * SUBW);
                     if (h == NSUB - 1) {   // the whole slot is drained and zeroed: give it back to the MMA issuer
                         tmem_st_wait();
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive_cluster(free0 + (slot << 3));
                     }
+                    PROF_ADD(p_drain, p_td);
                     if (!emit) continue;
+                    PROF_T0(p_tm);
+#ifdef RESR_PROFILE_WAITS
+                    ++p_rows;
+#endif
 
-#pragma unroll
-                    for (int i = 0; i < SUBW; ++i) val[i] = __fadd_rn(val[i], bias_s[h * SUBW + i]);
+                    // (no bias add here: the accumulator was armed with the bias, tmem_init_bias)
                     if (use_res1 && a.res16) {  // widen the 16-bit residual in place (consumed below as fp32)
                         float wide[SUBW];
 #pragma unroll
@@ -501,14 +519,16 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
                                 val[4 * i + 1] = __fadd_rn(r4.y, val[4 * i + 1]);
                                 val[4 * i + 2] = __fadd_rn(r4.z, val[4 * i + 2]);
                                 val[4 * i + 3] = __fadd_rn(r4.w, val[4 * i + 3]);
-                            } else {
-                                val[4 * i + 0] = __fadd_rn(__fmul_rn(val[4 * i + 0], 0.2f), r4.x);
-                                val[4 * i + 1] = __fadd_rn(__fmul_rn(val[4 * i + 1], 0.2f), r4.y);
-                                val[4 * i + 2] = __fadd_rn(__fmul_rn(val[4 * i + 2], 0.2f), r4.z);
-                                val[4 * i + 3] = __fadd_rn(__fmul_rn(val[4 * i + 3], 0.2f), r4.w);
+                            } else {   // v * 0.2 + r: separately rounded product and sum (reference order), two lanes per instruction
+                                const float2 p01 = __fmul2_rn(make_float2(val[4 * i + 0], val[4 * i + 1]), make_float2(0.2f, 0.2f));
+                                const float2 p23 = __fmul2_rn(make_float2(val[4 * i + 2], val[4 * i + 3]), make_float2(0.2f, 0.2f));
+                                const float2 s01 = __fadd2_rn(p01, make_float2(r4.x, r4.y));
+                                const float2 s23 = __fadd2_rn(p23, make_float2(r4.z, r4.w));
+                                val[4 * i + 0] = s01.x; val[4 * i + 1] = s01.y; val[4 * i + 2] = s23.x; val[4 * i + 3] = s23.y;
                             }
                         }
                     }
+                    PROF_ADD(p_math, p_tm);
                     uint8_t* const tileR = tile_base + ((two_bufs && (pass & 1u)) ? buf_bytes : 0);  // fp32 output tile
                     uint8_t* const tile16 = tileR + (a.has_outf ? kTileFBytes : 0);                  // 16-bit output tile
                     if (staged) {
@@ -520,6 +540,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
                         PROF_ADD(p_tile, p_t);
                         ++pass;
                     }
+                    PROF_T0(p_ts);
                     if (a.ep_mode == EP_RRDB) {
                         if (a.res16) {
                             // plain (coherent) loads: in the inference trunk res2 is the RRDB input held in the very buffer
@@ -531,7 +552,11 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
                                 float f8[8];
                                 unpack16x8(r2[i], a.res16_fmt, f8);
 #pragma unroll
-                                for (int e = 0; e < 8; ++e) val[8 * i + e] = __fadd_rn(__fmul_rn(val[8 * i + e], 0.2f), f8[e]);
+                                for (int e = 0; e < 8; e += 2) {
+                                    const float2 pp = __fmul2_rn(make_float2(val[8 * i + e], val[8 * i + e + 1]), make_float2(0.2f, 0.2f));
+                                    const float2 ss = __fadd2_rn(pp, make_float2(f8[e], f8[e + 1]));
+                                    val[8 * i + e] = ss.x; val[8 * i + e + 1] = ss.y;
+                                }
                             }
                         } else {
                             const float4* r2 = reinterpret_cast<const float4*>(static_cast<const float*>(a.res2) + pix * a.res2_cstride +
@@ -557,9 +582,13 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
                             val[4 * i + 3] = fmaf(a.res2_scale, r4.w, val[4 * i + 3]);
                         }
                     }
-                    if (a.lrelu) {
+                    if (a.lrelu) {   // max(v, 0.2 v) == (v > 0 ? v : 0.2 v) for every finite v; the product is one packed FMUL2 per pair
 #pragma unroll
-                        for (int i = 0; i < SUBW; ++i) val[i] = val[i] > 0.f ? val[i] : __fmul_rn(val[i], 0.2f);
+                        for (int i = 0; i < SUBW / 2; ++i) {
+                            const float2 t = __fmul2_rn(make_float2(val[2 * i], val[2 * i + 1]), make_float2(0.2f, 0.2f));
+                            val[2 * i] = fmaxf(val[2 * i], t.x);
+                            val[2 * i + 1] = fmaxf(val[2 * i + 1], t.y);
+                        }
                     }
                     if (a.out_nchw_raw && valid) {
                         const size_t plane = static_cast<size_t>(a.H) * a.W;
@@ -603,11 +632,11 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
                                 __nv_bfloat162 hh = __floats2bfloat162_rn(val[2 * i], val[2 * i + 1]);
                                 pk[i] = *reinterpret_cast<uint32_t*>(&hh);
                             } else {
-                                __half2 hh = __floats2half2_rn(fminf(fmaxf(val[2 * i], -65504.f), 65504.f),
-                                                               fminf(fmaxf(val[2 * i + 1], -65504.f), 65504.f));  // saturate, never inf
-                                pk[i] = *reinterpret_cast<uint32_t*>(&hh);
+                                pk[i] = pack_f16x2_sat(val[2 * i], val[2 * i + 1]);  // saturate, never inf
                             }
                         }
+                        // (Storing the pixel's channels straight from registers instead -- no staging tile, no proxy fence, no
+                        // block barrier -- was tried and is slower: 45.5 vs 43.0 ms per cfg3 forward, profiles/r02_direct_store_ab.txt.)
                         uint4* dst = reinterpret_cast<uint4*>(tile16 + m * (SUBW * 2));
 #pragma unroll
                         for (int i = 0; i < SUBW / 8; ++i) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
@@ -632,6 +661,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
                             __syncwarp();
                         }
                     }
+                    PROF_ADD(p_store, p_ts);
                     if (a.out_nchw && valid) {
                         const size_t plane = static_cast<size_t>(a.H) * a.W;
                         float* o = a.out_nchw + static_cast<size_t>(n) * a.out_nchw_c * plane + static_cast<size_t>(y) * a.W + x;
@@ -656,7 +686,10 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
         }
         if (lead_warp) tma_store_wait_all();
 #ifdef RESR_PROFILE_WAITS
-        if (warp == 4) { PROF_FLUSH(6, clock64() - p_t0); PROF_FLUSH(7, p_acc); PROF_FLUSH(8, p_tile); }
+        if (warp == 4) {
+            PROF_FLUSH(6, clock64() - p_t0); PROF_FLUSH(7, p_acc); PROF_FLUSH(8, p_tile);
+            PROF_FLUSH(9, p_drain); PROF_FLUSH(10, p_math); PROF_FLUSH(11, p_store); PROF_FLUSH(12, p_rows);
+        }
 #endif
     }
 

@@ -537,9 +537,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
                             __nv_bfloat162 h = __floats2bfloat162_rn(val[2 * i], val[2 * i + 1]);
                             pk[i] = *reinterpret_cast<uint32_t*>(&h);
                         } else {
-                            __half2 h = __floats2half2_rn(fminf(fmaxf(val[2 * i], -65504.f), 65504.f),
-                                                          fminf(fmaxf(val[2 * i + 1], -65504.f), 65504.f));  // saturate, never inf
-                            pk[i] = *reinterpret_cast<uint32_t*>(&h);
+
+                            pk[i] = pack_f16x2_sat(val[2 * i], val[2 * i + 1]);  // saturate, never inf
                         }
                     }
                     // rotate the 16-byte chunk order per lane so that a quarter-warp does not hammer two bank groups
@@ -662,9 +661,17 @@ int conv3x3_make_tmap_act(CUtensorMap* out, const void* base, int N, int H, int 
                                    static_cast<cuuint64_t>(H) * W * C * 2};
     cuuint32_t box[4] = {64, static_cast<cuuint32_t>(mode == 0 ? BW + 2 : BW), 1, static_cast<cuuint32_t>(mode == 0 ? 1 : BN)};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
+    // L2 promotion: 128 B fetches suit full 64-channel chunks (128 B per pixel); a layer whose last chunk holds only 32
+    // channels (Cin = 96 / 160) would drag the other half of every 128-byte line in from DRAM (ncu: 278 MB read for the
+    // 201 MB a 96-channel layer needs), so those maps promote to 64 B. RESR_TMAP_PROMO = 0 / 1 / 2 / 3 forces none / 64 / 128 / 256.
+    static const int env_promo = getenv("RESR_TMAP_PROMO") ? atoi(getenv("RESR_TMAP_PROMO")) : -1;
+    CUtensorMapL2promotion promo = (cdim % 64 != 0) ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    if (env_promo == 0) promo = CU_TENSOR_MAP_L2_PROMOTION_NONE;
+    else if (env_promo == 1) promo = CU_TENSOR_MAP_L2_PROMOTION_L2_64B;
+    else if (env_promo == 2) promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    else if (env_promo == 3) promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
     const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
 }
 

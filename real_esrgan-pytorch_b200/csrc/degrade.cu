@@ -33,9 +33,12 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {  // ATen reflection_p
 // 4 at 128^2, 2 at 64^2 (the 64 x 64 tile of round 1 left 100 of the 148 SMs idle there).
 static constexpr int kF2dTileW = 64;
 
+// The two columns of a thread (x, x + 32) ride in ONE packed fp32x2 FMA (Blackwell FFMA2, `__ffma2_rn`: two IEEE fmas per
+// instruction, the tap broadcast to both halves by the operand selector): the same arithmetic bit for bit in half the issue
+// slots. ncu had this kernel issue-bound (issue slots 78 % busy, FMA pipe 48 %, 60 % of the instructions FMAs).
 template <int KS, int R, int tpitch>
 __device__ __forceinline__ void filter2d_body(const float* __restrict__ tile, const float* __restrict__ taps, int k,
-                                              int off, int tx, int ty0, float (&acc)[2][R]) {
+                                              int off, int tx, int ty0, float2 (&acc)[R]) {
     // taps: full k x k array; the KS x KS centred window starts at (off, off). tile row 0 / col 0 correspond to output
     // (0,0) shifted by -(k/2); the window adds `off` again.
     for (int kx = 0; kx < KS; ++kx) {
@@ -45,14 +48,11 @@ __device__ __forceinline__ void filter2d_body(const float* __restrict__ tile, co
         const float* col = tile + (ty0 + off) * tpitch + tx + off + kx;
 #pragma unroll
         for (int rr = 0; rr < KS + R - 1; ++rr) {
-            const float v0 = col[rr * tpitch], v1 = col[rr * tpitch + 32];
+            const float2 v = make_float2(col[rr * tpitch], col[rr * tpitch + 32]);
 #pragma unroll
             for (int j = 0; j < R; ++j) {
                 const int ky = rr - j;
-                if (ky >= 0 && ky < KS) {
-                    acc[0][j] = fmaf(v0, w[ky], acc[0][j]);
-                    acc[1][j] = fmaf(v1, w[ky], acc[1][j]);
-                }
+                if (ky >= 0 && ky < KS) acc[j] = __ffma2_rn(v, make_float2(w[ky], w[ky]), acc[j]);
             }
         }
     }
@@ -119,9 +119,9 @@ __global__ void __launch_bounds__(R == 16 ? 128 : 256) filter2d_kernel(const flo
     __syncthreads();
     const int tx = threadIdx.x & 31;
     const int ty0 = (threadIdx.x >> 5) * R;   // NW warps x R rows
-    float acc[2][R];
+    float2 acc[R];   // .x: column tx, .y: column tx + 32
 #pragma unroll
-    for (int j = 0; j < R; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; }
+    for (int j = 0; j < R; ++j) acc[j] = make_float2(0.f, 0.f);
     switch (2 * ext + 1) {
         case 1: filter2d_body<1, R, PITCH>(tile, taps, k, off, tx, ty0, acc); break;
         case 3: filter2d_body<3, R, PITCH>(tile, taps, k, off, tx, ty0, acc); break;
@@ -145,8 +145,8 @@ __global__ void __launch_bounds__(R == 16 ? 128 : 256) filter2d_kernel(const flo
                         const int ky = rr - j;
                         if (ky >= 0 && ky < ks) {
                             const float wv = taps[(off + ky) * k + off + kx];
-                            acc[0][j] = fmaf(v0, wv, acc[0][j]);
-                            acc[1][j] = fmaf(v1, wv, acc[1][j]);
+                            acc[j].x = fmaf(v0, wv, acc[j].x);
+                            acc[j].y = fmaf(v1, wv, acc[j].y);
                         }
                     }
                 }
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(R == 16 ? 128 : 256) filter2d_kernel(const flo
 #pragma unroll
             for (int j = 0; j < R; ++j) {
                 const int gy = y0 + ty0 + j;
-                if (gy < H) out[static_cast<size_t>(plane) * H * W + static_cast<size_t>(gy) * W + gx] = acc[c][j];
+                if (gy < H) out[static_cast<size_t>(plane) * H * W + static_cast<size_t>(gy) * W + gx] = c ? acc[j].y : acc[j].x;
             }
         }
     }
@@ -280,37 +280,40 @@ __global__ void __launch_bounds__(256) usm_vpass_kernel(const float* __restrict_
 
 // The 51-tap case the training loops use (USMSharp(50, 0)): each blur is a horizontal pass into a scratch image (it
 // stays in the 126 MB L2) and a vertical pass with the pointwise tail fused. Both passes are plain 1-D stencils with NO
-// recomputation: a thread slides a register window over 16 consecutive outputs ALONG the filter direction (66 shared
-// loads + 816 FMAs with the taps as uniform-register operands), and the lane index runs ACROSS it, so that the window
-// loads of a warp are conflict-free (horizontal pass: lane = row, odd row pitch; vertical pass: lane = column).
-// Global loads are issued in batches ahead of their use (tile rows four at a time, the tail's operands before the
-// window): ncu showed the first version of these kernels waiting on the long scoreboard for most of its cycles.
-static constexpr int kUsmK = 51, kUsmR = kUsmK / 2, kUsmO = 16;   // outputs per thread
-static constexpr int kUsmHCols = 64, kUsmHRows = 32, kUsmHPitch = kUsmHCols + kUsmK - 1 + 1;  // 115: odd
+// recomputation. A thread slides a register window over 8 consecutive outputs ALONG the filter direction for TWO
+// independent lines at once (two rows in the horizontal pass, two columns in the vertical one): the two lines share every
+// tap, so each step is one packed fp32x2 FMA (FFMA2, tap broadcast by the operand selector) -- 408 packed FMAs + 116
+// conflict-free shared loads per 16 outputs, taps in uniform registers. The lane index runs ACROSS the filter direction
+// (horizontal pass: lane = row, odd row pitch; vertical pass: lane = column). Global loads are issued in batches ahead
+// of their use (ncu showed the first version of these kernels waiting on the long scoreboard for most of its cycles).
+static constexpr int kUsmK = 51, kUsmR = kUsmK / 2, kUsmO = 8;   // outputs per thread and line
+static constexpr int kUsmHCols = 64, kUsmHRows = 64, kUsmHPitch = kUsmHCols + kUsmK - 1 + 1;  // 115: odd
 static constexpr int kUsmVCols = 64, kUsmVRows = 64, kUsmVIn = kUsmVRows + kUsmK - 1;         // 114 input rows
 
-__device__ __forceinline__ void usm_window16(const float* __restrict__ p, int stride, float (&acc)[kUsmO]) {
+__device__ __forceinline__ void usm_window8x2(const float* __restrict__ p0, const float* __restrict__ p1, int stride,
+                                              float2 (&acc)[kUsmO]) {
 #pragma unroll
-    for (int j = 0; j < kUsmO; ++j) acc[j] = 0.f;
+    for (int j = 0; j < kUsmO; ++j) acc[j] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int t = 0; t < kUsmK + kUsmO - 1; ++t) {
-        const float v = p[t * stride];
+        const float2 v = make_float2(p0[t * stride], p1[t * stride]);
 #pragma unroll
         for (int j = 0; j < kUsmO; ++j) {
             const int tap = t - j;
-            if (tap >= 0 && tap < kUsmK) acc[j] = fmaf(v, c_usm_taps[tap], acc[j]);
+            if (tap >= 0 && tap < kUsmK) acc[j] = __ffma2_rn(v, make_float2(c_usm_taps[tap], c_usm_taps[tap]), acc[j]);
         }
     }
 }
 
-// tmp = conv_x(src), reflect padding. Block = 32 rows x 64 columns of outputs, 128 threads: lane = row, warp = 16 columns.
-__global__ void __launch_bounds__(128) usm_h51_kernel(const float* __restrict__ src, float* __restrict__ tmp, int H, int W) {
+// tmp = conv_x(src), reflect padding. Block = 64 rows x 64 columns of outputs, 256 threads: lane = rows (l, l + 32),
+// warp = 8 columns.
+__global__ void __launch_bounds__(256) usm_h51_kernel(const float* __restrict__ src, float* __restrict__ tmp, int H, int W) {
     __shared__ float A[kUsmHRows * kUsmHPitch];
     const int plane = blockIdx.z;
     const int x0 = blockIdx.x * kUsmHCols, y0 = blockIdx.y * kUsmHRows;
     const size_t pbase = static_cast<size_t>(plane) * H * W;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    {   // tile rows: warp w takes rows w, w+4, ...; 4 rows (16 loads per lane) in flight, coalesced along x
+    {   // tile rows: warp w takes rows w, w+8, ...; 4 rows (16 loads per lane) in flight, coalesced along x
         int gxk[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) gxk[k] = min(max(reflect_idx(x0 + lane + 32 * k - kUsmR, W), 0), W - 1);
@@ -320,14 +323,14 @@ __global__ void __launch_bounds__(128) usm_h51_kernel(const float* __restrict__ 
             float v[4][4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int ty = warp + 4 * (pass * 4 + u);
+                const int ty = warp + 8 * (pass * 4 + u);
                 const float* srow = src + pbase + static_cast<size_t>(min(y0 + ty, H - 1)) * W;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) v[u][k] = srow[gxk[k]];
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int ty = warp + 4 * (pass * 4 + u);
+                const int ty = warp + 8 * (pass * 4 + u);
 #pragma unroll
                 for (int k = 0; k < 3; ++k) A[ty * kUsmHPitch + lane + 32 * k] = v[u][k];
                 if (last_ok) A[ty * kUsmHPitch + lane + 96] = v[u][3];
@@ -335,24 +338,29 @@ __global__ void __launch_bounds__(128) usm_h51_kernel(const float* __restrict__ 
         }
     }
     __syncthreads();
-    const int gy = y0 + lane;
     const int c0 = warp * kUsmO;
-    float acc[kUsmO];
-    usm_window16(A + lane * kUsmHPitch + c0, 1, acc);
-    if (gy < H) {
+    float2 acc[kUsmO];
+    usm_window8x2(A + lane * kUsmHPitch + c0, A + (lane + 32) * kUsmHPitch + c0, 1, acc);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int gy = y0 + lane + 32 * half;
+        if (gy >= H) continue;
+        float o8[kUsmO];
+#pragma unroll
+        for (int j = 0; j < kUsmO; ++j) o8[j] = half ? acc[j].y : acc[j].x;
         float* o = tmp + pbase + static_cast<size_t>(gy) * W + x0 + c0;
         if (x0 + c0 + kUsmO <= W && (W & 3) == 0) {
-#pragma unroll
-            for (int j = 0; j < kUsmO; j += 4) reinterpret_cast<float4*>(o)[j >> 2] = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+            reinterpret_cast<float4*>(o)[0] = make_float4(o8[0], o8[1], o8[2], o8[3]);
+            reinterpret_cast<float4*>(o)[1] = make_float4(o8[4], o8[5], o8[6], o8[7]);
         } else {
 #pragma unroll
             for (int j = 0; j < kUsmO; ++j)
-                if (x0 + c0 + j < W) o[j] = acc[j];
+                if (x0 + c0 + j < W) o[j] = o8[j];
         }
     }
 }
 
-// conv_y(tmp) + the pointwise tail. Block = 64 x 64 outputs, 256 threads: thread = column, 16 consecutive rows each.
+// conv_y(tmp) + the pointwise tail. Block = 64 x 64 outputs, 256 threads: thread = columns (c, c + 32), 8 consecutive rows.
 //   stage 0: blur = conv_y(tmp); res = x - blur; mask = |res| * 255 > threshold     -> res, mask_or_out
 //   stage 1: soft = conv_y(tmp); out = soft * clip(x + weight * res, 0, 1) + (1 - soft) * x
 __global__ void __launch_bounds__(256) usm_v51_kernel(const float* __restrict__ tmp, const float* __restrict__ x,
@@ -362,9 +370,9 @@ __global__ void __launch_bounds__(256) usm_v51_kernel(const float* __restrict__ 
     const int plane = blockIdx.z;
     const int x0 = blockIdx.x * kUsmVCols, y0 = blockIdx.y * kUsmVRows;
     const size_t pbase = static_cast<size_t>(plane) * H * W;
-    const int cx = threadIdx.x & 63;
-    const int gxc = min(x0 + cx, W - 1);
     {   // 114 rows x 64 columns, coalesced; this thread's rows are g, g+4, ...: 8 loads in flight per batch
+        const int cx = threadIdx.x & 63;
+        const int gxc = min(x0 + cx, W - 1);
         const int g = threadIdx.x >> 6;
 #pragma unroll
         for (int base = 0; base < kUsmVIn; base += 32) {
@@ -382,33 +390,40 @@ __global__ void __launch_bounds__(256) usm_v51_kernel(const float* __restrict__ 
             }
         }
     }
-    const int r0 = (threadIdx.x >> 6) * kUsmO;
-    const int gx = x0 + cx;
-    // the tail's operands, requested before the window so that their latency hides behind 816 FMAs
-    float xv[kUsmO], rv[kUsmO];
+    const int cx = threadIdx.x & 31;
+    const int r0 = (threadIdx.x >> 5) * kUsmO;
+    // the tail's operands, requested before the window so that their latency hides behind the FMAs
+    float2 xv[kUsmO], rv[kUsmO];
 #pragma unroll
     for (int j = 0; j < kUsmO; ++j) {
-        const size_t o = pbase + static_cast<size_t>(min(y0 + r0 + j, H - 1)) * W + gxc;
-        xv[j] = x[o];
-        rv[j] = stage == 0 ? 0.f : res[o];
+        const size_t o = pbase + static_cast<size_t>(min(y0 + r0 + j, H - 1)) * W;
+        const int ga = min(x0 + cx, W - 1), gb = min(x0 + cx + 32, W - 1);
+        xv[j] = make_float2(x[o + ga], x[o + gb]);
+        rv[j] = stage == 0 ? make_float2(0.f, 0.f) : make_float2(res[o + ga], res[o + gb]);
     }
     __syncthreads();
-    float acc[kUsmO];
-    usm_window16(Bm + r0 * kUsmVCols + cx, kUsmVCols, acc);
-    if (gx >= W) return;
+    float2 acc[kUsmO];
+    usm_window8x2(Bm + r0 * kUsmVCols + cx, Bm + r0 * kUsmVCols + cx + 32, kUsmVCols, acc);
 #pragma unroll
-    for (int j = 0; j < kUsmO; ++j) {
-        const int gy = y0 + r0 + j;
-        if (gy >= H) break;
-        const size_t o = pbase + static_cast<size_t>(gy) * W + gx;
-        if (stage == 0) {
-            const float r = xv[j] - acc[j];                                       // imgproc.py:1528
-            res[o] = r;
-            mask_or_out[o] = (fabsf(r) * 255.f > threshold) ? 1.f : 0.f;          // imgproc.py:1530-1531
-        } else {
-            float sh = __fadd_rn(xv[j], __fmul_rn(weight, rv[j]));                // imgproc.py:1533
-            sh = fminf(fmaxf(sh, 0.f), 1.f);                                      // imgproc.py:1534
-            mask_or_out[o] = __fadd_rn(__fmul_rn(acc[j], sh), __fmul_rn(1.f - acc[j], xv[j]));  // imgproc.py:1535
+    for (int half = 0; half < 2; ++half) {
+        const int gx = x0 + cx + 32 * half;
+        if (gx >= W) continue;
+#pragma unroll
+        for (int j = 0; j < kUsmO; ++j) {
+            const int gy = y0 + r0 + j;
+            if (gy >= H) break;
+            const size_t o = pbase + static_cast<size_t>(gy) * W + gx;
+            const float a = half ? acc[j].y : acc[j].x, xx = half ? xv[j].y : xv[j].x;
+            if (stage == 0) {
+                const float r = xx - a;                                               // imgproc.py:1528
+                res[o] = r;
+                mask_or_out[o] = (fabsf(r) * 255.f > threshold) ? 1.f : 0.f;          // imgproc.py:1530-1531
+            } else {
+                const float rr = half ? rv[j].y : rv[j].x;
+                float sh = __fadd_rn(xx, __fmul_rn(weight, rr));                      // imgproc.py:1533
+                sh = fminf(fmaxf(sh, 0.f), 1.f);                                      // imgproc.py:1534
+                mask_or_out[o] = __fadd_rn(__fmul_rn(a, sh), __fmul_rn(1.f - a, xx));  // imgproc.py:1535
+            }
         }
     }
 }
@@ -453,9 +468,9 @@ static int usm_impl(const float* x, float* out, float* ws, int B, int C, int H, 
     if (k == kUsmK) {
         const dim3 g51h((W + kUsmHCols - 1) / kUsmHCols, (H + kUsmHRows - 1) / kUsmHRows, B * C);
         const dim3 g51v((W + kUsmVCols - 1) / kUsmVCols, (H + kUsmVRows - 1) / kUsmVRows, B * C);
-        usm_h51_kernel<<<g51h, 128, 0, s>>>(x, tmp, H, W);
+        usm_h51_kernel<<<g51h, 256, 0, s>>>(x, tmp, H, W);
         usm_v51_kernel<<<g51v, 256, 0, s>>>(tmp, x, res, mask, H, W, 0, weight, threshold);
-        usm_h51_kernel<<<g51h, 128, 0, s>>>(mask, tmp, H, W);
+        usm_h51_kernel<<<g51h, 256, 0, s>>>(mask, tmp, H, W);
         usm_v51_kernel<<<g51v, 256, 0, s>>>(tmp, x, res, out, H, W, 1, weight, threshold);
     } else {
         usm_hpass_kernel<<<gh, 256, sh, s>>>(x, tmp, H, W, k);

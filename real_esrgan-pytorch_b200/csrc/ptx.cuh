@@ -260,6 +260,28 @@ __device__ __forceinline__ void tmem_st_zero16(uint32_t taddr) {
         ::"r"(taddr), "r"(z)
         : "memory");
 }
+// registers -> TMEM: 32 (or 16) consecutive fp32 columns of this warp's 32 lanes from v[]
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
+    const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+        "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+        "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+    const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------- CTA pairs (cluster of 2, tcgen05 cta_group::2)
@@ -329,6 +351,14 @@ __device__ __forceinline__ void tma_load_4d_pair(void* smem_dst, const void* des
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar_cluster_addr), "r"(c0), "r"(c1),
         "r"(c2), "r"(c3)
         : "memory");
+}
+
+// two fp32 -> packed fp16x2 (lo = a, hi = b), round to nearest, SATURATING to +-65504 instead of overflowing to inf: one
+// F2FP.SATFINITE instead of four FMNMX + F2FP per pair (the epilogue warps are instruction-issue bound)
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
 }
 
 // Programmatic dependent launch: wait for the previous kernel in the stream / let the next one start its prologue.

@@ -41,10 +41,13 @@ for cin, cout in ((64, 32), (96, 32), (128, 32), (160, 32), (192, 64)):
     torch.cuda.synchronize()
     buf = (ctypes.c_ulonglong * 16)()
     L.check(L.lib().resr_debug_wait_profile(buf, 0))
-    v = [float(buf[i]) for i in range(9)]
+    v = [float(buf[i]) for i in range(13)]
     steps = max(v[3], 1.0)
     leaders = 74.0
     print(f"conv {cin:3d}->{cout:2d}: per step (cycles): MMA-warp total {v[0] / steps:7.0f} | wait full {v[1] / steps:6.0f} | wait slot {v[2] / steps:6.0f}"
           f" || producer total/step {v[4] / 2 / steps:7.0f} wait-empty {v[5] / 2 / steps:6.0f}"
           f" || epilogue(g0) total/step {v[6] / 2 / steps:7.0f} wait-acc {v[7] / 2 / steps:6.0f} wait-tile {v[8] / 2 / steps:6.0f}"
           f" | steps per launch per leader {steps / reps / leaders:.0f}")
+    rows = max(v[12], 1.0)
+    print(f"      epilogue per emitted pass of group 0 (cycles): drain (ld + zero + arrive) {v[9] / rows:6.0f} | bias/residual math {v[10] / rows:6.0f}"
+          f" | tile wait {v[8] / rows:6.0f} | activation + pack + stage + TMA store {v[11] / rows:6.0f} | accumulator wait {v[7] / rows:6.0f}")
