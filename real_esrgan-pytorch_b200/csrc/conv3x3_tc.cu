@@ -126,6 +126,19 @@ __device__ __forceinline__ void issue_half(int ks, uint32_t s0, uint32_t d0, uin
 #undef RESR_HALF
 }
 
+// Re-arm an accumulator slot with the layer's BIAS instead of zero (see conv3x3_pair.cu tmem_init_bias): the MMAs
+// accumulate on top of it and the epilogue needs no bias add.
+template <int W>
+__device__ __forceinline__ void tmem_init_bias_w(uint32_t taddr, const float* __restrict__ bias_w) {
+    float b[W];
+#pragma unroll
+    for (int i = 0; i < W / 4; ++i) {
+        const float4 q = reinterpret_cast<const float4*>(bias_w)[i];
+        b[4 * i] = q.x; b[4 * i + 1] = q.y; b[4 * i + 2] = q.z; b[4 * i + 3] = q.w;
+    }
+    if (W == 32) tmem_st32(taddr, b); else tmem_st16(taddr, b);
+}
+
 // eight 16-bit values (fp16 or bf16) of a uint4 -> fp32
 __device__ __forceinline__ void unpack16x8(const uint4 q, int fmt, float (&f)[8]) {
     const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
@@ -358,9 +371,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         const int x_in_tile = m % a.BW;
         {   // zero this group's share of the accumulator ring, then hand the slots to the MMA issuer
             const int s_lo = gi * kSlots / a.nepi, s_hi = (gi + 1) * kSlots / a.nepi;
-            for (int s = s_lo; s < s_hi; ++s) {
-                if (NOUT == 32) tmem_st_zero32(lane_base + s * NOUT); else tmem_st_zero16(lane_base + s * NOUT);
-            }
+            for (int s = s_lo; s < s_hi; ++s) tmem_init_bias_w<NOUT>(lane_base + s * NOUT, bias_s);
             tmem_st_wait();
             tc_fence_before();
             for (int s = s_lo; s < s_hi; ++s) mbar_arrive(slot_free + s);
@@ -409,14 +420,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
                 float val[NOUT];
                 if (NOUT == 32) tmem_ld32(lane_base + slot * NOUT, val); else tmem_ld16(lane_base + slot * NOUT, val);
                 tmem_ld_wait();
-                if (NOUT == 32) tmem_st_zero32(lane_base + slot * NOUT); else tmem_st_zero16(lane_base + slot * NOUT);
+                tmem_init_bias_w<NOUT>(lane_base + slot * NOUT, bias_s);
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(slot_free + slot);
                 if (!emit) continue;
 
-#pragma unroll
-                for (int i = 0; i < NOUT; ++i) val[i] = __fadd_rn(val[i], bias_s[i]);
+                // (no bias add here: the accumulator was armed with the bias)
                 if (use_res1 && a.res16) {  // widen the 16-bit residual in place (consumed below as fp32)
                     float wide[NOUT];
 #pragma unroll
@@ -490,9 +500,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
                         val[4 * i + 3] = fmaf(a.res2_scale, r4.w, val[4 * i + 3]);
                     }
                 }
-                if (a.lrelu) {
+                if (a.lrelu) {   // max(v, 0.2 v) == (v > 0 ? v : 0.2 v); the product is one packed FMUL2 per pair
 #pragma unroll
-                    for (int i = 0; i < NOUT; ++i) val[i] = val[i] > 0.f ? val[i] : __fmul_rn(val[i], 0.2f);
+                    for (int i = 0; i < NOUT / 2; ++i) {
+                        const float2 t = __fmul2_rn(make_float2(val[2 * i], val[2 * i + 1]), make_float2(0.2f, 0.2f));
+                        val[2 * i] = fmaxf(val[2 * i], t.x);
+                        val[2 * i + 1] = fmaxf(val[2 * i + 1], t.y);
+                    }
                 }
                 if (a.out_nchw_raw && valid) {
                     const size_t plane = static_cast<size_t>(a.H) * a.W;
