@@ -536,6 +536,19 @@ def run_ours(args):
 
     head = forward_leg(n_strong)
     weak = forward_leg(TOTAL_BATCH) if (world > 1 and not args.batch and not args.no_weak) else None
+    # the other precision recipe on the same box, device-resident only (north_star names bf16; fp16 is the default)
+    other = "bf16" if args.precision == "fp16" else "fp16"
+    other_ms = None
+    if not args.no_other_precision:
+        try:
+            gen.set_precision(other)
+            gen.invalidate()
+            xo = torch.rand(n_strong, 3, H, W, generator=torch.Generator().manual_seed(99 + rank)).to(device)
+            other_ms = D.max_ms(timed(lambda k: gen(xo), max(3, args.steps // 2), D, warm=3))[0]
+        finally:
+            gen.set_precision(args.precision)
+            gen.invalidate()
+            gen._workspace = None
 
     line = None
     if rank == 0:
@@ -551,6 +564,10 @@ def run_ours(args):
             "config": {"workload": f"RRDBNet x4 (23 RRDB, nf=64, gc=32) inference, {world * head['n']}x3x{H}x{W} LR in total "
                                    f"(BASELINE.json configs[2]), {head['n']} images per GPU, random init; batch-sharded, no collective",
                        "precision": prec[args.precision],
+                       "other_precision": None if other_ms is None else {
+                           "recipe": other, "what": prec[other], "value": px / (other_ms * 1e-3) / 1e6, "unit": "LR Mpix/s",
+                           "ms_per_step": other_ms,
+                           "roofline_frac": FLOP_PER_LR_PIXEL * px / (other_ms * 1e-3) / 1e12 / (peaks["tf_sustained"] * world)},
                        "l2": "working set (GBs of activations per forward) is far larger than the 126 MB L2; no flush needed"},
             "e2e": {"value": px / (head["ms_pipe"] * 1e-3) / 1e6, "unit": "LR Mpix/s", "ms_per_step": head["ms_pipe"],
                     "h2d_bytes_per_step": head["h2d"], "d2h_bytes_per_step": head["d2h"],
@@ -664,6 +681,7 @@ def main():
                     help="MMA operand / activation format of the generator (bf16 = north_star's recipe with fp32 residual masters)")
     ap.add_argument("--batch", type=int, default=0, help="LR images per GPU (default 64 / n_gpus: strong scaling of configs[2])")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--no-other-precision", action="store_true", help="skip the secondary forward leg in the other precision recipe")
     ap.add_argument("--no-weak", action="store_true", help="skip the secondary weak-scaling forward leg (N > 1)")
     ap.add_argument("--no-tiled", action="store_true", help="skip the secondary tiled-inference leg (configs[4])")
     ap.add_argument("--no-degrade", action="store_true", help="skip the secondary degradation leg")

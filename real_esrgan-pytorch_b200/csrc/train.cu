@@ -608,6 +608,8 @@ int backward_common(resr_generator* g, float* grads, int N, int H, int W, const 
                     tb.db[cs] = grads + c.p_off + static_cast<size_t>(c.cout) * c.cin * 9 + tb.co_base[cs];
                 }
                 tb.dbcat = B.dbcat;
+                // (giving the two chains disjoint SM subsets instead of letting them interleave was tried: 22.6 - 24.4 ms
+                // against 21.5 ms, profiles/r02_train_sm_partition_ab.txt)
                 const int rc = wgrad_launch_rdb(B.xt, B.dyt, N, H, W, B.partial, tb, g->num_sms, wst);
                 if (rc != 0) return set_error(RESR_E_CUDA, "dense-block wgrad failed (%d)", rc);
             }
