@@ -294,7 +294,7 @@ def degradation_bench(D, steps, warmup, peaks, B=16, want_e2e=True):
 # ------------------------------------------------------------------------------------------------- training step
 
 
-def training_bench(D, steps, warmup, peaks):
+def training_bench(D, steps, warmup, peaks, precision="bf16", with_optimizer=True):
     """configs[3]: RealESRNet training-step core per GPU — plan-driven degradation of 16 HR crops (256^2 -> LR 64^2),
     generator forward + L1 + backward, and (world > 1) the NCCL all-reduce of the flat gradient vector. Optimizer / EMA
     are outside the north-star path."""
@@ -309,6 +309,7 @@ def training_bench(D, steps, warmup, peaks):
     pipe = ip.DegradePipeline(hr, k1, k2, sk, plan)
     torch.manual_seed(0)
     gen = resr_b200.model.Generator(3, 3, 4).to(device).train()
+    gen.set_precision(precision)
     ts = resr_b200.autograd.TrainStep(gen, B, H // 4, W // 4, device, None, world)
     state = {}
 
@@ -321,6 +322,8 @@ def training_bench(D, steps, warmup, peaks):
     tflops = 3 * FLOP_PER_LR_PIXEL * B * (H // 4) * (W // 4) / (ms * 1e-3) / 1e12
     opt_info = None
     try:
+        if not with_optimizer:
+            raise RuntimeError("skipped")
         opt = resr_b200.optim.FlatAdamEMA(gen)
         flat = ts.flat
         for _ in range(2):
@@ -337,9 +340,12 @@ def training_bench(D, steps, warmup, peaks):
         opt_info = {"ms_per_step": o0.elapsed_time(o1) / 5,
                     "what": "resr_adam_ema_step (36 B per parameter) + repack of all tensor-core weight tiles (2 launches)"}
     except Exception as e:
-        opt_info = {"error": repr(e)}
+        opt_info = None if not with_optimizer else {"error": repr(e)}
     return {"metric": "training pairs/s", "value": world * B / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms, "n_gpus": world,
             "scaling": "weak", "loss": float(state["loss"].item()), "cuda_graph": bool(ts.is_graph), "optimizer": opt_info,
+            "precision": {"fp16": "fp16 activations, bf16 gradients, weight gradients through channels-first copies (wgrad_tc.cu)",
+                          "bf16": "bf16 activations and gradients (north_star's recipe), fp32 residual stream, weight gradients "
+                                  "straight from the NHWC buffers (wgrad_mn.cu)"}[precision],
             "config": {"workload": "per GPU: degradation (plan S0, mixed / sinc kernels, CUDA graph) of 16x3x256x256 HR + RRDBNet x4 "
                                    "forward/L1/backward on 16x3x64x64 LR (one CUDA graph), flat-gradient NCCL all-reduce when n_gpus > 1; "
                                    "no optimizer"},
@@ -656,7 +662,15 @@ def run_ours(args):
     train = None
     if not args.no_train:  # every rank takes part (all-reduce)
         try:
-            train = training_bench(D, max(5, min(args.steps, 20)), args.warmup, peaks)
+            train = training_bench(D, max(5, min(args.steps, 20)), args.warmup, peaks, args.train_precision)
+            if not args.no_other_precision:
+                other_t = "fp16" if args.train_precision == "bf16" else "bf16"
+                try:
+                    o = training_bench(D, max(5, min(args.steps, 10)), args.warmup, peaks, other_t, with_optimizer=False)
+                    train["other_precision"] = {"recipe": other_t, "what": o["precision"], "value": o["value"], "unit": o["unit"],
+                                                "ms_per_step": o["ms_per_step"], "loss": o["loss"]}
+                except Exception as e:
+                    train["other_precision"] = {"recipe": other_t, "error": repr(e)}
         except Exception as e:
             train = {"error": repr(e)}
     if rank == 0:
@@ -681,6 +695,8 @@ def main():
                     help="MMA operand / activation format of the generator (bf16 = north_star's recipe with fp32 residual masters)")
     ap.add_argument("--batch", type=int, default=0, help="LR images per GPU (default 64 / n_gpus: strong scaling of configs[2])")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--train-precision", choices=["fp16", "bf16"], default="bf16",
+                    help="recipe of the training leg (bf16: north_star's recipe, NHWC weight-gradient kernel)")
     ap.add_argument("--no-other-precision", action="store_true", help="skip the secondary forward leg in the other precision recipe")
     ap.add_argument("--no-weak", action="store_true", help="skip the secondary weak-scaling forward leg (N > 1)")
     ap.add_argument("--no-tiled", action="store_true", help="skip the secondary tiled-inference leg (configs[4])")

@@ -273,6 +273,15 @@ size_t resr_conv3x3_wgrad_workspace_bytes(int n, int h, int w, int cin, int cout
 int resr_conv3x3_wgrad(const void* x16, int x_cstride, int fmt_x, const void* dy16_bf16, int n, int h, int w, int cin,
                        int cout, float* dw, float* db, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same gradients straight from NHWC bf16 operands (no channels-first copies): both operands are MN-major tcgen05
+ * operands, pixel shifts are descriptor / TMA-coordinate shifts (csrc/wgrad_mn.cu). x_bf16: [n,h,w,x_cstride] (first cin
+ * channels, cin <= 256); dy_bf16: [n,h,w,dy_cstride] (first cout channels, cout <= 192; when cout is not a multiple of 8
+ * the channels up to the next multiple of 8 must be zero). No restriction on w. This is the kernel the bf16 training
+ * recipe uses for every layer (autograd of model.py:75-79, 87-98). */
+size_t resr_conv3x3_wgrad_nhwc_workspace_bytes(void);
+int resr_conv3x3_wgrad_nhwc(const void* x_bf16, int x_cstride, const void* dy_bf16, int dy_cstride, int n, int h, int w,
+                            int cin, int cout, float* dw, float* db, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- the whole degradation block in one call (train_realesrnet.py:267-377 == train_realesrgan.py:347-457) ---------------
  * A POD plan holds every host decision of one execution of the block; per-sample parameters and host-fed random draws
  * are DEVICE pointers owned by the caller. Stage order, kernels and arithmetic are those of the op-level entry points. */

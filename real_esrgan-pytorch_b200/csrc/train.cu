@@ -312,7 +312,10 @@ static TrainWs train_layout(size_t N, size_t H, size_t W, int num_sms) {
     L.midb = take(4 * P * 64 * 2);
     L.xt = take(16 * P * 64 * 2 > P * 192 * 2 ? 16 * P * 64 * 2 : P * 192 * 2);
     L.dyt = take(3 * 16 * P * 64 * 2);  // also holds the three 192-channel copies of a dense block's dYcat (3 * 192 * P)
-    L.partial = take(wgrad_partial_bytes(num_sms));
+    {
+        const size_t pa = wgrad_partial_bytes(num_sms), pb = wgrad_mn_workspace_bytes(num_sms);
+        L.partial = take(pa > pb ? pa : pb);
+    }
     L.loss = take(64);
     L.total = o;
     return L;
@@ -377,8 +380,11 @@ ConvIO fwd_io(const resr_generator* g, int k) {
     const ConvSpec& c = table().c[k];
     ConvIO io;
     io.wpack = g->wpack + c.w_off; io.bias = g->bias + c.b_off;
-    io.nout = c.nout; io.nslices = c.nslices; io.nchunks = c.nchunks; io.fmt = c.fmt; io.kvalid = c.cin;
-    io.out16_fmt = 0;  // forward activations are fp16 (the operand format of every consumer)
+    io.nout = c.nout; io.nslices = c.nslices; io.nchunks = c.nchunks; io.kvalid = c.cin;
+    // forward activations are stored in the operand format of every consumer: fp16 (default recipe) or bf16 (precision 1;
+    // the residual stream is fp32 in both, B.f[])
+    io.fmt = g->precision == 1 ? 1 : c.fmt;
+    io.out16_fmt = g->precision == 1 ? 1 : 0;
     return io;
 }
 
@@ -387,7 +393,7 @@ int forward_train(resr_generator* g, const float* x, float* y, int N, int H, int
     const size_t P = static_cast<size_t>(N) * H * W;
     // (no clearing of the concat buffers: a layer's activation tensor map ends at its last input channel, the rest of
     // the tail chunk is zero-filled by TMA, so never-written growth channels are never read)
-    RESR_TRY(resr_nchw_to_nhwc16(x, B.xin, N, 3, H, W, 64, 0, s));
+    RESR_TRY(resr_nchw_to_nhwc16(x, B.xin, N, 3, H, W, 64, g->precision == 1 ? 1 : 0, s));
     int k = 0;
     {
         ConvIO io = fwd_io(g, k++);
@@ -418,22 +424,22 @@ int forward_train(resr_generator* g, const float* x, float* y, int N, int H, int
     {   // conv2 + skip, stored nearest-upsampled x2 (fp16)
         ConvIO io = fwd_io(g, k++);
         io.in16 = B.c[69]; io.in_c = 192; io.ep_mode = EP_SKIP; io.res1 = B.f[0];
-        io.out16 = B.t1; io.out16_c = 64; io.out16_fmt = 0; io.out16_up2 = 1;
+        io.out16 = B.t1; io.out16_c = 64; io.out16_up2 = 1;
         RESR_TRY(launch_conv_io(g, g0, N, io, s));
     }
     {
         ConvIO io = fwd_io(g, k++);
-        io.in16 = B.t1; io.lrelu = 1; io.out16 = B.t2; io.out16_fmt = 0; io.out16_up2 = 1;
+        io.in16 = B.t1; io.lrelu = 1; io.out16 = B.t2; io.out16_up2 = 1;
         RESR_TRY(launch_conv_io(g, g1, N, io, s));
     }
     {
         ConvIO io = fwd_io(g, k++);
-        io.in16 = B.t2; io.lrelu = 1; io.out16 = B.t3; io.out16_fmt = 0;
+        io.in16 = B.t2; io.lrelu = 1; io.out16 = B.t3;
         RESR_TRY(launch_conv_io(g, g2, N, io, s));
     }
     {
         ConvIO io = fwd_io(g, k++);
-        io.in16 = B.t3; io.lrelu = 1; io.out16 = B.t4; io.out16_fmt = 0;
+        io.in16 = B.t3; io.lrelu = 1; io.out16 = B.t4;
         RESR_TRY(launch_conv_io(g, g2, N, io, s));
     }
     {
@@ -475,6 +481,25 @@ int layer_wgrad(resr_generator* g, int k, const uint16_t* x16, int x_cstride, in
     const size_t P = static_cast<size_t>(N) * q.H * q.W;
     cudaStream_t w = wgrad_stream(g, s);
     fork_to(g, s, w);  // dY of this layer (and everything before it) is complete on the main stream
+    if (g->precision == 1) {
+        // bf16 recipe: X and dY share one operand format, the MN-major kernel reads both NHWC buffers in place
+        WgradMnTable tb;
+        float* dw = grads + c.p_off;
+        for (int cs = 0; cs < 6; ++cs) {
+            tb.dw[cs] = dw; tb.db[cs] = dw + static_cast<size_t>(c.cout) * c.cin * 9;
+            tb.cin[cs] = c.cin; tb.cout[cs] = c.cout; tb.co_base[cs] = cs * 32;
+        }
+        const int dyc = (c.cout + 7) / 8 * 8 > 64 ? 64 : (c.cout + 7) / 8 * 8;
+        int units[2][3] = {{0, 0, 64}, {128, 0, 64}};
+        const int rc = wgrad_mn_launch(x16, x_cstride, c.cin, dy16, 64, dyc, N, q.H, q.W, units, c.cin > 128 ? 2 : 1, tb, true, B.partial,
+                                       g->num_sms, w);
+        if (rc != 0) return set_error(RESR_E_CUDA, "wgrad (nhwc) of layer %d failed (%d)", k, rc);
+        if (w != s) {  // the main stream overwrites this dY buffer two layers later: wait for its reader here
+            cudaEventRecord(g->ev_dy, w);
+            cudaStreamWaitEvent(s, g->ev_dy, 0);
+        }
+        return RESR_OK;
+    }
     if (!x_already_transposed) {
         xt_rows = (c.cin + 31) / 32 * 32;
         nhwc16_to_cf_kernel<false><<<dim3(static_cast<unsigned>((P + 255) / 256), xt_rows / 32), 256, 0, w>>>(x16, x_cstride, 0, c.cin, xt_rows, P, q.W,
@@ -514,33 +539,33 @@ int backward_common(resr_generator* g, float* grads, int N, int H, int W, const 
     const int kConv2 = 346, kUp1 = 347, kUp2 = 348, kConv3 = 349, kConv4 = 350;
 
     // ---- tail (model.py:264-270 backwards)
-    RESR_TRY(layer_wgrad(g, kConv4, B.t4, 64, 0, false, 0, B.biga, N, g2, B, grads, s));
+    RESR_TRY(layer_wgrad(g, kConv4, B.t4, 64, g->precision, false, 0, B.biga, N, g2, B, grads, s));
     {   // d(T4) masked by LeakyReLU'(conv3 out) -> conv3's dY
         ConvIO io = bwd_io(g, kConv4);
         io.in16 = B.biga; io.out16 = B.bigb; io.mask16 = B.t4;
         RESR_TRY(launch_conv_io(g, g2, N, io, s));
     }
-    RESR_TRY(layer_wgrad(g, kConv3, B.t3, 64, 0, false, 0, B.bigb, N, g2, B, grads, s));
+    RESR_TRY(layer_wgrad(g, kConv3, B.t3, 64, g->precision, false, 0, B.bigb, N, g2, B, grads, s));
     {
         ConvIO io = bwd_io(g, kConv3);
         io.in16 = B.bigb; io.out16 = B.biga; io.mask16 = B.t3;
         RESR_TRY(launch_conv_io(g, g2, N, io, s));
     }
-    RESR_TRY(layer_wgrad(g, kUp2, B.t2, 64, 0, false, 0, B.biga, N, g2, B, grads, s));
+    RESR_TRY(layer_wgrad(g, kUp2, B.t2, 64, g->precision, false, 0, B.biga, N, g2, B, grads, s));
     {   // d(T2) at 4x, masked by LeakyReLU'(up1 out) (T2 holds its upsampled copy), then the 2x2 sum of nearest x2
         ConvIO io = bwd_io(g, kUp2);
         io.in16 = B.biga; io.out16 = B.bigb; io.mask16 = B.t2;
         RESR_TRY(launch_conv_io(g, g2, N, io, s));
         sum2x2_kernel<<<egrid(4 * P * 32), 256, 0, s>>>(B.bigb, nullptr, B.mida, N, 2 * H, 2 * W);
     }
-    RESR_TRY(layer_wgrad(g, kUp1, B.t1, 64, 0, false, 0, B.mida, N, g1, B, grads, s));
+    RESR_TRY(layer_wgrad(g, kUp1, B.t1, 64, g->precision, false, 0, B.mida, N, g1, B, grads, s));
     {   // d(T1) at 2x (no activation on the skip sum), 2x2 sum -> d(out) at LR: fp32 (skip branch) + bf16 (conv2's dY)
         ConvIO io = bwd_io(g, kUp1);
         io.in16 = B.mida; io.out16 = B.midb;
         RESR_TRY(launch_conv_io(g, g1, N, io, s));
         sum2x2_kernel<<<egrid(P * 32), 256, 0, s>>>(B.midb, B.dskip, B.dya, N, H, W);
     }
-    RESR_TRY(layer_wgrad(g, kConv2, B.c[69], 192, 0, false, 0, B.dya, N, g0, B, grads, s));
+    RESR_TRY(layer_wgrad(g, kConv2, B.c[69], 192, g->precision, false, 0, B.dya, N, g0, B, grads, s));
     {   // d(trunk output), fp32
         ConvIO io = bwd_io(g, kConv2);
         io.in16 = B.dya; io.outf = B.dx[0];
@@ -590,6 +615,28 @@ int backward_common(resr_generator* g, float* grads, int N, int H, int W, const 
             }
             {   // weight + bias gradients of the five layers (side stream): dYcat is complete once conv2's launch is done
                 fork_to(g, s, wst);
+                if (g->precision == 1) {
+                    // bf16 recipe: ONE MN-major GEMM straight from the concat buffer and dYcat' (no transposed copies).
+                    // Units (128 ci x n co'): [0,128) x [0,128), [0,128) x [128,192), [128,192(+64 zero rows)) x [0,128);
+                    // the reduction keeps ci < cin of the layer owning each 32-channel slice of dYcat'.
+                    WgradMnTable tb;
+                    for (int cs = 0; cs < 6; ++cs) {
+                        const int kl = 1 + 5 * r + (cs < 2 ? 4 : 5 - cs);
+                        const ConvSpec& c = table().c[kl];
+                        tb.dw[cs] = grads + c.p_off;
+                        tb.db[cs] = grads + c.p_off + static_cast<size_t>(c.cout) * c.cin * 9;
+                        tb.cin[cs] = c.cin; tb.cout[cs] = c.cout;
+                        tb.co_base[cs] = cs < 2 ? cs * 32 : 0;
+                    }
+                    const int units[3][3] = {{0, 0, 128}, {0, 128, 64}, {128, 0, 128}};
+                    const int rc = wgrad_mn_launch(B.c[r], 192, 192, dyc, 192, 192, N, H, W, units, 3, tb, true, B.partial, g->num_sms, wst);
+                    if (rc != 0) return set_error(RESR_E_CUDA, "dense-block wgrad (nhwc) failed (%d)", rc);
+                    if (wst != s) {
+                        cudaEventRecord(g->ev_dyc[r & 1], wst);
+                        g->ev_dyc_valid[r & 1] = true;
+                    }
+                    continue;
+                }
                 const dim3 tg(static_cast<unsigned>((P + 255) / 256), 6);
                 nhwc16_to_cf_kernel<false><<<tg, 256, 0, wst>>>(B.c[r], 192, 0, 192, 192, P, W, 0, B.xt, nullptr);
                 cudaMemsetAsync(B.dbcat, 0, 192 * sizeof(float), wst);
@@ -619,7 +666,7 @@ int backward_common(resr_generator* g, float* grads, int N, int H, int W, const 
     }
     // ---- conv1 (model.py:258): dY = d(trunk input) + d(skip)
     scale_f32_to_bf16_kernel<<<egrid(P * 64), 256, 0, s>>>(B.dx[0], 1.f, B.dskip, 1.f, B.dya, P * 64);
-    RESR_TRY(layer_wgrad(g, 0, B.xin, 64, 0, false, 0, B.dya, N, g0, B, grads, s));
+    RESR_TRY(layer_wgrad(g, 0, B.xin, 64, g->precision, false, 0, B.dya, N, g0, B, grads, s));
     if (g->side_stream && wgrad_stream(g, s) != s) {  // join: the gradient vector is complete when the main stream continues
         cudaEventRecord(g->ev_join, g->side_stream);
         cudaStreamWaitEvent(s, g->ev_join, 0);
@@ -632,8 +679,8 @@ int backward_common(resr_generator* g, float* grads, int N, int H, int W, const 
 int check_train_args(resr_generator_t* g, int n, int h, int w, void* ws, size_t ws_bytes) {
     if (!g || !ws) return set_error(RESR_E_INVALID, "null argument");
     if (n <= 0 || h <= 0 || w <= 0) return set_error(RESR_E_INVALID, "bad shape");
-    if (w % 8 != 0) return set_error(RESR_E_INVALID, "training path needs W %% 8 == 0 (channels-first TMA strides), got %d", w);
-    if (g->precision != 0) return set_error(RESR_E_INVALID, "the training path uses the fp16 forward recipe: resr_generator_set_precision(g, 0) first");
+    if (g->precision != 1 && w % 8 != 0)
+        return set_error(RESR_E_INVALID, "the fp16 training recipe needs W %% 8 == 0 (channels-first TMA strides), got %d; the bf16 recipe has no such limit", w);
     if (!g->loaded || !g->flat_params) return set_error(RESR_E_INVALID, "resr_generator_load_params has not been called");
     if (ws_bytes < resr_generator_train_workspace_bytes(n, h, w)) return set_error(RESR_E_NOMEM, "training workspace too small");
     if ((reinterpret_cast<uintptr_t>(ws) & 1023) != 0) return set_error(RESR_E_INVALID, "workspace must be 1024-byte aligned");
@@ -745,6 +792,37 @@ int resr_conv3x3_wgrad(const void* x16, int x_cstride, int fmt_x, const void* dy
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int rc = wgrad_launch(xt, xr, dyt, yr, n, h, w, cin, cout, partial, dw, nullptr, sms, s);
     if (rc != 0) return set_error(RESR_E_CUDA, "wgrad failed (%d)", rc);
+    return RESR_OK;
+}
+
+size_t resr_conv3x3_wgrad_nhwc_workspace_bytes(void) { return wgrad_mn_workspace_bytes(160) + 1024; }
+
+int resr_conv3x3_wgrad_nhwc(const void* x_bf16, int x_cstride, const void* dy_bf16, int dy_cstride, int n, int h, int w, int cin, int cout,
+                            float* dw, float* db, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!x_bf16 || !dy_bf16 || !dw || !workspace) return set_error(RESR_E_INVALID, "null argument");
+    if (n <= 0 || h <= 0 || w <= 0 || cin <= 0 || cout <= 0 || cin > 256 || cout > 192 || cin > x_cstride || cout > dy_cstride ||
+        (x_cstride & 7) || (dy_cstride & 7))
+        return set_error(RESR_E_INVALID, "unsupported wgrad shape (cin <= 256, cout <= 192, channel strides multiples of 8)");
+    if (workspace_bytes < resr_conv3x3_wgrad_nhwc_workspace_bytes()) return set_error(RESR_E_NOMEM, "wgrad workspace too small");
+    if ((reinterpret_cast<uintptr_t>(workspace) & 15) != 0) return set_error(RESR_E_INVALID, "workspace must be 16-byte aligned");
+    int units[4][3], nu = 0;
+    for (int ci0 = 0; ci0 < cin; ci0 += 128)
+        for (int co0 = 0; co0 < cout;) {
+            const int nn = cout - co0 > 64 ? 128 : 64;
+            units[nu][0] = ci0; units[nu][1] = co0; units[nu][2] = nn; ++nu;
+            co0 += nn;
+        }
+    WgradMnTable tb;
+    for (int cs = 0; cs < 6; ++cs) { tb.dw[cs] = dw; tb.db[cs] = db; tb.cin[cs] = cin; tb.cout[cs] = cout; tb.co_base[cs] = cs * 32; }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms > 160) sms = 160;
+    int dyc = (cout + 7) / 8 * 8;
+    if (dyc > dy_cstride) dyc = dy_cstride;
+    const int rc = wgrad_mn_launch(static_cast<const uint16_t*>(x_bf16), x_cstride, cin, static_cast<const uint16_t*>(dy_bf16), dy_cstride, dyc,
+                                   n, h, w, units, nu, tb, db != nullptr, static_cast<float*>(workspace), sms, static_cast<cudaStream_t>(stream));
+    if (rc != 0) return set_error(RESR_E_CUDA, "wgrad (nhwc) failed (%d)", rc);
     return RESR_OK;
 }
 

@@ -40,4 +40,29 @@ int wgrad_launch_rdb(const uint16_t* xt, const uint16_t* dyt, int N, int H, int 
 int wgrad_launch(const uint16_t* xt, int x_channels, const uint16_t* dyt, int dy_channels, int N, int H, int W, int cin, int cout,
                  float* partial, float* dw, float* db, int num_sms, cudaStream_t s);
 
+// ---- MN-major variant (wgrad_mn.cu): operands straight from the NHWC buffers, one 16-bit format (bf16) for X and dY
+static constexpr int kMnMaxKinds = 12;
+struct WgradMnKind { int ci0, co0, n, dy, cta0, nsplit; };   // unit (128 input channels from ci0) x (n = 64 / 128 dY channels from co0), one dy
+struct WgradMnArgs {
+    int N, H, W;
+    int segs_per_row;         // ceil(W / 64)
+    long long kslabs;         // N * H * segs_per_row (one stage = 64 pixels of one row)
+    float* partial;           // [cta][3 dx][128 ci][128 co] fp32
+    int nkinds;
+    WgradMnKind kind[kMnMaxKinds];
+};
+// dY channel slice cs (32 channels) belongs to the layer with gradient dw[cs] (OIHW, cin[cs] x cout[cs]); the slice's first
+// channel is output channel co_base[cs] of that layer; db[cs] is the layer's bias gradient (indexed by output channel).
+struct WgradMnTable {
+    float* dw[6];
+    float* db[6];
+    int cin[6], cout[6], co_base[6];
+};
+size_t wgrad_mn_workspace_bytes(int num_sms);
+// x: NHWC bf16 [N][H][W][x_cstride] (channels >= x_channels are never read); dy: NHWC bf16 [N][H][W][dy_cstride], channels
+// [0, dy_channels). units: (ci0, co0, n) triples with n = 64 or 128. workspace: wgrad_mn_workspace_bytes(num_sms).
+int wgrad_mn_launch(const uint16_t* x, int x_cstride, int x_channels, const uint16_t* dy, int dy_cstride, int dy_channels,
+                    int N, int H, int W, const int (*units)[3], int nunits, const WgradMnTable& tb, bool with_bias,
+                    float* workspace, int num_sms, cudaStream_t s);
+
 }  // namespace resr

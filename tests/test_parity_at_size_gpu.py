@@ -266,31 +266,36 @@ def test_cfg3_batch_sampled_against_oracle():
 
 
 def test_cfg4_train_step_at_size():
+    """Both training recipes (fp16 activations + channels-first weight-gradient copies; bf16 activations + the NHWC MN-major
+    weight-gradient kernel) against ONE run of the oracle's fp32 autograd on the full batch."""
     import resr_b200
     from oracle import generator as og
     sd = og.random_state_dict(1)
-    g = resr_b200.model.Generator(3, 3, 4)
-    g.load_state_dict(sd)
-    g = g.cuda().train()
     gen = torch.Generator().manual_seed(4)
     n = 16
     lr = torch.rand(n, 3, 64, 64, generator=gen)
     hr = torch.rand(n, 3, 256, 256, generator=gen)
-    ts = resr_b200.autograd.TrainStep(g, n, 64, 64)
-    loss, sr, flat = ts.step(lr.cuda(), hr.cuda(), scatter=False)
-    torch.cuda.synchronize()
-    assert ts.is_graph
-    got = flat.cpu()
     # the oracle's fp32 autograd on a quarter of the batch at a time would change the mean: run the full batch
     ref_loss, ref_grads, ref_sr = og.l1_loss_and_grads(lr, hr, sd)
     ref_flat = torch.cat([ref_grads[k].reshape(-1) for k in sd])
-    rel = abs(loss.item() - ref_loss.item()) / ref_loss.item()
-    cos = float(torch.dot(got.double(), ref_flat.double()) / (got.double().norm() * ref_flat.double().norm()))
-    rl2 = float((got - ref_flat).double().norm() / ref_flat.double().norm())
-    sr_err = (sr.cpu() - ref_sr).abs().max().item()
-    print(f"cfg4 16x3x64x64: loss rel err {rel:.2e}; grad cosine {cos:.6f}; rel-L2 {rl2:.3%}; sr max-abs {sr_err:.2e}")
-    assert torch.isfinite(got).all()
-    assert rel <= 1e-3 and cos >= 0.9995 and rl2 <= 0.03 and sr_err <= 2e-2
+    for precision in ("fp16", "bf16"):
+        g = resr_b200.model.Generator(3, 3, 4)
+        g.load_state_dict(sd)
+        g = g.cuda().train()
+        g.set_precision(precision)
+        ts = resr_b200.autograd.TrainStep(g, n, 64, 64)
+        loss, sr, flat = ts.step(lr.cuda(), hr.cuda(), scatter=False)
+        torch.cuda.synchronize()
+        assert ts.is_graph
+        got = flat.cpu()
+        rel = abs(loss.item() - ref_loss.item()) / ref_loss.item()
+        cos = float(torch.dot(got.double(), ref_flat.double()) / (got.double().norm() * ref_flat.double().norm()))
+        rl2 = float((got - ref_flat).double().norm() / ref_flat.double().norm())
+        sr_err = (sr.cpu() - ref_sr).abs().max().item()
+        print(f"cfg4 16x3x64x64 [{precision}]: loss rel err {rel:.2e}; grad cosine {cos:.6f}; rel-L2 {rl2:.3%}; sr max-abs {sr_err:.2e}")
+        assert torch.isfinite(got).all()
+        assert rel <= 1e-3 and cos >= 0.9995 and rl2 <= 0.03 and sr_err <= 2e-2
+        del ts, g
 
 
 # ---------------------------------------------------------------------------------------------------------- cfg5

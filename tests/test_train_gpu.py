@@ -40,13 +40,50 @@ def test_wgrad_kernel(n, h, w, cin, c_total, cout):
     assert (db - ref_b).abs().max().item() <= 1e-3 * ref_b.abs().max().item() + 1e-3
 
 
+@pytest.mark.parametrize("n,h,w,cin,xs,cout,ys", [(2, 12, 64, 64, 64, 32, 64), (1, 9, 128, 160, 192, 32, 64), (2, 16, 64, 192, 192, 64, 64),
+                                                 (1, 8, 72, 64, 64, 3, 64), (3, 5, 16, 96, 192, 32, 192), (1, 7, 9, 3, 64, 64, 64),
+                                                 (2, 6, 150, 192, 192, 192, 192), (1, 3, 1, 130, 136, 70, 72), (4, 32, 32, 128, 192, 128, 128)])
+def test_wgrad_nhwc_kernel(n, h, w, cin, xs, cout, ys):
+    """MN-major weight-gradient kernel (csrc/wgrad_mn.cu: both operands straight from NHWC bf16 buffers, pixel shifts as
+    descriptor / TMA-coordinate shifts) vs torch's conv2d_weight in float64 on the same bf16-rounded operands. Ragged and odd
+    widths, one-pixel rows, 3 input channels, 3 ci blocks x 2 co chunks (every unit shape), garbage in the unused channels."""
+    import resr_b200
+    L = resr_b200._lib
+    torch.manual_seed(n + h + w + cin + cout)
+    dev = "cuda"
+    x = torch.randn(n, cin, h, w, device=dev).bfloat16().float()
+    dy = torch.randn(n, cout, h, w, device=dev).bfloat16().float()
+    x16 = torch.randn(n, h, w, xs, device=dev).bfloat16()
+    x16[..., :cin] = x.permute(0, 2, 3, 1).bfloat16()
+    dy16 = torch.randn(n, h, w, ys, device=dev).bfloat16()
+    dy16[..., :cout] = dy.permute(0, 2, 3, 1).bfloat16()
+    dy16[..., cout:(cout + 7) // 8 * 8] = 0
+    dw = torch.full((cout, cin, 3, 3), float("nan"), device=dev)
+    db = torch.full((cout,), float("nan"), device=dev)
+    need = L.lib().resr_conv3x3_wgrad_nhwc_workspace_bytes()
+    ws = torch.empty(need + 1024, dtype=torch.uint8, device=dev)
+    wp = ws.data_ptr() + (-ws.data_ptr()) % 1024
+    for _ in range(2):  # twice: the second call runs on a dirty partial buffer
+        L.check(L.lib().resr_conv3x3_wgrad_nhwc(L.ptr(x16), xs, L.ptr(dy16), ys, n, h, w, cin, cout, L.ptr(dw), L.ptr(db),
+                                                ctypes.c_void_p(wp), need, L.stream_ptr()))
+    torch.cuda.synchronize()
+    ref_w = torch.nn.grad.conv2d_weight(x.double(), (cout, cin, 3, 3), dy.double(), padding=1).float()
+    ref_b = dy.double().sum((0, 2, 3)).float()
+    scale = ref_w.abs().max().item()
+    assert torch.isfinite(dw).all() and torch.isfinite(db).all()
+    err = (dw - ref_w).abs().max().item()
+    print(f"wgrad nhwc max err {err:.3e} (scale {scale:.3e})")
+    assert err <= 1e-4 * scale + 1e-4
+    assert (db - ref_b).abs().max().item() <= 1e-3 * ref_b.abs().max().item() + 1e-3
+
+
 def _cos(a, b):
     return float(torch.dot(a.double(), b.double()) / (a.double().norm() * b.double().norm() + 1e-300))
 
 
 @pytest.mark.parametrize("seed,shape", [(0, (1, 3, 16, 24)), (1, (2, 3, 16, 64)), (2, (3, 3, 5, 8)), (3, (1, 3, 9, 136))])
-@pytest.mark.parametrize("policy", [1, 2])
-def test_generator_loss_and_gradients_vs_oracle_autograd(seed, shape, policy):
+@pytest.mark.parametrize("policy,precision", [(1, "fp16"), (2, "fp16"), (1, "bf16"), (2, "bf16")])
+def test_generator_loss_and_gradients_vs_oracle_autograd(seed, shape, policy, precision):
     import resr_b200
     from oracle import generator as og
     prev = resr_b200._lib.lib().resr_set_conv_pair_policy(policy)  # 2: forward / data-gradient convs on CTA pairs
@@ -54,6 +91,7 @@ def test_generator_loss_and_gradients_vs_oracle_autograd(seed, shape, policy):
     g = resr_b200.model.Generator(3, 3, 4)
     g.load_state_dict(sd)
     g = g.cuda()
+    g.set_precision(precision)  # bf16: activations and gradients in one format, MN-major weight-gradient kernel (wgrad_mn.cu)
     torch.manual_seed(50 + seed)
     x = torch.rand(*shape)
     hr = torch.rand(shape[0], 3, 4 * shape[2], 4 * shape[3])
@@ -75,11 +113,34 @@ def test_generator_loss_and_gradients_vs_oracle_autograd(seed, shape, policy):
         if nel >= 1024:
             worst = min(worst, _cos(got[pos:pos + nel], ref_flat[pos:pos + nel]))
         pos += nel
-    print(f"loss rel err {rel:.2e}; grad cosine {cos:.5f}; rel-L2 {rl2:.3%}; worst per-tensor cosine {worst:.4f}")
+    print(f"[{precision}] loss rel err {rel:.2e}; grad cosine {cos:.5f}; rel-L2 {rl2:.3%}; worst per-tensor cosine {worst:.4f}")
     assert rel <= 1e-3 and cos >= 0.999 and rl2 <= 0.03 and worst >= 0.98
     # param.grad populated in state_dict order
     p0 = next(g.parameters())
     assert torch.allclose(p0.grad.cpu(), ref_grads["conv1.weight"], atol=5e-2 * ref_grads["conv1.weight"].abs().max().item() + 1e-7)
+
+
+def test_bf16_recipe_trains_on_widths_that_are_not_multiples_of_8():
+    """The NHWC weight-gradient path has no W % 8 restriction (the fp16 recipe's channels-first copies do)."""
+    import resr_b200
+    from oracle import generator as og
+    sd = og.random_state_dict(4)
+    g = resr_b200.model.Generator(3, 3, 4)
+    g.load_state_dict(sd)
+    g = g.cuda()
+    torch.manual_seed(54)
+    x = torch.rand(2, 3, 7, 13)
+    hr = torch.rand(2, 3, 28, 52)
+    with pytest.raises(resr_b200._lib.ResrError):
+        resr_b200.autograd.l1_loss_backward(g, x.cuda(), hr.cuda())
+    g.set_precision("bf16")
+    ref_loss, ref_grads, _ = og.l1_loss_and_grads(x, hr, sd)
+    loss, _, flat = resr_b200.autograd.l1_loss_backward(g, x.cuda(), hr.cuda())
+    ref_flat = torch.cat([ref_grads[k].reshape(-1) for k in sd])
+    cos = _cos(flat.cpu(), ref_flat)
+    rl2 = float((flat.cpu() - ref_flat).double().norm() / ref_flat.double().norm())
+    print(f"13-wide bf16 step: grad cosine {cos:.5f}; rel-L2 {rl2:.3%}")
+    assert abs(loss.item() - ref_loss.item()) / ref_loss.item() <= 1e-3 and cos >= 0.999 and rl2 <= 0.03
 
 
 def test_autograd_function_matches_fused_path():
@@ -102,13 +163,15 @@ def test_autograd_function_matches_fused_path():
     assert _cos(got, flat) >= 0.99999
 
 
-def test_train_step_graph_replay_matches_eager():
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+def test_train_step_graph_replay_matches_eager(precision):
     """The CUDA-graph training step (persistent buffers) reproduces the eager fused call, also after a weight update."""
     import resr_b200
     from oracle import generator as og
     g = resr_b200.model.Generator(3, 3, 4)
     g.load_state_dict(og.random_state_dict(2))
     g = g.cuda().train()
+    g.set_precision(precision)
     torch.manual_seed(11)
     lr = torch.rand(2, 3, 16, 32, device="cuda")
     hr = torch.rand(2, 3, 64, 128, device="cuda")

@@ -7,6 +7,7 @@ import resr_b200
 n, h, w = 16, 64, 64
 torch.manual_seed(0)
 g = resr_b200.model.Generator(3, 3, 4).cuda().train()
+g.set_precision(os.environ.get("RESR_PREC", "bf16"))
 lr = torch.rand(n, 3, h, w, device="cuda"); hr = torch.rand(n, 3, 4 * h, 4 * w, device="cuda")
 ts = resr_b200.autograd.TrainStep(g, n, h, w)
 for _ in range(3):
@@ -24,7 +25,7 @@ print("streams", streams)
 # overlap between conv kernels and wgrad kernels
 import bisect
 conv = [(e["ts"], e["ts"] + e["dur"]) for e in ev if "conv3x3" in e["name"]]
-wg = [(e["ts"], e["ts"] + e["dur"]) for e in ev if "wgrad_tc" in e["name"]]
+wg = [(e["ts"], e["ts"] + e["dur"]) for e in ev if ("wgrad_tc" in e["name"] or "wgrad_mn_kernel" in e["name"])]
 ov = 0.0
 for a0, a1 in wg:
     for b0, b1 in conv:
