@@ -46,8 +46,9 @@ struct WgradMnKind { int ci0, co0, n, dy, cta0, nsplit; };   // unit (128 input 
 struct WgradMnArgs {
     int N, H, W;
     int segs_per_row;         // ceil(W / 64)
-    long long kslabs;         // N * H * segs_per_row (one stage = 64 pixels of one row)
+    uint32_t kslabs;          // N * H * segs_per_row (one slab = 64 pixels of one row)
     float* partial;           // [cta][3 dx][128 ci][128 co] fp32
+    float* bias_partial;      // [cta][256 / n row groups][n] column sums of dY from the (ci0 = 0, dy = 1) CTAs, or null
     int nkinds;
     WgradMnKind kind[kMnMaxKinds];
 };

@@ -30,14 +30,21 @@ namespace resr {
 
 static constexpr int kMnXChunk = 72 * 128;                       // 66 rows loaded, rounded up to whole 8-row groups
 static constexpr int kMnYChunk = 64 * 128;
-static constexpr int kMnStageBytes = 2 * kMnXChunk + 2 * kMnYChunk;  // 34,816
-static constexpr int kMnStages = 6;
-static constexpr int kMnTileFloats = 3 * 128 * 128;              // one CTA's partial tile [dx][ci][co]
+static constexpr int kMnSlabBytes = 2 * kMnXChunk + 2 * kMnYChunk;  // 34,816: one 64-pixel slab (X tile + dY tile)
+static constexpr int kMnSub = 2;                                 // slabs per pipeline stage (one barrier round trip per 24 MMAs)
+static constexpr int kMnStageBytes = kMnSub * kMnSlabBytes;      // 69,632
+static constexpr int kMnStages = 3;
+static constexpr int kMnTileFloats = 3 * 128 * 128;              // one CTA's partial tile [dx][ci][co (16-byte groups XOR-swizzled by ci & 7)]
 
 // MN-major, 128B-swizzled operand: start address | LBO (bits 16..29) in the low word; SBO = 1024 B, version 1, SWIZZLE_128B.
 static constexpr uint32_t kMnDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
 __device__ __forceinline__ uint64_t mn_desc(uint32_t addr16, uint32_t lbo16) {
     return (static_cast<uint64_t>(kMnDescHi) << 32) | (lbo16 << 16) | (addr16 & 0x3FFFu);
+}
+__device__ __forceinline__ void bulk_store_1d(void* gdst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(reinterpret_cast<uint64_t>(gdst)),
+                 "r"(smem_u32(smem_src)), "r"(bytes)
+                 : "memory");
 }
 
 __global__ void __launch_bounds__(256, 1)
@@ -55,15 +62,20 @@ wgrad_mn_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constant
     int kind = 0;
     while (kind + 1 < a.nkinds && static_cast<int>(blockIdx.x) >= a.kind[kind + 1].cta0) ++kind;
     const WgradMnKind kd = a.kind[kind];
-    const int split = blockIdx.x - kd.cta0;
-    const long long k0 = a.kslabs * split / kd.nsplit;
-    const long long k1 = a.kslabs * (split + 1) / kd.nsplit;
+    const uint32_t split = blockIdx.x - kd.cta0;
+    // 32-bit index arithmetic throughout (the launcher checks kslabs * nsplit < 2^32): 64-bit divisions are subroutine
+    // calls of ~1 us each on one warp
+    const uint32_t k0 = a.kslabs * split / static_cast<uint32_t>(kd.nsplit);
+    const uint32_t k1 = a.kslabs * (split + 1) / static_cast<uint32_t>(kd.nsplit);
     const int nyc = kd.n >> 6;  // 64-channel chunks of dY
+    // bias gradient = column sums of dY: the CTAs of the (ci block 0, dy = 1) kinds see every dY tile exactly once, their
+    // four epilogue warps (idle during the main loop) sum the tiles out of shared memory
+    const bool bias_cta = a.bias_partial != nullptr && kd.dy == 1 && kd.ci0 == 0;
 
     if (threadIdx.x == 0) {
         prefetch_tmap(&tmapX);
         prefetch_tmap(&tmapDY);
-        for (int i = 0; i < kMnStages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+        for (int i = 0; i < kMnStages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, bias_cta ? 5 : 1); }
         mbar_init(done, 1);
         fence_mbar_init();
     }
@@ -72,44 +84,54 @@ wgrad_mn_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tbase = *tmem_ptr;
-    const int segs = a.segs_per_row;
+    const uint32_t segs = a.segs_per_row;
 
     if (warp == 0) {
         int stage = 0; uint32_t phase = 0;
-        for (long long k = k0; k < k1; ++k) {
-            const int xs = static_cast<int>(k % segs);
-            const int y = static_cast<int>((k / segs) % a.H);
-            const int n = static_cast<int>(k / (static_cast<long long>(segs) * a.H));
+        // (xs, y, n) of the first slab, then incremented
+        uint32_t xs = k0 % segs, y = (k0 / segs) % static_cast<uint32_t>(a.H), n = k0 / (segs * static_cast<uint32_t>(a.H));
+        for (uint32_t k = k0; k < k1; k += kMnSub) {
+            const int cnt = k1 - k < kMnSub ? static_cast<int>(k1 - k) : kMnSub;
             mbar_wait(empty + stage, phase ^ 1);
             if (elect_one()) {
                 uint8_t* st = smem + stage * kMnStageBytes;
-                mbar_expect_tx(full + stage, 2 * 66 * 128 + nyc * kMnYChunk);
-                tma_load_4d(st, &tmapX, full + stage, kd.ci0, xs * 64 - 1, y + kd.dy - 1, n);
-                tma_load_4d(st + kMnXChunk, &tmapX, full + stage, kd.ci0 + 64, xs * 64 - 1, y + kd.dy - 1, n);
-                for (int j = 0; j < nyc; ++j)
-                    tma_load_4d(st + 2 * kMnXChunk + j * kMnYChunk, &tmapDY, full + stage, kd.co0 + 64 * j, xs * 64, y, n);
+                mbar_expect_tx(full + stage, cnt * (2 * 66 * 128 + nyc * kMnYChunk));
+                uint32_t xs2 = xs, y2 = y, n2 = n;
+                for (int sub = 0; sub < cnt; ++sub, st += kMnSlabBytes) {
+                    const int px = static_cast<int>(xs2) * 64, yy = static_cast<int>(y2), nn = static_cast<int>(n2);
+                    tma_load_4d(st, &tmapX, full + stage, kd.ci0, px - 1, yy + kd.dy - 1, nn);
+                    tma_load_4d(st + kMnXChunk, &tmapX, full + stage, kd.ci0 + 64, px - 1, yy + kd.dy - 1, nn);
+                    for (int j = 0; j < nyc; ++j)
+                        tma_load_4d(st + 2 * kMnXChunk + j * kMnYChunk, &tmapDY, full + stage, kd.co0 + 64 * j, px, yy, nn);
+                    if (++xs2 == segs) { xs2 = 0; if (++y2 == static_cast<uint32_t>(a.H)) { y2 = 0; ++n2; } }
+                }
             }
             __syncwarp();
             if (++stage == kMnStages) { stage = 0; phase ^= 1; }
+            for (int sub = 0; sub < kMnSub; ++sub)
+                if (++xs == segs) { xs = 0; if (++y == static_cast<uint32_t>(a.H)) { y = 0; ++n; } }
         }
     } else if (warp == 1) {
-        const uint32_t idesc = make_idesc_f16(1, 128, kd.n) | (1u << 15) | (1u << 16);
+        const uint32_t idesc = make_idesc_f16(1, 128, kd.n) | (1u << 15) | (1u << 16);   // A and B MN-major
         const uint32_t s16 = (smem_u32(smem) & 0x3FFFFu) >> 4;
         int stage = 0; uint32_t phase = 0;
         uint32_t acc = 0;
-        for (long long k = k0; k < k1; ++k) {
+        for (uint32_t k = k0; k < k1; k += kMnSub) {
+            const int cnt = k1 - k < kMnSub ? static_cast<int>(k1 - k) : kMnSub;
             mbar_wait(full + stage, phase);
             tc_fence_after();
             if (elect_one()) {
-                const uint32_t xa = s16 + stage * (kMnStageBytes >> 4);
-                const uint32_t ya = xa + ((2 * kMnXChunk) >> 4);
+                for (int sub = 0; sub < cnt; ++sub) {
+                    const uint32_t xa = s16 + ((stage * kMnStageBytes + sub * kMnSlabBytes) >> 4);
+                    const uint32_t ya = xa + ((2 * kMnXChunk) >> 4);
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                    const uint64_t bd = mn_desc(ya + ks * (2048 >> 4), kMnYChunk >> 4);
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint64_t bd = mn_desc(ya + ks * (2048 >> 4), kMnYChunk >> 4);
 #pragma unroll
-                    for (int dx = 0; dx < 3; ++dx)
-                        umma_f16(tbase + dx * kd.n, mn_desc(xa + ks * (2048 >> 4) + dx * (128 >> 4), kMnXChunk >> 4), bd, idesc,
-                                 (acc | ks) ? 1u : 0u);
+                        for (int dx = 0; dx < 3; ++dx)
+                            umma_f16(tbase + dx * kd.n, mn_desc(xa + ks * (2048 >> 4) + dx * (128 >> 4), kMnXChunk >> 4), bd, idesc,
+                                     (acc | sub | ks) ? 1u : 0u);
+                    }
                 }
                 umma_commit(empty + stage);
             }
@@ -122,13 +144,42 @@ wgrad_mn_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constant
     } else if (warp >= 4) {
         const int q = warp & 3;
         const int m = q * 32 + lane;  // ci row within the unit
+        if (bias_cta) {
+            const int t = threadIdx.x - 128, half = kd.n >> 1;     // thread -> (channel pair, row group)
+            const int cp = t % half, rg = t / half, rows = (64 * half) >> 7;   // 256 / n row groups of 64 / (256 / n) rows
+            const uint32_t coff = 2 * kMnXChunk + (cp >> 5) * kMnYChunk + (cp & 3) * 4;
+            const int c16 = (cp & 31) >> 2;
+            float s0 = 0.f, s1 = 0.f;
+            int stage = 0; uint32_t phase = 0;
+            for (uint32_t k = k0; k < k1; k += kMnSub) {
+                const int cnt = k1 - k < kMnSub ? static_cast<int>(k1 - k) : kMnSub;
+                mbar_wait(full + stage, phase);
+                for (int sub = 0; sub < cnt; ++sub) {
+                    const uint8_t* yt = smem + stage * kMnStageBytes + sub * kMnSlabBytes + coff;
+#pragma unroll 8
+                    for (int r = rg * rows; r < (rg + 1) * rows; ++r) {
+                        const uint32_t v = *reinterpret_cast<const uint32_t*>(yt + r * 128 + ((c16 ^ (r & 7)) << 4));
+                        s0 += __uint_as_float(v << 16);
+                        s1 += __uint_as_float(v & 0xFFFF0000u);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty + stage);
+                if (++stage == kMnStages) { stage = 0; phase ^= 1; }
+            }
+            float* bp = a.bias_partial + static_cast<size_t>(blockIdx.x) * 256 + rg * kd.n + 2 * cp;
+            bp[0] = s0; bp[1] = s1;
+        }
         mbar_wait(done, 0);
         tc_fence_after();
-        float* dst = a.partial + static_cast<size_t>(blockIdx.x) * kMnTileFloats + static_cast<size_t>(m) * 128;
+        named_bar_sync(1, 128);   // every warp has left the bias loop: the stage buffers may be overwritten
+        // Accumulators -> shared memory (the pipeline buffers are free now) -> ONE 64 KB bulk store per dx. Row m of a tile
+        // is 512 B; its 16-byte groups are XOR-swizzled by (m & 7) so that a quarter-warp's float4 stores hit distinct
+        // banks; the global partial tile keeps that layout and the reduction kernel un-swizzles.
         const bool any = k1 > k0;
 #pragma unroll 1
         for (int dx = 0; dx < 3; ++dx) {
-            float* row = dst + static_cast<size_t>(dx) * 128 * 128;
+            float4* row = reinterpret_cast<float4*>(smem + dx * 65536 + m * 512);
 #pragma unroll 1
             for (int c = 0; c < kd.n; c += 32) {
                 float v[32];
@@ -136,9 +187,16 @@ wgrad_mn_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constant
                 tmem_ld_wait();
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
-                    reinterpret_cast<float4*>(row + c)[i] =
-                        any ? make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    row[((c >> 2) + i) ^ (m & 7)] = any ? make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (threadIdx.x == 128) {
+            float* dst = a.partial + static_cast<size_t>(blockIdx.x) * kMnTileFloats;
+            for (int dx = 0; dx < 3; ++dx) bulk_store_1d(dst + dx * 16384, smem + dx * 65536, 65536);
+            tma_store_commit();
+            tma_store_wait_read();
         }
     }
     tc_fence_before();
@@ -149,8 +207,7 @@ wgrad_mn_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constant
 // dW of the layer owning each 32-channel slice of dY: sum over the splits of a kind. One thread per partial element
 // (kind, dx, ci, co): the split-strided reads are coalesced along co, the OIHW write happens once. The first `nbias`
 // threads also finish the bias gradients from the per-block column sums.
-__global__ void __launch_bounds__(256) wgrad_mn_reduce_kernel(const WgradMnArgs a, const WgradMnTable tb, const float* __restrict__ colsum,
-                                                             int ncolblocks, int nbias) {
+__global__ void __launch_bounds__(256) wgrad_mn_reduce_kernel(const WgradMnArgs a, const WgradMnTable tb, int nbias) {
     const size_t total = static_cast<size_t>(a.nkinds) * kMnTileFloats;
     for (size_t e = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; e < total; e += static_cast<size_t>(gridDim.x) * blockDim.x) {
         const int col = e & 127;
@@ -162,54 +219,35 @@ __global__ void __launch_bounds__(256) wgrad_mn_reduce_kernel(const WgradMnArgs 
         const int ci = kd.ci0 + m, cc = kd.co0 + col, cs = cc >> 5;
         const int co = tb.co_base[cs] + (cc & 31);
         if (ci >= tb.cin[cs] || co >= tb.cout[cs]) continue;
-        const float* p = a.partial + static_cast<size_t>(kd.cta0) * kMnTileFloats + (e - static_cast<size_t>(kind) * kMnTileFloats);
+        // (dx, m) tile row, 16-byte group XOR-swizzled by m & 7 (the epilogue's shared-memory layout, kept in global memory)
+        const float* p = a.partial + static_cast<size_t>(kd.cta0) * kMnTileFloats + (static_cast<size_t>(dx) * 128 + m) * 128 +
+                         ((((col >> 2) ^ (m & 7)) << 2) | (col & 3));
+        // fixed summation order (bit-reproducible), four independent loads in flight per thread
         float s = 0.f;
-        for (int sp = 0; sp < kd.nsplit; ++sp) s += p[static_cast<size_t>(sp) * kMnTileFloats];
+        int sp = 0;
+        for (; sp + 4 <= kd.nsplit; sp += 4) {
+            const float v0 = p[static_cast<size_t>(sp) * kMnTileFloats], v1 = p[static_cast<size_t>(sp + 1) * kMnTileFloats];
+            const float v2 = p[static_cast<size_t>(sp + 2) * kMnTileFloats], v3 = p[static_cast<size_t>(sp + 3) * kMnTileFloats];
+            s += v0; s += v1; s += v2; s += v3;
+        }
+        for (; sp < kd.nsplit; ++sp) s += p[static_cast<size_t>(sp) * kMnTileFloats];
         tb.dw[cs][((static_cast<size_t>(co) * tb.cin[cs] + ci) * 3 + kd.dy) * 3 + dx] = s;
     }
     const size_t gt = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-    if (gt < static_cast<size_t>(nbias) && colsum) {
-        const int cs = static_cast<int>(gt >> 5);
-        const int co = tb.co_base[cs] + static_cast<int>(gt & 31);
+    if (gt < static_cast<size_t>(nbias) && a.bias_partial) {
+        const int cc = static_cast<int>(gt), cs = cc >> 5;
+        const int co = tb.co_base[cs] + (cc & 31);
         if (co < tb.cout[cs]) {
             float s = 0.f;
-            for (int b = 0; b < ncolblocks; ++b) s += colsum[static_cast<size_t>(b) * 192 + gt];
+            for (int kind = 0; kind < a.nkinds; ++kind) {
+                const WgradMnKind kd = a.kind[kind];
+                if (kd.dy != 1 || kd.ci0 != 0 || cc < kd.co0 || cc >= kd.co0 + kd.n) continue;
+                const int nrg = 256 / kd.n;
+                for (int sp = 0; sp < kd.nsplit; ++sp)
+                    for (int rg = 0; rg < nrg; ++rg) s += a.bias_partial[static_cast<size_t>(kd.cta0 + sp) * 256 + rg * kd.n + (cc - kd.co0)];
+            }
             tb.db[cs][co] = s;
         }
-    }
-}
-
-// Per-block column sums of a 16-bit NHWC gradient buffer: out[block][c] = sum over the block's pixels of dy[p][choff + c]
-// (c < C <= 192, C % 8 == 0). 16-byte loads, fixed summation order (the bias gradient is bit-reproducible).
-__global__ void __launch_bounds__(384) colsum_bf16_kernel(const uint16_t* __restrict__ dy, int cstride, int choff, int C, size_t P,
-                                                         float* __restrict__ out) {
-    __shared__ float red[16][192];
-    const int tpr = C >> 3;                 // threads per pixel row
-    const int rows = 384 / tpr;             // pixel rows in flight
-    const int r = threadIdx.x / tpr, t = threadIdx.x % tpr;
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    const size_t per = (P + gridDim.x - 1) / gridDim.x;
-    const size_t p0 = blockIdx.x * per, p1 = p0 + per < P ? p0 + per : P;
-    if (r < rows && r < 16) {
-        const int rr = rows < 16 ? rows : 16;
-        for (size_t p = p0 + r; p < p1; p += rr) {
-            const uint4 v = *reinterpret_cast<const uint4*>(dy + p * cstride + choff + t * 8);
-            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                acc[2 * j] += __uint_as_float(w4[j] << 16);
-                acc[2 * j + 1] += __uint_as_float(w4[j] & 0xFFFF0000u);
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) red[r][t * 8 + j] = acc[j];
-    }
-    __syncthreads();
-    if (static_cast<int>(threadIdx.x) < C) {
-        const int rr = rows < 16 ? rows : 16;
-        float s = 0.f;
-        for (int i = 0; i < rr; ++i) s += red[i][threadIdx.x];
-        out[static_cast<size_t>(blockIdx.x) * 192 + threadIdx.x] = s;
     }
 }
 
@@ -243,10 +281,8 @@ static int make_nhwc_map(CUtensorMap* out, const void* base, int C, int cstride,
     return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
 }
 
-static constexpr int kMnColBlocks = 128;
-
 size_t wgrad_mn_workspace_bytes(int num_sms) {
-    return static_cast<size_t>(num_sms + 16) * kMnTileFloats * sizeof(float) + static_cast<size_t>(kMnColBlocks) * 192 * sizeof(float);
+    return static_cast<size_t>(num_sms + 16) * (kMnTileFloats + 256) * sizeof(float);
 }
 
 static int wgrad_mn_set_smem_attr(int smem) {
@@ -269,7 +305,9 @@ int wgrad_mn_launch(const uint16_t* x, int x_cstride, int x_channels, const uint
     memset(&a, 0, sizeof(a));
     a.N = N; a.H = H; a.W = W;
     a.segs_per_row = (W + 63) / 64;
-    a.kslabs = static_cast<long long>(N) * H * a.segs_per_row;
+    const long long kslabs = static_cast<long long>(N) * H * a.segs_per_row;
+    if (kslabs * (num_sms + 16) >= (1ll << 32)) return -2;   // the kernel's index arithmetic is 32-bit
+    a.kslabs = static_cast<uint32_t>(kslabs);
     a.partial = workspace;
     a.nkinds = nunits * 3;
     int weight[kMnMaxKinds], share[kMnMaxKinds];
@@ -282,7 +320,7 @@ int wgrad_mn_launch(const uint16_t* x, int x_cstride, int x_channels, const uint
             weight[u * 3 + d] = k.n + 32;
             wsum += weight[u * 3 + d];
         }
-    long long cap = a.kslabs / 4;
+    long long cap = kslabs / 4;
     if (cap < 1) cap = 1;
     int used = 0;
     for (int i = 0; i < a.nkinds; ++i) {
@@ -305,15 +343,10 @@ int wgrad_mn_launch(const uint16_t* x, int x_cstride, int x_channels, const uint
     if (rc != 0) return rc;
     const int smem = 1024 + kMnStages * kMnStageBytes + 256;
     if (wgrad_mn_set_smem_attr(smem) != 0) return -3;
-    float* colsum = workspace + static_cast<size_t>(num_sms + 16) * kMnTileFloats;
-    const size_t P = static_cast<size_t>(N) * H * W;
-    int colblocks = static_cast<int>((P + 255) / 256);
-    if (colblocks > kMnColBlocks) colblocks = kMnColBlocks;
-    if (with_bias) colsum_bf16_kernel<<<colblocks, 384, 0, s>>>(dy, dy_cstride, 0, dy_channels, P, colsum);
+    a.bias_partial = with_bias ? workspace + static_cast<size_t>(num_sms + 16) * kMnTileFloats : nullptr;
     wgrad_mn_kernel<<<cta, 256, smem, s>>>(mx, my, a);
     const size_t total = static_cast<size_t>(a.nkinds) * kMnTileFloats;
-    wgrad_mn_reduce_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(a, tb, with_bias ? colsum : nullptr, colblocks,
-                                                                                     with_bias ? dy_channels : 0);
+    wgrad_mn_reduce_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(a, tb, with_bias ? dy_channels : 0);
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 

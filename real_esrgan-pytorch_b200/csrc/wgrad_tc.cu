@@ -63,10 +63,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constant
 
     if (warp == 0) {
         int stage = 0; uint32_t phase = 0;
+        // (xs, y, n) once, then incremented (64-bit divisions per stage were this loop's critical path)
+        int xs = static_cast<int>(k0 % segs);
+        int y = static_cast<int>((k0 / segs) % a.H);
+        int n = static_cast<int>(k0 / (static_cast<long long>(segs) * a.H));
         for (long long k = k0; k < k1; ++k) {
-            const int xs = static_cast<int>(k % segs);
-            const int y = static_cast<int>((k / segs) % a.H);
-            const int n = static_cast<int>(k / (static_cast<long long>(segs) * a.H));
             wg_wait(empty + stage, phase ^ 1, a, 1);
             if (elect_one()) {
                 uint8_t* st = smem + stage * kWgStageBytes;
@@ -78,6 +79,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constant
             }
             __syncwarp();
             if (++stage == a.nstages) { stage = 0; phase ^= 1; }
+            if (++xs == segs) { xs = 0; if (++y == a.H) { y = 0; ++n; } }
         }
     } else if (warp == 1) {
         const uint32_t idesc = make_idesc_f16(1, 128, 96);
