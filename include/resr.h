@@ -153,6 +153,14 @@ int resr_filter2d(const float* image, const float* kernel, float* out, int b, in
 size_t resr_usm_workspace_bytes(int b, int c, int h, int w);
 int resr_usm_sharp(const float* image, float* out, int b, int c, int h, int w, int radius, int sigma, float weight,
                    float threshold, void* workspace, size_t workspace_bytes, void* stream);
+/* Backward of USMSharp.forward: d loss / d image from d loss / d out. train_realesrgan.py:476-478 sharpens the generator
+ * output inside the pixel and content losses, so the loss gradient passes through imgproc.py:1526-1535 (autograd of the
+ * reflect-padded blur, the clip and the blend; the 0/1 mask and hence the soft mask are constants). The forward
+ * quantities are recomputed from `image`. */
+size_t resr_usm_backward_workspace_bytes(int b, int c, int h, int w);
+int resr_usm_sharp_backward(const float* image, const float* grad_out, float* grad_in, int b, int c, int h, int w,
+                            int radius, int sigma, float weight, float threshold, void* workspace,
+                            size_t workspace_bytes, void* stream);
 
 /* torch.nn.functional.interpolate(image, size= | scale_factor=, mode=) as called at train_realesrnet.py:288, 326,
  * 349, 366. mode: 0 area, 1 bilinear, 2 bicubic (align_corners=False, no antialias). scale_h/scale_w: the

@@ -242,7 +242,8 @@ __global__ void __launch_bounds__(256) usm_hpass_kernel(const float* __restrict_
 //   stage 1: soft = conv_y(tmp); out = soft * clip(x + weight * res, 0, 1) + (1 - soft) * x
 __global__ void __launch_bounds__(256) usm_vpass_kernel(const float* __restrict__ tmp, const float* __restrict__ x,
                                                         float* __restrict__ res, float* __restrict__ mask_or_out, int H,
-                                                        int W, int k, int stage, float weight, float threshold) {
+                                                        int W, int k, int stage, float weight, float threshold,
+                                                        float* __restrict__ soft_out) {
     extern __shared__ float tile[];  // [64 + k - 1][32]
     const int r = k / 2;
     const int plane = blockIdx.z;
@@ -274,6 +275,7 @@ __global__ void __launch_bounds__(256) usm_vpass_kernel(const float* __restrict_
             float sh = __fadd_rn(xv, __fmul_rn(weight, rv));                // imgproc.py:1533 (separate mul, add)
             sh = fminf(fmaxf(sh, 0.f), 1.f);                               // imgproc.py:1534
             mask_or_out[o] = __fadd_rn(__fmul_rn(acc, sh), __fmul_rn(1.f - acc, xv));  // imgproc.py:1535
+            if (soft_out) soft_out[o] = acc;   // kept for the backward pass (resr_usm_sharp_backward)
         }
     }
 }
@@ -365,7 +367,7 @@ __global__ void __launch_bounds__(256) usm_h51_kernel(const float* __restrict__ 
 //   stage 1: soft = conv_y(tmp); out = soft * clip(x + weight * res, 0, 1) + (1 - soft) * x
 __global__ void __launch_bounds__(256) usm_v51_kernel(const float* __restrict__ tmp, const float* __restrict__ x,
                                                       float* __restrict__ res, float* __restrict__ mask_or_out, int H, int W,
-                                                      int stage, float weight, float threshold) {
+                                                      int stage, float weight, float threshold, float* __restrict__ soft_out) {
     __shared__ float Bm[kUsmVIn * kUsmVCols];
     const int plane = blockIdx.z;
     const int x0 = blockIdx.x * kUsmVCols, y0 = blockIdx.y * kUsmVRows;
@@ -423,6 +425,7 @@ __global__ void __launch_bounds__(256) usm_v51_kernel(const float* __restrict__ 
                 float sh = __fadd_rn(xx, __fmul_rn(weight, rr));                      // imgproc.py:1533
                 sh = fminf(fmaxf(sh, 0.f), 1.f);                                      // imgproc.py:1534
                 mask_or_out[o] = __fadd_rn(__fmul_rn(a, sh), __fmul_rn(1.f - a, xx));  // imgproc.py:1535
+                if (soft_out) soft_out[o] = a;   // kept for the backward pass (resr_usm_sharp_backward)
             }
         }
     }
@@ -454,7 +457,7 @@ static int usm_set_taps(int radius, int sigma, int* k_out) {
 }
 
 static int usm_impl(const float* x, float* out, float* ws, int B, int C, int H, int W, int radius, int sigma, float weight,
-                    float threshold, cudaStream_t s) {
+                    float threshold, cudaStream_t s, float* soft_out = nullptr) {
     int k = 0;
     const int rc = usm_set_taps(radius, sigma, &k);
     if (rc != RESR_OK) return rc;
@@ -469,17 +472,58 @@ static int usm_impl(const float* x, float* out, float* ws, int B, int C, int H, 
         const dim3 g51h((W + kUsmHCols - 1) / kUsmHCols, (H + kUsmHRows - 1) / kUsmHRows, B * C);
         const dim3 g51v((W + kUsmVCols - 1) / kUsmVCols, (H + kUsmVRows - 1) / kUsmVRows, B * C);
         usm_h51_kernel<<<g51h, 256, 0, s>>>(x, tmp, H, W);
-        usm_v51_kernel<<<g51v, 256, 0, s>>>(tmp, x, res, mask, H, W, 0, weight, threshold);
+        usm_v51_kernel<<<g51v, 256, 0, s>>>(tmp, x, res, mask, H, W, 0, weight, threshold, nullptr);
         usm_h51_kernel<<<g51h, 256, 0, s>>>(mask, tmp, H, W);
-        usm_v51_kernel<<<g51v, 256, 0, s>>>(tmp, x, res, out, H, W, 1, weight, threshold);
+        usm_v51_kernel<<<g51v, 256, 0, s>>>(tmp, x, res, out, H, W, 1, weight, threshold, soft_out);
     } else {
         usm_hpass_kernel<<<gh, 256, sh, s>>>(x, tmp, H, W, k);
-        usm_vpass_kernel<<<gv, 256, sv, s>>>(tmp, x, res, mask, H, W, k, 0, weight, threshold);
+        usm_vpass_kernel<<<gv, 256, sv, s>>>(tmp, x, res, mask, H, W, k, 0, weight, threshold, nullptr);
         usm_hpass_kernel<<<gh, 256, sh, s>>>(mask, tmp, H, W, k);
-        usm_vpass_kernel<<<gv, 256, sv, s>>>(tmp, x, res, out, H, W, k, 1, weight, threshold);
+        usm_vpass_kernel<<<gv, 256, sv, s>>>(tmp, x, res, out, H, W, k, 1, weight, threshold, soft_out);
     }
     RESR_LAUNCH_CHECK("usm");
     return RESR_OK;
+}
+
+// ---- backward of USMSharp (train_realesrgan.py:476-478 sharpens SR inside the pixel / content losses, so the loss
+// gradient has to pass through imgproc.py:1526-1535). The 0/1 mask is a comparison, so the soft mask s is a constant:
+//     out = s * clip(x + w * (x - K x), 0, 1) + (1 - s) * x
+//     g_sh = g * s * [0 <= x + w * r <= 1]                (torch.clip passes the gradient on the closed interval)
+//     dL/dx = g * (1 - s) + (1 + w) * g_sh - w * K^T g_sh
+// K^T is the adjoint of the REFLECT-padded separable blur: position j also collects what the padded positions -j (for
+// 1 <= j <= R) and 2 (L - 1) - j (for L - 1 - R <= j <= L - 2) received in the forward pass.
+__global__ void __launch_bounds__(256) usm_gsh_kernel(const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ res,
+                                                      const float* __restrict__ soft, float* __restrict__ gsh, size_t total, float weight) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const float v = __fadd_rn(x[i], __fmul_rn(weight, res[i]));
+        gsh[i] = (v >= 0.f && v <= 1.f) ? g[i] * soft[i] : 0.f;
+    }
+}
+
+// out[j] = sum over the padded positions p that reflect onto j of  sum_i taps[p - i + R] * in[i]   along x (dir 0) or y (dir 1).
+// dir 1 also applies the pointwise tail of the backward when g is given: out = g * (1 - soft) + (1 + w) * gsh - w * K^T gsh.
+__global__ void __launch_bounds__(256) usm_adjoint_kernel(const float* __restrict__ in, float* __restrict__ out, int planes, int H, int W,
+                                                          int k, int dir, const float* __restrict__ g, const float* __restrict__ soft,
+                                                          const float* __restrict__ gsh, float weight) {
+    const int R = k / 2;
+    const size_t total = static_cast<size_t>(planes) * H * W;
+    for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int x = static_cast<int>(idx % W), y = static_cast<int>((idx / W) % H);
+        const size_t pbase = idx - static_cast<size_t>(y) * W - x;
+        const int L = dir ? H : W, j = dir ? y : x;
+        const size_t stride = dir ? W : 1;
+        const float* line = in + pbase + (dir ? static_cast<size_t>(x) : static_cast<size_t>(y) * W);
+        float acc = 0.f;
+        auto gather = [&](int p) {   // G(p): what padded position p received
+            const int i0 = max(0, p - R), i1 = min(L - 1, p + R);
+            for (int i = i0; i <= i1; ++i) acc = fmaf(c_usm_taps[p - i + R], line[i * stride], acc);
+        };
+        gather(j);
+        if (j >= 1 && j <= R) gather(-j);
+        if (j >= L - 1 - R && j <= L - 2) gather(2 * (L - 1) - j);
+        if (dir && g) acc = g[idx] * (1.f - soft[idx]) + (1.f + weight) * gsh[idx] - weight * acc;
+        out[idx] = acc;
+    }
 }
 
 // ===================================================================================== resize (a9)
@@ -1094,6 +1138,27 @@ int resr_usm_sharp(const float* image, float* out, int b, int c, int h, int w, i
     if (workspace_bytes < resr_usm_workspace_bytes(b, c, h, w)) return set_error(RESR_E_NOMEM, "USM workspace too small");
     return usm_impl(image, out, static_cast<float*>(workspace), b, c, h, w, radius, sigma, weight, threshold,
                     static_cast<cudaStream_t>(stream));
+}
+
+size_t resr_usm_backward_workspace_bytes(int b, int c, int h, int w) { return static_cast<size_t>(b) * c * h * w * 4 * 6; }
+
+int resr_usm_sharp_backward(const float* image, const float* grad_out, float* grad_in, int b, int c, int h, int w, int radius, int sigma,
+                            float weight, float threshold, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!image || !grad_out || !grad_in || !workspace) return set_error(RESR_E_INVALID, "null argument");
+    if (workspace_bytes < resr_usm_backward_workspace_bytes(b, c, h, w)) return set_error(RESR_E_NOMEM, "USM backward workspace too small");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t E = static_cast<size_t>(b) * c * h * w;
+    float* ws = static_cast<float*>(workspace);           // [0, 3E): forward scratch (tmp, res, mask)
+    float *soft = ws + 3 * E, *gsh = ws + 4 * E, *t = ws + 5 * E;
+    // recompute the forward quantities the gradient needs (residual, soft mask); the sharpened image itself lands in `t`
+    const int rc = usm_impl(image, t, ws, b, c, h, w, radius, sigma, weight, threshold, s, soft);
+    if (rc != RESR_OK) return rc;
+    int k = radius % 2 == 0 ? radius + 1 : radius;
+    usm_gsh_kernel<<<grid1d(E), 256, 0, s>>>(grad_out, image, ws + E, soft, gsh, E, weight);
+    usm_adjoint_kernel<<<grid1d(E), 256, 0, s>>>(gsh, t, b * c, h, w, k, 0, nullptr, nullptr, nullptr, weight);
+    usm_adjoint_kernel<<<grid1d(E), 256, 0, s>>>(t, grad_in, b * c, h, w, k, 1, grad_out, soft, gsh, weight);
+    RESR_LAUNCH_CHECK("usm backward");
+    return RESR_OK;
 }
 
 int resr_resize(const float* image, float* out, int planes, int h_in, int w_in, int h_out, int w_out, int mode,

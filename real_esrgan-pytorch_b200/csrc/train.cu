@@ -390,7 +390,6 @@ ConvIO fwd_io(const resr_generator* g, int k) {
 
 int forward_train(resr_generator* g, const float* x, float* y, int N, int H, int W, const Bufs& B, cudaStream_t s) {
     const Geo g0 = make_geo(g, H, W), g1 = make_geo(g, 2 * H, 2 * W), g2 = make_geo(g, 4 * H, 4 * W);
-    const size_t P = static_cast<size_t>(N) * H * W;
     // (no clearing of the concat buffers: a layer's activation tensor map ends at its last input channel, the rest of
     // the tail chunk is zero-filled by TMA, so never-written growth channels are never read)
     RESR_TRY(resr_nchw_to_nhwc16(x, B.xin, N, 3, H, W, 64, g->precision == 1 ? 1 : 0, s));

@@ -140,15 +140,47 @@ class USMSharp(nn.Module):
 
     @_on_device
     def forward(self, x: torch.Tensor, weight: float, threshold: int) -> torch.Tensor:
+        if torch.is_grad_enabled() and x.requires_grad:
+            # RealESRGAN sharpens the generator output inside its losses (train_realesrgan.py:476-478): differentiable path
+            return _USMFn.apply(x, self.radius, int(self.sigma), float(weight), float(threshold))
+        return _usm_forward(x, self.radius, int(self.sigma), float(weight), float(threshold))
+
+
+def _usm_forward(x, radius, sigma, weight, threshold):
+    b, c, h, w = x.size()
+    xi = _prep(x)
+    out = torch.empty_like(xi)
+    need = _lib.lib().resr_usm_workspace_bytes(b, c, h, w)
+    ws = _workspace(need, xi.device)
+    _lib.check(_lib.lib().resr_usm_sharp(_lib.ptr(xi), _lib.ptr(out), b, c, h, w, radius, sigma, weight, threshold, _lib.ptr(ws),
+                                         ws.numel(), _lib.stream_ptr()))
+    return out
+
+
+class _USMFn(torch.autograd.Function):
+    """USMSharp with its backward (C ABI resr_usm_sharp_backward): autograd of imgproc.py:1526-1535 with the thresholded
+    mask treated as the constant it is."""
+
+    @staticmethod
+    def forward(ctx, x, radius, sigma, weight, threshold):
+        ctx.save_for_backward(x)
+        ctx.args = (radius, sigma, weight, threshold)
+        with torch.cuda.device(x.device):
+            return _usm_forward(x.detach(), radius, sigma, weight, threshold)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (x,) = ctx.saved_tensors
+        radius, sigma, weight, threshold = ctx.args
         b, c, h, w = x.size()
-        xi = _prep(x)
+        xi, gi = _prep(x.detach()), _prep(grad_out)
         out = torch.empty_like(xi)
-        need = _lib.lib().resr_usm_workspace_bytes(b, c, h, w)
-        ws = _workspace(need, xi.device)
-        _lib.check(_lib.lib().resr_usm_sharp(_lib.ptr(xi), _lib.ptr(out), b, c, h, w, self.radius, int(self.sigma),
-                                             float(weight), float(threshold), _lib.ptr(ws), ws.numel(),
-                                             _lib.stream_ptr()))
-        return out
+        with torch.cuda.device(x.device):
+            need = _lib.lib().resr_usm_backward_workspace_bytes(b, c, h, w)
+            ws = _workspace(need, xi.device)
+            _lib.check(_lib.lib().resr_usm_sharp_backward(_lib.ptr(xi), _lib.ptr(gi), _lib.ptr(out), b, c, h, w, radius, sigma, weight,
+                                                          threshold, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+        return out, None, None, None, None
 
 
 class DiffJPEG(nn.Module):

@@ -261,9 +261,9 @@ def test_bf16_recipe_within_contract(policy):
     assert ebf <= MAX_ABS and _psnr(ybf, ref) >= MIN_PSNR
     assert e16 <= MAX_ABS and torch.equal(y16, y16b)
     assert not torch.equal(y16, ybf)
-    g.set_precision("bf16")
-    with pytest.raises(resr_b200._lib.ResrError):
-        resr_b200.autograd.l1_loss_backward(g, x[:, :, :8, :8].cuda(), torch.rand(2, 3, 32, 32).cuda())
+    g.set_precision("bf16")   # the training path runs in either recipe (tests/test_train_gpu.py holds the parity tests)
+    loss, _, flat = resr_b200.autograd.l1_loss_backward(g, x[:, :, :8, :8].cuda(), torch.rand(2, 3, 32, 32).cuda())
+    assert torch.isfinite(loss) and torch.isfinite(flat).all()
 
 
 def test_u8_image_io_is_the_reference_conversion_fused():
