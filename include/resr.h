@@ -215,6 +215,15 @@ int resr_poisson_noise_sampled(const float* image, float* out, const float* scal
 int resr_jpeg(const float* image, float* out, const float* quality, float* factor_out, int b, int h, int w,
               int clamp_input, float* q_y, float* q_cb, float* q_cr, void* stream);
 
+/* Training-image augmentation of the dataset (dataset.py:66-79) for a whole batch: random_rotate by 0 / 90 / 180 / 270 degrees
+ * about (w//2, h//2) (imgproc.py:1937-1963, cv2.warpAffine: exact pixel copies, zeros where the canvas has no source),
+ * random horizontal / vertical flip (imgproc.py:1966-2001), BGR -> RGB, image_to_tensor (HWC -> CHW) and the / 255 of
+ * dataset.py:67. images_bgr_hwc: decoded u8 images [b,h,w,3]; out_rgb_nchw: fp32 [b,3,h,w]; ops[b] (device):
+ * bits 0-1 = angle index (0, 90, 180, 270), bit 2 = horizontal flip, bit 3 = vertical flip -- the caller's draws
+ * (imgproc.draw_augment_ops keeps the reference's RNG order). Bit-exact against the reference functions. */
+int resr_augment_batch_u8(const unsigned char* images_bgr_hwc, float* out_rgb_nchw, const int* ops, int b, int h, int w,
+                          void* stream);
+
 /* Paired crop (imgproc.random_crop, imgproc.py:1894-1934) and the u8-grid rounding of train_realesrnet.py:374. */
 int resr_crop(const float* image, float* out, int planes, int h_in, int w_in, int top, int left, int h_out, int w_out,
               int round_to_u8, void* stream);

@@ -634,6 +634,44 @@ def degrade_batch_native(hr: torch.Tensor, kernel1: torch.Tensor, kernel2: torch
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# Training-image augmentation of the dataset (dataset.py:66-79) for a whole batch of decoded images.
+
+def draw_augment_ops(batch: int, angles=(0, 90, 180, 270), p_hflip: float = 0.5, p_vflip: float = 0.5):
+    """The random decisions of dataset.py:71-73 for `batch` images, drawn from Python's `random` in the reference's order
+    (per image: random.choice(angles) in random_rotate, random.random() < p in the horizontal, then the vertical flip).
+    Returns an int32 CPU tensor of packed ops (bits 0-1 angle index, bit 2 horizontal flip, bit 3 vertical flip)."""
+    import random
+    if tuple(angles) != (0, 90, 180, 270):
+        raise ValueError("the device augmentation implements the reference's angles [0, 90, 180, 270]")
+    ops = []
+    for _ in range(batch):
+        ai = angles.index(random.choice(list(angles)))
+        hf = random.random() < p_hflip
+        vf = random.random() < p_vflip
+        ops.append(ai | (int(hf) << 2) | (int(vf) << 3))
+    return torch.tensor(ops, dtype=torch.int32)
+
+
+@_on_device
+def augment_batch(images_u8_bgr: torch.Tensor, ops: torch.Tensor) -> torch.Tensor:
+    """dataset.py:67-79 on the device: decoded u8 HWC BGR images [b, h, w, 3] -> fp32 RGB tensors [b, 3, h, w] in [0, 1],
+    rotated / flipped per sample as `ops` says (see draw_augment_ops). One gather kernel, bit-exact against
+    random_rotate + random_*_flip + cvtColor + image_to_tensor of the reference (C ABI resr_augment_batch_u8)."""
+    if not images_u8_bgr.is_cuda:
+        raise _lib.ResrError("resr_b200.imgproc runs on CUDA tensors only; there is no CPU path")
+    if images_u8_bgr.dtype != torch.uint8 or images_u8_bgr.dim() != 4 or images_u8_bgr.size(-1) != 3:
+        raise ValueError("expected a uint8 tensor [b, h, w, 3]")
+    x = images_u8_bgr.contiguous()
+    b, h, w, _ = x.shape
+    o = ops.to(device=x.device, dtype=torch.int32).contiguous()
+    if o.numel() != b:
+        raise ValueError("one op per image")
+    out = torch.empty(b, 3, h, w, dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().resr_augment_batch_u8(_lib.ptr(x), _lib.ptr(out), _lib.ptr(o), b, h, w, _lib.stream_ptr()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
 # Blur-kernel synthesis (reference imgproc.py:225-603, dataset.py:81-141): random draws on the host in the reference's
 # RNG order, arithmetic in float64 on the device (C ABI resr_synthesize_kernels).
 

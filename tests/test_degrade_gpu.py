@@ -461,3 +461,32 @@ def test_device_side_kernel_parameter_draws_follow_the_reference_distributions()
     k1b, _, _ = ip.draw_degradation_kernels_device(16, P, seed=123)
     k1c, _, _ = ip.draw_degradation_kernels_device(16, P, seed=123)
     assert not torch.equal(k1b, k1c)
+
+
+@pytest.mark.gpu
+def test_augment_batch_is_the_reference_chain_bit_for_bit():
+    """SURVEY.md §8 f3 (data path): rotate / flip / BGR->RGB / image_to_tensor of dataset.py:67-79 as one device gather,
+    against the golden outputs of the reference's own functions and against the oracle on a 400 x 400 batch."""
+    import os
+    import numpy as np
+    import resr_b200
+    from oracle import augment as oa
+    ip = resr_b200.imgproc
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "augment.npz"))
+    for idx in range(6):
+        img = gold[f"img{idx}"]
+        combos = [(ai, hf, vf) for ai in range(4) for hf in (0, 1) for vf in (0, 1)]
+        batch = torch.from_numpy(np.stack([img] * len(combos))).cuda()
+        ops = torch.tensor([oa.pack_op(*c) for c in combos], dtype=torch.int32)
+        out = ip.augment_batch(batch, ops).cpu().numpy()
+        for k, (ai, hf, vf) in enumerate(combos):
+            assert np.array_equal(out[k], gold[f"out{idx}_{ai}_{hf}_{vf}"]), (idx, ai, hf, vf)
+    rng = np.random.default_rng(3)
+    imgs = rng.integers(0, 256, (16, 400, 400, 3), dtype=np.uint8)   # the reference's dataset images are 400 x 400
+    import random
+    random.seed(9)
+    ops = ip.draw_augment_ops(16)
+    out = ip.augment_batch(torch.from_numpy(imgs).cuda(), ops).cpu().numpy()
+    for k in range(16):
+        op = int(ops[k])
+        assert np.array_equal(out[k], oa.augment(imgs[k], op & 3, bool(op & 4), bool(op & 8)))

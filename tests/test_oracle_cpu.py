@@ -176,3 +176,32 @@ def test_filter2d_fft_path_equals_direct_definition():
     assert np.abs(od.filter2d(x, k, "direct").astype(np.float64) - od.filter2d(x, k, "fft")).max() <= 1e-7
     ku = od.usm_kernel_2d()
     assert np.abs(od.filter2d(x, ku, "direct").astype(np.float64) - od.filter2d(x, ku, "fft")).max() <= 1e-7
+
+
+def test_augment_oracle_matches_reference_golden():
+    """dataset.py:67-79 (rotate / flips / BGR->RGB / image_to_tensor): the numpy restatement reproduces the reference's own
+    functions bit for bit on every (angle, hflip, vflip) of six image shapes (odd, even, non-square)."""
+    import numpy as np
+    from oracle import augment as oa
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "augment.npz"))
+    n = 0
+    for idx in range(6):
+        img = gold[f"img{idx}"]
+        for ai in range(4):
+            for hf in (0, 1):
+                for vf in (0, 1):
+                    assert np.array_equal(oa.augment(img, ai, hf, vf), gold[f"out{idx}_{ai}_{hf}_{vf}"])
+                    n += 1
+    assert n == 96
+
+
+def test_draw_augment_ops_keeps_the_reference_rng_order():
+    import random
+    import resr_b200
+    random.seed(5)
+    ops = resr_b200.imgproc.draw_augment_ops(6).tolist()
+    random.seed(5)
+    for op in ops:
+        assert [0, 90, 180, 270][op & 3] == random.choice([0, 90, 180, 270])
+        assert bool(op & 4) == (random.random() < 0.5)
+        assert bool(op & 8) == (random.random() < 0.5)
