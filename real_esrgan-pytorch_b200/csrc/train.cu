@@ -108,20 +108,29 @@ __global__ void __launch_bounds__(256) scale_f32_to_bf16_kernel(const float* __r
     }
 }
 
-// out[p][choff + c] = bf16(sa * a[p][c]) for c < 64: a dense [P][64] fp32 tensor into a channel slice of a wider NHWC buffer
+// out[p][choff + c] = bf16(sa * a[p][c]) for c < 64: a dense [P][64] fp32 tensor into a channel slice of a wider NHWC buffer.
+// One thread per four channels (16-byte load, 8-byte store; cstride and choff are multiples of 4).
 __global__ void __launch_bounds__(256) scale_f32_to_bf16_slice_kernel(const float* __restrict__ a, float sa, uint16_t* __restrict__ out,
                                                                      size_t P, int cstride, int choff) {
-    const size_t n = P * 64;
-    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const __nv_bfloat16 h = __float2bfloat16_rn(sa * a[i]);
-        out[(i >> 6) * cstride + choff + (i & 63)] = *reinterpret_cast<const uint16_t*>(&h);
+    const size_t n4 = P * 16;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const float4 v = reinterpret_cast<const float4*>(a)[i];
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(sa * v.x, sa * v.y), hi = __floats2bfloat162_rn(sa * v.z, sa * v.w);
+        uint2 o;
+        o.x = *reinterpret_cast<const uint32_t*>(&lo);
+        o.y = *reinterpret_cast<const uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(out + (i >> 4) * cstride + choff + ((i & 15) << 2)) = o;
     }
 }
 
+// out = sa * a + sb * b, n a multiple of 4 (float4 traffic)
 __global__ void __launch_bounds__(256) axpby_f32_kernel(const float* __restrict__ a, float sa, const float* __restrict__ b, float sb,
                                                        float* __restrict__ out, size_t n) {
-    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
-        out[i] = sa * a[i] + sb * b[i];
+    const size_t n4 = n >> 2;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const float4 x = reinterpret_cast<const float4*>(a)[i], y = reinterpret_cast<const float4*>(b)[i];
+        reinterpret_cast<float4*>(out)[i] = make_float4(sa * x.x + sb * y.x, sa * x.y + sb * y.y, sa * x.z + sb * y.z, sa * x.w + sb * y.w);
+    }
 }
 
 // Backward of nearest x2 upsampling (model.py:264-265): out[n,y,x,c] = sum of the 2x2 block of in[n,2y+a,2x+b,c].
@@ -594,7 +603,7 @@ int backward_common(resr_generator* g, float* grads, int N, int H, int W, const 
             cudaStream_t wst = wgrad_stream(g, s);
             if (wst != s && g->ev_dyc_valid[r & 1]) cudaStreamWaitEvent(s, g->ev_dyc[r & 1], 0);  // its previous user was transposed
             // dY5 = 0.2 * d(xout)
-            scale_f32_to_bf16_slice_kernel<<<egrid(P * 64), 256, 0, s>>>(D, 0.2f * dscale[jj], dyc, P, 192, 0);
+            scale_f32_to_bf16_slice_kernel<<<egrid(P * 16), 256, 0, s>>>(D, 0.2f * dscale[jj], dyc, P, 192, 0);
             for (int b = 4; b >= 0; --b) {
                 const ConvSpec& shape = table().c[1 + 5 * r + (4 - b)];   // step b has the shape of forward conv(5 - b)
                 ConvIO io;
@@ -661,7 +670,7 @@ int backward_common(resr_generator* g, float* grads, int N, int H, int W, const 
             }
         }
         // d(x0) = d(rdb1 input) + d(out)   (model.py:129-130)
-        axpby_f32_kernel<<<egrid(P * 64), 256, 0, s>>>(B.dx[1], 1.f, B.dx[0], 1.f, B.dx[0], P * 64);
+        axpby_f32_kernel<<<egrid(P * 16), 256, 0, s>>>(B.dx[1], 1.f, B.dx[0], 1.f, B.dx[0], P * 64);
     }
     // ---- conv1 (model.py:258): dY = d(trunk input) + d(skip)
     scale_f32_to_bf16_kernel<<<egrid(P * 64), 256, 0, s>>>(B.dx[0], 1.f, B.dskip, 1.f, B.dya, P * 64);

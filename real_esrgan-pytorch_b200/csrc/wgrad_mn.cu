@@ -295,7 +295,7 @@ static int wgrad_mn_set_smem_attr(int smem) {
 }
 
 // units: (ci0, co0, n) triples; every unit is expanded into its three dy kinds. CTAs are dealt to the kinds in proportion
-// to their per-stage cost (MMA columns + the fixed X tile), every kind gets at least one.
+// to their per-slab MMA cost, every kind gets at least one.
 int wgrad_mn_launch(const uint16_t* x, int x_cstride, int x_channels, const uint16_t* dy, int dy_cstride, int dy_channels,
                     int N, int H, int W, const int (*units)[3], int nunits, const WgradMnTable& tb, bool with_bias,
                     float* workspace, int num_sms, cudaStream_t s) {
@@ -317,7 +317,8 @@ int wgrad_mn_launch(const uint16_t* x, int x_cstride, int x_channels, const uint
             WgradMnKind& k = a.kind[u * 3 + d];
             k.ci0 = units[u][0]; k.co0 = units[u][1]; k.n = units[u][2]; k.dy = d;
             if (k.n != 64 && k.n != 128) return -2;
-            weight[u * 3 + d] = k.n + 32;
+            // cost of a slab = 12 MMAs: 64 cycles each at N = 128, 48 at N = 64 (shared-memory operand bound, tools/mma_mn_bench.cu)
+            weight[u * 3 + d] = k.n == 128 ? 4 : 3;
             wsum += weight[u * 3 + d];
         }
     long long cap = kslabs / 4;
@@ -333,7 +334,7 @@ int wgrad_mn_launch(const uint16_t* x, int x_cstride, int x_channels, const uint
     // hand the SMs left over by the rounding to the heaviest kinds first
     for (int pass = 0; pass < 2 && used < num_sms; ++pass)
         for (int i = 0; i < a.nkinds && used < num_sms; ++i)
-            if (weight[i] >= (pass == 0 ? 160 : 0) && share[i] < cap) { ++share[i]; ++used; }
+            if (weight[i] >= (pass == 0 ? 4 : 0) && share[i] < cap) { ++share[i]; ++used; }
     int cta = 0;
     for (int i = 0; i < a.nkinds; ++i) { a.kind[i].cta0 = cta; a.kind[i].nsplit = share[i]; cta += share[i]; }
     if (cta > num_sms + 16) return -2;
