@@ -279,6 +279,14 @@ int resr_generator_train_step_l1(resr_generator_t* g, const float* x, const floa
                                  float* loss_out, int n, int h, int w, void* workspace, size_t workspace_bytes,
                                  void* stream);
 int resr_generator_step_is_graph(resr_generator_t* g);
+/* Data-parallel training (the reference trains on one GPU): the backward finishes gradients from the END of
+ * the flat vector towards its front (tail, trunk.22 ... trunk.0, conv1), so the vector is cut into 4 contiguous buckets that
+ * complete in the order 3, 2, 1, 0 of their position: bucket k = [offsets[k], offsets[k+1]) (returns the bucket count, 4).
+ * resr_generator_wait_grad_bucket makes `stream` wait until bucket k of the most recently enqueued training step is complete
+ * (k = 3 finishes first; k = 0 finishes with the step itself: no wait is inserted), so that an all-reduce of that slice can run under the
+ * rest of the backward. Works for the eager step and for the CUDA-graph replay (external event-record nodes). */
+int resr_generator_grad_buckets(size_t* offsets, int max_entries);
+int resr_generator_wait_grad_bucket(resr_generator_t* g, int bucket, void* stream);
 /* Backward from an upstream gradient dL/dy (fp32 NCHW [n,3,4h,4w]); the clamp of model.py:270 is applied inside. */
 int resr_generator_backward(resr_generator_t* g, const float* dy, float* grads_flat, int n, int h, int w, void* workspace,
                             size_t workspace_bytes, void* stream);

@@ -132,6 +132,13 @@ class TrainStep:
         # CUDA graphs cannot be captured on the legacy default stream: the step runs on its own stream, ordered
         # against the caller's current stream on both sides
         self.stream = torch.cuda.Stream(device=dev)
+        # data parallel: the flat gradient vector is all-reduced in 4 buckets on a communication stream, each as soon as
+        # the backward has finished it (C ABI resr_generator_grad_buckets / resr_generator_wait_grad_bucket)
+        self.comm = torch.cuda.Stream(device=dev) if world_size > 1 else None
+        offs = (ctypes.c_size_t * 5)()
+        self.nbuckets = _lib.lib().resr_generator_grad_buckets(offs, 5)
+        self.bucket_offsets = [int(o) for o in offs]
+        self.overlap = True
 
     def step(self, lr: torch.Tensor = None, hr: torch.Tensor = None, scatter: bool = True):
         n, h, w = self.shape
@@ -151,11 +158,33 @@ class TrainStep:
                     gen._native(), _lib.ptr(self.lr), _lib.ptr(self.hr), _lib.ptr(self.sr), _lib.ptr(self.flat), _lib.ptr(self.loss), n, h,
                     w, wp, wbytes, _lib.stream_ptr(self.lr.device)))
             if self.world > 1:
-                allreduce_mean_(self.flat, self.group, self.world)
+                if self.overlap and self.nbuckets == 4:
+                    self._allreduce_buckets()
+                else:
+                    allreduce_mean_(self.flat, self.group, self.world)
         cur.wait_stream(self.stream)
         if scatter:
             _scatter_grads(gen, self.flat, accumulate=False)
         return self.loss, self.sr, self.flat
+
+    def _allreduce_buckets(self):
+        """Gradient all-reduce overlapped with the backward: the communication stream waits for each
+        bucket's completion event inside the running step (tail and trunk.22-17 first), reduces that slice of the flat
+        vector over NCCL while the rest of the backward is still executing, and the step's stream joins at the end."""
+        import torch.distributed as dist
+        dev = self.lr.device
+        with torch.cuda.device(dev):
+            for k in (3, 2, 1, 0):
+                if k == 0:
+                    self.comm.wait_stream(self.stream)     # the front of the vector completes with the step itself
+                else:
+                    _lib.check(_lib.lib().resr_generator_wait_grad_bucket(self.gen._native(), k, ctypes.c_void_p(self.comm.cuda_stream)))
+                a, b = self.bucket_offsets[k], self.bucket_offsets[k + 1]
+                with torch.cuda.stream(self.comm):
+                    sl = self.flat[a:b]
+                    dist.all_reduce(sl, op=dist.ReduceOp.SUM, group=self.group)
+                    sl.div_(self.world)
+        self.stream.wait_stream(self.comm)
 
     @property
     def is_graph(self) -> bool:

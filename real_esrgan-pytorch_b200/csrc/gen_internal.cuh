@@ -113,6 +113,9 @@ struct resr_generator {
     cudaEvent_t ev_fork = nullptr, ev_dy = nullptr, ev_join = nullptr;
     cudaEvent_t ev_dyc[2] = {nullptr, nullptr};  // dYcat buffer of a dense block has been transposed (side stream)
     bool ev_dyc_valid[2] = {false, false};
+    // gradient buckets (data-parallel training): bucket i of the flat gradient vector is complete when ev_bucket[i] fires
+    // (recorded on the weight-gradient stream inside the backward, as an EXTERNAL event when the step is being captured)
+    cudaEvent_t ev_bucket[4] = {nullptr, nullptr, nullptr, nullptr};
     uint8_t* wpack_t = nullptr;   // transposed packs for the backward data-gradient convolutions (lazily allocated)
     uint8_t* wpack_t2 = nullptr;  // mirrored dense-block data-gradient packs (train.cu), laid out like the forward packs
     float* zero_bias = nullptr;

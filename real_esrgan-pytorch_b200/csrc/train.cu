@@ -535,6 +535,19 @@ ConvIO bwd_io(const resr_generator* g, int k) {
     return io;
 }
 
+// Gradient buckets for data-parallel training (the all-reduce overlapped with the backward). The backward
+// finishes gradients tail first, then trunk.22 ... trunk.0, conv1 -- in the flat vector (state_dict order) that is from
+// the END towards the front, so "everything from RRDB i on" is one contiguous suffix. Bucket 0 = [trunk.17, end),
+// 1 = [trunk.11, trunk.17), 2 = [trunk.5, trunk.11), 3 = [0, trunk.5) (complete when the step itself is).
+static const int kBucketRRDB[3] = {17, 11, 5};
+
+static void record_bucket(resr_generator* g, int i, cudaStream_t st) {
+    if (!g->ev_bucket[i] && cudaEventCreateWithFlags(&g->ev_bucket[i], cudaEventDisableTiming) != cudaSuccess) { g->ev_bucket[i] = nullptr; return; }
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cs);
+    cudaEventRecordWithFlags(g->ev_bucket[i], st, cs == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault);
+}
+
 // Common backward: B.biga holds conv4's output gradient (NHWC bf16 [16P][64], 3 channels used).
 int backward_common(resr_generator* g, float* grads, int N, int H, int W, const Bufs& B, cudaStream_t s) {
     const Geo g0 = make_geo(g, H, W), g1 = make_geo(g, 2 * H, 2 * W), g2 = make_geo(g, 4 * H, 4 * W);
@@ -669,6 +682,8 @@ int backward_common(resr_generator* g, float* grads, int N, int H, int W, const 
                 if (rc != 0) return set_error(RESR_E_CUDA, "dense-block wgrad failed (%d)", rc);
             }
         }
+        for (int bi = 0; bi < 3; ++bi)   // every gradient from RRDB i upwards has been enqueued on the weight-gradient stream
+            if (i == kBucketRRDB[bi]) record_bucket(g, bi, wgrad_stream(g, s));
         // d(x0) = d(rdb1 input) + d(out)   (model.py:129-130)
         axpby_f32_kernel<<<egrid(P * 16), 256, 0, s>>>(B.dx[1], 1.f, B.dx[0], 1.f, B.dx[0], P * 64);
     }
@@ -779,6 +794,28 @@ int resr_generator_train_step_l1(resr_generator_t* g, const float* x, const floa
 }
 
 int resr_generator_step_is_graph(resr_generator_t* g) { return g && g->step_exec ? 1 : 0; }
+
+int resr_generator_grad_buckets(size_t* offsets, int max_entries) {
+    if (!offsets || max_entries < 5) return set_error(RESR_E_INVALID, "need room for 5 offsets");
+    const Table& T = table();
+    // layer index of the first convolution of RRDB i: 1 + 15 * i (conv1 is layer 0, 15 convolutions per RRDB)
+    offsets[0] = 0;
+    offsets[1] = T.c[1 + 15 * kBucketRRDB[2]].p_off;
+    offsets[2] = T.c[1 + 15 * kBucketRRDB[1]].p_off;
+    offsets[3] = T.c[1 + 15 * kBucketRRDB[0]].p_off;
+    offsets[4] = T.n_params;
+    return 4;
+}
+
+int resr_generator_wait_grad_bucket(resr_generator_t* g, int bucket, void* stream) {
+    if (!g || bucket < 0 || bucket > 3) return set_error(RESR_E_INVALID, "bad bucket");
+    if (bucket == 0) return RESR_OK;                       // the front of the vector (conv1 ... trunk.4) completes with the step itself
+    cudaEvent_t ev = g->ev_bucket[3 - bucket];             // bucket 3 (the end of the vector) is closed by the first event
+    if (!ev) return set_error(RESR_E_INVALID, "no training step has recorded bucket %d yet", bucket);
+    const cudaError_t e = cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), ev, 0);
+    if (e != cudaSuccess) return set_error(RESR_E_CUDA, "cudaStreamWaitEvent: %s", cudaGetErrorString(e));
+    return RESR_OK;
+}
 
 int resr_conv3x3_wgrad(const void* x16, int x_cstride, int fmt_x, const void* dy16_bf16, int n, int h, int w, int cin, int cout,
                        float* dw, float* db, void* workspace, size_t workspace_bytes, void* stream) {

@@ -328,3 +328,31 @@ def test_checkpoint_round_trip_in_reference_format(tmp_path):
     assert torch.equal(opt2.flat, opt.flat) and torch.equal(opt2.shadow, opt.shadow)
     ref_flat = torch.cat([p.detach().reshape(-1) for p in g_ref.parameters()])
     assert (ref_flat - opt.flat).abs().max().item() <= 2e-7
+
+
+def test_gradient_buckets_follow_the_backward_order():
+    """Data-parallel plumbing: four contiguous buckets of the flat gradient vector, cut at trunk.5 / 11 / 17 in
+    state_dict order; after a step the completion events of buckets 3, 2, 1 can be waited on from another stream (bucket 0
+    closes with the step). The 2- and 8-GPU runs of tools/ddp_overlap_check.py (profiles/r02_ddp_overlap.txt) check that the
+    bucketed all-reduce is bit-identical to the single all-reduce after the step."""
+    import resr_b200
+    L = resr_b200._lib
+    g = resr_b200.model.Generator(3, 3, 4).cuda().train()
+    g.set_precision("bf16")
+    offs = (ctypes.c_size_t * 5)()
+    assert L.lib().resr_generator_grad_buckets(offs, 5) == 4
+    offs = [int(o) for o in offs]
+    pos, want = 0, {}
+    for k, v in g.state_dict().items():
+        if k in ("trunk.5.rdb1.conv1.weight", "trunk.11.rdb1.conv1.weight", "trunk.17.rdb1.conv1.weight"):
+            want[k] = pos
+        pos += v.numel()
+    assert offs == [0, want["trunk.5.rdb1.conv1.weight"], want["trunk.11.rdb1.conv1.weight"], want["trunk.17.rdb1.conv1.weight"], pos]
+    ts = resr_b200.autograd.TrainStep(g, 1, 8, 8)
+    side = torch.cuda.Stream()
+    for it in range(2):   # eager step, then the graph replay
+        _, _, flat = ts.step(torch.rand(1, 3, 8, 8).cuda(), torch.rand(1, 3, 32, 32).cuda(), scatter=False)
+        for k in (3, 2, 1, 0):
+            L.check(L.lib().resr_generator_wait_grad_bucket(g._native(), k, ctypes.c_void_p(side.cuda_stream)))
+        side.synchronize()
+        assert torch.isfinite(flat).all()
