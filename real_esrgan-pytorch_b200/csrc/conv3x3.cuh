@@ -66,6 +66,7 @@ struct ConvArgs {
     const void* mask16;         // LeakyReLU' mask source: NHWC 16-bit activations; v *= (act > 0 ? 1 : 0.2) before out16
     int mask16_cstride, mask16_choff;
     float res2_scale;           // EP_ADD2
+    float out16_scale;          // != 0: the 16-bit output stores out16_scale * v (the fp32 output keeps v): the next dense block's dY5
     float* out_nchw_raw;        // pre-clamp copy of the NCHW output (training: clamp backward needs it)
     int dbg_flags;            // experiments only: 1 = skip output stores, 2 = producer re-reads row 0, 4 = issue 1/4 of the MMAs
     unsigned long long* dbg;  // optional: CTA (0,0) writes phase timestamps (globaltimer ns) here, 16 slots

@@ -624,6 +624,10 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
                             }
                         }
                     }
+                    if (use_o16 && a.out16_scale != 0.f) {
+#pragma unroll
+                        for (int i = 0; i < SUBW; ++i) val[i] = __fmul_rn(val[i], a.out16_scale);
+                    }
                     if (use_o16) {
                         uint32_t pk[SUBW / 2];
 #pragma unroll

@@ -543,6 +543,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
                         }
                     }
                 }
+                if (use_o16 && a.out16_scale != 0.f) {
+#pragma unroll
+                    for (int i = 0; i < NOUT; ++i) val[i] = __fmul_rn(val[i], a.out16_scale);
+                }
                 if (use_o16) {
                     uint32_t pk[NOUT / 2];
 #pragma unroll

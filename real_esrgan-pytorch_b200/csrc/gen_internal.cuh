@@ -111,8 +111,8 @@ struct resr_generator {
     // second stream of the backward pass: the weight-gradient chain of a layer runs beside the data-gradient chain
     cudaStream_t side_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_dy = nullptr, ev_join = nullptr;
-    cudaEvent_t ev_dyc[2] = {nullptr, nullptr};  // dYcat buffer of a dense block has been transposed (side stream)
-    bool ev_dyc_valid[2] = {false, false};
+    cudaEvent_t ev_dyc[3] = {nullptr, nullptr, nullptr};  // the weight gradient has read this dYcat buffer (side stream)
+    bool ev_dyc_valid[3] = {false, false, false};
     // gradient buckets (data-parallel training): bucket i of the flat gradient vector is complete when ev_bucket[i] fires
     // (recorded on the weight-gradient stream inside the backward, as an EXTERNAL event when the step is being captured)
     cudaEvent_t ev_bucket[4] = {nullptr, nullptr, nullptr, nullptr};

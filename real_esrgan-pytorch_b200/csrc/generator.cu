@@ -522,8 +522,8 @@ void resr_generator_destroy(resr_generator_t* g) {
     if (g->ev_fork) cudaEventDestroy(g->ev_fork);
     if (g->ev_dy) cudaEventDestroy(g->ev_dy);
     if (g->ev_join) cudaEventDestroy(g->ev_join);
-    if (g->ev_dyc[0]) cudaEventDestroy(g->ev_dyc[0]);
-    if (g->ev_dyc[1]) cudaEventDestroy(g->ev_dyc[1]);
+    for (int i = 0; i < 3; ++i)
+        if (g->ev_dyc[i]) cudaEventDestroy(g->ev_dyc[i]);
     for (int i = 0; i < 4; ++i)
         if (g->ev_bucket[i]) cudaEventDestroy(g->ev_bucket[i]);
     delete g;

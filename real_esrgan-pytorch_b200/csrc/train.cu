@@ -108,31 +108,6 @@ __global__ void __launch_bounds__(256) scale_f32_to_bf16_kernel(const float* __r
     }
 }
 
-// out[p][choff + c] = bf16(sa * a[p][c]) for c < 64: a dense [P][64] fp32 tensor into a channel slice of a wider NHWC buffer.
-// One thread per four channels (16-byte load, 8-byte store; cstride and choff are multiples of 4).
-__global__ void __launch_bounds__(256) scale_f32_to_bf16_slice_kernel(const float* __restrict__ a, float sa, uint16_t* __restrict__ out,
-                                                                     size_t P, int cstride, int choff) {
-    const size_t n4 = P * 16;
-    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const float4 v = reinterpret_cast<const float4*>(a)[i];
-        const __nv_bfloat162 lo = __floats2bfloat162_rn(sa * v.x, sa * v.y), hi = __floats2bfloat162_rn(sa * v.z, sa * v.w);
-        uint2 o;
-        o.x = *reinterpret_cast<const uint32_t*>(&lo);
-        o.y = *reinterpret_cast<const uint32_t*>(&hi);
-        *reinterpret_cast<uint2*>(out + (i >> 4) * cstride + choff + ((i & 15) << 2)) = o;
-    }
-}
-
-// out = sa * a + sb * b, n a multiple of 4 (float4 traffic)
-__global__ void __launch_bounds__(256) axpby_f32_kernel(const float* __restrict__ a, float sa, const float* __restrict__ b, float sb,
-                                                       float* __restrict__ out, size_t n) {
-    const size_t n4 = n >> 2;
-    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const float4 x = reinterpret_cast<const float4*>(a)[i], y = reinterpret_cast<const float4*>(b)[i];
-        reinterpret_cast<float4*>(out)[i] = make_float4(sa * x.x + sb * y.x, sa * x.y + sb * y.y, sa * x.z + sb * y.z, sa * x.w + sb * y.w);
-    }
-}
-
 // Backward of nearest x2 upsampling (model.py:264-265): out[n,y,x,c] = sum of the 2x2 block of in[n,2y+a,2x+b,c].
 // in: bf16 [N,2H,2W,64]; outputs (either may be null): fp32 and bf16 [N,H,W,64].
 __global__ void __launch_bounds__(256) sum2x2_kernel(const uint16_t* __restrict__ in, float* __restrict__ outf,
@@ -239,6 +214,7 @@ struct ConvIO {
     const float* res2 = nullptr; int res2_c = 64; float res2_scale = 1.f;
     const void* mask16 = nullptr; int mask16_c = 64, mask16_choff = 0;
     int ep_mode = EP_PLAIN, lrelu = 0, clamp01 = 0;
+    float out16_scale = 0.f;
     float* out_nchw = nullptr; float* out_nchw_raw = nullptr; int out_nchw_c = 3;
 };
 
@@ -273,6 +249,7 @@ static int launch_conv_io(const resr_generator* g, const Geo& q, int N, const Co
         a.res1 = io.res1; a.res1_cstride = io.res1_c;
     }
     a.res2 = io.res2; a.res2_cstride = io.res2_c; a.res2_scale = io.res2_scale;
+    a.out16_scale = io.out16_scale;
     a.mask16 = io.mask16; a.mask16_cstride = io.mask16_c; a.mask16_choff = io.mask16_choff;
     a.out_nchw = io.out_nchw; a.out_nchw_raw = io.out_nchw_raw; a.out_nchw_c = io.out_nchw_c;
     ConvLaunchCfg cfg;  // CTA-pair kernel whenever two column groups can be paired (conv3x3_pair.cu)
@@ -289,7 +266,7 @@ static size_t up1k(size_t v) { return (v + 1023) / 1024 * 1024; }
 
 struct TrainWs {
     size_t xin, c[70], f[4], t1, t2, t3, t4, yraw;       // forward
-    size_t dycat[2], dbcat;
+    size_t dycat[3], dbcat;
     size_t g, dya, dyb, dx[3], dskip, biga, bigb, mida, midb, xt, dyt, partial, loss;  // backward
     size_t total;
 };
@@ -308,8 +285,7 @@ static TrainWs train_layout(size_t N, size_t H, size_t W, int num_sms) {
     L.t4 = take(16 * P * 64 * 2);
     L.yraw = take(16 * P * 3 * 4);
     L.g = take(P * 192 * 4);
-    L.dycat[0] = take(P * 192 * 2);
-    L.dycat[1] = take(P * 192 * 2);
+    for (int i = 0; i < 3; ++i) L.dycat[i] = take(P * 192 * 2);
     L.dbcat = take(192 * 4);
     L.dya = take(P * 64 * 2);
     L.dyb = take(P * 64 * 2);
@@ -352,7 +328,7 @@ using namespace resr;
 namespace {
 
 struct Bufs {
-    uint16_t *dycat[2];
+    uint16_t *dycat[3];
     float* dbcat;
     uint16_t *xin, *c[70], *t1, *t2, *t3, *t4, *dya, *dyb, *biga, *bigb, *mida, *midb, *xt, *dyt;
     float *f[4], *yraw, *g, *dx[3], *dskip, *partial;
@@ -369,7 +345,7 @@ Bufs carve(void* ws, const TrainWs& L) {
     B.t3 = reinterpret_cast<uint16_t*>(b + L.t3); B.t4 = reinterpret_cast<uint16_t*>(b + L.t4);
     B.yraw = reinterpret_cast<float*>(b + L.yraw);
     B.g = reinterpret_cast<float*>(b + L.g);
-    B.dycat[0] = reinterpret_cast<uint16_t*>(b + L.dycat[0]); B.dycat[1] = reinterpret_cast<uint16_t*>(b + L.dycat[1]);
+    for (int i = 0; i < 3; ++i) B.dycat[i] = reinterpret_cast<uint16_t*>(b + L.dycat[i]);
     B.dbcat = reinterpret_cast<float*>(b + L.dbcat);
     B.dya = reinterpret_cast<uint16_t*>(b + L.dya); B.dyb = reinterpret_cast<uint16_t*>(b + L.dyb);
     for (int i = 0; i < 3; ++i) B.dx[i] = reinterpret_cast<float*>(b + L.dx[i]);
@@ -471,8 +447,7 @@ cudaStream_t wgrad_stream(resr_generator* g, cudaStream_t s) {
         cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&g->ev_dy, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&g->ev_join, cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&g->ev_dyc[0], cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&g->ev_dyc[1], cudaEventDisableTiming);
+        for (int i = 0; i < 3; ++i) cudaEventCreateWithFlags(&g->ev_dyc[i], cudaEventDisableTiming);
     }
     return g->side_stream;
 }
@@ -553,7 +528,7 @@ int backward_common(resr_generator* g, float* grads, int N, int H, int W, const 
     const Geo g0 = make_geo(g, H, W), g1 = make_geo(g, 2 * H, 2 * W), g2 = make_geo(g, 4 * H, 4 * W);
     const size_t P = static_cast<size_t>(N) * H * W;
     ensure_transposed_packs(g, s, true);
-    g->ev_dyc_valid[0] = g->ev_dyc_valid[1] = false;
+    g->ev_dyc_valid[0] = g->ev_dyc_valid[1] = g->ev_dyc_valid[2] = false;
     cudaMemsetAsync(grads, 0, table().n_params * sizeof(float), s);  // bias gradients are accumulated with atomics
     cudaMemsetAsync(B.dya, 0, P * 64 * 2, s);
     cudaMemsetAsync(B.dyb, 0, P * 64 * 2, s);
@@ -587,9 +562,10 @@ int backward_common(resr_generator* g, float* grads, int N, int H, int W, const 
         sum2x2_kernel<<<egrid(P * 32), 256, 0, s>>>(B.midb, B.dskip, B.dya, N, H, W);
     }
     RESR_TRY(layer_wgrad(g, kConv2, B.c[69], 192, g->precision, false, 0, B.dya, N, g0, B, grads, s));
-    {   // d(trunk output), fp32
+    {   // d(trunk output), fp32, and its bf16 copy x 0.2 x 0.2 = dY5 of the last dense block (trunk.22.rdb3)
         ConvIO io = bwd_io(g, kConv2);
         io.in16 = B.dya; io.outf = B.dx[0];
+        io.out16 = B.dycat[(3 * kNumRRDB - 1) % 3]; io.out16_c = 192; io.out16_choff = 0; io.out16_fmt = 1; io.out16_scale = 0.2f * 0.2f;
         RESR_TRY(launch_conv_io(g, g0, N, io, s));
     }
 
@@ -606,17 +582,17 @@ int backward_common(resr_generator* g, float* grads, int N, int H, int W, const 
             // Data gradient of the block as a MIRRORED DENSE BLOCK. The five output gradients live side by side in ONE
             // 192-channel buffer, latest layer first,
             //     dYcat' = [dY5 (64) | dY4 (32) | dY3 | dY2 | dY1]
-            // (double-buffered across blocks). The gradient of out_b needs every later layer's dY, which is exactly a
+            // (three buffers rotate across blocks). The gradient of out_b needs every later layer's dY, which is exactly a
             // channel PREFIX of dYcat': step b = 4, 3, 2, 1 is a convolution 64 / 96 / 128 / 160 -> 32 with the
             // mirrored packs (generator.cu pack_rdb_bwd_kernel), masked by LeakyReLU'(out_b) and written in place as
             // the next 32 channels; step 0 is 192 -> 64 and yields d(block input). Same launch shapes as the forward
             // block, all accumulation over layers happens in the MMA's K dimension: the fp32 gradient buffer that
             // round 1 read and re-wrote once per layer (210 MB per block) and its 20 K = 32 / 64 output slices are gone.
-            uint16_t* dyc = B.dycat[r & 1];
+            // dY5 = 0.2 * d(xout) is already in channels 0..63 of this block's buffer: the convolution that produced
+            // d(xout) (the previous block's step 0, or conv2's data gradient for the first block) stored it as its scaled
+            // 16-bit output. Three buffers rotate, so a buffer's previous reader (the weight gradient of block r + 3) is long done.
+            uint16_t* dyc = B.dycat[r % 3];
             cudaStream_t wst = wgrad_stream(g, s);
-            if (wst != s && g->ev_dyc_valid[r & 1]) cudaStreamWaitEvent(s, g->ev_dyc[r & 1], 0);  // its previous user was transposed
-            // dY5 = 0.2 * d(xout)
-            scale_f32_to_bf16_slice_kernel<<<egrid(P * 16), 256, 0, s>>>(D, 0.2f * dscale[jj], dyc, P, 192, 0);
             for (int b = 4; b >= 0; --b) {
                 const ConvSpec& shape = table().c[1 + 5 * r + (4 - b)];   // step b has the shape of forward conv(5 - b)
                 ConvIO io;
@@ -631,6 +607,16 @@ int backward_common(resr_generator* g, float* grads, int N, int H, int W, const 
                     io.ep_mode = EP_ADD2;
                     io.res2 = D; io.res2_c = 64; io.res2_scale = dscale[jj];
                     io.outf = dxin[jj]; io.outf_c = 64;
+                    if (jj == 2) {   // rdb1: d(x0) = d(rdb1 input) + d(out) (model.py:129-130) accumulated in place into dx[0]
+                        io.res1 = B.dx[0]; io.res1_c = 64;
+                        io.outf = B.dx[0];
+                    }
+                    if (r > 0) {     // ... and the next block's dY5 = 0.2 * (its d(xout)) [* 0.2 for an rdb3], bf16
+                        const int rn = (r - 1) % 3;
+                        if (wst != s && g->ev_dyc_valid[rn]) cudaStreamWaitEvent(s, g->ev_dyc[rn], 0);   // its previous reader is done
+                        io.out16 = B.dycat[rn]; io.out16_c = 192; io.out16_choff = 0; io.out16_fmt = 1;
+                        io.out16_scale = jj == 2 ? 0.2f * 0.2f : 0.2f;
+                    }
                 }
                 RESR_TRY(launch_conv_io(g, g0, N, io, s));
             }
@@ -653,8 +639,8 @@ int backward_common(resr_generator* g, float* grads, int N, int H, int W, const 
                     const int rc = wgrad_mn_launch(B.c[r], 192, 192, dyc, 192, 192, N, H, W, units, 3, tb, true, B.partial, g->num_sms, wst);
                     if (rc != 0) return set_error(RESR_E_CUDA, "dense-block wgrad (nhwc) failed (%d)", rc);
                     if (wst != s) {
-                        cudaEventRecord(g->ev_dyc[r & 1], wst);
-                        g->ev_dyc_valid[r & 1] = true;
+                        cudaEventRecord(g->ev_dyc[r % 3], wst);
+                        g->ev_dyc_valid[r % 3] = true;
                     }
                     continue;
                 }
@@ -663,8 +649,8 @@ int backward_common(resr_generator* g, float* grads, int N, int H, int W, const 
                 cudaMemsetAsync(B.dbcat, 0, 192 * sizeof(float), wst);
                 nhwc16_to_cf_kernel<true><<<tg, 256, 0, wst>>>(dyc, 192, 0, 192, 192, P, W, 1, B.dyt, B.dbcat);
                 if (wst != s) {
-                    cudaEventRecord(g->ev_dyc[r & 1], wst);
-                    g->ev_dyc_valid[r & 1] = true;
+                    cudaEventRecord(g->ev_dyc[r % 3], wst);
+                    g->ev_dyc_valid[r % 3] = true;
                 }
                 WgradRdbTable tb;
                 for (int cs = 0; cs < 6; ++cs) {   // slices of dYcat': conv5 (two halves), conv4, conv3, conv2, conv1
@@ -684,8 +670,7 @@ int backward_common(resr_generator* g, float* grads, int N, int H, int W, const 
         }
         for (int bi = 0; bi < 3; ++bi)   // every gradient from RRDB i upwards has been enqueued on the weight-gradient stream
             if (i == kBucketRRDB[bi]) record_bucket(g, bi, wgrad_stream(g, s));
-        // d(x0) = d(rdb1 input) + d(out)   (model.py:129-130)
-        axpby_f32_kernel<<<egrid(P * 16), 256, 0, s>>>(B.dx[1], 1.f, B.dx[0], 1.f, B.dx[0], P * 64);
+        // (d(x0) = d(rdb1 input) + d(out), model.py:129-130, was accumulated in place by rdb1's last convolution)
     }
     // ---- conv1 (model.py:258): dY = d(trunk input) + d(skip)
     scale_f32_to_bf16_kernel<<<egrid(P * 64), 256, 0, s>>>(B.dx[0], 1.f, B.dskip, 1.f, B.dya, P * 64);
