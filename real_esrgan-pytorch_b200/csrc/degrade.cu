@@ -9,8 +9,24 @@
 #include "../../include/resr.h"
 #include "device_state.h"
 #include "errors.h"
+#include "ptx.cuh"
 
 namespace resr {
+
+// Every kernel of this file is launched with programmatic stream serialization (PDL) and starts with griddepcontrol.wait:
+// inside the degradation chain (a CUDA graph of ~15 dependent launches of 3 - 50 us each) the next kernel's blocks are
+// scheduled while the previous kernel drains, instead of after a full launch round trip per edge.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    static const bool no_pdl = getenv("RESR_NO_PDL") != nullptr;   // A/B switch (profiles/r02_degrade_pdl_ab.txt)
+    cfg.attrs = at; cfg.numAttrs = no_pdl ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 #define RESR_LAUNCH_CHECK(what)                                                                   \
     do {                                                                                          \
@@ -64,6 +80,8 @@ template <int R, int PITCH>
 __global__ void __launch_bounds__(R == 16 ? 128 : 256) filter2d_kernel(const float* __restrict__ in, const float* __restrict__ kern,
                                                        float* __restrict__ out, int B, int C, int H, int W, int k,
                                                        int kern_batched) {
+    grid_dep_wait();      // programmatic dependent launch: everything the previous kernel wrote is visible from here on
+    grid_dep_launch();    // the next kernel of the chain may be scheduled behind this one
     constexpr int NW = R == 16 ? 4 : 8;   // warps per block
     constexpr int TH = NW * R;            // tile height
     extern __shared__ float sm[];
@@ -179,7 +197,7 @@ static void filter2d_launch(const float* in, const float* kern, float* out, int 
             cudaFuncSetAttribute(filter2d_kernel<R, 85>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
             attr_set.cur() = smem;
         }
-        filter2d_kernel<R, 85><<<grid, 32 * NW, smem, s>>>(in, kern, out, B, C, H, W, k, kb);
+        launch_pdl(filter2d_kernel<R, 85>, grid, 32 * NW, smem, s, in, kern, out, B, C, H, W, k, kb);
     } else {
         const size_t smem = (static_cast<size_t>(th) * 127 + static_cast<size_t>(k) * k) * sizeof(float);
         static PerDevice<size_t> attr_set;
@@ -187,7 +205,7 @@ static void filter2d_launch(const float* in, const float* kern, float* out, int 
             cudaFuncSetAttribute(filter2d_kernel<R, 127>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
             attr_set.cur() = smem;
         }
-        filter2d_kernel<R, 127><<<grid, 32 * NW, smem, s>>>(in, kern, out, B, C, H, W, k, kb);
+        launch_pdl(filter2d_kernel<R, 127>, grid, 32 * NW, smem, s, in, kern, out, B, C, H, W, k, kb);
     }
 }
 
@@ -219,6 +237,8 @@ __constant__ float c_usm_taps[kUsmMaxTaps];
 // out = conv_x(in) with reflect padding; one block = one row segment of 256 outputs.
 __global__ void __launch_bounds__(256) usm_hpass_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W,
                                                         int k) {
+    grid_dep_wait();      // programmatic dependent launch: everything the previous kernel wrote is visible from here on
+    grid_dep_launch();    // the next kernel of the chain may be scheduled behind this one
     extern __shared__ float row[];
     const int r = k / 2;
     const size_t line = static_cast<size_t>(blockIdx.z) * H + blockIdx.y;
@@ -244,6 +264,8 @@ __global__ void __launch_bounds__(256) usm_vpass_kernel(const float* __restrict_
                                                         float* __restrict__ res, float* __restrict__ mask_or_out, int H,
                                                         int W, int k, int stage, float weight, float threshold,
                                                         float* __restrict__ soft_out) {
+    grid_dep_wait();      // programmatic dependent launch: everything the previous kernel wrote is visible from here on
+    grid_dep_launch();    // the next kernel of the chain may be scheduled behind this one
     extern __shared__ float tile[];  // [64 + k - 1][32]
     const int r = k / 2;
     const int plane = blockIdx.z;
@@ -310,6 +332,8 @@ __device__ __forceinline__ void usm_window8x2(const float* __restrict__ p0, cons
 // tmp = conv_x(src), reflect padding. Block = 64 rows x 64 columns of outputs, 256 threads: lane = rows (l, l + 32),
 // warp = 8 columns.
 __global__ void __launch_bounds__(256) usm_h51_kernel(const float* __restrict__ src, float* __restrict__ tmp, int H, int W) {
+    grid_dep_wait();      // programmatic dependent launch: everything the previous kernel wrote is visible from here on
+    grid_dep_launch();    // the next kernel of the chain may be scheduled behind this one
     __shared__ float A[kUsmHRows * kUsmHPitch];
     const int plane = blockIdx.z;
     const int x0 = blockIdx.x * kUsmHCols, y0 = blockIdx.y * kUsmHRows;
@@ -368,6 +392,8 @@ __global__ void __launch_bounds__(256) usm_h51_kernel(const float* __restrict__ 
 __global__ void __launch_bounds__(256) usm_v51_kernel(const float* __restrict__ tmp, const float* __restrict__ x,
                                                       float* __restrict__ res, float* __restrict__ mask_or_out, int H, int W,
                                                       int stage, float weight, float threshold, float* __restrict__ soft_out) {
+    grid_dep_wait();      // programmatic dependent launch: everything the previous kernel wrote is visible from here on
+    grid_dep_launch();    // the next kernel of the chain may be scheduled behind this one
     __shared__ float Bm[kUsmVIn * kUsmVCols];
     const int plane = blockIdx.z;
     const int x0 = blockIdx.x * kUsmVCols, y0 = blockIdx.y * kUsmVRows;
@@ -471,15 +497,15 @@ static int usm_impl(const float* x, float* out, float* ws, int B, int C, int H, 
     if (k == kUsmK) {
         const dim3 g51h((W + kUsmHCols - 1) / kUsmHCols, (H + kUsmHRows - 1) / kUsmHRows, B * C);
         const dim3 g51v((W + kUsmVCols - 1) / kUsmVCols, (H + kUsmVRows - 1) / kUsmVRows, B * C);
-        usm_h51_kernel<<<g51h, 256, 0, s>>>(x, tmp, H, W);
-        usm_v51_kernel<<<g51v, 256, 0, s>>>(tmp, x, res, mask, H, W, 0, weight, threshold, nullptr);
-        usm_h51_kernel<<<g51h, 256, 0, s>>>(mask, tmp, H, W);
-        usm_v51_kernel<<<g51v, 256, 0, s>>>(tmp, x, res, out, H, W, 1, weight, threshold, soft_out);
+        launch_pdl(usm_h51_kernel, g51h, 256, 0, s, x, tmp, H, W);
+        launch_pdl(usm_v51_kernel, g51v, 256, 0, s, tmp, x, res, mask, H, W, 0, weight, threshold, nullptr);
+        launch_pdl(usm_h51_kernel, g51h, 256, 0, s, mask, tmp, H, W);
+        launch_pdl(usm_v51_kernel, g51v, 256, 0, s, tmp, x, res, out, H, W, 1, weight, threshold, soft_out);
     } else {
-        usm_hpass_kernel<<<gh, 256, sh, s>>>(x, tmp, H, W, k);
-        usm_vpass_kernel<<<gv, 256, sv, s>>>(tmp, x, res, mask, H, W, k, 0, weight, threshold, nullptr);
-        usm_hpass_kernel<<<gh, 256, sh, s>>>(mask, tmp, H, W, k);
-        usm_vpass_kernel<<<gv, 256, sv, s>>>(tmp, x, res, out, H, W, k, 1, weight, threshold, soft_out);
+        launch_pdl(usm_hpass_kernel, gh, 256, sh, s, x, tmp, H, W, k);
+        launch_pdl(usm_vpass_kernel, gv, 256, sv, s, tmp, x, res, mask, H, W, k, 0, weight, threshold, nullptr);
+        launch_pdl(usm_hpass_kernel, gh, 256, sh, s, mask, tmp, H, W, k);
+        launch_pdl(usm_vpass_kernel, gv, 256, sv, s, tmp, x, res, out, H, W, k, 1, weight, threshold, soft_out);
     }
     RESR_LAUNCH_CHECK("usm");
     return RESR_OK;
@@ -494,6 +520,8 @@ static int usm_impl(const float* x, float* out, float* ws, int B, int C, int H, 
 // 1 <= j <= R) and 2 (L - 1) - j (for L - 1 - R <= j <= L - 2) received in the forward pass.
 __global__ void __launch_bounds__(256) usm_gsh_kernel(const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ res,
                                                       const float* __restrict__ soft, float* __restrict__ gsh, size_t total, float weight) {
+    grid_dep_wait();      // programmatic dependent launch: everything the previous kernel wrote is visible from here on
+    grid_dep_launch();    // the next kernel of the chain may be scheduled behind this one
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
         const float v = __fadd_rn(x[i], __fmul_rn(weight, res[i]));
         gsh[i] = (v >= 0.f && v <= 1.f) ? g[i] * soft[i] : 0.f;
@@ -505,6 +533,8 @@ __global__ void __launch_bounds__(256) usm_gsh_kernel(const float* __restrict__ 
 __global__ void __launch_bounds__(256) usm_adjoint_kernel(const float* __restrict__ in, float* __restrict__ out, int planes, int H, int W,
                                                           int k, int dir, const float* __restrict__ g, const float* __restrict__ soft,
                                                           const float* __restrict__ gsh, float weight) {
+    grid_dep_wait();      // programmatic dependent launch: everything the previous kernel wrote is visible from here on
+    grid_dep_launch();    // the next kernel of the chain may be scheduled behind this one
     const int R = k / 2;
     const size_t total = static_cast<size_t>(planes) * H * W;
     for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -533,6 +563,8 @@ __device__ __forceinline__ float cubic2(float x) { const float A = -0.75f; retur
 
 __global__ void __launch_bounds__(256) resize_kernel(const float* __restrict__ in, float* __restrict__ out, int planes, int Hi,
                                                      int Wi, int Ho, int Wo, int mode, float sy, float sx) {
+    grid_dep_wait();      // programmatic dependent launch: everything the previous kernel wrote is visible from here on
+    grid_dep_launch();    // the next kernel of the chain may be scheduled behind this one
     const size_t total = static_cast<size_t>(planes) * Ho * Wo;
     for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -593,7 +625,7 @@ static int resize_impl(const float* in, float* out, int planes, int Hi, int Wi, 
     const float sy = scale_h > 0 ? static_cast<float>(1.0 / scale_h) : static_cast<float>(Hi) / static_cast<float>(Ho);
     const float sx = scale_w > 0 ? static_cast<float>(1.0 / scale_w) : static_cast<float>(Wi) / static_cast<float>(Wo);
     const size_t total = static_cast<size_t>(planes) * Ho * Wo;
-    resize_kernel<<<grid1d(total), 256, 0, s>>>(in, out, planes, Hi, Wi, Ho, Wo, mode, sy, sx);
+    launch_pdl(resize_kernel, grid1d(total), 256, 0, s, in, out, planes, Hi, Wi, Ho, Wo, mode, sy, sx);
     RESR_LAUNCH_CHECK("resize");
     return RESR_OK;
 }
@@ -619,6 +651,8 @@ __global__ void __launch_bounds__(256) gaussian_noise_kernel(const float* __rest
                                                              const float* __restrict__ ncolor,
                                                              const float* __restrict__ ngray, int B, int C, int HW, int clip,
                                                              int rounds) {
+    grid_dep_wait();      // programmatic dependent launch: everything the previous kernel wrote is visible from here on
+    grid_dep_launch();    // the next kernel of the chain may be scheduled behind this one
     const size_t total = static_cast<size_t>(B) * C * HW;
     for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -643,6 +677,8 @@ __global__ void __launch_bounds__(256) gaussian_noise_sampled_kernel(const float
                                                                      const float* __restrict__ sigma, const float* __restrict__ gray,
                                                                      unsigned long long seed, unsigned long long* __restrict__ state,
                                                                      int with_gray, int B, int C, int HW, int clip, int rounds) {
+    grid_dep_wait();      // programmatic dependent launch: everything the previous kernel wrote is visible from here on
+    grid_dep_launch();    // the next kernel of the chain may be scheduled behind this one
     const size_t total = static_cast<size_t>(B) * C * HW;
     const unsigned long long call = state[0];
     for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
@@ -675,6 +711,8 @@ __global__ void __launch_bounds__(256) gaussian_noise_sampled_kernel(const float
 // torch.unique host syncs of imgproc.py:892, 903. bitmaps: [B][2][8] uint32 (0 = colour, 1 = gray), pre-zeroed.
 __global__ void __launch_bounds__(256) u8_presence_kernel(const float* __restrict__ x, unsigned* __restrict__ bitmaps, int C,
                                                           int HW, int want_gray, unsigned long long* __restrict__ call_counter) {
+    grid_dep_wait();      // programmatic dependent launch: everything the previous kernel wrote is visible from here on
+    grid_dep_launch();    // the next kernel of the chain may be scheduled behind this one
     if (call_counter && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *call_counter += 1;  // sampled mode
     __shared__ unsigned sbits[16];
     if (threadIdx.x < 16) sbits[threadIdx.x] = 0;
@@ -699,6 +737,8 @@ __global__ void __launch_bounds__(256) u8_presence_kernel(const float* __restric
 
 __global__ void unique_counts_kernel(const unsigned* __restrict__ bitmaps, int* __restrict__ counts, float* __restrict__ vals,
                                      int B) {
+    grid_dep_wait();      // programmatic dependent launch: everything the previous kernel wrote is visible from here on
+    grid_dep_launch();    // the next kernel of the chain may be scheduled behind this one
     const int i = blockIdx.x * blockDim.x + threadIdx.x;  // b*2 + which
     if (i >= 2 * B) return;
     int n = 0;
@@ -715,6 +755,8 @@ __global__ void __launch_bounds__(256) poisson_noise_kernel(const float* __restr
                                                             const float* __restrict__ scolor,
                                                             const float* __restrict__ sgray, const float* __restrict__ vals,
                                                             int B, int HW, int clip, int rounds) {
+    grid_dep_wait();      // programmatic dependent launch: everything the previous kernel wrote is visible from here on
+    grid_dep_launch();    // the next kernel of the chain may be scheduled behind this one
     const size_t total = static_cast<size_t>(B) * HW;
     for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -796,6 +838,8 @@ __global__ void __launch_bounds__(256) poisson_noise_sampled_kernel(const float*
                                                                     const unsigned long long* __restrict__ counter,
                                                                     unsigned long long seed, int with_gray, int B, int HW, int clip,
                                                                     int rounds) {
+    grid_dep_wait();      // programmatic dependent launch: everything the previous kernel wrote is visible from here on
+    grid_dep_launch();    // the next kernel of the chain may be scheduled behind this one
     // four threads per pixel: lanes 0..2 of a quad draw the colour channels, lane 3 the luma sample (the sampler's loop
     // count grows with the rate, so the draws are spread over threads instead of being made one after the other)
     const size_t total = static_cast<size_t>(B) * HW;
@@ -837,6 +881,8 @@ __global__ void __launch_bounds__(256) poisson_noise_sampled_kernel(const float*
 __global__ void __launch_bounds__(256) poisson_rates_kernel(const float* __restrict__ x, const float* __restrict__ vals,
                                                             float* __restrict__ rate_color, float* __restrict__ rate_gray,
                                                             int B, int HW) {
+    grid_dep_wait();      // programmatic dependent launch: everything the previous kernel wrote is visible from here on
+    grid_dep_launch();    // the next kernel of the chain may be scheduled behind this one
     const size_t total = static_cast<size_t>(B) * HW;
     for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -868,6 +914,8 @@ __global__ void __launch_bounds__(32 * kJpegWarps) jpeg_kernel(const float* __re
                                                                const float* __restrict__ quality, float* __restrict__ factor_out,
                                                                int B, int H, int W, int clamp_in, float* __restrict__ qy,
                                                                float* __restrict__ qcb, float* __restrict__ qcr) {
+    grid_dep_wait();      // programmatic dependent launch: everything the previous kernel wrote is visible from here on
+    grid_dep_launch();    // the next kernel of the chain may be scheduled behind this one
     __shared__ __align__(16) float s_pix[kJpegWarps][6][64];   // samples -> dequantised coefficients -> reconstruction
     __shared__ __align__(16) float s_tmp[kJpegWarps][6][64];   // row-transformed intermediate
     __shared__ __align__(16) float s_chr[kJpegWarps][2][256];  // full-resolution Cb, Cr of the MCU
@@ -1097,7 +1145,7 @@ static int jpeg_impl(const float* x, float* out, const float* quality, float* fa
     const int nmcu = B * ((H + 15) / 16) * ((W + 15) / 16);
     int grid = (nmcu + kJpegWarps - 1) / kJpegWarps;
     if (grid > 148 * 8) grid = 148 * 8;   // beyond that, warps loop over MCUs
-    jpeg_kernel<<<grid, 32 * kJpegWarps, 0, s>>>(x, out, quality, factor_out, B, H, W, clamp_in, qy, qcb, qcr);
+    launch_pdl(jpeg_kernel, grid, 32 * kJpegWarps, 0, s, x, out, quality, factor_out, B, H, W, clamp_in, qy, qcb, qcr);
     RESR_LAUNCH_CHECK("jpeg");
     return RESR_OK;
 }
@@ -1105,6 +1153,8 @@ static int jpeg_impl(const float* x, float* out, const float* quality, float* fa
 // ===================================================================================== round + crop (a13)
 __global__ void __launch_bounds__(256) crop_kernel(const float* __restrict__ in, float* __restrict__ out, int planes, int Hi,
                                                    int Wi, int top, int left, int Ho, int Wo, int round_to_u8) {
+    grid_dep_wait();      // programmatic dependent launch: everything the previous kernel wrote is visible from here on
+    grid_dep_launch();    // the next kernel of the chain may be scheduled behind this one
     const size_t total = static_cast<size_t>(planes) * Ho * Wo;
     for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -1154,9 +1204,9 @@ int resr_usm_sharp_backward(const float* image, const float* grad_out, float* gr
     const int rc = usm_impl(image, t, ws, b, c, h, w, radius, sigma, weight, threshold, s, soft);
     if (rc != RESR_OK) return rc;
     int k = radius % 2 == 0 ? radius + 1 : radius;
-    usm_gsh_kernel<<<grid1d(E), 256, 0, s>>>(grad_out, image, ws + E, soft, gsh, E, weight);
-    usm_adjoint_kernel<<<grid1d(E), 256, 0, s>>>(gsh, t, b * c, h, w, k, 0, nullptr, nullptr, nullptr, weight);
-    usm_adjoint_kernel<<<grid1d(E), 256, 0, s>>>(t, grad_in, b * c, h, w, k, 1, grad_out, soft, gsh, weight);
+    launch_pdl(usm_gsh_kernel, grid1d(E), 256, 0, s, grad_out, image, ws + E, soft, gsh, E, weight);
+    launch_pdl(usm_adjoint_kernel, grid1d(E), 256, 0, s, gsh, t, b * c, h, w, k, 0, nullptr, nullptr, nullptr, weight);
+    launch_pdl(usm_adjoint_kernel, grid1d(E), 256, 0, s, t, grad_in, b * c, h, w, k, 1, grad_out, soft, gsh, weight);
     RESR_LAUNCH_CHECK("usm backward");
     return RESR_OK;
 }
@@ -1173,7 +1223,7 @@ int resr_gaussian_noise_apply(const float* image, float* out, const float* sigma
     if (!image || !out || !sigma || !noise_color) return set_error(RESR_E_INVALID, "null argument");
     if (noise_gray && !gray) return set_error(RESR_E_INVALID, "noise_gray needs gray flags");
     const size_t total = static_cast<size_t>(b) * c * h * w;
-    gaussian_noise_kernel<<<grid1d(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(image, out, sigma, gray, noise_color,
+    launch_pdl(gaussian_noise_kernel, grid1d(total), 256, 0, static_cast<cudaStream_t>(stream), image, out, sigma, gray, noise_color,
                                                                                        noise_gray, b, c, h * w, clip, rounds);
     RESR_LAUNCH_CHECK("gaussian_noise");
     return RESR_OK;
@@ -1183,7 +1233,7 @@ int resr_gaussian_noise_sampled(const float* image, float* out, const float* sig
                                 int clip, int rounds, unsigned long long seed, unsigned long long* call_state, void* stream) {
     if (!image || !out || !sigma || !call_state) return set_error(RESR_E_INVALID, "null argument");
     const size_t total = static_cast<size_t>(b) * c * h * w;
-    gaussian_noise_sampled_kernel<<<grid1d(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(image, out, sigma, gray, seed, call_state,
+    launch_pdl(gaussian_noise_sampled_kernel, grid1d(total), 256, 0, static_cast<cudaStream_t>(stream), image, out, sigma, gray, seed, call_state,
                                                                                                gray != nullptr, b, c, h * w, clip, rounds);
     RESR_LAUNCH_CHECK("gaussian_noise_sampled");
     return RESR_OK;
@@ -1203,8 +1253,8 @@ static int poisson_prepare(const float* image, int b, int c, int h, int w, int w
     const int HW = h * w;
     int gx = (HW + 255) / 256;
     if (gx > 64) gx = 64;
-    u8_presence_kernel<<<dim3(gx, b), 256, 0, s>>>(image, *bm, c, HW, want_gray, nullptr);
-    unique_counts_kernel<<<(2 * b + 127) / 128, 128, 0, s>>>(*bm, *counts, *vals, b);
+    launch_pdl(u8_presence_kernel, dim3(gx, b), 256, 0, s, image, *bm, c, HW, want_gray, nullptr);
+    launch_pdl(unique_counts_kernel, (2 * b + 127) / 128, 128, 0, s, *bm, *counts, *vals, b);
     RESR_LAUNCH_CHECK("poisson_prepare");
     return RESR_OK;
 }
@@ -1229,7 +1279,7 @@ int resr_poisson_rates(const float* image, float* rate_color, float* rate_gray, 
     unsigned* bm; int* counts; float* vals;
     const int rc = poisson_prepare(image, b, c, h, w, rate_gray != nullptr, workspace, workspace_bytes, s, &bm, &counts, &vals);
     if (rc != RESR_OK) return rc;
-    poisson_rates_kernel<<<grid1d(static_cast<size_t>(b) * h * w), 256, 0, s>>>(image, vals, rate_color, rate_gray, b, h * w);
+    launch_pdl(poisson_rates_kernel, grid1d(static_cast<size_t>(b) * h * w), 256, 0, s, image, vals, rate_color, rate_gray, b, h * w);
     RESR_LAUNCH_CHECK("poisson_rates");
     return RESR_OK;
 }
@@ -1244,7 +1294,7 @@ int resr_poisson_noise_apply(const float* image, float* out, const float* scale,
     const int rc = poisson_prepare(image, b, c, h, w, samples_gray != nullptr, workspace, workspace_bytes, s, &bm, &counts, &vals,
                                    reuse_counts != 0);
     if (rc != RESR_OK) return rc;
-    poisson_noise_kernel<<<grid1d(static_cast<size_t>(b) * h * w), 256, 0, s>>>(image, out, scale, gray, samples_color,
+    launch_pdl(poisson_noise_kernel, grid1d(static_cast<size_t>(b) * h * w), 256, 0, s, image, out, scale, gray, samples_color,
                                                                               samples_gray, vals, b, h * w, clip, rounds);
     RESR_LAUNCH_CHECK("poisson_noise");
     return RESR_OK;
@@ -1263,8 +1313,8 @@ int resr_poisson_noise_sampled(const float* image, float* out, const float* scal
     const int HW = h * w;
     int gx = (HW + 255) / 256;
     if (gx > 64) gx = 64;
-    u8_presence_kernel<<<dim3(gx, b), 256, 0, s>>>(image, bm, c, HW, gray != nullptr, counter);
-    poisson_noise_sampled_kernel<<<static_cast<unsigned>((static_cast<size_t>(b) * HW * 4 + 255) / 256), 256, 0, s>>>(image, out, scale, gray, bm, counter, seed,
+    launch_pdl(u8_presence_kernel, dim3(gx, b), 256, 0, s, image, bm, c, HW, gray != nullptr, counter);
+    launch_pdl(poisson_noise_sampled_kernel, static_cast<unsigned>((static_cast<size_t>(b) * HW * 4 + 255) / 256), 256, 0, s, image, out, scale, gray, bm, counter, seed,
                                                                                   gray != nullptr, b, HW, clip, rounds);
     RESR_LAUNCH_CHECK("poisson_noise_sampled");
     return RESR_OK;
@@ -1288,7 +1338,7 @@ int resr_crop(const float* image, float* out, int planes, int h_in, int w_in, in
             return set_error(RESR_E_CUDA, "crop copy failed");
         return RESR_OK;
     }
-    crop_kernel<<<grid1d(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(image, out, planes, h_in, w_in, top, left, h_out,
+    launch_pdl(crop_kernel, grid1d(total), 256, 0, static_cast<cudaStream_t>(stream), image, out, planes, h_in, w_in, top, left, h_out,
                                                                             w_out, round_to_u8);
     RESR_LAUNCH_CHECK("crop");
     return RESR_OK;

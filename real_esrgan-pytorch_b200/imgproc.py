@@ -653,7 +653,7 @@ def draw_augment_ops(batch: int, angles=(0, 90, 180, 270), p_hflip: float = 0.5,
 
 
 @_on_device
-def augment_batch(images_u8_bgr: torch.Tensor, ops: torch.Tensor) -> torch.Tensor:
+def augment_batch(images_u8_bgr: torch.Tensor, ops: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
     """dataset.py:67-79 on the device: decoded u8 HWC BGR images [b, h, w, 3] -> fp32 RGB tensors [b, 3, h, w] in [0, 1],
     rotated / flipped per sample as `ops` says (see draw_augment_ops). One gather kernel, bit-exact against
     random_rotate + random_*_flip + cvtColor + image_to_tensor of the reference (C ABI resr_augment_batch_u8)."""
@@ -666,7 +666,10 @@ def augment_batch(images_u8_bgr: torch.Tensor, ops: torch.Tensor) -> torch.Tenso
     o = ops.to(device=x.device, dtype=torch.int32).contiguous()
     if o.numel() != b:
         raise ValueError("one op per image")
-    out = torch.empty(b, 3, h, w, dtype=torch.float32, device=x.device)
+    if out is None:
+        out = torch.empty(b, 3, h, w, dtype=torch.float32, device=x.device)
+    elif out.shape != (b, 3, h, w) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != x.device:
+        raise ValueError("out must be a contiguous fp32 tensor [b, 3, h, w] on the images' device")
     _lib.check(_lib.lib().resr_augment_batch_u8(_lib.ptr(x), _lib.ptr(out), _lib.ptr(o), b, h, w, _lib.stream_ptr()))
     return out
 
