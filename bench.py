@@ -705,8 +705,8 @@ def run_ours(args):
 
 
 # ncu-measured DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum), see profiles/README.md for the captures
-TRAFFIC_PER_LAUNCH = 408.7e6   # bytes per conv launch, mean over the 351 launches of one cfg3 forward (profiles/r02_generator_launches.csv)
-DEGRADE_TRAFFIC = 133.6e6      # bytes per S0 batch, sum over the 15 launches, cold L2 (profiles/r02_degrade_launches.csv)
+TRAFFIC_PER_LAUNCH = 380.2e6   # bytes per conv launch, mean over the 351 launches of one cfg3 forward (profiles/r02_generator_launches_v2.csv)
+DEGRADE_TRAFFIC = 133.6e6      # bytes per S0 batch, sum over the 15 launches, cold L2 (profiles/r02_degrade_launches_v2.csv)
 DEGRADE_LAUNCHES = 15
 
 
