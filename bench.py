@@ -326,16 +326,36 @@ def training_bench(D, steps, warmup, peaks, precision="bf16", with_optimizer=Tru
     g = torch.Generator(device="cpu").manual_seed(2)
     hr = torch.rand(B, 3, H, W, generator=g).to(device)
     k1, k2, sk = s0_kernels(B, device, seed=3)   # reference-range supports (7 .. 21), real sinc
-    pipe = ip.DegradePipeline(hr, k1, k2, sk, plan)
+    # software-pipelined data path: the degradation of batch k + 1 (its own CUDA graph, on a data stream) runs under the
+    # training step of batch k, which is latency-bound at this size and leaves SM time free; two pipelines alternate
+    pipes = [ip.DegradePipeline(hr, k1, k2, sk, plan) for _ in range(2)]
     torch.manual_seed(0)
     gen = resr_b200.model.Generator(3, 3, 4).to(device).train()
     gen.set_precision(precision)
     ts = resr_b200.autograd.TrainStep(gen, B, H // 4, W // 4, device, None, world)
-    state = {}
+    data = torch.cuda.Stream(device=device)
+    ready = [torch.cuda.Event() for _ in range(2)]   # degradation output i is complete
+    done = [torch.cuda.Event() for _ in range(2)]    # the training step that read output i has finished
+    state = {"k": 0}
+    cur = torch.cuda.current_stream(device)
+    data.wait_stream(cur)
+    with torch.cuda.stream(data):
+        pipes[0]()
+        ready[0].record(data)
+    for e in done:
+        e.record(cur)
 
-    def step(k):
-        lr, hr_c = pipe()
-        state["loss"], _, _ = ts.step(lr, hr_c, scatter=False)
+    def step(_):
+        k = state["k"]
+        state["k"] = k + 1
+        i, nxt = k & 1, (k + 1) & 1
+        data.wait_event(done[nxt])
+        with torch.cuda.stream(data):
+            pipes[nxt]()
+            ready[nxt].record(data)
+        cur.wait_event(ready[i])
+        state["loss"], _, _ = ts.step(pipes[i].lr, pipes[i].hr_crop, scatter=False)
+        done[i].record(cur)
 
     ms = timed(step, steps, D, warm=max(3, warmup))
     ms = D.max_ms(ms)[0]
@@ -366,9 +386,10 @@ def training_bench(D, steps, warmup, peaks, precision="bf16", with_optimizer=Tru
             "precision": {"fp16": "fp16 activations, bf16 gradients, weight gradients through channels-first copies (wgrad_tc.cu)",
                           "bf16": "bf16 activations and gradients (north_star's recipe), fp32 residual stream, weight gradients "
                                   "straight from the NHWC buffers (wgrad_mn.cu)"}[precision],
-            "config": {"workload": "per GPU: degradation (plan S0, mixed / sinc kernels, CUDA graph) of 16x3x256x256 HR + RRDBNet x4 "
-                                   "forward/L1/backward on 16x3x64x64 LR (one CUDA graph), flat-gradient NCCL all-reduce when n_gpus > 1; "
-                                   "no optimizer"},
+            "config": {"workload": "per GPU and step: degradation (plan S0, mixed / sinc kernels, CUDA graph) of 16x3x256x256 HR + RRDBNet x4 "
+                                   "forward/L1/backward on 16x3x64x64 LR (one CUDA graph), flat-gradient NCCL all-reduce (4 buckets under "
+                                   "the backward) when n_gpus > 1; no optimizer. The degradation of batch k + 1 runs on a data stream "
+                                   "under the training step of batch k"},
             "roofline": {"bound": "tensor", "achieved": tflops, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                          "frac": tflops / peaks["tf_sustained"], "traffic": None,
                          "note": "algorithmic FLOPs = 3 x forward (SURVEY.md §8d): 7.05 TFLOP per GPU-step"}}
