@@ -418,20 +418,53 @@ def tiled_bench(D, gen, steps, peaks):
     px = Hh * Ww
     halo_factor = sum((t[5] - t[4]) for t in tiles) / Hh
 
-    def run(u8):
+    def shared_host(shape, dtype, tag):
+        """One result buffer in POSIX shared memory, mapped and page-locked (cudaHostRegister) by every rank: each rank's
+        bands go device -> host over its OWN PCIe link straight into their rows of the one 8192^2 image."""
+        import shutil
+        numel = int(np.prod(shape))
+        nbytes = numel * torch.empty((), dtype=dtype).element_size()
+        base = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > nbytes + (64 << 20) else "/tmp"
+        path = f"{base}/resr_tiled_{os.environ.get('MASTER_PORT', '0')}_{tag}"
+        if rank == 0:
+            with open(path, "wb") as f:
+                f.truncate(nbytes)
+        D.barrier()
+        t = torch.from_file(path, shared=True, size=numel, dtype=dtype).view(shape)
+        rc = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), nbytes, 0)
+        if int(rc) != 0:
+            raise RuntimeError(f"cudaHostRegister failed ({rc})")
+        D.barrier()
+        if rank == 0:
+            os.unlink(path)   # the mappings keep the memory alive
+        return t
+
+    def run(u8, shared=False):
+        tag = ("u8" if u8 else "f32")
         if u8:
-            out = torch.empty((1, s * Hh, s * Ww, 3), dtype=torch.uint8, device=device) if rank == 0 else None
-            y_host = torch.empty((1, s * Hh, s * Ww, 3), dtype=torch.uint8).pin_memory() if rank == 0 else None
+            shape, dt = (1, s * Hh, s * Ww, 3), torch.uint8
             x_dev = torch.empty((1, Hh, Ww, 3), dtype=torch.uint8, device=device)
             src = img_host
         else:
-            out = torch.empty((1, 3, s * Hh, s * Ww), dtype=torch.float32, device=device) if rank == 0 else None
-            y_host = torch.empty((1, 3, s * Hh, s * Ww), dtype=torch.float32).pin_memory() if rank == 0 else None
+            shape, dt = (1, 3, s * Hh, s * Ww), torch.float32
             x_dev = torch.empty((1, 3, Hh, Ww), dtype=torch.float32, device=device)
             src = x_host
+        if shared:
+            out, y_host = None, shared_host(shape, dt, tag)
+        else:
+            out = torch.empty(shape, dtype=dt, device=device) if rank == 0 else None
+            y_host = torch.empty(shape, dtype=dt).pin_memory() if rank == 0 else None
 
         def step(k):
-            x_dev.copy_(src, non_blocking=True)
+            if shared:   # only the windows this rank computes are uploaded
+                for i, (y0, y1, x0, x1, wy0, wy1, wx0, wx1) in enumerate(tiles):
+                    if i % world == rank:
+                        if u8:
+                            x_dev[:, wy0:wy1].copy_(src[:, wy0:wy1], non_blocking=True)
+                        else:
+                            x_dev[:, :, wy0:wy1].copy_(src[:, :, wy0:wy1], non_blocking=True)
+            else:
+                x_dev.copy_(src, non_blocking=True)
             ops, keep = [], []
             for i, (y0, y1, x0, x1, wy0, wy1, wx0, wx1) in enumerate(tiles):
                 owner = i % world
@@ -439,34 +472,47 @@ def tiled_bench(D, gen, steps, peaks):
                 if owner == rank:
                     if u8:
                         piece = gen.infer_u8(x_dev[:, wy0:wy1])[:, r0:r1]               # [1, rows, 4W, 3]: one contiguous block
-                        parts = [(piece[0], out[0, s * y0:s * y1] if rank == 0 else None)]
+                        parts = [(piece[0], (y_host if shared else out)[0, s * y0:s * y1] if (shared or rank == 0) else None)]
                     else:
                         sr = gen.infer(x_dev[:, :, wy0:wy1, :])
-                        parts = [(sr[0, c, r0:r1], out[0, c, s * y0:s * y1] if rank == 0 else None) for c in range(3)]
+                        parts = [(sr[0, c, r0:r1], (y_host if shared else out)[0, c, s * y0:s * y1] if (shared or rank == 0) else None)
+                                 for c in range(3)]
                     for piece_c, dst in parts:
-                        if rank == 0:
+                        if shared:
+                            dst.copy_(piece_c, non_blocking=True)   # D2H of this rank's rows into the shared pinned image
+                            keep.append(piece_c)
+                        elif rank == 0:
                             dst.copy_(piece_c)
                         else:
                             t = piece_c.contiguous()
                             keep.append(t)
                             ops.append(dist.P2POp(dist.isend, t, 0))
-                elif rank == 0:
+                elif rank == 0 and not shared:
                     dsts = [out[0, s * y0:s * y1]] if u8 else [out[0, c, s * y0:s * y1] for c in range(3)]
                     for dst in dsts:
                         ops.append(dist.P2POp(dist.irecv, dst, owner))
             if ops:
                 for w in dist.batch_isend_irecv(ops):
                     w.wait()
-            if rank == 0:
+            if rank == 0 and not shared:
                 y_host.copy_(out, non_blocking=True)
+            if shared:
+                torch.cuda.current_stream(device).synchronize()   # `keep` may go: this rank's copies have landed
 
         ms = timed(step, steps, D, warm=1)
         ms = D.max_ms(ms)[0]
         chk = None
         if rank == 0:
             chk = float(y_host[0, ::512, ::512].double().sum()) if u8 else float(y_host[0, :, ::512, ::512].double().sum())
+        if shared:
+            D.barrier()
+            torch.cuda.cudart().cudaHostUnregister(y_host.data_ptr())
         nbytes_in = src.numel() * src.element_size()
         nbytes_out = 3 * 16 * px * (1 if u8 else 4)
+        if shared:
+            return {"value": px / (ms * 1e-3) / 1e6, "unit": "LR Mpix/s", "ms_per_step": ms,
+                    "h2d_bytes_per_step": int(nbytes_in * halo_factor), "d2h_bytes_per_step": nbytes_out, "gather_bytes_per_step": 0,
+                    "checksum": chk}
         return {"value": px / (ms * 1e-3) / 1e6, "unit": "LR Mpix/s", "ms_per_step": ms, "h2d_bytes_per_step": nbytes_in * world,
                 "d2h_bytes_per_step": nbytes_out, "gather_bytes_per_step": nbytes_out * (world - 1) // world, "checksum": chk}
 
@@ -474,6 +520,17 @@ def tiled_bench(D, gen, steps, peaks):
     gen._workspace = None
     torch.cuda.empty_cache()
     u8 = run(True)
+    sh = {}
+    for name, is_u8 in (("fp32", False), ("u8_image", True)):
+        gen._workspace = None
+        torch.cuda.empty_cache()
+        try:
+            sh[name] = run(is_u8, shared=True)
+        except Exception as e:   # e.g. no /dev/shm: keep the NCCL-gather numbers
+            sh[name] = {"error": repr(e)}
+        if "checksum" in sh[name] and rank == 0:
+            ref = (u8 if is_u8 else f32)["checksum"]
+            sh[name]["matches_nccl_gather"] = bool(sh[name]["checksum"] == ref)
     ms = f32["ms_per_step"]
     tflops = FLOP_PER_LR_PIXEL * px * halo_factor / (ms * 1e-3) / 1e12
     tflops8 = FLOP_PER_LR_PIXEL * px * halo_factor / (u8["ms_per_step"] * 1e-3) / 1e12
@@ -483,6 +540,10 @@ def tiled_bench(D, gen, steps, peaks):
                                    f"+ 16-row halo ({halo_factor:.3f}x pixels computed), round-robin over {world} rank(s), NCCL send/recv "
                                    "gather into rank 0's buffer; timed end to end from / to pinned host memory (fp32 tensors)"},
             "e2e": f32,
+            "shared_pinned_host": dict(sh, api="no gather at all: the result image lives in ONE page-locked host buffer in POSIX shared "
+                                               "memory mapped by every rank (cudaHostRegister); each rank uploads only its windows and "
+                                               "copies its bands device -> host over its own PCIe link into their rows (SURVEY.md §8e: "
+                                               "'gather by P2P copy into one GPU's buffer or pinned host')"),
             "u8_image": dict(u8, api="Generator.infer_u8 per band (resr_generator_forward_u8): u8 HWC image in, u8 HWC image out, the "
                                      "conversions of inference.py:40-46, 56 fused into the first / last kernel",
                              roofline_frac=tflops8 / (peaks["tf_sustained"] * world)),
