@@ -531,15 +531,21 @@ def tiled_bench(D, gen, steps, peaks):
         if "checksum" in sh[name] and rank == 0:
             ref = (u8 if is_u8 else f32)["checksum"]
             sh[name]["matches_nccl_gather"] = bool(sh[name]["checksum"] == ref)
-    ms = f32["ms_per_step"]
+    # headline of the leg: the faster of the two ways of assembling the fp32 result in ONE pinned host buffer
+    best, how = f32, "NCCL send/recv gather into rank 0's buffer, then one device -> host copy"
+    if sh["fp32"].get("matches_nccl_gather") or (world > 1 and rank != 0):
+        if sh["fp32"].get("ms_per_step", float("inf")) < f32["ms_per_step"]:
+            best, how = sh["fp32"], "no gather: every rank copies its bands into one page-locked host image in shared memory"
+    ms = best["ms_per_step"]
     tflops = FLOP_PER_LR_PIXEL * px * halo_factor / (ms * 1e-3) / 1e12
     tflops8 = FLOP_PER_LR_PIXEL * px * halo_factor / (u8["ms_per_step"] * 1e-3) / 1e12
-    return {"metric": "tiled x4 inference LR Mpix/s", "value": f32["value"], "unit": "LR Mpix/s", "ms_per_step": ms,
+    return {"metric": "tiled x4 inference LR Mpix/s", "value": best["value"], "unit": "LR Mpix/s", "ms_per_step": ms,
             "n_gpus": world, "scaling": "strong", "steps": steps,
             "config": {"workload": "1x3x2048x2048 LR -> 1x3x8192x8192 SR (BASELINE.json configs[4]), 8 full-width bands of 256 LR rows "
-                                   f"+ 16-row halo ({halo_factor:.3f}x pixels computed), round-robin over {world} rank(s), NCCL send/recv "
-                                   "gather into rank 0's buffer; timed end to end from / to pinned host memory (fp32 tensors)"},
-            "e2e": f32,
+                                   f"+ 16-row halo ({halo_factor:.3f}x pixels computed), round-robin over {world} rank(s); timed end to "
+                                   f"end from / to pinned host memory (fp32 tensors); result assembled by: {how}"},
+            "e2e": best,
+            "nccl_gather": f32,
             "shared_pinned_host": dict(sh, api="no gather at all: the result image lives in ONE page-locked host buffer in POSIX shared "
                                                "memory mapped by every rank (cudaHostRegister); each rank uploads only its windows and "
                                                "copies its bands device -> host over its own PCIe link into their rows (SURVEY.md §8e: "
