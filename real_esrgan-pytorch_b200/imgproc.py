@@ -477,23 +477,30 @@ class DegradePipeline:
     Inputs live in static device buffers (`hr`, `kernel1`, `kernel2`, `sinc_kernel` and the tensors inside `plan`);
     update them in place (``pipe.hr.copy_(new_hr)``) and call the pipeline again."""
 
-    def __init__(self, hr, kernel1, kernel2, sinc_kernel, plan, use_graph: bool = True):
+    def __init__(self, hr, kernel1, kernel2, sinc_kernel, plan, use_graph: bool = True, u8_images: bool = False):
         dev = hr.device
         self.hr, self.kernel1, self.kernel2, self.sinc_kernel = (t.detach().clone().float().contiguous()
                                                                  for t in (hr, kernel1, kernel2, sinc_kernel))
         self.plan = plan_to_device(plan, dev)
         self.graph = None
+        # u8_images: the batch arrives as decoded u8 HWC BGR images (`pipe.images_u8`, with the per-sample augmentation ops in
+        # `pipe.augment_ops`); the augmentation gather that turns them into `hr` (dataset.py:67-79) is the graph's first node
+        self.images_u8 = self.augment_ops = None
+        if u8_images:
+            b, _, h, w = self.hr.shape
+            self.images_u8 = torch.zeros(b, h, w, 3, dtype=torch.uint8, device=dev)
+            self.augment_ops = torch.zeros(b, dtype=torch.int32, device=dev)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(2):  # warm-up outside the capture: constant-table uploads, function attributes, workspaces
-                self.lr, self.hr_crop = degrade_batch(self.hr, self.kernel1, self.kernel2, self.sinc_kernel, self.plan)
+                self.lr, self.hr_crop = self._run()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         if use_graph:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self.lr, self.hr_crop = degrade_batch(self.hr, self.kernel1, self.kernel2, self.sinc_kernel, self.plan)
+                self.lr, self.hr_crop = self._run()
             self.graph = g
         self.launches = None
 
@@ -501,8 +508,13 @@ class DegradePipeline:
         if self.graph is not None:
             self.graph.replay()
         else:
-            self.lr, self.hr_crop = degrade_batch(self.hr, self.kernel1, self.kernel2, self.sinc_kernel, self.plan)
+            self.lr, self.hr_crop = self._run()
         return self.lr, self.hr_crop
+
+    def _run(self):
+        if self.images_u8 is not None:
+            augment_batch(self.images_u8, self.augment_ops, out=self.hr)
+        return degrade_batch(self.hr, self.kernel1, self.kernel2, self.sinc_kernel, self.plan)
 
 
 _block_mods = None

@@ -490,3 +490,37 @@ def test_augment_batch_is_the_reference_chain_bit_for_bit():
     for k in range(16):
         op = int(ops[k])
         assert np.array_equal(out[k], oa.augment(imgs[k], op & 3, bool(op & 4), bool(op & 8)))
+
+
+@pytest.mark.gpu
+def test_degrade_pipeline_fed_with_u8_images():
+    """DegradePipeline(u8_images=True): the augmentation gather is the first node of the captured graph; the result equals
+    augment_batch followed by the plain pipeline."""
+    import random
+    import resr_b200
+    ip = resr_b200.imgproc
+    B, H, W = 4, 64, 72
+    plan = resr_b200.plan.canonical_plan_s0(B, H, W, seed=2)
+    rng = np.random.default_rng(5)   # host-fed second noise: the in-kernel Poisson draws advance a per-device call counter
+    plan["noise2"] = {"type": "gaussian", "sigma": rng.uniform(1, 25, size=B).astype(np.float32), "gray": plan["noise1"]["gray"],
+                      "noise_color": rng.standard_normal((B, 3, H // 4, W // 4), dtype=np.float32),
+                      "noise_gray": rng.standard_normal((H // 4, W // 4), dtype=np.float32)}
+    torch.manual_seed(0)
+    k = torch.zeros(B, 21, 21)
+    k[:, 8:13, 8:13] = 1.0 / 25
+    sk = torch.zeros(B, 21, 21)
+    sk[:, 10, 10] = 1
+    k, sk = k.cuda(), sk.cuda()
+    imgs = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8).cuda()
+    random.seed(4)
+    ops = ip.draw_augment_ops(B)
+    hr = ip.augment_batch(imgs, ops)
+    ref = ip.DegradePipeline(hr, k, k, sk, plan)
+    lr_ref, hrc_ref = ref()
+    pipe = ip.DegradePipeline(torch.zeros_like(hr), k, k, sk, plan, u8_images=True)
+    pipe.images_u8.copy_(imgs)
+    pipe.augment_ops.copy_(ops)
+    for _ in range(2):
+        lr, hrc = pipe()
+    torch.cuda.synchronize()
+    assert torch.equal(lr, lr_ref) and torch.equal(hrc, hrc_ref)
