@@ -307,6 +307,19 @@ size_t resr_conv3x3_wgrad_nhwc_workspace_bytes(void);
 int resr_conv3x3_wgrad_nhwc(const void* x_bf16, int x_cstride, const void* dy_bf16, int dy_cstride, int n, int h, int w,
                             int cin, int cout, float* dw, float* db, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * NIQE on the device (image_quality_assessment.py:886-998 `_niqe_torch`, class NIQE :1001-1033): the per-block feature
+ * extraction. image_rgb: fp32 NCHW [b,3,h,w] in [0,1]; features: float64 [b, nblocks, 36] (18 AGGD features of the MSCN
+ * coefficients per block at two scales; block order row-major -- the reference's column-first order only permutes the
+ * rows of a matrix whose mean and covariance are taken). crop_border pixels are dropped on every side, then the image
+ * is cropped to whole block x block tiles (block must be even: the second scale uses block / 2 on the half-size image).
+ * The 36-dimensional Gaussian fit against the pristine statistics (nanmean / nancov / pinv, :879-884) is a 36 x 36
+ * problem left to the caller (resr_b200/iqa.py). */
+int resr_niqe_num_blocks(int h, int w, int crop_border, int block);
+size_t resr_niqe_workspace_bytes(int b, int h, int w, int crop_border, int block);
+int resr_niqe_features(const float* image_rgb, double* features, int b, int h, int w, int crop_border, int block,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- the whole degradation block in one call (train_realesrnet.py:267-377 == train_realesrgan.py:347-457) ---------------
  * A POD plan holds every host decision of one execution of the block; per-sample parameters and host-fed random draws
  * are DEVICE pointers owned by the caller. Stage order, kernels and arithmetic are those of the op-level entry points. */

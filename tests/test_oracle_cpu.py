@@ -205,3 +205,20 @@ def test_draw_augment_ops_keeps_the_reference_rng_order():
         assert [0, 90, 180, 270][op & 3] == random.choice([0, 90, 180, 270])
         assert bool(op & 4) == (random.random() < 0.5)
         assert bool(op & 8) == (random.random() < 0.5)
+
+
+def test_niqe_oracle_matches_reference_golden():
+    """image_quality_assessment.py:886-998 restated in numpy (oracle/niqe.py) against the unmodified reference run with
+    synthetic pristine statistics (tests/golden/niqe.npz): per-block features and the final score."""
+    import numpy as np
+    from oracle import niqe as on
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "niqe.npz"))
+    for ci in range(3):
+        x = g[f"x{ci}"].astype(np.float32) / np.float32(255.0)
+        score, feat = on.niqe(x, int(g[f"border{ci}"]), g["mu_prisparam"], g["cov_prisparam"])
+        ref_feat = g[f"feat{ci}"]
+        for b in range(feat.shape[0]):      # block order differs (the reference stores blocks column-first): compare as sets
+            a = np.array(sorted(map(tuple, feat[b])))
+            r = np.array(sorted(map(tuple, ref_feat[b])))
+            assert np.abs(a - r).max() <= 1e-6
+        assert np.abs(score - g[f"niqe{ci}"]).max() <= 1e-5 * g[f"niqe{ci}"].max()
