@@ -457,6 +457,119 @@ __global__ void __launch_bounds__(256) usm_v51_kernel(const float* __restrict__ 
     }
 }
 
+// One blur (horizontal + vertical 51-tap pass + the pointwise tail) in ONE kernel: a block owns a 32-column strip of a plane
+// over its FULL height, so the horizontal-pass results it needs for the vertical pass are exactly the strip's own rows --
+// no halo recomputation, no scratch image, two launches per USM instead of four. The strip's horizontal results live in
+// shared memory ([H + 50][33] floats with the 25 reflected rows on either side); the per-output FMA order is that of
+// usm_h51_kernel / usm_v51_kernel (same usm_window8x2), so the results are bit-identical. 128 threads: horizontal pass
+// in chunks of 64 rows (lane = rows l, l + 32; warp = 8 columns), vertical pass in chunks of 64 rows (lane = column,
+// warp = 8 rows of each of the two 32-row halves).
+static constexpr int kUsmFCols = 32, kUsmFPitchT = 33, kUsmFPitchA = kUsmFCols + kUsmK - 1 + 1;   // 83: odd
+__global__ void __launch_bounds__(128) usm_fused51_kernel(const float* __restrict__ src, const float* __restrict__ x,
+                                                          float* __restrict__ res, float* __restrict__ mask_or_out, int H, int W,
+                                                          int stage, float weight, float threshold, float* __restrict__ soft_out) {
+    grid_dep_wait();
+    grid_dep_launch();
+    extern __shared__ float usm_sm[];
+    float* T = usm_sm;                                   // [H + 2 * kUsmR][33]: row i <-> image row i - 25
+    float* A = usm_sm + (H + 2 * kUsmR) * kUsmFPitchT;   // [64][83] staging of the horizontal pass
+    const int plane = blockIdx.y, x0 = blockIdx.x * kUsmFCols;
+    const size_t pbase = static_cast<size_t>(plane) * H * W;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int gxk[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) gxk[k] = min(max(reflect_idx(x0 + lane + 32 * k - kUsmR, W), 0), W - 1);
+    const bool last_ok = lane + 64 < kUsmFCols + kUsmK - 1;
+    // Horizontal pass in chunks of 64 rows. The global loads of chunk i + 1 are issued (into registers) before the FMAs of
+    // chunk i, so their latency hides behind the arithmetic: warp w holds rows w, w + 4, ... of the chunk, 3 columns per lane.
+    float v[16][3];
+    auto load_chunk = [&](int row0) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const float* srow = src + pbase + static_cast<size_t>(min(row0 + warp + 4 * u, H - 1)) * W;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) v[u][k] = srow[gxk[k]];
+        }
+    };
+    load_chunk(0);
+    for (int row0 = 0; row0 < H; row0 += 64) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int ty = warp + 4 * u;
+            A[ty * kUsmFPitchA + lane] = v[u][0];
+            A[ty * kUsmFPitchA + lane + 32] = v[u][1];
+            if (last_ok) A[ty * kUsmFPitchA + lane + 64] = v[u][2];
+        }
+        __syncthreads();
+        if (row0 + 64 < H) load_chunk(row0 + 64);
+        const int c0 = warp * kUsmO;
+        float2 acc[kUsmO];
+        usm_window8x2(A + lane * kUsmFPitchA + c0, A + (lane + 32) * kUsmFPitchA + c0, 1, acc);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int gy = row0 + lane + 32 * half;
+            if (gy < H) {
+                float* t = T + (gy + kUsmR) * kUsmFPitchT + c0;
+#pragma unroll
+                for (int j = 0; j < kUsmO; ++j) t[j] = half ? acc[j].y : acc[j].x;
+            }
+        }
+        __syncthreads();
+    }
+    // reflected halo rows: image row -k = row k, row H - 1 + k = row H - 1 - k  (k = 1 .. 25)
+    for (int i = threadIdx.x; i < 2 * kUsmR * kUsmFCols; i += blockDim.x) {
+        const int k = i / (2 * kUsmFCols) + 1, side = (i / kUsmFCols) & 1, c = i % kUsmFCols;
+        if (side == 0) T[(kUsmR - k) * kUsmFPitchT + c] = T[(kUsmR + k) * kUsmFPitchT + c];
+        else T[(kUsmR + H - 1 + k) * kUsmFPitchT + c] = T[(kUsmR + H - 1 - k) * kUsmFPitchT + c];
+    }
+    __syncthreads();
+    const int gx = x0 + lane;
+    // Vertical pass in chunks of 64 rows; the tail's operands (x, res) of chunk i + 1 are requested before chunk i's FMAs.
+    float2 xv[kUsmO], rv[kUsmO], xn[kUsmO], rn[kUsmO];
+    auto load_tail = [&](int row0, float2 (&xo)[kUsmO], float2 (&ro)[kUsmO]) {
+        const int r0 = row0 + warp * kUsmO, r1 = r0 + 32;
+#pragma unroll
+        for (int j = 0; j < kUsmO; ++j) {
+            const size_t oa = pbase + static_cast<size_t>(min(r0 + j, H - 1)) * W + min(gx, W - 1);
+            const size_t ob = pbase + static_cast<size_t>(min(r1 + j, H - 1)) * W + min(gx, W - 1);
+            xo[j] = make_float2(x[oa], x[ob]);
+            ro[j] = stage == 0 ? make_float2(0.f, 0.f) : make_float2(res[oa], res[ob]);
+        }
+    };
+    load_tail(0, xn, rn);
+    for (int row0 = 0; row0 < H; row0 += 64) {
+        const int r0 = row0 + warp * kUsmO, r1 = r0 + 32;      // two lines: the same column, rows r0.. and r0 + 32..
+#pragma unroll
+        for (int j = 0; j < kUsmO; ++j) { xv[j] = xn[j]; rv[j] = rn[j]; }
+        if (row0 + 64 < H) load_tail(row0 + 64, xn, rn);
+        float2 acc[kUsmO];
+        // T row index of image row r is r + 25, and the window of output row r starts at image row r - 25: T row r
+        usm_window8x2(T + min(r0, H - 1) * kUsmFPitchT + lane, T + min(r1, H - 1) * kUsmFPitchT + lane, kUsmFPitchT, acc);
+        if (gx >= W) continue;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+            for (int j = 0; j < kUsmO; ++j) {
+                const int gy = (half ? r1 : r0) + j;
+                if (gy >= H) break;
+                const size_t o = pbase + static_cast<size_t>(gy) * W + gx;
+                const float a = half ? acc[j].y : acc[j].x, xx = half ? xv[j].y : xv[j].x;
+                if (stage == 0) {
+                    const float r = xx - a;                                               // imgproc.py:1528
+                    res[o] = r;
+                    mask_or_out[o] = (fabsf(r) * 255.f > threshold) ? 1.f : 0.f;          // imgproc.py:1530-1531
+                } else {
+                    const float rr = half ? rv[j].y : rv[j].x;
+                    float sh = __fadd_rn(xx, __fmul_rn(weight, rr));                      // imgproc.py:1533
+                    sh = fminf(fmaxf(sh, 0.f), 1.f);                                      // imgproc.py:1534
+                    mask_or_out[o] = __fadd_rn(__fmul_rn(a, sh), __fmul_rn(1.f - a, xx));  // imgproc.py:1535
+                    if (soft_out) soft_out[o] = a;
+                }
+            }
+        }
+    }
+}
+
 static int usm_set_taps(int radius, int sigma, int* k_out) {
     if (radius % 2 == 0) radius += 1;  // imgproc.py:1518-1519
     if (radius > kUsmMaxTaps) return set_error(RESR_E_INVALID, "USM radius %d too large", radius);
@@ -494,7 +607,18 @@ static int usm_impl(const float* x, float* out, float* ws, int B, int C, int H, 
     float* mask = ws + 2 * E;
     const dim3 gh((W + 255) / 256, H, B * C), gv((W + 31) / 32, (H + 63) / 64, B * C);
     const size_t sh = (256 + k - 1) * sizeof(float), sv = static_cast<size_t>(64 + k - 1) * 32 * sizeof(float);
-    if (k == kUsmK) {
+    static const int env_fused = getenv("RESR_USM_FUSED") ? atoi(getenv("RESR_USM_FUSED")) : 1;
+    const size_t fsm = (static_cast<size_t>(H + 2 * kUsmR) * kUsmFPitchT + 64 * kUsmFPitchA) * sizeof(float);
+    if (k == kUsmK && env_fused && fsm <= 100 * 1024) {   // strip height bounded by shared memory (H <= ~570)
+        static PerDevice<size_t> attr_set;
+        if (fsm > 48 * 1024 && fsm > attr_set.cur()) {
+            cudaFuncSetAttribute(usm_fused51_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fsm));
+            attr_set.cur() = fsm;
+        }
+        const dim3 gf((W + kUsmFCols - 1) / kUsmFCols, B * C);
+        launch_pdl(usm_fused51_kernel, gf, 128, fsm, s, x, x, res, mask, H, W, 0, weight, threshold, nullptr);
+        launch_pdl(usm_fused51_kernel, gf, 128, fsm, s, static_cast<const float*>(mask), x, res, out, H, W, 1, weight, threshold, soft_out);
+    } else if (k == kUsmK) {
         const dim3 g51h((W + kUsmHCols - 1) / kUsmHCols, (H + kUsmHRows - 1) / kUsmHRows, B * C);
         const dim3 g51v((W + kUsmVCols - 1) / kUsmVCols, (H + kUsmVRows - 1) / kUsmVRows, B * C);
         launch_pdl(usm_h51_kernel, g51h, 256, 0, s, x, tmp, H, W);
