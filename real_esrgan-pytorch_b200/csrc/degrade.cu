@@ -39,6 +39,15 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {  // ATen reflection_p
     return i >= n ? 2 * (n - 1) - i : i;
 }
 
+// a / b and a % b in 32-bit arithmetic whenever the dividend fits: a 64-bit division is a ~100-instruction subroutine, and
+// the elementwise kernels below decode one linear index per element
+__device__ __forceinline__ size_t div_u(size_t a, unsigned b) {
+    return a <= 0xffffffffull ? static_cast<size_t>(static_cast<unsigned>(a) / b) : a / b;
+}
+__device__ __forceinline__ unsigned mod_u(size_t a, unsigned b) {
+    return a <= 0xffffffffull ? static_cast<unsigned>(a) % b : static_cast<unsigned>(a % b);
+}
+
 // ===================================================================================== filter2d (a8)
 // One block = 64 x (8 * R) output tile of one (sample, channel) plane; 256 threads = 32 columns x 8 row groups, each
 // thread owns R consecutive rows of 2 columns (x and x+32). The reflect-padded halo tile and the taps live in shared
@@ -98,11 +107,14 @@ __global__ void __launch_bounds__(R == 16 ? 128 : 256) filter2d_kernel(const flo
     const float* kp = kern + (kern_batched ? static_cast<size_t>(b) * k * k : 0);
     if (threadIdx.x == 0) s_ext = 0;
     __syncthreads();
-    for (int i = threadIdx.x; i < k * k; i += blockDim.x) {
+    int ext_mine = 0;                  // per-thread, then per-warp maximum: ONE shared atomic per warp (a dense 21 x 21 sinc
+    for (int i = threadIdx.x; i < k * k; i += blockDim.x) {   // kernel used to serialise 441 of them per block)
         const float v = kp[i];
         taps[i] = v;
-        if (v != 0.f) atomicMax(&s_ext, max(abs(i / k - r), abs(i % k - r)));
+        if (v != 0.f) ext_mine = max(ext_mine, max(abs(i / k - r), abs(i % k - r)));
     }
+    ext_mine = __reduce_max_sync(0xffffffffu, ext_mine);
+    if ((threadIdx.x & 31) == 0 && ext_mine > 0) atomicMax(&s_ext, ext_mine);
     __syncthreads();
     const int ext = s_ext;
     const int off = r - ext;           // first row/col of the centred support inside the k x k array
@@ -692,9 +704,10 @@ __global__ void __launch_bounds__(256) resize_kernel(const float* __restrict__ i
     const size_t total = static_cast<size_t>(planes) * Ho * Wo;
     for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int ox = idx % Wo;
-        const int oy = (idx / Wo) % Ho;
-        const size_t p = idx / (static_cast<size_t>(Wo) * Ho);
+        const size_t rowi = div_u(idx, Wo);
+        const int ox = static_cast<int>(mod_u(idx, Wo));
+        const int oy = static_cast<int>(mod_u(rowi, Ho));
+        const size_t p = div_u(rowi, Ho);
         const float* src = in + p * Hi * Wi;
         float v;
         if (mode == 0) {  // area == adaptive_avg_pool2d
@@ -780,8 +793,8 @@ __global__ void __launch_bounds__(256) gaussian_noise_kernel(const float* __rest
     const size_t total = static_cast<size_t>(B) * C * HW;
     for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int b = idx / (static_cast<size_t>(C) * HW);
-        const int p = idx % HW;
+        const int b = static_cast<int>(div_u(idx, static_cast<unsigned>(C) * HW));
+        const int p = static_cast<int>(mod_u(idx, HW));
         const float sg = sigma[b];
         float n = __fdiv_rn(__fmul_rn(ncolor[idx], sg), 255.f);  // imgproc.py:858
         if (ngray) {                                             // imgproc.py:853-861
@@ -807,8 +820,8 @@ __global__ void __launch_bounds__(256) gaussian_noise_sampled_kernel(const float
     const unsigned long long call = state[0];
     for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int b = idx / (static_cast<size_t>(C) * HW);
-        const int p = idx % HW;
+        const int b = static_cast<int>(div_u(idx, static_cast<unsigned>(C) * HW));
+        const int p = static_cast<int>(mod_u(idx, HW));
         const float sg = sigma[b];
         curandStatePhilox4_32_10_t st;
         curand_init(seed, idx, call * 8ull, &st);
@@ -884,8 +897,8 @@ __global__ void __launch_bounds__(256) poisson_noise_kernel(const float* __restr
     const size_t total = static_cast<size_t>(B) * HW;
     for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int b = idx / HW;
-        const int p = idx % HW;
+        const int b = static_cast<int>(div_u(idx, HW));
+        const int p = static_cast<int>(mod_u(idx, HW));
         const size_t base = static_cast<size_t>(b) * 3 * HW + p;
         const float r = x[base], g = x[base + HW], bl = x[base + 2 * static_cast<size_t>(HW)];
         const float vc = vals[2 * b], sc = scale[b];
@@ -973,8 +986,8 @@ __global__ void __launch_bounds__(256) poisson_noise_sampled_kernel(const float*
     const int k = static_cast<int>(tid & 3);
     const bool live = idx < total;
     const size_t pi = live ? idx : 0;
-    const int b = pi / HW;
-    const int p = pi % HW;
+    const int b = static_cast<int>(div_u(pi, HW));
+    const int p = static_cast<int>(mod_u(pi, HW));
     const size_t base = static_cast<size_t>(b) * 3 * HW + p;
     const float r = x[base], g = x[base + HW], bl = x[base + 2 * static_cast<size_t>(HW)];
     const float vc = vals_of(bitmaps + b * 16);
@@ -1010,8 +1023,8 @@ __global__ void __launch_bounds__(256) poisson_rates_kernel(const float* __restr
     const size_t total = static_cast<size_t>(B) * HW;
     for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int b = idx / HW;
-        const int p = idx % HW;
+        const int b = static_cast<int>(div_u(idx, HW));
+        const int p = static_cast<int>(mod_u(idx, HW));
         const size_t base = static_cast<size_t>(b) * 3 * HW + p;
         const float r = x[base], g = x[base + HW], bl = x[base + 2 * static_cast<size_t>(HW)];
         const float vc = vals[2 * b];
@@ -1282,9 +1295,10 @@ __global__ void __launch_bounds__(256) crop_kernel(const float* __restrict__ in,
     const size_t total = static_cast<size_t>(planes) * Ho * Wo;
     for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int ox = idx % Wo;
-        const int oy = (idx / Wo) % Ho;
-        const size_t p = idx / (static_cast<size_t>(Wo) * Ho);
+        const size_t rowi = div_u(idx, Wo);
+        const int ox = static_cast<int>(mod_u(idx, Wo));
+        const int oy = static_cast<int>(mod_u(rowi, Ho));
+        const size_t p = div_u(rowi, Ho);
         float v = in[(p * Hi + top + oy) * Wi + left + ox];
         if (round_to_u8) v = round_u8(v);  // train_realesrnet.py:374
         out[idx] = v;
