@@ -203,3 +203,20 @@ def test_param_version_key_sees_data_swaps():
     with torch.no_grad():
         p.mul_(1.0)
     assert g._param_version() != v0
+
+
+def test_gradient_bucket_offsets_follow_state_dict_order():
+    """resr_generator_grad_buckets (host-only): the flat gradient vector is cut at trunk.5 / trunk.11 / trunk.17."""
+    import ctypes
+    import resr_b200
+    g = resr_b200.model.Generator(3, 3, 4)
+    offs = (ctypes.c_size_t * 5)()
+    assert resr_b200._lib.lib().resr_generator_grad_buckets(offs, 5) == 4
+    pos, want = 0, {}
+    for k, v in g.state_dict().items():
+        if k in ("trunk.5.rdb1.conv1.weight", "trunk.11.rdb1.conv1.weight", "trunk.17.rdb1.conv1.weight"):
+            want[k] = pos
+        pos += v.numel()
+    assert [int(o) for o in offs] == [0, want["trunk.5.rdb1.conv1.weight"], want["trunk.11.rdb1.conv1.weight"],
+                                      want["trunk.17.rdb1.conv1.weight"], pos]
+    assert resr_b200._lib.lib().resr_niqe_num_blocks(200, 304, 4, 96) == 6 and resr_b200._lib.lib().resr_niqe_num_blocks(90, 200, 0, 96) == 0
