@@ -233,13 +233,15 @@ def test_flat_adam_ema_matches_torch_adam_and_reference_ema():
 
 
 @pytest.mark.gpu
-def test_training_loop_step_graph_plus_fused_optimizer_reduces_the_loss():
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+def test_training_loop_step_graph_plus_fused_optimizer_reduces_the_loss(precision):
     """The pieces together as train_realesrnet.py:383-394 uses them: TrainStep (one CUDA-graph replay per step), flat Adam +
     EMA, weights repacked from the flat master copy — eight iterations on one fixed batch must drive the L1 loss down, and
     the first step must equal a torch.optim.Adam step taken from the same gradients."""
     import resr_b200
     torch.manual_seed(3)
     g = resr_b200.model.Generator(3, 3, 4).cuda().train()
+    g.set_precision(precision)
     opt = resr_b200.optim.FlatAdamEMA(g, lr=2e-4, betas=(0.9, 0.99))
     ts = resr_b200.autograd.TrainStep(g, 2, 16, 24)
     lr = torch.rand(2, 3, 16, 24, device="cuda")
@@ -257,7 +259,7 @@ def test_training_loop_step_graph_plus_fused_optimizer_reduces_the_loss():
         if it == 0:
             assert (opt.flat - ref.detach()).abs().max().item() <= 2e-7
     assert ts.is_graph
-    print("losses", [round(v, 5) for v in losses])
+    print(f"[{precision}] losses", [round(v, 5) for v in losses])
     assert losses[-1] < losses[0] * 0.9 and min(losses[4:]) < min(losses[:2])
     assert torch.isfinite(opt.flat).all() and torch.isfinite(opt.shadow).all()
 
