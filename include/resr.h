@@ -263,7 +263,10 @@ int resr_draw_degradation_kernel_params(const resr_kernel_draw_config* cfg, int 
  * Replaces `sr = model(lr); loss = L1(sr, hr); loss.backward()` (train_realesrnet.py:383-388) for the generator.
  * grads_flat: fp32 [resr_generator_num_params()] in state_dict order (layout of resr_generator_tensor_span); every
  * element is overwritten. The flat parameter vector given to resr_generator_load_params must stay alive (the
- * transposed weight packs of the data-gradient convolutions are built from it on the first backward). w % 8 == 0.
+ * transposed weight packs of the data-gradient convolutions are built from it on the first backward).
+ * Two recipes (resr_generator_set_precision): 0 = fp16 activations + bf16 gradients, weight gradients through
+ * channels-first copies (w % 8 == 0 required); 1 = bf16 activations and gradients with an fp32 residual stream, weight
+ * gradients straight from the NHWC buffers (csrc/wgrad_mn.cu; no shape rule, ~27 % faster per step).
  * ---------------------------------------------------------------------------------------------------------- */
 size_t resr_generator_train_workspace_bytes(int n, int h, int w);
 int resr_generator_forward_train(resr_generator_t* g, const float* x, float* y, int n, int h, int w, void* workspace,
