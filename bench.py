@@ -426,17 +426,34 @@ def tiled_bench(D, gen, steps, peaks):
         nbytes = numel * torch.empty((), dtype=dtype).element_size()
         base = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > nbytes + (64 << 20) else "/tmp"
         path = f"{base}/resr_tiled_{os.environ.get('MASTER_PORT', '0')}_{tag}"
+        def all_ok(ok):   # every rank learns whether every rank succeeded: nobody is left waiting in a barrier
+            return D.max_ms(0.0 if ok else 1.0)[0] == 0.0
+
+        ok = True
         if rank == 0:
-            with open(path, "wb") as f:
-                f.truncate(nbytes)
-        D.barrier()
-        t = torch.from_file(path, shared=True, size=numel, dtype=dtype).view(shape)
-        rc = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), nbytes, 0)
-        if int(rc) != 0:
-            raise RuntimeError(f"cudaHostRegister failed ({rc})")
-        D.barrier()
+            try:
+                with open(path, "wb") as f:
+                    f.truncate(nbytes)
+            except OSError:
+                ok = False
+        if not all_ok(ok):
+            raise RuntimeError(f"could not create {path}")
+        t, ok = None, True
+        try:
+            t = torch.from_file(path, shared=True, size=numel, dtype=dtype).view(shape)
+            ok = int(torch.cuda.cudart().cudaHostRegister(t.data_ptr(), nbytes, 0)) == 0
+        except Exception:
+            ok = False
+        everyone = all_ok(ok)
         if rank == 0:
-            os.unlink(path)   # the mappings keep the memory alive
+            try:
+                os.unlink(path)   # the mappings keep the memory alive
+            except OSError:
+                pass
+        if not everyone:
+            if ok and t is not None:
+                torch.cuda.cudart().cudaHostUnregister(t.data_ptr())
+            raise RuntimeError("mapping / page-locking the shared result image failed on some rank")
         return t
 
     def run(u8, shared=False):
