@@ -57,8 +57,8 @@ constexpr int kMiscBytes = 1024;
 constexpr int kSmemMax = 232448;    // 227 KB opt-in limit per CTA
 constexpr int kTileFBytes = 16384;  // 128 px x 32 fp32
 
-struct RowRange {
-    long long g0, g1;
+struct RowRange {   // 32-bit on purpose: 64-bit divisions are ~100-instruction subroutines and every role decodes its strips
+    int g0, g1;     // (the launcher refuses problems with rows_total * grid >= 2^31)
 };
 
 // K-major, 128B-swizzled operand descriptor: constant high word (SBO = 1024 B, version 1, SWIZZLE_128B) + low word.
@@ -139,9 +139,9 @@ __device__ __forceinline__ void mma_role(const ConvArgs& a, const RowRange rr, c
     uint32_t acq = 0;                // accumulators acquired so far (virtual indices < acq)
     PROF_DECL(p_full); PROF_DECL(p_slot); PROF_DECL(p_steps);
     PROF_T0(p_t0);
-    for (long long g = rr.g0; g < rr.g1;) {
-        const int ya = static_cast<int>(g % H);
-        const int yb = static_cast<int>(min(static_cast<long long>(H), ya + (rr.g1 - g)));
+    for (int g = rr.g0; g < rr.g1;) {
+        const int ya = g % H;
+        const int yb = min(H, ya + (rr.g1 - g));
         const int ra = max(ya - 1, 0), rb = min(yb, H - 1);
         vnew += 1;                   // a strip touches rows ra-1 .. rb+1: first row's newest accumulator is v0 + 2
         for (int r = ra; r <= rb; ++r, ++vnew) {
@@ -293,9 +293,9 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
     // the pair's work: a contiguous range of (pair column group, row); this CTA takes column group 2 * cg2 + rank
     RowRange rr;
     {
-        const long long npairs = gridDim.x >> 1, pidx = blockIdx.x >> 1;
-        rr.g0 = a.rows_total_pair * pidx / npairs;
-        rr.g1 = a.rows_total_pair * (pidx + 1) / npairs;
+        const unsigned npairs = gridDim.x >> 1, pidx = blockIdx.x >> 1, rows = static_cast<unsigned>(a.rows_total_pair);
+        rr.g0 = static_cast<int>(rows * pidx / npairs);
+        rr.g1 = static_cast<int>(rows * (pidx + 1) / npairs);
     }
     const int H = a.H;
 
@@ -338,11 +338,11 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
         PROF_DECL(p_empty);
         PROF_T0(p_t0);
         const int ncg2 = (a.ncg + 1) >> 1;
-        for (long long g = rr.g0; g < rr.g1;) {
-            const int cg2 = static_cast<int>(g / H);
+        for (int g = rr.g0; g < rr.g1;) {
+            const int cg2 = g / H;
             const int cg = 2 * (a.reverse ? ncg2 - 1 - cg2 : cg2) + static_cast<int>(rank);  // may be == ncg (odd count): all out of bounds
-            const int ya = static_cast<int>(g % H);
-            const int yb = static_cast<int>(min(static_cast<long long>(H), ya + (rr.g1 - g)));
+            const int ya = g % H;
+            const int yb = min(H, ya + (rr.g1 - g));
             const int n0 = (cg / a.nxs) * a.BN;
             const int x0 = (cg % a.nxs) * a.BW;
             const int ra = max(ya - 1, 0), rb = min(yb, H - 1);
@@ -413,11 +413,11 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
         PROF_T0(p_t0);
         uint32_t v0 = 0;
         const int ncg2 = (a.ncg + 1) >> 1;
-        for (long long g = rr.g0; g < rr.g1;) {
-            const int cg2 = static_cast<int>(g / H);
+        for (int g = rr.g0; g < rr.g1;) {
+            const int cg2 = g / H;
             const int cg = 2 * (a.reverse ? ncg2 - 1 - cg2 : cg2) + static_cast<int>(rank);
-            const int ya = static_cast<int>(g % H);
-            const int yb = static_cast<int>(min(static_cast<long long>(H), ya + (rr.g1 - g)));
+            const int ya = g % H;
+            const int yb = min(H, ya + (rr.g1 - g));
             const int n0 = (cg / a.nxs) * a.BN;
             const int x0 = (cg % a.nxs) * a.BW;
             const int n = n0 + img_in_tile;
@@ -772,6 +772,7 @@ cudaError_t conv3x3_pair_launch(const ConvMaps& maps, const ConvArgs& args_in, i
     const long long cap = (args.rows_total_pair + min_rows - 1) / min_rows;
     if (npairs > cap) npairs = cap;
     if (npairs < 1) npairs = 1;
+    if (args.rows_total_pair * (npairs + 1) >= (1ll << 31)) return cudaErrorInvalidValue;   // the kernel's strip arithmetic is 32-bit
     if (args.tail_ksteps != 1 && args.tail_ksteps != 2 && args.tail_ksteps != 4) args.tail_ksteps = 4;
     const dim3 grid(static_cast<unsigned>(2 * npairs), static_cast<unsigned>(nslices), 1);
     const int threads = 128 + 128 * args.nepi;

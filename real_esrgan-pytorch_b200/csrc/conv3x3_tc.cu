@@ -47,14 +47,15 @@ static constexpr int kMiscBytes = 1024;
 static constexpr int kSmemMax = 232448;    // 227 KB opt-in limit per CTA
 static constexpr int kTileFBytes = 16384;  // 128 px x 32 fp32
 
-struct RowRange {
-    long long g0, g1;
+struct RowRange {   // 32-bit on purpose: 64-bit divisions are ~100-instruction subroutines and every role decodes its strips
+    int g0, g1;     // (the launcher refuses problems with rows_total * grid >= 2^31)
 };
 
 __device__ __forceinline__ RowRange cta_rows(const ConvArgs& a) {
     RowRange r;
-    r.g0 = a.rows_total * static_cast<long long>(blockIdx.x) / gridDim.x;
-    r.g1 = a.rows_total * static_cast<long long>(blockIdx.x + 1) / gridDim.x;
+    const unsigned rows = static_cast<unsigned>(a.rows_total);
+    r.g0 = static_cast<int>(rows * blockIdx.x / gridDim.x);
+    r.g1 = static_cast<int>(rows * (blockIdx.x + 1) / gridDim.x);
     return r;
 }
 
@@ -65,7 +66,7 @@ __device__ __forceinline__ unsigned long long gtimer() {
 }
 #define RESR_DBG(slot) do { if (a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0) a.dbg[slot] = gtimer(); } while (0)
 
-__device__ __forceinline__ uint32_t slot_of(long long v) { return static_cast<uint32_t>((16 - (v & 15)) & 15); }
+__device__ __forceinline__ uint32_t slot_of(uint32_t v) { return (16u - (v & 15u)) & 15u; }
 
 __host__ __device__ inline int epi_group_bytes(const ConvArgs& a, int nout) {
     const int f = a.has_outf ? kTileFBytes : 0;  // fp32 output tile (TMA store)
@@ -182,9 +183,9 @@ __device__ __forceinline__ void mma_role(const ConvArgs& a, const RowRange rr, c
     bool full_ready = false, slot_ready = false;
     uint32_t vnew = 1;               // virtual index of the NEWEST accumulator the next row touches (out row r+1)
     uint32_t acq = 0;                // accumulators acquired so far (virtual indices < acq)
-    for (long long g = rr.g0; g < rr.g1;) {
-        const int ya = static_cast<int>(g % H);
-        const int yb = static_cast<int>(min(static_cast<long long>(H), ya + (rr.g1 - g)));
+    for (int g = rr.g0; g < rr.g1;) {
+        const int ya = g % H;
+        const int yb = min(H, ya + (rr.g1 - g));
         const int ra = max(ya - 1, 0), rb = min(yb, H - 1);
         vnew += 1;                   // a strip touches rows ra-1 .. rb+1: first row's newest accumulator is v0 + 2
         for (int r = ra; r <= rb; ++r, ++vnew) {
@@ -317,10 +318,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         uint32_t phase = 0;
         const int ndx = a.mode == 0 ? 1 : 3;
         const uint32_t tx_bytes = a.mode == 0 ? (a.BW + 2) * 128 : 128 * 128;
-        for (long long g = rr.g0; g < rr.g1;) {
-            const int cg = static_cast<int>(g / H);
-            const int ya = static_cast<int>(g % H);
-            const int yb = static_cast<int>(min(static_cast<long long>(H), ya + (rr.g1 - g)));
+        for (int g = rr.g0; g < rr.g1;) {
+            const int cg = g / H;
+            const int ya = g % H;
+            const int yb = min(H, ya + (rr.g1 - g));
             const int n0 = (cg / a.nxs) * a.BN;
             const int x0 = (cg % a.nxs) * a.BW;
             const int ra = max(ya - 1, 0), rb = min(yb, H - 1);
@@ -377,11 +378,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
             for (int s = s_lo; s < s_hi; ++s) mbar_arrive(slot_free + s);
         }
         grid_dep_wait();  // residual reads / output writes below touch buffers of the previous kernel
-        long long v0 = 0;
-        for (long long g = rr.g0; g < rr.g1;) {
-            const int cg = static_cast<int>(g / H);
-            const int ya = static_cast<int>(g % H);
-            const int yb = static_cast<int>(min(static_cast<long long>(H), ya + (rr.g1 - g)));
+        uint32_t v0 = 0;
+        for (int g = rr.g0; g < rr.g1;) {
+            const int cg = g / H;
+            const int ya = g % H;
+            const int yb = min(H, ya + (rr.g1 - g));
             const int n0 = (cg / a.nxs) * a.BN;
             const int x0 = (cg % a.nxs) * a.BW;
             const int n = n0 + img_in_tile;
@@ -390,8 +391,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
             const int ra = max(ya - 1, 0), rb = min(yb, H - 1);
             const int n_acc = rb - ra + 3;
             for (int j = 0; j < n_acc; ++j) {
-                const long long v = v0 + j;
-                if (static_cast<int>(v % a.nepi) != gi) continue;
+                const uint32_t v = v0 + j;
+                if (static_cast<int>(v % static_cast<uint32_t>(a.nepi)) != gi) continue;
                 const int y = ra - 1 + j;
                 const bool emit = (y >= ya) && (y < yb) && !DBGF(8);
                 const uint32_t slot = slot_of(v);
@@ -769,6 +770,7 @@ cudaError_t conv3x3_launch(const ConvMaps& maps, const ConvArgs& args, int cout_
     const long long cap = (args.rows_total + min_rows - 1) / min_rows;
     if (gx > cap) gx = cap;
     if (gx < 1) gx = 1;
+    if (args.rows_total * (gx + 1) >= (1ll << 31)) return cudaErrorInvalidValue;   // the kernel's strip arithmetic is 32-bit
     const dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(nslices), 1);
     const int threads = 128 + 128 * args.nepi;
     static const int env_flags = getenv("RESR_CONV_DBGFLAGS") ? atoi(getenv("RESR_CONV_DBGFLAGS")) : 0;  // experiments only
