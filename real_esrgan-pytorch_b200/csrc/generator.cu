@@ -24,9 +24,9 @@ __device__ __forceinline__ void pack_conv_body(const float* __restrict__ w, cons
                                                int transposed, size_t first, size_t stride) {
     const int NT = 3 * nout;
     const size_t total = static_cast<size_t>(nslices) * nchunks * 3 * NT * 64;
-    for (size_t idx = first; idx < total; idx += stride) {
-        const int k = idx % 64;
-        size_t t = idx / 64;
+    for (size_t idx = first; idx < total; idx += stride) {   // (a layer's pack has < 2^32 elements: 32-bit index decoding)
+        const int k = static_cast<int>(idx & 63);
+        unsigned t = static_cast<unsigned>(idx >> 6);
         const int n = t % NT;
         t /= NT;
         const int dx = t % 3;
@@ -100,8 +100,8 @@ __global__ void __launch_bounds__(256) pack_rdb_bwd_kernel(const float* __restri
     const size_t total = static_cast<size_t>(shape.nslices) * shape.nchunks * 3 * NT * 64;
     for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int k = idx % 64;
-        size_t t = idx / 64;
+        const int k = static_cast<int>(idx & 63);
+        unsigned t = static_cast<unsigned>(idx >> 6);   // (a layer's pack has < 2^32 elements: 32-bit index decoding)
         const int n = t % NT;
         t /= NT;
         const int dx = t % 3;

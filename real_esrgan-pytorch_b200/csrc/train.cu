@@ -114,11 +114,16 @@ __global__ void __launch_bounds__(256) sum2x2_kernel(const uint16_t* __restrict_
                                                     uint16_t* __restrict__ out16, int N, int H, int W) {
     const size_t total = static_cast<size_t>(N) * H * W * 32;  // one thread per channel pair
     for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int cp = idx % 32;
-        const size_t pix = idx / 32;
-        const int x = pix % W;
-        const int y = (pix / W) % H;
-        const size_t n = pix / (static_cast<size_t>(W) * H);
+        const int cp = static_cast<int>(idx & 31);
+        const size_t pix = idx >> 5;
+        size_t rowi, n;   // 32-bit divisions whenever the index fits (64-bit ones are ~100-instruction subroutines)
+        int x, y;
+        if (pix <= 0xffffffffull) {
+            const unsigned p32 = static_cast<unsigned>(pix), r32 = p32 / static_cast<unsigned>(W);
+            x = static_cast<int>(p32 % static_cast<unsigned>(W)); y = static_cast<int>(r32 % static_cast<unsigned>(H)); n = r32 / static_cast<unsigned>(H);
+        } else {
+            rowi = pix / W; x = static_cast<int>(pix % W); y = static_cast<int>(rowi % H); n = rowi / H;
+        }
         float s0 = 0.f, s1 = 0.f;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
