@@ -491,6 +491,8 @@ int resr_generator_create(resr_generator_t** out, int in_channels, int out_chann
     if (prop.major != 10) return set_error(RESR_E_CUDA, "libresr needs an sm_100a device (found sm_%d%d)", prop.major, prop.minor);
     resr_generator* g = new resr_generator();
     g->num_sms = prop.multiProcessorCount;
+    if (getenv("RESR_NUM_SMS") && atoi(getenv("RESR_NUM_SMS")) > 0 && atoi(getenv("RESR_NUM_SMS")) < g->num_sms)
+        g->num_sms = atoi(getenv("RESR_NUM_SMS"));   // experiment knob: grids sized for a subset of the SMs (concurrent chains)
     const char* fm = getenv("RESR_CONV_MODE");
     if (fm) g->force_mode = atoi(fm);
     if (cudaMalloc(&g->wpack, table().pack_bytes) != cudaSuccess || cudaMalloc(&g->bias, table().bias_floats * 4) != cudaSuccess) {
