@@ -328,7 +328,15 @@ def training_bench(D, steps, warmup, peaks, precision="bf16", with_optimizer=Tru
     k1, k2, sk = s0_kernels(B, device, seed=3)   # reference-range supports (7 .. 21), real sinc
     # software-pipelined data path: the degradation of batch k + 1 (its own CUDA graph, on a data stream) runs under the
     # training step of batch k, which is latency-bound at this size and leaves SM time free; two pipelines alternate
-    pipes = [ip.DegradePipeline(hr, k1, k2, sk, plan) for _ in range(2)]
+    # (the pipelines take decoded u8 images: the end-to-end variant below uploads a fresh batch from pinned host memory per
+    # step; the device-resident variant replays them on the batch that is already there)
+    pipes = [ip.DegradePipeline(hr, k1, k2, sk, plan, u8_images=True) for _ in range(2)]
+    img_host = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, generator=g).pin_memory()
+    loss_host = torch.zeros(1).pin_memory()
+    random.seed(12)
+    for p_ in pipes:
+        p_.images_u8.copy_(img_host)
+        p_.augment_ops.copy_(ip.draw_augment_ops(B))
     torch.manual_seed(0)
     gen = resr_b200.model.Generator(3, 3, 4).to(device).train()
     gen.set_precision(precision)
@@ -345,20 +353,25 @@ def training_bench(D, steps, warmup, peaks, precision="bf16", with_optimizer=Tru
     for e in done:
         e.record(cur)
 
-    def step(_):
+    def step(_, e2e=False):
         k = state["k"]
         state["k"] = k + 1
         i, nxt = k & 1, (k + 1) & 1
         data.wait_event(done[nxt])
         with torch.cuda.stream(data):
+            if e2e:
+                pipes[nxt].images_u8.copy_(img_host, non_blocking=True)   # the next batch: decoded u8 images from pinned host memory
             pipes[nxt]()
             ready[nxt].record(data)
         cur.wait_event(ready[i])
         state["loss"], _, _ = ts.step(pipes[i].lr, pipes[i].hr_crop, scatter=False)
+        if e2e:
+            loss_host.copy_(state["loss"].reshape(1), non_blocking=True)   # the step's result read back
         done[i].record(cur)
 
     ms = timed(step, steps, D, warm=max(3, warmup))
-    ms = D.max_ms(ms)[0]
+    ms_e2e = timed(lambda k: step(k, True), steps, D, warm=2)
+    ms, ms_e2e = D.max_ms(ms, ms_e2e)
     tflops = 3 * FLOP_PER_LR_PIXEL * B * (H // 4) * (W // 4) / (ms * 1e-3) / 1e12
     opt_info = None
     try:
@@ -383,6 +396,11 @@ def training_bench(D, steps, warmup, peaks, precision="bf16", with_optimizer=Tru
         opt_info = None if not with_optimizer else {"error": repr(e)}
     return {"metric": "training pairs/s", "value": world * B / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms, "n_gpus": world,
             "scaling": "weak", "loss": float(state["loss"].item()), "cuda_graph": bool(ts.is_graph), "optimizer": opt_info,
+            "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": img_host.numel(), "d2h_bytes_per_step": 4,
+                    "api": "per step: 16 decoded u8 HR images from pinned host memory -> DegradePipeline(u8_images=True) (augmentation + "
+                           "degradation, one CUDA graph, on the data stream under the previous step) -> autograd.TrainStep.step; the loss "
+                           "is read back to pinned host memory"},
             "precision": {"fp16": "fp16 activations, bf16 gradients, weight gradients through channels-first copies (wgrad_tc.cu)",
                           "bf16": "bf16 activations and gradients (north_star's recipe), fp32 residual stream, weight gradients "
                                   "straight from the NHWC buffers (wgrad_mn.cu)"}[precision],
